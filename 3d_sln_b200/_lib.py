@@ -1,0 +1,158 @@
+"""ctypes binding of libsln_b200.so (C ABI declared in include/sln_b200.h).
+
+There is no CPU fallback: if the shared library cannot be loaded (and cannot be built with nvcc), every hot-path
+call raises.  The library is built in-tree (``3d_sln_b200/libsln_b200.so``) so that it travels with the repo snapshot.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG_DIR, "csrc")
+LIB_PATH = os.path.join(_PKG_DIR, "libsln_b200.so")
+INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
+
+SOURCES = ["vae_engine.cu", "raster.cu", "spade.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _sources():
+    return [os.path.join(_CSRC, s) for s in SOURCES if os.path.exists(os.path.join(_CSRC, s))]
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [os.path.join(INCLUDE_DIR, "sln_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into libsln_b200.so (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("3d_sln_b200: nvcc not found and %s is missing/stale; cannot build the CUDA library" % LIB_PATH)
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + [f for f in NVCC_FLAGS] + ["-I", INCLUDE_DIR, "-o", tmp] + _sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("3d_sln_b200: nvcc failed\n%s\n%s" % (" ".join(cmd), res.stderr[-8000:]))
+    if verbose:
+        print(res.stderr)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+class VaeDesc(ctypes.Structure):
+    """Mirror of ``sln_vae_desc`` (include/sln_b200.h)."""
+    _fields_ = [
+        ("embedding_dim", ctypes.c_int32), ("n_layers", ctypes.c_int32), ("recurrent", ctypes.c_int32),
+        ("norm", ctypes.c_int32), ("training", ctypes.c_int32), ("box_dim", ctypes.c_int32),
+        ("n_angle", ctypes.c_int32), ("num_objs", ctypes.c_int32), ("num_preds", ctypes.c_int32),
+        ("num_attrs", ctypes.c_int32), ("bn_eps", ctypes.c_float), ("bn_momentum", ctypes.c_float),
+        ("gconv_dim_override", ctypes.c_int32), ("gconv_hidden_override", ctypes.c_int32),
+    ]
+
+
+_P = ctypes.c_void_p
+_I64 = ctypes.c_int64
+_I32 = ctypes.c_int32
+_SZ = ctypes.c_size_t
+_F = ctypes.c_float
+_DESC = ctypes.POINTER(VaeDesc)
+
+# name -> (restype, argtypes); one entry per symbol declared in include/sln_b200.h
+SIGNATURES = {
+    "sln_version": (ctypes.c_int, []),
+    "sln_last_error": (ctypes.c_char_p, []),
+    "sln_vae_num_params": (ctypes.c_int, [_DESC]),
+    "sln_vae_num_bn": (ctypes.c_int, [_DESC]),
+    "sln_vae_workspace_bytes": (_SZ, [_DESC, _I64, _I64, ctypes.c_int]),
+    "sln_vae_encoder_fwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),
+    "sln_vae_encoder_bwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _I64, _I64, _P, _SZ, _P]),
+    "sln_vae_decoder_fwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),
+    "sln_vae_decoder_bwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, ctypes.c_int, _P, _I64, _I64, _P, _SZ, _P]),
+    "sln_gconv_layer_fwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),
+    "sln_gconv_layer_bwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),
+    "sln_gconv_pool_workspace_bytes": (_SZ, [_I64, _I64]),
+    "sln_csr_build": (ctypes.c_int, [_P, _I64, _I64, _I64, _P, _SZ, _P]),
+    "sln_gconv_pool_fwd": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P, _SZ, _P]),
+    "sln_csr_pointers": (ctypes.c_int, [_P, _I64, _I64, ctypes.POINTER(_P), ctypes.POINTER(_P)]),
+    "sln_reparam_fwd": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P]),
+    "sln_reparam_bwd": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P, _P]),
+    "sln_vae_loss": (ctypes.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P, _I32, _F, _I64, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P]),
+    "sln_adam_step": (ctypes.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P, _I32, _P]),
+}
+
+
+def declared_symbols():
+    """Symbols declared in include/sln_b200.h (parsed from the header, used by the CPU-side ABI test)."""
+    import re
+    with open(os.path.join(INCLUDE_DIR, "sln_b200.h")) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sln_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    """Load (building if needed) the CUDA library.  Raises RuntimeError when it is unavailable — no fallback."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if _stale():
+            build()
+        try:
+            lib = ctypes.CDLL(LIB_PATH)
+        except OSError as e:
+            raise RuntimeError("3d_sln_b200: cannot load %s (%s); the hot path has no CPU/PyTorch fallback" % (LIB_PATH, e))
+        for name, (res, args) in SIGNATURES.items():
+            if not hasattr(lib, name):
+                continue  # optional components (raster/spade) may be absent in a partial build; checked by tests
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.sln_version() != 1:
+            raise RuntimeError("3d_sln_b200: ABI version mismatch (library %d, binding 1)" % lib.sln_version())
+        _lib = lib
+        return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().sln_last_error()
+        raise RuntimeError("3d_sln_b200 %s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None) as an int for ctypes."""
+    return None if t is None else t.data_ptr()
+
+
+def cur_stream(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr_array(items):
+    """Host array of device pointers (void*[]) from tensors / ints / None."""
+    arr = (ctypes.c_void_p * max(len(items), 1))()
+    for i, it in enumerate(items):
+        if it is None:
+            arr[i] = None
+        elif isinstance(it, int):
+            arr[i] = it
+        else:
+            arr[i] = it.data_ptr()
+    return arr

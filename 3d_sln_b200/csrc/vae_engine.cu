@@ -1,0 +1,831 @@
+// Host-side orchestration + C ABI of the VAE-graph hot path (see include/sln_b200.h).
+// One call = one whole encoder/decoder forward or backward: a fixed sequence of launches on the caller's stream,
+// no allocation, no synchronisation -> capturable in a CUDA graph.
+//
+// Reference being replaced: models/graph.py:57-143 (GraphTripleConv[Net]), models/Sg2ScVAE_model.py:115-188
+// (encoder / decoder / forward), utils.py:12-33 (losses), train.py:82-84 (Adam).
+#include <stdarg.h>
+
+#include "../../include/sln_b200.h"
+#include "vae_kernels.cuh"
+
+namespace sln {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+namespace {
+
+constexpr int kMaxLayers = 32;
+
+struct Lin {
+  const float* W; const float* b; float* dW; float* db; int in, out;
+};
+struct Blk {  // Linear [+ BatchNorm1d] [+ ReLU]   (reference graph.py:10-27)
+  Lin lin;
+  int has_bn, relu;
+  const float* gamma; const float* beta; float* dgamma; float* dbeta;
+  float* rm; float* rv; long long* nbt;
+};
+struct BlkState {  // per-instance saved tensors (workspace)
+  float* y;  // pre-BN output [M, out]
+  int M;
+  float *mean, *rstd, *scale, *shift;  // BN statistics / lazy affine [out]
+  float *p, *q, *r;                    // BN-backward coefficients [out]
+  float* partial;                      // [2 * ceil(M/64) * out]
+  unsigned* counter;
+  float* g;  // masked gradient w.r.t. the post-activation output [M, out] (backward scratch)
+};
+
+struct Dims {
+  int E, D, H, Z, L, Lw, obj_w, attr_w, box_w, ang_w, box_dim, n_angle;
+  int norm, training;
+  float eps, momentum;
+};
+
+struct Model {
+  const float* emb[7];
+  float* demb[7];
+  Blk box_emb;
+  Blk enc[kMaxLayers][4], dec[kMaxLayers][4];
+  Blk bmv[2], amv[2], box_mean, box_var, angle_mean, angle_var, box_net[2], angle_net[2];
+};
+
+struct Ctx {
+  cudaStream_t st;
+  Dims dm;
+};
+
+int make_dims(const sln_vae_desc* d, Dims* o) {
+  SLN_CHECK_ARG(d != nullptr, "null model descriptor");
+  SLN_CHECK_ARG(d->embedding_dim > 0 && d->embedding_dim % 4 == 0, "embedding_dim must be a positive multiple of 4 (got %d)", d->embedding_dim);
+  SLN_CHECK_ARG(d->n_layers >= 1 && d->n_layers <= kMaxLayers, "gconv_num_layers must be in [1,%d] (got %d)", kMaxLayers, d->n_layers);
+  SLN_CHECK_ARG(d->norm == 0 || d->norm == 1, "norm must be 0 ('none') or 1 ('batch')");
+  SLN_CHECK_ARG(d->box_dim == 6 || d->box_dim == 4, "box_dim must be 6 or 4");
+  SLN_CHECK_ARG(d->n_angle > 0 && d->num_objs > 0 && d->num_preds > 0 && d->num_attrs > 0, "vocabulary sizes must be positive");
+  o->E = d->embedding_dim; o->D = 2 * o->E; o->H = 4 * o->E; o->Z = o->E;
+  if (d->gconv_dim_override > 0) o->D = d->gconv_dim_override;      // standalone GraphTripleConv only
+  if (d->gconv_hidden_override > 0) o->H = d->gconv_hidden_override;
+  SLN_CHECK_ARG(o->D % 4 == 0 && o->H % 4 == 0, "gconv dims must be multiples of 4 (D=%d, H=%d)", o->D, o->H);
+  o->L = d->n_layers; o->Lw = d->recurrent ? 1 : d->n_layers;
+  o->obj_w = o->E * 3 / 4; o->attr_w = o->E / 4; o->box_w = o->E * 3 / 4; o->ang_w = o->E / 4;
+  o->box_dim = d->box_dim; o->n_angle = d->n_angle;
+  o->norm = d->norm; o->training = d->training;
+  o->eps = d->bn_eps; o->momentum = d->bn_momentum;
+  return SLN_OK;
+}
+
+int count_params(const Dims& dm) {
+  int bn = dm.norm ? 2 : 0;
+  int n = 7;
+  n += 2;                              // box_embeddings
+  n += 2 * dm.Lw * 4 * (2 + bn);       // enc + dec gconv
+  n += 4 * (2 + bn);                   // box_mean_var, angle_mean_var
+  n += 4 * 2;                          // box_mean/var, angle_mean/var
+  n += (2 + bn) + 2 + (2 + bn) + 2;    // box_net, angle_net
+  return n;
+}
+int count_bn(const Dims& dm) { return dm.norm ? (2 * dm.Lw * 4 + 4 + 2) : 0; }
+
+struct TableReader {
+  const void* const* params; void* const* grads; void* const* bn; int ip, ib; int norm;
+  Blk take(int in, int out, bool with_bn, bool relu) {
+    Blk b; memset(&b, 0, sizeof(b));
+    b.lin.in = in; b.lin.out = out; b.relu = relu ? 1 : 0;
+    b.lin.W = (const float*)params[ip]; b.lin.dW = grads ? (float*)grads[ip] : nullptr; ++ip;
+    b.lin.b = (const float*)params[ip]; b.lin.db = grads ? (float*)grads[ip] : nullptr; ++ip;
+    if (with_bn && norm) {
+      b.has_bn = 1;
+      b.gamma = (const float*)params[ip]; b.dgamma = grads ? (float*)grads[ip] : nullptr; ++ip;
+      b.beta = (const float*)params[ip]; b.dbeta = grads ? (float*)grads[ip] : nullptr; ++ip;
+      if (bn) { b.rm = (float*)bn[ib]; b.rv = (float*)bn[ib + 1]; b.nbt = (long long*)bn[ib + 2]; }
+      ib += 3;
+    }
+    return b;
+  }
+};
+
+void take_gconv(TableReader& tr, const Dims& dm, Blk* blk) {
+  blk[0] = tr.take(3 * dm.D, dm.H, true, true);
+  blk[1] = tr.take(dm.H, 2 * dm.H + dm.D, true, true);
+  blk[2] = tr.take(dm.H, dm.H, true, true);
+  blk[3] = tr.take(dm.H, dm.D, true, true);
+}
+
+int parse_model(const Dims& dm, const void* const* params, void* const* grads, void* const* bn, Model* m) {
+  SLN_CHECK_ARG(params != nullptr, "null parameter table");
+  memset(m, 0, sizeof(Model));
+  for (int i = 0; i < 7; ++i) { m->emb[i] = (const float*)params[i]; m->demb[i] = grads ? (float*)grads[i] : nullptr; }
+  TableReader tr{params, grads, bn, 7, 0, dm.norm};
+  m->box_emb = tr.take(dm.box_dim, dm.box_w, false, false);
+  for (int l = 0; l < dm.Lw; ++l) take_gconv(tr, dm, m->enc[l]);
+  for (int l = dm.Lw; l < dm.L; ++l) for (int k = 0; k < 4; ++k) m->enc[l][k] = m->enc[0][k];
+  for (int l = 0; l < dm.Lw; ++l) take_gconv(tr, dm, m->dec[l]);
+  for (int l = dm.Lw; l < dm.L; ++l) for (int k = 0; k < 4; ++k) m->dec[l][k] = m->dec[0][k];
+  m->bmv[0] = tr.take(dm.D, dm.H, true, true);
+  m->bmv[1] = tr.take(dm.H, dm.D, true, true);
+  m->amv[0] = tr.take(dm.D, dm.H, true, true);
+  m->amv[1] = tr.take(dm.H, dm.D, true, true);
+  m->box_mean = tr.take(dm.D, dm.box_w, false, false);
+  m->box_var = tr.take(dm.D, dm.box_w, false, false);
+  m->angle_mean = tr.take(dm.D, dm.ang_w, false, false);
+  m->angle_var = tr.take(dm.D, dm.ang_w, false, false);
+  m->box_net[0] = tr.take(dm.D + dm.attr_w, dm.H, true, true);
+  m->box_net[1] = tr.take(dm.H, dm.box_dim, false, false);
+  m->angle_net[0] = tr.take(dm.D, dm.H, true, true);
+  m->angle_net[1] = tr.take(dm.H, dm.n_angle, false, false);
+  if (tr.ip != count_params(dm)) { set_error("internal: parameter table walk mismatch (%d vs %d)", tr.ip, count_params(dm)); return SLN_EINVAL; }
+  return SLN_OK;
+}
+
+// ---------------------------------------------------------------- workspace plans
+struct CounterPool { unsigned* base; int n, cap; };
+
+void plan_state(Arena& ar, CounterPool& cp, int M, int out, BlkState* s) {
+  s->M = M;
+  s->y = ar.take<float>((size_t)M * out);
+  s->mean = ar.take<float>(out); s->rstd = ar.take<float>(out); s->scale = ar.take<float>(out); s->shift = ar.take<float>(out);
+  s->p = ar.take<float>(out); s->q = ar.take<float>(out); s->r = ar.take<float>(out);
+  s->partial = ar.take<float>((size_t)2 * max_row_tiles(M) * out);
+  s->counter = cp.base + cp.n; cp.n++;
+  s->g = nullptr;
+}
+
+void plan_graph(Arena& ar, int O, int T, Graph* g, int** deg, int** err) {
+  g->O = O; g->T = T;
+  g->s_idx = ar.take<int>(T); g->p_idx = ar.take<int>(T); g->o_idx = ar.take<int>(T);
+  g->row_ptr = ar.take<int>(O + 1); g->ent = ar.take<int>((size_t)2 * T);
+  g->inv_cnt = ar.take<float>(O); g->cursor = ar.take<int>(O);
+  *deg = ar.take<int>(O); *err = ar.take<int>(1);
+}
+
+struct GconvScratch { float *g1, *g2, *g3, *g4, *dpooled, *dcat[2]; };
+void plan_gconv_scratch(Arena& ar, const Dims& dm, int O, int T, GconvScratch* s) {
+  s->g1 = ar.take<float>((size_t)T * dm.H);
+  s->g2 = ar.take<float>((size_t)T * (2 * dm.H + dm.D));
+  s->g3 = ar.take<float>((size_t)O * dm.H);
+  s->g4 = ar.take<float>((size_t)O * dm.D);
+  s->dpooled = ar.take<float>((size_t)O * dm.H);
+  s->dcat[0] = ar.take<float>((size_t)T * 3 * dm.D);
+  s->dcat[1] = ar.take<float>((size_t)T * 3 * dm.D);
+}
+
+struct NetPlan {
+  Graph g; int* deg; int* err;
+  int *objs32, *attrs32, *angles32;
+  float *obj0, *pred0;
+  BlkState st[kMaxLayers][4];
+  float* pooled[kMaxLayers];
+  GconvScratch sc;
+  float* dobj0;
+  // encoder heads
+  BlkState bmv[2], amv[2];
+  float *tmpA, *tmpB;
+  // decoder heads
+  BlkState box_net0, angle_net0;
+  float *logits, *logp, *dlogits, *tmpC;
+  CounterPool cp;
+  size_t bytes;
+};
+
+constexpr int kCounterCap = 4 * kMaxLayers + 16;
+
+// which: 0 encoder, 1 decoder, 2 single standalone layer
+void make_plan(const Dims& dm, int O, int T, int which, void* ws, NetPlan* p) {
+  Arena ar(ws, (size_t)-1);
+  memset(p, 0, sizeof(NetPlan));
+  p->cp.base = ar.take<unsigned>(kCounterCap); p->cp.n = 0; p->cp.cap = kCounterCap;
+  plan_graph(ar, O, T, &p->g, &p->deg, &p->err);
+  p->objs32 = ar.take<int>(O); p->attrs32 = ar.take<int>(O); p->angles32 = ar.take<int>(O);
+  p->obj0 = ar.take<float>((size_t)O * dm.D);
+  p->pred0 = ar.take<float>((size_t)T * dm.D);
+  const int L = which == 2 ? 1 : dm.L;
+  for (int l = 0; l < L; ++l) {
+    plan_state(ar, p->cp, T, dm.H, &p->st[l][0]);
+    plan_state(ar, p->cp, T, 2 * dm.H + dm.D, &p->st[l][1]);
+    plan_state(ar, p->cp, O, dm.H, &p->st[l][2]);
+    plan_state(ar, p->cp, O, dm.D, &p->st[l][3]);
+    p->pooled[l] = ar.take<float>((size_t)O * dm.H);
+  }
+  plan_gconv_scratch(ar, dm, O, T, &p->sc);
+  for (int l = 0; l < L; ++l) { p->st[l][0].g = p->sc.g1; p->st[l][1].g = p->sc.g2; p->st[l][2].g = p->sc.g3; p->st[l][3].g = p->sc.g4; }
+  p->dobj0 = ar.take<float>((size_t)O * dm.D);
+  if (which == 0) {
+    plan_state(ar, p->cp, O, dm.H, &p->bmv[0]); plan_state(ar, p->cp, O, dm.D, &p->bmv[1]);
+    plan_state(ar, p->cp, O, dm.H, &p->amv[0]); plan_state(ar, p->cp, O, dm.D, &p->amv[1]);
+    p->bmv[0].g = ar.take<float>((size_t)O * dm.H); p->bmv[1].g = ar.take<float>((size_t)O * dm.D);
+    p->amv[0].g = ar.take<float>((size_t)O * dm.H); p->amv[1].g = ar.take<float>((size_t)O * dm.D);
+    p->tmpA = ar.take<float>((size_t)O * dm.D); p->tmpB = ar.take<float>((size_t)O * dm.D);
+  } else if (which == 1) {
+    plan_state(ar, p->cp, O, dm.H, &p->box_net0); plan_state(ar, p->cp, O, dm.H, &p->angle_net0);
+    p->box_net0.g = ar.take<float>((size_t)O * dm.H); p->angle_net0.g = ar.take<float>((size_t)O * dm.H);
+    p->logits = ar.take<float>((size_t)O * dm.n_angle); p->logp = ar.take<float>((size_t)O * dm.n_angle);
+    p->dlogits = ar.take<float>((size_t)O * dm.n_angle);
+    p->tmpC = ar.take<float>((size_t)O * (dm.D + dm.attr_w));
+  }
+  p->bytes = ar.off;
+}
+
+// ---------------------------------------------------------------- building blocks
+int norm_mode(const Ctx& c, const Blk& b) { return !b.has_bn ? NORM_NONE : (c.dm.training ? NORM_BN_TRAIN : NORM_BN_EVAL); }
+
+MatView block_out(const Blk& b, const BlkState& s) {
+  return make_view(s.y, b.lin.out, s.M, b.lin.out, b.has_bn ? s.scale : nullptr, b.has_bn ? s.shift : nullptr, b.relu);
+}
+MatView slice_cols(const MatView& v, int off, int width) {
+  return make_view(v.p + off, v.ld, v.rows, width, v.scale ? v.scale + off : nullptr, v.shift ? v.shift + off : nullptr, v.relu);
+}
+MatView weight_view(const Lin& l) { return make_view(l.W, l.in, l.out, l.in); }
+
+template <class AOp>
+int block_fwd(const Ctx& c, const AOp& A, int M, const Blk& b, BlkState& s, float* out = nullptr, int ldo = 0) {
+  EpiStore epi; memset(&epi, 0, sizeof(epi));
+  epi.C = out ? out : s.y; epi.ldc = out ? ldo : b.lin.out; epi.bias = b.lin.b;
+  int mode = norm_mode(c, b);
+  if (mode == NORM_BN_TRAIN) {
+    BnFwdFin& f = epi.fin;
+    f.enabled = 1; f.partial = s.partial; f.counter = s.counter; f.gamma = b.gamma; f.beta = b.beta;
+    f.running_mean = b.rm; f.running_var = b.rv; f.nbt = b.nbt;
+    f.mean = s.mean; f.rstd = s.rstd; f.scale = s.scale; f.shift = s.shift;
+    f.eps = c.dm.eps; f.momentum = c.dm.momentum; f.M = M;
+  } else if (mode == NORM_BN_EVAL) {
+    SLN_CHECK_ARG(b.rm && b.rv, "eval-mode BatchNorm needs running statistics");
+    k_bn_eval_prep<<<ceil_div(b.lin.out, 128), 128, 0, c.st>>>(b.gamma, b.beta, b.rm, b.rv, c.dm.eps, b.lin.out, s.mean, s.rstd, s.scale, s.shift);
+    SLN_TRY(check_launch("bn_eval_prep"));
+  }
+  return launch_gemm<true, true>(c.st, A, weight_view(b.lin), epi, M, b.lin.out, b.lin.in, false, "linear_fwd");
+}
+
+DyView blk_dy(const Ctx& c, const Blk& b, const BlkState& s) {
+  int mode = norm_mode(c, b);
+  if (mode == NORM_NONE) return make_dy(s.g, b.lin.out, s.M, b.lin.out);
+  if (mode == NORM_BN_EVAL) return make_dy(s.g, b.lin.out, s.M, b.lin.out, nullptr, 0, s.p);
+  return make_dy(s.g, b.lin.out, s.M, b.lin.out, s.y, b.lin.out, s.p, s.q, s.r);
+}
+BnBwdFin blk_fin(const Ctx& c, const Blk& b, const BlkState& s) {
+  BnBwdFin f; memset(&f, 0, sizeof(f));
+  f.mode = norm_mode(c, b); f.partial = s.partial; f.counter = s.counter; f.gamma = b.gamma;
+  f.mean = s.mean; f.rstd = s.rstd; f.scale = s.scale; f.p = s.p; f.q = s.q; f.r = s.r;
+  f.dgamma = b.dgamma; f.dbeta = b.dbeta; f.dbias = b.lin.db; f.M = s.M;
+  return f;
+}
+ActInfo blk_act(const Blk& b, const BlkState& s) {
+  ActInfo a; memset(&a, 0, sizeof(a));
+  a.has_act = 1; a.y = s.y; a.ldy = b.lin.out;
+  if (b.has_bn) { a.scale = s.scale; a.shift = s.shift; a.mean = s.mean; a.rstd = s.rstd; }
+  return a;
+}
+
+// dW[out,in] += dy^T X     (split along the sample dimension, RED.ADD)
+template <class XOp>
+int bwd_w(const Ctx& c, const DyView& dy, const XOp& X, const Lin& lin, int M) {
+  if (!lin.dW) return SLN_OK;
+  EpiAtomic epi{lin.dW, lin.in};
+  return launch_gemm<false, false>(c.st, dy, X, epi, lin.out, lin.in, M, true, "linear_bwd_w");
+}
+// dX[M,in] = dy W
+int bwd_x_plain(const Ctx& c, const DyView& dy, const Lin& lin, int M, float* dX, int ldx) {
+  EpiStore epi; memset(&epi, 0, sizeof(epi));
+  epi.C = dX; epi.ldc = ldx;
+  return launch_gemm<true, false>(c.st, dy, weight_view(lin), epi, M, lin.in, lin.out, false, "linear_bwd_x");
+}
+// prev.g = relu_mask(prev) ? (dy W + add) : 0, with the BN-backward reduction of `prev` fused in the epilogue.
+int bwd_x_masked(const Ctx& c, const DyView& dy, const Lin& lin, int M, const Blk& pb, BlkState& ps, const float* add, int ldadd) {
+  EpiMaskReduce epi; memset(&epi, 0, sizeof(epi));
+  epi.G = ps.g; epi.ldg = pb.lin.out; epi.add = add; epi.ldadd = ldadd;
+  epi.yprev = ps.y; epi.ldy = pb.lin.out;
+  if (pb.has_bn) { epi.scale = ps.scale; epi.shift = ps.shift; epi.mean = ps.mean; epi.rstd = ps.rstd; }
+  epi.fin = blk_fin(c, pb, ps);
+  SLN_CHECK_ARG(lin.in == pb.lin.out, "internal: masked backward expects matching widths (%d vs %d)", lin.in, pb.lin.out);
+  return launch_gemm<true, false>(c.st, dy, weight_view(lin), epi, M, lin.in, lin.out, false, "linear_bwd_x_masked");
+}
+// bias gradient of a Linear whose dy is given directly: db += column sums
+int bwd_bias_plain(const Ctx& c, const float* dy, int ld, int M, const Lin& lin) {
+  if (!lin.db) return SLN_OK;
+  k_embed_bwd<<<1, 128, 0, c.st>>>(dy, ld, nullptr, 0, nullptr, M, lin.out, lin.db, lin.out);
+  return check_launch("bias_grad");
+}
+
+int graph_prep(const Ctx& c, NetPlan& p, const int64_t* triples_or_edges, int stride3) {
+  const Graph& g = p.g;
+  SLN_CUDA_TRY(cudaMemsetAsync(p.deg, 0, sizeof(int) * g.O, c.st));
+  SLN_CUDA_TRY(cudaMemsetAsync(g.cursor, 0, sizeof(int) * g.O, c.st));
+  SLN_CUDA_TRY(cudaMemsetAsync(p.err, 0, sizeof(int), c.st));
+  (void)stride3;
+  if (g.T > 0) {
+    k_split_triples<<<ceil_div(g.T, 256), 256, 0, c.st>>>((const long long*)triples_or_edges, g.T, g.O, g.s_idx, g.p_idx, g.o_idx, p.deg, p.err);
+    SLN_TRY(check_launch("split_triples"));
+  }
+  k_scan_deg<<<1, 1024, 0, c.st>>>(p.deg, g.O, g.row_ptr, g.inv_cnt);
+  SLN_TRY(check_launch("scan_deg"));
+  if (g.T > 0) {
+    k_fill_csr<<<ceil_div(g.T, 256), 256, 0, c.st>>>(g.s_idx, g.o_idx, g.T, g.row_ptr, g.cursor, g.ent);
+    SLN_TRY(check_launch("fill_csr"));
+    k_sort_rows<<<ceil_div(g.O, 128), 128, 0, c.st>>>(g.row_ptr, g.O, g.ent);
+    SLN_TRY(check_launch("sort_rows"));
+  }
+  return SLN_OK;
+}
+
+// edges [T,2] variant for the standalone layer: same kernel with a 2-wide stride
+__global__ void k_split_edges(const long long* __restrict__ edges, int T, int O, int* s_idx, int* o_idx, int* deg, int* err) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  long long s = edges[(size_t)t * 2 + 0], o = edges[(size_t)t * 2 + 1];
+  if (s < 0 || s >= O || o < 0 || o >= O) { atomicExch(err, 1); s = 0; o = 0; }
+  s_idx[t] = (int)s; o_idx[t] = (int)o;
+  atomicAdd(deg + s, 1);
+  atomicAdd(deg + o, 1);
+}
+int graph_prep_edges(cudaStream_t st, Graph& g, int* deg, int* err, const int64_t* edges) {
+  SLN_CUDA_TRY(cudaMemsetAsync(deg, 0, sizeof(int) * g.O, st));
+  SLN_CUDA_TRY(cudaMemsetAsync(g.cursor, 0, sizeof(int) * g.O, st));
+  SLN_CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
+  if (g.T > 0) {
+    k_split_edges<<<ceil_div(g.T, 256), 256, 0, st>>>((const long long*)edges, g.T, g.O, g.s_idx, g.o_idx, deg, err);
+    SLN_TRY(check_launch("split_edges"));
+  }
+  k_scan_deg<<<1, 1024, 0, st>>>(deg, g.O, g.row_ptr, g.inv_cnt);
+  SLN_TRY(check_launch("scan_deg"));
+  if (g.T > 0) {
+    k_fill_csr<<<ceil_div(g.T, 256), 256, 0, st>>>(g.s_idx, g.o_idx, g.T, g.row_ptr, g.cursor, g.ent);
+    SLN_TRY(check_launch("fill_csr"));
+    k_sort_rows<<<ceil_div(g.O, 128), 128, 0, st>>>(g.row_ptr, g.O, g.ent);
+    SLN_TRY(check_launch("sort_rows"));
+  }
+  return SLN_OK;
+}
+
+int gather_rows(const Ctx& c, const float* table, int ldt, const int* idx, int n, int width, float* out, int ldo, int off) {
+  if (n <= 0) return SLN_OK;
+  dim3 blk(32, 8);
+  k_gather_rows<<<ceil_div(n, 8), blk, 0, c.st>>>(table, ldt, idx, n, width, out, ldo, off);
+  return check_launch("gather_rows");
+}
+int embed_bwd(const Ctx& c, const float* a, int lda, const float* b, int ldb, const int* idx, int n, int width, float* tg, int rows) {
+  if (!tg || n <= 0) return SLN_OK;
+  k_embed_bwd<<<rows, 128, 0, c.st>>>(a, lda, b, ldb, idx, n, width, tg, width);
+  return check_launch("embed_bwd");
+}
+
+// ---------------------------------------------------------------- one GraphTripleConv layer
+int gconv_fwd(const Ctx& c, const Graph& g, const Blk* blk, BlkState* st, float* pooled, const MatView& obj_in,
+              const MatView& pred_in, MatView* obj_out, MatView* pred_out) {
+  const int D = c.dm.D, H = c.dm.H, O = g.O, T = g.T;
+  GatherCat gc{obj_in, pred_in, g.s_idx, g.o_idx, D, T, 3 * D};
+  SLN_TRY(block_fwd(c, gc, T, blk[0], st[0]));
+  SLN_TRY(block_fwd(c, block_out(blk[0], st[0]), T, blk[1], st[1]));
+  MatView a2 = block_out(blk[1], st[1]);
+  if (O > 0) {
+    int threads = min(256, max(32, ceil_div(H / 4, 32) * 32));
+    k_pool_fwd<<<O, threads, 0, c.st>>>(a2, g.row_ptr, g.ent, g.inv_cnt, O, H, D, pooled);
+    SLN_TRY(check_launch("pool_fwd"));
+  }
+  SLN_TRY(block_fwd(c, make_view(pooled, H, O, H), O, blk[2], st[2]));
+  SLN_TRY(block_fwd(c, block_out(blk[2], st[2]), O, blk[3], st[3]));
+  *obj_out = block_out(blk[3], st[3]);
+  *pred_out = slice_cols(a2, H, D);
+  return SLN_OK;
+}
+
+// Backward of one layer.  Precondition: st[3].g holds the masked gradient of the layer's obj output and its (p,q,r)
+// are finalised.  dpred_next: gradient w.r.t. the layer's pred output (null = 0).  Writes dcat [T,3D] = gradient w.r.t.
+// the virtual [obj[s] | pred | obj[o]] input.
+int gconv_bwd(const Ctx& c, const Graph& g, const Blk* blk, BlkState* st, const float* pooled, float* dpooled, const MatView& obj_in,
+              const MatView& pred_in, const float* dpred_next, int ld_dpred, float* dcat) {
+  const int D = c.dm.D, H = c.dm.H, O = g.O, T = g.T;
+  // net2, second Linear
+  DyView dy4 = blk_dy(c, blk[3], st[3]);
+  SLN_TRY(bwd_w(c, dy4, block_out(blk[2], st[2]), blk[3].lin, O));
+  SLN_TRY(bwd_x_masked(c, dy4, blk[3].lin, O, blk[2], st[2], nullptr, 0));
+  // net2, first Linear
+  DyView dy3 = blk_dy(c, blk[2], st[2]);
+  SLN_TRY(bwd_w(c, dy3, make_view(pooled, H, O, H), blk[2].lin, O));
+  SLN_TRY(bwd_x_plain(c, dy3, blk[2].lin, O, dpooled, H));
+  // pooling backward + BN-backward reduction of net1's second Linear
+  PoolBwdSrc src{dpooled, g.inv_cnt, g.s_idx, g.o_idx, dpred_next, ld_dpred, H, D};
+  SLN_TRY(launch_prep(c.st, src, blk_act(blk[1], st[1]), st[1].g, 2 * H + D, blk_fin(c, blk[1], st[1]), T, 2 * H + D, "pool_bwd_prep"));
+  // net1, second Linear
+  DyView dy2 = blk_dy(c, blk[1], st[1]);
+  SLN_TRY(bwd_w(c, dy2, block_out(blk[0], st[0]), blk[1].lin, T));
+  SLN_TRY(bwd_x_masked(c, dy2, blk[1].lin, T, blk[0], st[0], nullptr, 0));
+  // net1, first Linear
+  DyView dy1 = blk_dy(c, blk[0], st[0]);
+  GatherCat gc{obj_in, pred_in, g.s_idx, g.o_idx, D, T, 3 * D};
+  SLN_TRY(bwd_w(c, dy1, gc, blk[0].lin, T));
+  SLN_TRY(bwd_x_plain(c, dy1, blk[0].lin, T, dcat, 3 * D));
+  return SLN_OK;
+}
+
+// gradient of the node inputs from dcat: either masked against the previous layer's activation (+ its BN reduction)
+// or plain (first layer: the inputs are embeddings).
+int node_gather(const Ctx& c, const Graph& g, const float* dcat, const Blk* pblk, BlkState* pst, float* plain_out) {
+  const int D = c.dm.D;
+  NodeGatherSrc src{dcat, 3 * D, D, g.row_ptr, g.ent};
+  if (pblk) return launch_prep(c.st, src, blk_act(*pblk, *pst), pst->g, D, blk_fin(c, *pblk, *pst), g.O, D, "node_gather_prep");
+  ActInfo none; memset(&none, 0, sizeof(none));
+  BnBwdFin nofin; memset(&nofin, 0, sizeof(nofin));
+  return launch_prep(c.st, src, none, plain_out, D, nofin, g.O, D, "node_gather_plain");
+}
+
+int gconv_net_fwd(const Ctx& c, NetPlan& p, Blk (*blk)[4], MatView obj, MatView pred, MatView* obj_f) {
+  for (int l = 0; l < c.dm.L; ++l) {
+    MatView no, np;
+    SLN_TRY(gconv_fwd(c, p.g, blk[l], p.st[l], p.pooled[l], obj, pred, &no, &np));
+    obj = no; pred = np;
+  }
+  *obj_f = obj;
+  return SLN_OK;
+}
+
+MatView layer_obj_in(const Ctx& c, NetPlan& p, Blk (*blk)[4], int l) {
+  if (l == 0) return make_view(p.obj0, c.dm.D, p.g.O, c.dm.D);
+  return block_out(blk[l - 1][3], p.st[l - 1][3]);
+}
+MatView layer_pred_in(const Ctx& c, NetPlan& p, Blk (*blk)[4], int l) {
+  if (l == 0) return make_view(p.pred0, c.dm.D, p.g.T, c.dm.D);
+  return slice_cols(block_out(blk[l - 1][1], p.st[l - 1][1]), c.dm.H, c.dm.D);
+}
+
+// Precondition: p.st[L-1][3].g / (p,q,r) ready.  On return p.dobj0 [O,D] = gradient of the layer-0 node inputs,
+// *dpred0 points at the [T, ld 3D] slice holding the gradient of the layer-0 predicate inputs.
+int gconv_net_bwd(const Ctx& c, NetPlan& p, Blk (*blk)[4], const float** dpred0, int* ld_dpred0) {
+  const float* dpred_next = nullptr;
+  const int D = c.dm.D;
+  for (int l = c.dm.L - 1; l >= 0; --l) {
+    float* dcat = p.sc.dcat[l & 1];
+    SLN_TRY(gconv_bwd(c, p.g, blk[l], p.st[l], p.pooled[l], p.sc.dpooled, layer_obj_in(c, p, blk, l), layer_pred_in(c, p, blk, l),
+                      dpred_next, 3 * D, dcat));
+    if (l > 0) SLN_TRY(node_gather(c, p.g, dcat, &blk[l - 1][3], &p.st[l - 1][3], nullptr));
+    else SLN_TRY(node_gather(c, p.g, dcat, nullptr, nullptr, p.dobj0));
+    dpred_next = dcat + D;
+  }
+  *dpred0 = dpred_next; *ld_dpred0 = 3 * D;
+  return SLN_OK;
+}
+
+int check_ws(const NetPlan& p, const void* ws, size_t ws_bytes) {
+  SLN_CHECK_ARG(ws != nullptr, "null workspace");
+  SLN_CHECK_ARG((uintptr_t)ws % 256 == 0, "workspace must be 256-byte aligned");
+  if (ws_bytes < p.bytes) { set_error("workspace too small: %zu < %zu bytes", ws_bytes, p.bytes); return SLN_EWORKSPACE; }
+  return SLN_OK;
+}
+int to_i32(const Ctx& c, const int64_t* src, int n, int* dst, int limit, int* err) {
+  if (n <= 0) return SLN_OK;
+  k_i64_to_i32<<<ceil_div(n, 256), 256, 0, c.st>>>((const long long*)src, n, dst, limit, err);
+  return check_launch("i64_to_i32");
+}
+int check_dims(int64_t O, int64_t T) {
+  SLN_CHECK_ARG(O >= 1 && O < (1ll << 30), "O out of range: %lld", (long long)O);
+  SLN_CHECK_ARG(T >= 0 && T < (1ll << 30), "T out of range: %lld", (long long)T);
+  return SLN_OK;
+}
+
+}  // namespace
+}  // namespace sln
+
+using namespace sln;
+
+extern "C" {
+
+int sln_version(void) { return SLN_ABI_VERSION; }
+const char* sln_last_error(void) { return get_error(); }
+
+int sln_vae_num_params(const sln_vae_desc* d) { Dims dm; if (make_dims(d, &dm)) return -1; return count_params(dm); }
+int sln_vae_num_bn(const sln_vae_desc* d) { Dims dm; if (make_dims(d, &dm)) return -1; return count_bn(dm); }
+
+size_t sln_vae_workspace_bytes(const sln_vae_desc* d, int64_t O, int64_t T, int which) {
+  Dims dm;
+  if (make_dims(d, &dm) || check_dims(O, T)) return 0;
+  static thread_local NetPlan p;
+  make_plan(dm, (int)O, (int)T, which, nullptr, &p);
+  return p.bytes;
+}
+
+int sln_vae_encoder_fwd(const sln_vae_desc* d, const void* const* params, void* const* bn_bufs, const int64_t* objs,
+                        const int64_t* triples, const float* boxes, const int64_t* angles, const int64_t* attributes, int64_t O64,
+                        int64_t T64, float* mu, float* logvar, void* ws, size_t ws_bytes, void* stream) {
+  Ctx c; c.st = (cudaStream_t)stream;
+  SLN_TRY(make_dims(d, &c.dm)); SLN_TRY(check_dims(O64, T64));
+  SLN_CHECK_ARG(objs && boxes && angles && attributes && mu && logvar && (triples || T64 == 0), "null input/output pointer");
+  const Dims& dm = c.dm; const int O = (int)O64, T = (int)T64;
+  static thread_local Model m; static thread_local NetPlan p;
+  SLN_TRY(parse_model(dm, params, nullptr, bn_bufs, &m));
+  make_plan(dm, O, T, 0, ws, &p);
+  SLN_TRY(check_ws(p, ws, ws_bytes));
+  SLN_CUDA_TRY(cudaMemsetAsync(p.cp.base, 0, sizeof(unsigned) * kCounterCap, c.st));
+  SLN_TRY(graph_prep(c, p, triples, 1));
+  SLN_TRY(to_i32(c, objs, O, p.objs32, d->num_objs, p.err));
+  SLN_TRY(to_i32(c, attributes, O, p.attrs32, d->num_attrs, p.err));
+  SLN_TRY(to_i32(c, angles, O, p.angles32, d->n_angle, p.err));
+  // obj_vecs = [obj_emb | attr_emb | box_linear | angle_emb]   (Sg2ScVAE_model.py:121-129)
+  SLN_TRY(gather_rows(c, m.emb[0], dm.obj_w, p.objs32, O, dm.obj_w, p.obj0, dm.D, 0));
+  SLN_TRY(gather_rows(c, m.emb[1], dm.attr_w, p.attrs32, O, dm.attr_w, p.obj0, dm.D, dm.obj_w));
+  {
+    dim3 blk(32, 8);
+    k_small_linear<<<ceil_div(O, 8), blk, 0, c.st>>>(boxes, O, dm.box_dim, m.box_emb.lin.W, m.box_emb.lin.b, dm.box_w, p.obj0, dm.D, dm.obj_w + dm.attr_w);
+    SLN_TRY(check_launch("box_embeddings"));
+  }
+  SLN_TRY(gather_rows(c, m.emb[2], dm.ang_w, p.angles32, O, dm.ang_w, p.obj0, dm.D, dm.obj_w + dm.attr_w + dm.box_w));
+  SLN_TRY(gather_rows(c, m.emb[3], dm.D, p.g.p_idx, T, dm.D, p.pred0, dm.D, 0));
+  MatView obj_f;
+  SLN_TRY(gconv_net_fwd(c, p, m.enc, make_view(p.obj0, dm.D, O, dm.D), make_view(p.pred0, dm.D, T, dm.D), &obj_f));
+  // heads (Sg2ScVAE_model.py:134-143)
+  SLN_TRY(block_fwd(c, obj_f, O, m.bmv[0], p.bmv[0]));
+  SLN_TRY(block_fwd(c, block_out(m.bmv[0], p.bmv[0]), O, m.bmv[1], p.bmv[1]));
+  SLN_TRY(block_fwd(c, obj_f, O, m.amv[0], p.amv[0]));
+  SLN_TRY(block_fwd(c, block_out(m.amv[0], p.amv[0]), O, m.amv[1], p.amv[1]));
+  BlkState dummy; memset(&dummy, 0, sizeof(dummy)); dummy.M = O;
+  MatView hb = block_out(m.bmv[1], p.bmv[1]), ha = block_out(m.amv[1], p.amv[1]);
+  SLN_TRY(block_fwd(c, hb, O, m.box_mean, dummy, mu, dm.Z));
+  SLN_TRY(block_fwd(c, hb, O, m.box_var, dummy, logvar, dm.Z));
+  SLN_TRY(block_fwd(c, ha, O, m.angle_mean, dummy, mu + dm.box_w, dm.Z));
+  SLN_TRY(block_fwd(c, ha, O, m.angle_var, dummy, logvar + dm.box_w, dm.Z));
+  return SLN_OK;
+}
+
+int sln_vae_encoder_bwd(const sln_vae_desc* d, const void* const* params, void* const* grads, const float* boxes, const float* d_mu,
+                        const float* d_logvar, int64_t O64, int64_t T64, void* ws, size_t ws_bytes, void* stream) {
+  Ctx c; c.st = (cudaStream_t)stream;
+  SLN_TRY(make_dims(d, &c.dm)); SLN_TRY(check_dims(O64, T64));
+  SLN_CHECK_ARG(grads && boxes && d_mu && d_logvar, "null pointer");
+  const Dims& dm = c.dm; const int O = (int)O64, T = (int)T64;
+  static thread_local Model m; static thread_local NetPlan p;
+  SLN_TRY(parse_model(dm, params, grads, nullptr, &m));
+  make_plan(dm, O, T, 0, ws, &p);
+  SLN_TRY(check_ws(p, ws, ws_bytes));
+  const int L = dm.L;
+  MatView obj_f = block_out(m.enc[L - 1][3], p.st[L - 1][3]);
+  MatView hb = block_out(m.bmv[1], p.bmv[1]), ha = block_out(m.amv[1], p.amv[1]);
+  MatView hb1 = block_out(m.bmv[0], p.bmv[0]), ha1 = block_out(m.amv[0], p.amv[0]);
+  // --- box branch
+  DyView dmu_b = make_dy(d_mu, dm.Z, O, dm.box_w), dlv_b = make_dy(d_logvar, dm.Z, O, dm.box_w);
+  SLN_TRY(bwd_w(c, dmu_b, hb, m.box_mean.lin, O)); SLN_TRY(bwd_bias_plain(c, d_mu, dm.Z, O, m.box_mean.lin));
+  SLN_TRY(bwd_w(c, dlv_b, hb, m.box_var.lin, O)); SLN_TRY(bwd_bias_plain(c, d_logvar, dm.Z, O, m.box_var.lin));
+  SLN_TRY(bwd_x_plain(c, dmu_b, m.box_mean.lin, O, p.tmpA, dm.D));
+  SLN_TRY(bwd_x_masked(c, dlv_b, m.box_var.lin, O, m.bmv[1], p.bmv[1], p.tmpA, dm.D));
+  DyView dyb2 = blk_dy(c, m.bmv[1], p.bmv[1]);
+  SLN_TRY(bwd_w(c, dyb2, hb1, m.bmv[1].lin, O));
+  SLN_TRY(bwd_x_masked(c, dyb2, m.bmv[1].lin, O, m.bmv[0], p.bmv[0], nullptr, 0));
+  DyView dyb1 = blk_dy(c, m.bmv[0], p.bmv[0]);
+  SLN_TRY(bwd_w(c, dyb1, obj_f, m.bmv[0].lin, O));
+  SLN_TRY(bwd_x_plain(c, dyb1, m.bmv[0].lin, O, p.tmpB, dm.D));
+  // --- angle branch
+  DyView dmu_a = make_dy(d_mu + dm.box_w, dm.Z, O, dm.ang_w), dlv_a = make_dy(d_logvar + dm.box_w, dm.Z, O, dm.ang_w);
+  SLN_TRY(bwd_w(c, dmu_a, ha, m.angle_mean.lin, O)); SLN_TRY(bwd_bias_plain(c, d_mu + dm.box_w, dm.Z, O, m.angle_mean.lin));
+  SLN_TRY(bwd_w(c, dlv_a, ha, m.angle_var.lin, O)); SLN_TRY(bwd_bias_plain(c, d_logvar + dm.box_w, dm.Z, O, m.angle_var.lin));
+  SLN_TRY(bwd_x_plain(c, dmu_a, m.angle_mean.lin, O, p.tmpA, dm.D));
+  SLN_TRY(bwd_x_masked(c, dlv_a, m.angle_var.lin, O, m.amv[1], p.amv[1], p.tmpA, dm.D));
+  DyView dya2 = blk_dy(c, m.amv[1], p.amv[1]);
+  SLN_TRY(bwd_w(c, dya2, ha1, m.amv[1].lin, O));
+  SLN_TRY(bwd_x_masked(c, dya2, m.amv[1].lin, O, m.amv[0], p.amv[0], nullptr, 0));
+  DyView dya1 = blk_dy(c, m.amv[0], p.amv[0]);
+  SLN_TRY(bwd_w(c, dya1, obj_f, m.amv[0].lin, O));
+  // both branches meet at the last gconv layer's node output
+  SLN_TRY(bwd_x_masked(c, dya1, m.amv[0].lin, O, m.enc[L - 1][3], p.st[L - 1][3], p.tmpB, dm.D));
+  // --- graph conv stack
+  const float* dpred0; int ldp;
+  SLN_TRY(gconv_net_bwd(c, p, m.enc, &dpred0, &ldp));
+  // --- embeddings (Sg2ScVAE_model.py:121-129)
+  SLN_TRY(embed_bwd(c, p.dobj0, dm.D, nullptr, 0, p.objs32, O, dm.obj_w, m.demb[0], d->num_objs));
+  SLN_TRY(embed_bwd(c, p.dobj0 + dm.obj_w, dm.D, nullptr, 0, p.attrs32, O, dm.attr_w, m.demb[1], d->num_attrs));
+  {
+    const int off = dm.obj_w + dm.attr_w;
+    DyView dyb = make_dy(p.dobj0 + off, dm.D, O, dm.box_w);
+    SLN_TRY(bwd_w(c, dyb, make_view(boxes, dm.box_dim, O, dm.box_dim), m.box_emb.lin, O));
+    SLN_TRY(bwd_bias_plain(c, p.dobj0 + off, dm.D, O, m.box_emb.lin));
+  }
+  SLN_TRY(embed_bwd(c, p.dobj0 + dm.obj_w + dm.attr_w + dm.box_w, dm.D, nullptr, 0, p.angles32, O, dm.ang_w, m.demb[2], d->n_angle));
+  SLN_TRY(embed_bwd(c, dpred0, ldp, nullptr, 0, p.g.p_idx, T, dm.D, m.demb[3], d->num_preds));
+  return SLN_OK;
+}
+
+int sln_vae_decoder_fwd(const sln_vae_desc* d, const void* const* params, void* const* bn_bufs, const float* z, const int64_t* objs,
+                        const int64_t* triples, const int64_t* attributes, int64_t O64, int64_t T64, float* boxes_pred,
+                        float* angles_pred, void* ws, size_t ws_bytes, void* stream) {
+  Ctx c; c.st = (cudaStream_t)stream;
+  SLN_TRY(make_dims(d, &c.dm)); SLN_TRY(check_dims(O64, T64));
+  SLN_CHECK_ARG(z && objs && attributes && boxes_pred && angles_pred && (triples || T64 == 0), "null input/output pointer");
+  const Dims& dm = c.dm; const int O = (int)O64, T = (int)T64;
+  static thread_local Model m; static thread_local NetPlan p;
+  SLN_TRY(parse_model(dm, params, nullptr, bn_bufs, &m));
+  make_plan(dm, O, T, 1, ws, &p);
+  SLN_TRY(check_ws(p, ws, ws_bytes));
+  SLN_CUDA_TRY(cudaMemsetAsync(p.cp.base, 0, sizeof(unsigned) * kCounterCap, c.st));
+  SLN_TRY(graph_prep(c, p, triples, 1));
+  SLN_TRY(to_i32(c, objs, O, p.objs32, d->num_objs, p.err));
+  SLN_TRY(to_i32(c, attributes, O, p.attrs32, d->num_attrs, p.err));
+  // obj_vecs = [obj_emb_dc | attr_emb_dc | z]   (Sg2ScVAE_model.py:150-159, decoder_cat)
+  SLN_TRY(gather_rows(c, m.emb[4], dm.obj_w, p.objs32, O, dm.obj_w, p.obj0, dm.D, 0));
+  SLN_TRY(gather_rows(c, m.emb[5], dm.attr_w, p.attrs32, O, dm.attr_w, p.obj0, dm.D, dm.obj_w));
+  SLN_TRY(gather_rows(c, z, dm.Z, nullptr, O, dm.Z, p.obj0, dm.D, dm.obj_w + dm.attr_w));
+  SLN_TRY(gather_rows(c, m.emb[6], dm.D, p.g.p_idx, T, dm.D, p.pred0, dm.D, 0));
+  MatView obj_f;
+  SLN_TRY(gconv_net_fwd(c, p, m.dec, make_view(p.obj0, dm.D, O, dm.D), make_view(p.pred0, dm.D, T, dm.D), &obj_f));
+  // box_net on [obj_f | attr_vecs], angle_net on obj_f   (Sg2ScVAE_model.py:166-171)
+  Concat2 cat{obj_f, make_view(p.obj0 + dm.obj_w, dm.D, O, dm.attr_w), O, dm.D + dm.attr_w};
+  SLN_TRY(block_fwd(c, cat, O, m.box_net[0], p.box_net0));
+  BlkState dummy; memset(&dummy, 0, sizeof(dummy)); dummy.M = O;
+  SLN_TRY(block_fwd(c, block_out(m.box_net[0], p.box_net0), O, m.box_net[1], dummy, boxes_pred, dm.box_dim));
+  SLN_TRY(block_fwd(c, obj_f, O, m.angle_net[0], p.angle_net0));
+  SLN_TRY(block_fwd(c, block_out(m.angle_net[0], p.angle_net0), O, m.angle_net[1], dummy, p.logits, dm.n_angle));
+  k_log_softmax_fwd<<<ceil_div(O, 8), 256, 0, c.st>>>(p.logits, O, dm.n_angle, angles_pred);
+  SLN_TRY(check_launch("log_softmax_fwd"));
+  SLN_CUDA_TRY(cudaMemcpyAsync(p.logp, angles_pred, sizeof(float) * (size_t)O * dm.n_angle, cudaMemcpyDeviceToDevice, c.st));
+  return SLN_OK;
+}
+
+int sln_vae_decoder_bwd(const sln_vae_desc* d, const void* const* params, void* const* grads, const float* d_boxes, const float* d_angles,
+                        int angles_are_logits, float* d_z, int64_t O64, int64_t T64, void* ws, size_t ws_bytes, void* stream) {
+  Ctx c; c.st = (cudaStream_t)stream;
+  SLN_TRY(make_dims(d, &c.dm)); SLN_TRY(check_dims(O64, T64));
+  SLN_CHECK_ARG(grads && d_boxes && d_angles, "null pointer");
+  const Dims& dm = c.dm; const int O = (int)O64, T = (int)T64;
+  static thread_local Model m; static thread_local NetPlan p;
+  SLN_TRY(parse_model(dm, params, grads, nullptr, &m));
+  make_plan(dm, O, T, 1, ws, &p);
+  SLN_TRY(check_ws(p, ws, ws_bytes));
+  const int L = dm.L;
+  MatView obj_f = block_out(m.dec[L - 1][3], p.st[L - 1][3]);
+  const float* dlogits = d_angles;
+  if (!angles_are_logits) {
+    k_log_softmax_bwd<<<ceil_div(O, 8), 256, 0, c.st>>>(d_angles, p.logp, O, dm.n_angle, p.dlogits);
+    SLN_TRY(check_launch("log_softmax_bwd"));
+    dlogits = p.dlogits;
+  }
+  // angle_net
+  DyView dyl = make_dy(dlogits, dm.n_angle, O, dm.n_angle);
+  SLN_TRY(bwd_w(c, dyl, block_out(m.angle_net[0], p.angle_net0), m.angle_net[1].lin, O));
+  SLN_TRY(bwd_bias_plain(c, dlogits, dm.n_angle, O, m.angle_net[1].lin));
+  SLN_TRY(bwd_x_masked(c, dyl, m.angle_net[1].lin, O, m.angle_net[0], p.angle_net0, nullptr, 0));
+  // box_net
+  DyView dyb = make_dy(d_boxes, dm.box_dim, O, dm.box_dim);
+  SLN_TRY(bwd_w(c, dyb, block_out(m.box_net[0], p.box_net0), m.box_net[1].lin, O));
+  SLN_TRY(bwd_bias_plain(c, d_boxes, dm.box_dim, O, m.box_net[1].lin));
+  SLN_TRY(bwd_x_masked(c, dyb, m.box_net[1].lin, O, m.box_net[0], p.box_net0, nullptr, 0));
+  DyView dyb0 = blk_dy(c, m.box_net[0], p.box_net0);
+  Concat2 cat{obj_f, make_view(p.obj0 + dm.obj_w, dm.D, O, dm.attr_w), O, dm.D + dm.attr_w};
+  SLN_TRY(bwd_w(c, dyb0, cat, m.box_net[0].lin, O));
+  const int ldc = dm.D + dm.attr_w;
+  SLN_TRY(bwd_x_plain(c, dyb0, m.box_net[0].lin, O, p.tmpC, ldc));
+  DyView dya0 = blk_dy(c, m.angle_net[0], p.angle_net0);
+  SLN_TRY(bwd_w(c, dya0, obj_f, m.angle_net[0].lin, O));
+  SLN_TRY(bwd_x_masked(c, dya0, m.angle_net[0].lin, O, m.dec[L - 1][3], p.st[L - 1][3], p.tmpC, ldc));
+  // graph conv stack
+  const float* dpred0; int ldp;
+  SLN_TRY(gconv_net_bwd(c, p, m.dec, &dpred0, &ldp));
+  // embeddings + z
+  SLN_TRY(embed_bwd(c, p.dobj0, dm.D, nullptr, 0, p.objs32, O, dm.obj_w, m.demb[4], d->num_objs));
+  SLN_TRY(embed_bwd(c, p.dobj0 + dm.obj_w, dm.D, p.tmpC + dm.D, ldc, p.attrs32, O, dm.attr_w, m.demb[5], d->num_attrs));
+  SLN_TRY(embed_bwd(c, dpred0, ldp, nullptr, 0, p.g.p_idx, T, dm.D, m.demb[6], d->num_preds));
+  if (d_z) SLN_TRY(gather_rows(c, p.dobj0 + dm.obj_w + dm.attr_w, dm.D, nullptr, O, dm.Z, d_z, dm.Z, 0));
+  return SLN_OK;
+}
+
+// ---------------------------------------------------------------- standalone GraphTripleConv layer
+static int parse_layer(const Dims& dm, const void* const* lp, void* const* lg, void* const* lbn, Blk* blk) {
+  SLN_CHECK_ARG(lp != nullptr, "null layer parameter table");
+  TableReader tr{lp, lg, lbn, 0, 0, dm.norm};
+  take_gconv(tr, dm, blk);
+  return SLN_OK;
+}
+
+int sln_gconv_layer_fwd(const sln_vae_desc* d, const void* const* layer_params, void* const* layer_bn_bufs, const float* obj_vecs,
+                        const float* pred_vecs, const int64_t* edges, int64_t O64, int64_t T64, float* new_obj, float* new_pred,
+                        void* ws, size_t ws_bytes, void* stream) {
+  Ctx c; c.st = (cudaStream_t)stream;
+  SLN_TRY(make_dims(d, &c.dm)); SLN_TRY(check_dims(O64, T64));
+  SLN_CHECK_ARG(obj_vecs && new_obj && (T64 == 0 || (pred_vecs && edges && new_pred)), "null pointer");
+  const Dims& dm = c.dm; const int O = (int)O64, T = (int)T64;
+  Blk blk[4]; static thread_local NetPlan p;
+  SLN_TRY(parse_layer(dm, layer_params, nullptr, layer_bn_bufs, blk));
+  make_plan(dm, O, T, 2, ws, &p);
+  SLN_TRY(check_ws(p, ws, ws_bytes));
+  SLN_CUDA_TRY(cudaMemsetAsync(p.cp.base, 0, sizeof(unsigned) * kCounterCap, c.st));
+  SLN_TRY(graph_prep_edges(c.st, p.g, p.deg, p.err, edges));
+  MatView no, np;
+  SLN_TRY(gconv_fwd(c, p.g, blk, p.st[0], p.pooled[0], make_view(obj_vecs, dm.D, O, dm.D), make_view(pred_vecs, dm.D, T, dm.D), &no, &np));
+  dim3 b(32, 8);
+  k_materialize<<<ceil_div(O, 8), b, 0, c.st>>>(no, new_obj, dm.D);
+  SLN_TRY(check_launch("materialize_obj"));
+  if (T > 0) {
+    k_materialize<<<ceil_div(T, 8), b, 0, c.st>>>(np, new_pred, dm.D);
+    SLN_TRY(check_launch("materialize_pred"));
+  }
+  return SLN_OK;
+}
+
+int sln_gconv_layer_bwd(const sln_vae_desc* d, const void* const* layer_params, void* const* layer_grads, const float* obj_vecs,
+                        const float* pred_vecs, const float* d_new_obj, const float* d_new_pred, int64_t O64, int64_t T64, float* d_obj,
+                        float* d_pred, void* ws, size_t ws_bytes, void* stream) {
+  Ctx c; c.st = (cudaStream_t)stream;
+  SLN_TRY(make_dims(d, &c.dm)); SLN_TRY(check_dims(O64, T64));
+  SLN_CHECK_ARG(obj_vecs && d_new_obj && d_obj, "null pointer");
+  const Dims& dm = c.dm; const int O = (int)O64, T = (int)T64;
+  Blk blk[4]; static thread_local NetPlan p;
+  SLN_TRY(parse_layer(dm, layer_params, layer_grads, nullptr, blk));
+  make_plan(dm, O, T, 2, ws, &p);
+  SLN_TRY(check_ws(p, ws, ws_bytes));
+  // masked gradient of the node output + BN-backward reduction of net2's last Linear
+  PlainSrc src{d_new_obj, dm.D};
+  SLN_TRY(launch_prep(c.st, src, blk_act(blk[3], p.st[0][3]), p.st[0][3].g, dm.D, blk_fin(c, blk[3], p.st[0][3]), O, dm.D, "out_prep"));
+  float* dcat = p.sc.dcat[0];
+  SLN_TRY(gconv_bwd(c, p.g, blk, p.st[0], p.pooled[0], p.sc.dpooled, make_view(obj_vecs, dm.D, O, dm.D), make_view(pred_vecs, dm.D, T, dm.D),
+                    d_new_pred, dm.D, dcat));
+  SLN_TRY(node_gather(c, p.g, dcat, nullptr, nullptr, d_obj));
+  if (d_pred && T > 0) SLN_TRY(gather_rows(c, dcat + dm.D, 3 * dm.D, nullptr, T, dm.D, d_pred, dm.D, 0));
+  return SLN_OK;
+}
+
+// ---------------------------------------------------------------- pooling stage alone
+size_t sln_gconv_pool_workspace_bytes(int64_t O, int64_t T) {
+  Arena ar(nullptr, 0);
+  Graph g; int *deg, *err;
+  plan_graph(ar, (int)O, (int)T, &g, &deg, &err);
+  return ar.off;
+}
+int sln_csr_build(const int64_t* edges, int64_t edge_stride, int64_t O, int64_t T, void* ws, size_t ws_bytes, void* stream) {
+  SLN_TRY(check_dims(O, T));
+  SLN_CHECK_ARG(edge_stride == 2, "edges must be a contiguous [T,2] int64 tensor");
+  SLN_CHECK_ARG(ws && (uintptr_t)ws % 256 == 0 && ws_bytes >= sln_gconv_pool_workspace_bytes(O, T), "workspace missing, misaligned or too small");
+  Arena ar(ws, ws_bytes);
+  Graph g; int *deg, *err;
+  plan_graph(ar, (int)O, (int)T, &g, &deg, &err);
+  return graph_prep_edges((cudaStream_t)stream, g, deg, err, edges);
+}
+int sln_csr_pointers(void* ws, int64_t O, int64_t T, const int32_t** row_ptr, const int32_t** ent) {
+  Arena ar(ws, (size_t)-1);
+  Graph g; int *deg, *err;
+  plan_graph(ar, (int)O, (int)T, &g, &deg, &err);
+  *row_ptr = g.row_ptr; *ent = g.ent;
+  return SLN_OK;
+}
+int sln_gconv_pool_fwd(const float* new_t_vecs, int64_t O, int64_t T, int32_t H, int32_t Dout, float* pooled, const void* ws,
+                       size_t ws_bytes, void* stream) {
+  SLN_TRY(check_dims(O, T));
+  SLN_CHECK_ARG(new_t_vecs && pooled && ws, "null pointer");
+  SLN_CHECK_ARG(H > 0 && Dout >= 0, "bad feature sizes");
+  Arena ar((void*)ws, ws_bytes);
+  Graph g; int *deg, *err;
+  plan_graph(ar, (int)O, (int)T, &g, &deg, &err);
+  MatView a2 = make_view(new_t_vecs, 2 * H + Dout, (int)T, 2 * H + Dout);
+  int threads = min(256, max(32, ceil_div(H / 4, 32) * 32));
+  k_pool_fwd<<<(int)O, threads, 0, (cudaStream_t)stream>>>(a2, g.row_ptr, g.ent, g.inv_cnt, (int)O, H, Dout, pooled);
+  return check_launch("pool_fwd");
+}
+
+// ---------------------------------------------------------------- reparameterisation, losses, Adam
+int sln_reparam_fwd(const float* mu, const float* logvar, const float* eps, int64_t n, float* z, void* stream) {
+  SLN_CHECK_ARG(mu && logvar && eps && z && n >= 0, "bad argument");
+  if (n == 0) return SLN_OK;
+  k_reparam_fwd<<<(int)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(mu, logvar, eps, (int)n, z);
+  return check_launch("reparam_fwd");
+}
+int sln_reparam_bwd(const float* d_z, const float* logvar, const float* eps, int64_t n, float* d_mu, float* d_logvar, void* stream) {
+  SLN_CHECK_ARG(d_z && logvar && eps && d_mu && d_logvar && n >= 0, "bad argument");
+  if (n == 0) return SLN_OK;
+  k_reparam_bwd<<<(int)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(d_z, logvar, eps, (int)n, d_mu, d_logvar);
+  return check_launch("reparam_bwd");
+}
+
+int sln_vae_loss(const float* boxes_pred, const float* boxes_gt, int32_t box_dim, const float* angles_pred, const int64_t* angles_gt,
+                 int32_t n_angle, const float* mu, const float* logvar, int32_t Z, float kl_weight, int64_t O, float* losses, float* d_boxes,
+                 float* d_angles, int32_t angles_grad_is_logits, float* d_mu, float* d_logvar, void* scratch, size_t scratch_bytes, void* stream) {
+  SLN_CHECK_ARG(boxes_pred && boxes_gt && angles_pred && angles_gt && losses && scratch, "null pointer");
+  SLN_CHECK_ARG(O >= 1, "O must be >= 1");
+  SLN_CHECK_ARG((mu == nullptr) == (logvar == nullptr), "mu and logvar must both be given or both be null");
+  int blocks = (int)ceil_div64(O, 64);
+  SLN_CHECK_ARG(scratch_bytes >= 16 + (size_t)12 * blocks, "loss scratch too small");
+  LossArgs a;
+  a.boxes_pred = boxes_pred; a.boxes_gt = boxes_gt; a.BD = box_dim; a.logp = angles_pred; a.angles_gt = (const long long*)angles_gt;
+  a.NA = n_angle; a.mu = mu; a.logvar = logvar; a.Z = Z; a.kl_weight = kl_weight; a.O = (int)O;
+  a.logits_grad = angles_grad_is_logits;
+  a.d_boxes = d_boxes; a.d_logits = d_angles; a.d_mu = d_mu; a.d_logvar = d_logvar;
+  a.counter = (unsigned*)scratch; a.partial = (float*)((char*)scratch + 16); a.losses = losses;
+  k_vae_loss<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("vae_loss");
+}
+
+int sln_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float grad_scale, int64_t* step, int32_t advance_step, void* stream) {
+  SLN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && step && n >= 0, "bad argument");
+  SLN_CHECK_ARG(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0, "arenas must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (advance_step) {
+    k_inc_step<<<1, 1, 0, st>>>((long long*)step);
+    SLN_TRY(check_launch("adam_inc_step"));
+  }
+  if (n == 0) return SLN_OK;
+  long long threads = ceil_div64(n, 4);
+  k_adam<<<(int)ceil_div64(threads, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (long long)n, lr, beta1, beta2, eps, weight_decay,
+                                                       grad_scale, (const long long*)step);
+  return check_launch("adam");
+}
+
+}  // extern "C"

@@ -1,0 +1,443 @@
+// Non-contraction kernels of the VAE-graph hot path: graph preparation (CSR by node), embeddings,
+// avg-pool scatter expressed as a deterministic gather, BN-backward "prep" passes, losses, Adam.
+// All of them are HBM/L2-bound: one pass over their operands, coalesced along the feature dimension.
+#pragma once
+#include "gemm.cuh"
+
+namespace sln {
+
+// ================================================================ graph preparation
+// reference: Sg2ScVAE_model.py:117-119 (split triples), graph.py:74-75,92-107 (s/o indices, degree counts)
+struct Graph {
+  int O, T;
+  int* s_idx;    // [T]
+  int* p_idx;    // [T]
+  int* o_idx;    // [T]
+  int* row_ptr;  // [O+1]  CSR over nodes; entries = triples touching the node as subject (side 0) or object (side 1)
+  int* ent;      // [2T]   (side << 30) | t, sorted ascending inside each row (= reference scatter_add order)
+  float* inv_cnt;  // [O]  1 / max(deg,1)
+  int* cursor;     // [O]  scratch
+};
+
+__global__ void k_split_triples(const long long* __restrict__ triples, int T, int O, int* s_idx, int* p_idx, int* o_idx,
+                                int* deg, int* err) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  long long s = triples[(size_t)t * 3 + 0], p = triples[(size_t)t * 3 + 1], o = triples[(size_t)t * 3 + 2];
+  if (s < 0 || s >= O || o < 0 || o >= O) { atomicExch(err, 1); s = 0; o = 0; }
+  s_idx[t] = (int)s; p_idx[t] = (int)p; o_idx[t] = (int)o;
+  atomicAdd(deg + s, 1);
+  atomicAdd(deg + o, 1);
+}
+
+// single-CTA exclusive scan (O is at most a few 10^5; runs once per batch)
+__global__ void k_scan_deg(const int* __restrict__ deg, int O, int* row_ptr, float* inv_cnt) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int base = 0; base < O; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int v = i < O ? deg[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int tot = lane < nw ? warp_tot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, tot, o); if (lane >= o) tot += y; }
+      if (lane < nw) warp_tot[lane] = tot;  // inclusive over warps
+    }
+    __syncthreads();
+    int warp_off = w > 0 ? warp_tot[w - 1] : 0;
+    int carry = carry_s;
+    if (i < O) {
+      row_ptr[i] = carry + warp_off + x - v;
+      inv_cnt[i] = 1.f / (float)max(v, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + warp_tot[nw - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) row_ptr[O] = carry_s;
+}
+
+__global__ void k_fill_csr(const int* __restrict__ s_idx, const int* __restrict__ o_idx, int T, const int* __restrict__ row_ptr,
+                           int* cursor, int* ent) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  int s = s_idx[t], o = o_idx[t];
+  ent[row_ptr[s] + atomicAdd(cursor + s, 1)] = t;
+  ent[row_ptr[o] + atomicAdd(cursor + o, 1)] = (1 << 30) | t;
+}
+
+__global__ void k_sort_rows(const int* __restrict__ row_ptr, int O, int* ent) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  int b = row_ptr[o], e = row_ptr[o + 1];
+  for (int i = b + 1; i < e; ++i) {  // insertion sort: rows are short (degree of a scene-graph node)
+    int key = ent[i], j = i - 1;
+    while (j >= b && ent[j] > key) { ent[j + 1] = ent[j]; --j; }
+    ent[j + 1] = key;
+  }
+}
+
+__global__ void k_i64_to_i32(const long long* __restrict__ src, int n, int* dst, int limit, int* err) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long v = src[i];
+  if (v < 0 || v >= limit) { atomicExch(err, 1); v = 0; }
+  dst[i] = (int)v;
+}
+
+// ================================================================ embeddings
+// out[i, col_off + c] = table[idx ? idx[i] : i][c]           (reference Sg2ScVAE_model.py:121-129,150-154)
+__global__ void k_gather_rows(const float* __restrict__ table, int ldt, const int* __restrict__ idx, int n, int width,
+                              float* out, int ldo, int col_off) {
+  int i = blockIdx.x * blockDim.y + threadIdx.y;
+  if (i >= n) return;
+  int r = idx ? __ldg(idx + i) : i;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) out[(size_t)i * ldo + col_off + c] = __ldg(table + (size_t)r * ldt + c);
+}
+
+// out[i, col_off + c] = sum_k x[i,k] * W[c,k] + b[c]   for tiny k (box_embeddings: Linear(6 or 4, 3E/4))
+__global__ void k_small_linear(const float* __restrict__ x, int n, int kin, const float* __restrict__ W, const float* __restrict__ b,
+                               int width, float* out, int ldo, int col_off) {
+  int i = blockIdx.x * blockDim.y + threadIdx.y;
+  if (i >= n) return;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float acc = b ? __ldg(b + c) : 0.f;
+    for (int k = 0; k < kin; ++k) acc = fmaf(__ldg(x + (size_t)i * kin + k), __ldg(W + (size_t)c * kin + k), acc);
+    out[(size_t)i * ldo + col_off + c] = acc;
+  }
+}
+
+// table_grad[r, c] += sum_{i: idx[i]==r} ( a[i, c] (+ b[i, c]) ); idx == null -> single row 0 (column sum).
+// One CTA per table row (tables have <= 33 rows); threads own columns and walk the index list in order, so the
+// summation order is fixed (deterministic, no atomics).  The match test is warp-uniform.
+__global__ void k_embed_bwd(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb, const int* __restrict__ idx,
+                            int n, int width, float* table_grad, int ldt) {
+  const int r = blockIdx.x;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+      int id = idx ? __ldg(idx + i) : r;
+      if (id == r) {
+        float v = __ldg(a + (size_t)i * lda + c);
+        if (b) v += __ldg(b + (size_t)i * ldb + c);
+        acc += v;
+      }
+    }
+    table_grad[(size_t)r * ldt + c] += acc;
+  }
+}
+
+// ================================================================ avg pooling  (reference graph.py:92-108)
+// pooled[o, c] = inv_cnt[o] * ( sum_{t: s_t = o} a2[t, c] + sum_{t: o_t = o} a2[t, H + D + c] ),  a2 = relu(bn(y2)) lazily.
+// One CTA per node; threads own float4 columns; rows are read as contiguous 4*H-byte segments (coalesced).
+__global__ void k_pool_fwd(const MatView a2, const int* __restrict__ row_ptr, const int* __restrict__ ent,
+                           const float* __restrict__ inv_cnt, int O, int H, int D, float* pooled) {
+  int o = blockIdx.x;
+  int b = __ldg(row_ptr + o), e = __ldg(row_ptr + o + 1);
+  float ic = __ldg(inv_cnt + o);
+  for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = b; k < e; ++k) {
+      int en = __ldg(ent + k);
+      int t = en & ((1 << 30) - 1);
+      int off = (en >> 30) ? (H + D) : 0;
+      float4 v = a2.ld4(t, off + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    acc.x *= ic; acc.y *= ic; acc.z *= ic; acc.w *= ic;
+    float* dst = pooled + (size_t)o * H + c;
+    if (c + 3 < H) *reinterpret_cast<float4*>(dst) = acc;
+    else { dst[0] = acc.x; if (c + 1 < H) dst[1] = acc.y; if (c + 2 < H) dst[2] = acc.z; }
+  }
+}
+
+// ================================================================ backward "prep" passes
+// G[i,j] = mask(y[i,j]) ? src(i,j) : 0 and the BN-backward column sums, for gradients that are assembled by a gather
+// rather than produced by a contraction epilogue.
+struct PoolBwdSrc {  // gradient w.r.t. a2 = relu(bn(y2)) [T, 2H+D] from d pooled [O,H] and d new_pred [T,D]
+  const float* dpooled;  // [O,H]
+  const float* inv_cnt;
+  const int* s_idx;
+  const int* o_idx;
+  const float* dpred;  // [T, ldd] slice or null
+  int ldd, H, D;
+  __device__ __forceinline__ float at(int t, int c) const {
+    if (c < H) { int s = __ldg(s_idx + t); return __ldg(dpooled + (size_t)s * H + c) * __ldg(inv_cnt + s); }
+    if (c < H + D) return dpred ? __ldg(dpred + (size_t)t * ldd + (c - H)) : 0.f;
+    int o = __ldg(o_idx + t);
+    return __ldg(dpooled + (size_t)o * H + (c - H - D)) * __ldg(inv_cnt + o);
+  }
+};
+struct NodeGatherSrc {  // gradient w.r.t. obj_vecs [O,D] from d cat [T,3D]: transpose of the s/o gathers (graph.py:78-79)
+  const float* dcat;
+  int ld, D;
+  const int* row_ptr;
+  const int* ent;
+  __device__ __forceinline__ float at(int o, int c) const {
+    int b = __ldg(row_ptr + o), e = __ldg(row_ptr + o + 1);
+    float acc = 0.f;
+    for (int k = b; k < e; ++k) {
+      int en = __ldg(ent + k);
+      int t = en & ((1 << 30) - 1);
+      acc += __ldg(dcat + (size_t)t * ld + ((en >> 30) ? 2 * D + c : c));
+    }
+    return acc;
+  }
+};
+struct PlainSrc {
+  const float* p;
+  int ld;
+  __device__ __forceinline__ float at(int i, int c) const { return __ldg(p + (size_t)i * ld + c); }
+};
+
+struct ActInfo {  // the activation whose input gradient is being formed: a = relu(y*scale+shift)
+  int has_act;    // 0: plain copy (no mask, no statistics)
+  const float* y;
+  int ldy;
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+};
+
+// grid (ceil(N/128), row_tiles), block (128, 4); each CTA handles `rows_per_tile` rows.
+template <class Src>
+__global__ void __launch_bounds__(512) k_prep(const Src src, const ActInfo act, float* G, int ldg, BnBwdFin fin, int M, int N,
+                                              int rows_per_tile) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_tile;
+  const int r1 = min(M, r0 + rows_per_tile);
+  float s1 = 0.f, s2 = 0.f;
+  if (j < N) {
+    float sc = 1.f, sh = 0.f, mu = 0.f, rs = 0.f;
+    if (act.has_act && act.scale) { sc = __ldg(act.scale + j); sh = __ldg(act.shift + j); }
+    if (act.has_act && act.mean) { mu = __ldg(act.mean + j); rs = __ldg(act.rstd + j); }
+    for (int i = r0 + threadIdx.y; i < r1; i += 4) {
+      float d = src.at(i, j);
+      if (act.has_act) {
+        float y = __ldg(act.y + (size_t)i * act.ldy + j);
+        float g = fmaf(y, sc, sh) > 0.f ? d : 0.f;
+        G[(size_t)i * ldg + j] = g;
+        s1 += g;
+        s2 = fmaf(g, (y - mu) * rs, s2);
+      } else {
+        G[(size_t)i * ldg + j] = d;
+      }
+    }
+  }
+  if (!act.has_act) return;
+  __shared__ float red[2][4][128];
+  __shared__ int s_last;
+  red[0][threadIdx.y][threadIdx.x] = s1;
+  red[1][threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < N) {
+    float a = red[0][0][threadIdx.x] + red[0][1][threadIdx.x] + red[0][2][threadIdx.x] + red[0][3][threadIdx.x];
+    float c = red[1][0][threadIdx.x] + red[1][1][threadIdx.x] + red[1][2][threadIdx.x] + red[1][3][threadIdx.x];
+    fin.partial[((size_t)blockIdx.y * 2 + 0) * N + j] = a;
+    fin.partial[((size_t)blockIdx.y * 2 + 1) * N + j] = c;
+  }
+  __threadfence();
+  __syncthreads();
+  const int tid = threadIdx.y * 128 + threadIdx.x;
+  if (tid == 0) {
+    unsigned ticket = atomicAdd(fin.counter, 1u);
+    s_last = (ticket == gridDim.x * gridDim.y - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int col = tid; col < N; col += 512) bn_bwd_finalize(fin, col, N, gridDim.y);
+    if (tid == 0) *fin.counter = 0u;
+  }
+}
+
+template <class Src>
+int launch_prep(cudaStream_t st, const Src& src, const ActInfo& act, float* G, int ldg, const BnBwdFin& fin, int M, int N,
+                const char* what) {
+  if (M <= 0 || N <= 0) return SLN_OK;
+  // aim for ~2 waves of CTAs; partial buffer is sized for max_row_tiles(M) = ceil(M/64) tiles
+  int col_blocks = ceil_div(N, 128);
+  int want_tiles = max(1, (2 * kNumSMs) / col_blocks);
+  int rows = max(64, ceil_div(M, want_tiles));
+  rows = ceil_div(rows, 4) * 4;
+  dim3 grid(col_blocks, ceil_div(M, rows));
+  k_prep<Src><<<grid, dim3(128, 4), 0, st>>>(src, act, G, ldg, fin, M, N, rows);
+  return check_launch(what);
+}
+
+// scale/shift (+mean/rstd) of an eval-mode BatchNorm from its running statistics
+__global__ void k_bn_eval_prep(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rm,
+                               const float* __restrict__ rv, float eps, int C, float* mean, float* rstd, float* scale, float* shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float rs = 1.f / sqrtf(rv[c] + eps);
+  float sc = gamma[c] * rs;
+  mean[c] = rm[c]; rstd[c] = rs; scale[c] = sc; shift[c] = beta[c] - rm[c] * sc;
+}
+
+// out[i, c] = view(i, c)   (materialise a lazy BN+ReLU view)
+__global__ void k_materialize(const MatView v, float* out, int ldo) {
+  int i = blockIdx.x * blockDim.y + threadIdx.y;
+  if (i >= v.rows) return;
+  for (int c = threadIdx.x * 4; c < v.cols; c += blockDim.x * 4) {
+    float4 x = v.ld4(i, c);
+    float* d = out + (size_t)i * ldo + c;
+    d[0] = x.x; if (c + 1 < v.cols) d[1] = x.y; if (c + 2 < v.cols) d[2] = x.z; if (c + 3 < v.cols) d[3] = x.w;
+  }
+}
+
+// ================================================================ heads: log-softmax, reparameterisation, losses
+// reference Sg2ScVAE_model.py:171 — one warp per row (n_angle = 24 <= 32 columns fast path; generic loop otherwise)
+__global__ void k_log_softmax_fwd(const float* __restrict__ logits, int n, int C, float* out) {
+  int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, logits[(size_t)i * C + c]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(logits[(size_t)i * C + c] - m);
+  s = warp_sum(s);
+  float lse = m + logf(s);
+  for (int c = lane; c < C; c += 32) out[(size_t)i * C + c] = logits[(size_t)i * C + c] - lse;
+}
+// d logits = d out - exp(out) * sum_c d out
+__global__ void k_log_softmax_bwd(const float* __restrict__ dout, const float* __restrict__ out, int n, int C, float* dlogits) {
+  int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += dout[(size_t)i * C + c];
+  s = warp_sum(s);
+  for (int c = lane; c < C; c += 32) dlogits[(size_t)i * C + c] = dout[(size_t)i * C + c] - expf(out[(size_t)i * C + c]) * s;
+}
+
+// z = eps * exp(0.5*logvar) + mu      (reference Sg2ScVAE_model.py:180-183)
+__global__ void k_reparam_fwd(const float* __restrict__ mu, const float* __restrict__ logvar, const float* __restrict__ eps, int n, float* z) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) z[i] = fmaf(eps[i], expf(0.5f * logvar[i]), mu[i]);
+}
+// dmu += dz ; dlogvar += dz * eps * 0.5 * exp(0.5*logvar)
+__global__ void k_reparam_bwd(const float* __restrict__ dz, const float* __restrict__ logvar, const float* __restrict__ eps, int n,
+                              float* dmu, float* dlogvar) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float d = dz[i];
+    dmu[i] += d;
+    dlogvar[i] += d * eps[i] * 0.5f * expf(0.5f * logvar[i]);
+  }
+}
+
+// Fused loss forward + gradient seeds (reference utils.py:12-33,139-146):
+//   bbox = mean|pred-gt| ; angle = -mean logp[i, gt_i] ; kld = -0.5*sum(1+lv-mu^2-e^lv)/O ; total = bbox + angle + w*kld
+// losses[0..3] = {bbox, angle, w*kld, total}.  Deterministic: per-CTA partials, last CTA sums in order.
+struct LossArgs {
+  const float* boxes_pred; const float* boxes_gt; int BD;
+  const float* logp; const long long* angles_gt; int NA;
+  const float* mu; const float* logvar; int Z;  // mu == null -> AE mode, no KL
+  float kl_weight;
+  int O;
+  int logits_grad;  // 1: d_logits = d total / d logits (log-softmax backward fused); 0: gradient w.r.t. the log-probs
+  float* d_boxes; float* d_logits; float* d_mu; float* d_logvar;  // gradient outputs (may be null: loss only)
+  float* partial;   // [gridDim.x][3]
+  unsigned* counter;
+  float* losses;    // [4]
+};
+__global__ void __launch_bounds__(256) k_vae_loss(const LossArgs a) {
+  const int rows_per = 64;
+  int r0 = blockIdx.x * rows_per, r1 = min(a.O, r0 + rows_per);
+  float l1 = 0.f, nll = 0.f, kl = 0.f;
+  const float inv_bb = 1.f / ((float)a.O * (float)a.BD), inv_o = 1.f / (float)a.O;
+  for (int e = threadIdx.x; e < (r1 - r0) * a.BD; e += blockDim.x) {
+    size_t k = (size_t)r0 * a.BD + e;
+    float d = a.boxes_pred[k] - a.boxes_gt[k];
+    l1 += fabsf(d);
+    if (a.d_boxes) a.d_boxes[k] = (d > 0.f ? inv_bb : (d < 0.f ? -inv_bb : 0.f));
+  }
+  for (int e = threadIdx.x; e < (r1 - r0) * a.NA; e += blockDim.x) {
+    int i = r0 + e / a.NA, c = e % a.NA;
+    float lp = a.logp[(size_t)i * a.NA + c];
+    bool hit = ((long long)c == a.angles_gt[i]);
+    if (hit) nll -= lp;
+    if (a.d_logits) a.d_logits[(size_t)i * a.NA + c] = a.logits_grad ? (expf(lp) - (hit ? 1.f : 0.f)) * inv_o : (hit ? -inv_o : 0.f);
+  }
+  if (a.mu) {
+    for (int e = threadIdx.x; e < (r1 - r0) * a.Z; e += blockDim.x) {
+      size_t k = (size_t)r0 * a.Z + e;
+      float m = a.mu[k], lv = a.logvar[k], ex = expf(lv);
+      kl += 1.f + lv - m * m - ex;
+      if (a.d_mu) { a.d_mu[k] = a.kl_weight * m * inv_o; a.d_logvar[k] = a.kl_weight * 0.5f * (ex - 1.f) * inv_o; }
+    }
+  }
+  __shared__ float red[3][8];
+  __shared__ int s_last;
+  l1 = warp_sum(l1); nll = warp_sum(nll); kl = warp_sum(kl);
+  int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][w] = l1; red[1][w] = nll; red[2][w] = kl; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { s0 += red[0][k]; s1 += red[1][k]; s2 += red[2][k]; }
+    a.partial[blockIdx.x * 3 + 0] = s0; a.partial[blockIdx.x * 3 + 1] = s1; a.partial[blockIdx.x * 3 + 2] = s2;
+    __threadfence();
+    unsigned ticket = atomicAdd(a.counter, 1u);
+    s_last = (ticket == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double t0 = 0, t1 = 0, t2 = 0;
+    for (unsigned b = 0; b < gridDim.x; ++b) {
+      t0 += (double)__ldcg(a.partial + b * 3 + 0); t1 += (double)__ldcg(a.partial + b * 3 + 1); t2 += (double)__ldcg(a.partial + b * 3 + 2);
+    }
+    float bbox = (float)(t0 / ((double)a.O * a.BD));
+    float ang = (float)(t1 / (double)a.O);
+    float kld = a.mu ? a.kl_weight * (float)(-0.5 * t2 / (double)a.O) : 0.f;
+    a.losses[0] = bbox; a.losses[1] = ang; a.losses[2] = kld; a.losses[3] = bbox + ang + kld;
+    *a.counter = 0u;
+  }
+}
+
+// ================================================================ Adam over one flat parameter arena
+// torch.optim.Adam semantics (train.py:15,82-84): m = b1*m+(1-b1)g ; v = b2*v+(1-b2)g^2 ;
+// p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps), bc_i = 1 - b_i^step.  `step` lives on the device so the launch is graph-safe.
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                       float lr, float b1, float b2, float eps, float weight_decay, float grad_scale, const long long* step_ptr) {
+  long long step = *step_ptr;
+  float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+  float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 pp = *reinterpret_cast<float4*>(p + i), gg = *reinterpret_cast<const float4*>(g + i);
+    float4 mm = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+    float* P = &pp.x; float* G = &gg.x; float* Mm = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float gr = G[e] * grad_scale + weight_decay * P[e];
+      Mm[e] = b1 * Mm[e] + (1.f - b1) * gr;
+      V[e] = b2 * V[e] + (1.f - b2) * gr * gr;
+      P[e] -= step_size * Mm[e] / (sqrtf(V[e]) * inv_sqrt_bc2 + eps);
+    }
+    *reinterpret_cast<float4*>(p + i) = pp; *reinterpret_cast<float4*>(m + i) = mm; *reinterpret_cast<float4*>(v + i) = vv;
+  } else {
+    for (long long k = i; k < n; ++k) {
+      float gr = g[k] * grad_scale + weight_decay * p[k];
+      m[k] = b1 * m[k] + (1.f - b1) * gr;
+      v[k] = b2 * v[k] + (1.f - b2) * gr * gr;
+      p[k] -= step_size * m[k] / (sqrtf(v[k]) * inv_sqrt_bc2 + eps);
+    }
+  }
+}
+__global__ void k_inc_step(long long* step_ptr) { *step_ptr += 1; }
+
+}  // namespace sln

@@ -1,0 +1,329 @@
+"""Drop-ins for the hot-path helpers of the reference's ``utils.py`` plus the fused train step.
+
+* ``calculate_model_losses`` (reference utils.py:12-33) — same signature and return value; one fused kernel computes the
+  three loss terms and their gradient seeds, and the ``losses`` dict is filled from ONE device->host read (the reference
+  does three ``.item()`` syncs, utils.py:141).
+* ``tensor_aug`` (utils.py:114-124), ``add_loss`` (:139-146), ``get_model_attr`` (:149-153) — unchanged behaviour.
+* ``FusedAdam`` — ``torch.optim.Adam``-compatible step over flat arenas (train.py:15,82-84): 1 launch instead of a
+  multi-tensor foreach sequence.
+* ``VAETrainStep`` — the whole ``train.py:69-84`` loop body (H2D, forward, losses, backward, Adam) as a replayable CUDA graph.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+# ---------------------------------------------------------------------------------------------- reference helpers
+def tensor_aug(tensors, volatile=False, use_gpu=True):
+    out = []
+    for t in tensors:
+        v = t.cuda(non_blocking=True) if use_gpu else t
+        if volatile:
+            v.requires_grad = False
+        out.append(v)
+    return tuple(out)
+
+
+def add_loss(total_loss, curr_loss, loss_dict, loss_name, weight=1):
+    weighted = curr_loss * weight
+    loss_dict[loss_name] = weighted.item()
+    return weighted if total_loss is None else total_loss + weighted
+
+
+def get_model_attr(_object, attr):
+    if isinstance(_object, nn.DataParallel):
+        return getattr(_object.module, attr)
+    return getattr(_object, attr)
+
+
+def _loss_scratch(dev, O):
+    n = 16 + 12 * ((O + 63) // 64)
+    return torch.zeros((n + 3) // 4, dtype=torch.int32, device=dev)
+
+
+class _FusedLossFn(torch.autograd.Function):
+    """total = L1(bbox) + NLL(angle) + KL_weight * KLD, with the gradient seeds produced by the same kernel."""
+
+    @staticmethod
+    def forward(ctx, bbox_pred, bbox, angles_pred, angles, mu, logvar, kl_weight, holder):
+        lib = _lib.load()
+        dev = bbox_pred.device
+        bbox_pred, bbox, angles_pred = bbox_pred.contiguous().float(), bbox.contiguous().float(), angles_pred.contiguous().float()
+        angles = angles.contiguous().long()
+        O, BD, NA = bbox_pred.size(0), bbox_pred.size(1), angles_pred.size(1)
+        has_kl = mu is not None
+        if has_kl:
+            mu, logvar = mu.contiguous().float(), logvar.contiguous().float()
+        losses = torch.empty(4, device=dev, dtype=torch.float32)
+        d_boxes = torch.empty_like(bbox_pred)
+        d_angles = torch.empty_like(angles_pred)
+        d_mu = torch.empty_like(mu) if has_kl else None
+        d_logvar = torch.empty_like(logvar) if has_kl else None
+        scratch = _loss_scratch(dev, O)
+        _lib.check(lib.sln_vae_loss(bbox_pred.data_ptr(), bbox.data_ptr(), BD, angles_pred.data_ptr(), angles.data_ptr(), NA,
+                                    _lib.ptr(mu), _lib.ptr(logvar), mu.size(1) if has_kl else 0, float(kl_weight if has_kl else 0.0), O,
+                                    losses.data_ptr(), d_boxes.data_ptr(), d_angles.data_ptr(), 0, _lib.ptr(d_mu), _lib.ptr(d_logvar),
+                                    scratch.data_ptr(), scratch.numel() * 4, _lib.cur_stream(dev)), "vae_loss")
+        holder.append(losses)
+        ctx.save_for_backward(d_boxes, d_angles, *([d_mu, d_logvar] if has_kl else []))
+        ctx.has_kl = has_kl
+        return losses[3].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        d_boxes, d_angles = saved[0] * g, saved[1] * g
+        d_mu = saved[2] * g if ctx.has_kl else None
+        d_logvar = saved[3] * g if ctx.has_kl else None
+        return d_boxes, None, d_angles, None, d_mu, d_logvar, None, None
+
+
+def calculate_model_losses(args, model, bbox, bbox_pred, angles, angles_pred, mu=None, logvar=None, KL_weight=None):
+    """Same contract as the reference: returns (total_loss tensor, {'bbox_pred','angle_pred','KLD_Gauss'} floats)."""
+    if not bbox_pred.is_cuda:
+        raise RuntimeError("3d_sln_b200.calculate_model_losses runs on CUDA only (no CPU fallback)")
+    use_kl = not args.use_AE
+    holder = []
+    total = _FusedLossFn.apply(bbox_pred, bbox, angles_pred, angles, mu if use_kl else None, logvar if use_kl else None,
+                               KL_weight if use_kl else 0.0, holder)
+    vals = holder[0].tolist()   # the single device->host synchronisation of the loss computation
+    losses = {'bbox_pred': vals[0], 'angle_pred': vals[1]}
+    if use_kl:
+        losses['KLD_Gauss'] = vals[2]
+    return total, losses
+
+
+# ---------------------------------------------------------------------------------------------- fused Adam
+class FusedAdam(torch.optim.Optimizer):
+    """Adam with torch.optim.Adam's update rule, run by sln_adam_step over flat parameter / gradient / state arenas.
+
+    On the first ``step()`` the parameters are re-homed (``p.data`` re-pointed, values preserved) into one arena ordered
+    like their gradients, so that a model whose gradients live in the Sg2ScVAEModel gradient arena is updated by a single
+    launch.  Parameters whose gradients are not laid out contiguously are updated run by run.
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super(FusedAdam, self).__init__(params, defaults)
+        self.grad_scale = grad_scale
+        self._plans = {}
+
+    @staticmethod
+    def _key(ps):
+        return tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+
+    def _plan(self, gi, group):
+        ps = [p for p in group['params'] if p.grad is not None]
+        if not ps:
+            return None
+        old = self._plans.get(gi)
+        if old is not None and len(old['params']) == len(ps) and old['key'] == self._key(old['params']):
+            return old
+        for p in ps:
+            if not (p.is_cuda and p.dtype == torch.float32 and p.grad.is_contiguous()):
+                raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters and gradients")
+        ps.sort(key=lambda p: p.grad.data_ptr())
+        n = sum((p.numel() + 3) // 4 * 4 for p in ps)
+        dev = ps[0].device
+        arena = torch.zeros(n, device=dev, dtype=torch.float32)
+        m = torch.zeros(n, device=dev, dtype=torch.float32)
+        v = torch.zeros(n, device=dev, dtype=torch.float32)
+        off, runs, offsets = 0, [], {}
+        for p in ps:
+            k, g0 = p.numel(), p.grad.data_ptr()
+            cont = bool(runs) and runs[-1][2] + runs[-1][1] * 4 == g0 and runs[-1][0] + runs[-1][1] == off
+            if not cont:
+                off = (off + 3) // 4 * 4      # a new run starts 16-byte aligned
+            arena[off:off + k].copy_(p.data.reshape(-1))
+            if old is not None and id(p) in old['offsets']:   # carry optimizer state across a re-plan
+                o = old['offsets'][id(p)]
+                m[off:off + k].copy_(old['m'][o:o + k])
+                v[off:off + k].copy_(old['v'][o:o + k])
+            p.data = arena[off:off + k].view_as(p)
+            offsets[id(p)] = off
+            if cont:
+                runs[-1][1] += k
+            else:
+                runs.append([off, k, g0])
+            off += k
+        step = old['step'] if old is not None else torch.zeros(1, device=dev, dtype=torch.int64)
+        plan = dict(key=self._key(ps), arena=arena, m=m, v=v, runs=runs, step=step, offsets=offsets, params=ps)
+        self._plans[gi] = plan
+        return plan
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        for gi, group in enumerate(self.param_groups):
+            plan = self._plan(gi, group)
+            if plan is None:
+                continue
+            b1, b2 = group['betas']
+            st = _lib.cur_stream(plan['arena'].device)
+            for ri, (off, k, gptr) in enumerate(plan['runs']):
+                if gptr % 16:
+                    raise RuntimeError("FusedAdam: gradient run not 16-byte aligned")
+                _lib.check(lib.sln_adam_step(plan['arena'].data_ptr() + off * 4, gptr, plan['m'].data_ptr() + off * 4,
+                                             plan['v'].data_ptr() + off * 4, k, group['lr'], b1, b2, group['eps'],
+                                             group['weight_decay'], self.grad_scale, plan['step'].data_ptr(), int(ri == 0), st),
+                           "adam_step")
+        return loss
+
+
+# ---------------------------------------------------------------------------------------------- fused train step
+class VAETrainStep(object):
+    """The reference train-loop body (train.py:69-84) for a fixed batch shape, replayed as a CUDA graph.
+
+    step(batch) : batch = (objs, triples, boxes, angles, attributes) HOST (pinned) or device tensors of the captured
+                  shape -> device tensor losses[4] = {bbox, angle, KL_weight*KLD, total}
+    The timed body is: H2D copies into static buffers, encoder fwd, eps ~ N(0,1), reparameterise, decoder fwd, fused
+    losses + gradient seeds, decoder bwd, reparam bwd, encoder bwd, [all-reduce], Adam.
+    """
+
+    def __init__(self, model, O, T, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, kl_weight=0.1, use_graph=True, process_group=None,
+                 world_size=1):
+        self.lib = _lib.load()
+        self.model = model
+        dev = next(model.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError("VAETrainStep needs a CUDA model")
+        self.dev, self.O, self.T = dev, O, T
+        self.kl_weight, self.lr, self.betas, self.eps = kl_weight, lr, betas, eps
+        self.world_size, self.pg = world_size, process_group
+        E, BD, NA = model.embedding_dim, model.box_dim, model.Nangle
+        model._tables()
+        cache = model._cache
+        sink = model._grad_sink()
+        # flat parameter arena in the gradient arena's order -> one Adam launch, one all-reduce bucket
+        n = sink.flat.numel()
+        self.p_arena = torch.empty(n, device=dev, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for i in sink.order:
+                p = cache['params'][i]
+                k = p.numel()
+                self.p_arena[off:off + k].copy_(p.data.reshape(-1))
+                p.data = self.p_arena[off:off + k].view_as(p)
+                off += k
+        model._cache = None
+        model._tables()
+        model._sink, model._gtable = sink, None
+        sink.params = model._cache['params']
+        for g in ('enc', 'dec'):
+            sink.publish(g)
+        self.sink = sink
+        self.m = torch.zeros(n, device=dev); self.v = torch.zeros(n, device=dev)
+        self.step_count = torch.zeros(1, device=dev, dtype=torch.int64)
+        i64 = dict(device=dev, dtype=torch.int64)
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.objs = torch.zeros(O, **i64); self.triples = torch.zeros(T, 3, **i64); self.boxes = torch.zeros(O, BD, **f32)
+        self.angles = torch.zeros(O, **i64); self.attrs = torch.zeros(O, **i64)
+        self.mu = torch.zeros(O, E, **f32); self.logvar = torch.zeros(O, E, **f32); self.epsn = torch.zeros(O, E, **f32)
+        self.z = torch.zeros(O, E, **f32); self.boxes_pred = torch.zeros(O, BD, **f32); self.angles_pred = torch.zeros(O, NA, **f32)
+        self.d_boxes = torch.zeros(O, BD, **f32); self.d_logits = torch.zeros(O, NA, **f32)
+        self.d_mu = torch.zeros(O, E, **f32); self.d_logvar = torch.zeros(O, E, **f32); self.d_z = torch.zeros(O, E, **f32)
+        self.losses = torch.zeros(4, **f32)
+        self.loss_scratch = _loss_scratch(dev, O)
+        self.ws_enc = torch.empty(self.lib.sln_vae_workspace_bytes(model._desc(), O, T, 0), dtype=torch.uint8, device=dev)
+        self.ws_dec = torch.empty(self.lib.sln_vae_workspace_bytes(model._desc(), O, T, 1), dtype=torch.uint8, device=dev)
+        self.launches_per_step = None
+        self.graph_fb = None
+        self.graph_opt = None
+        self.use_graph = use_graph
+        self._static_inputs = (self.objs, self.triples, self.boxes, self.angles, self.attrs)
+
+    # -- the launch sequences -------------------------------------------------------------------
+    def _fwd_bwd(self):
+        lib, m, O, T = self.lib, self.model, self.O, self.T
+        st = _lib.cur_stream(self.dev)
+        desc = m._desc()
+        params, bufs = m._tables()
+        grads = m._grad_table()
+        E = m.embedding_dim
+        use_kl = not m.use_AE
+        self.sink.flat.zero_()
+        _lib.check(lib.sln_vae_encoder_fwd(desc, params, bufs, self.objs.data_ptr(), self.triples.data_ptr(), self.boxes.data_ptr(),
+                                           self.angles.data_ptr(), self.attrs.data_ptr(), O, T, self.mu.data_ptr(), self.logvar.data_ptr(),
+                                           self.ws_enc.data_ptr(), self.ws_enc.numel(), st), "encoder_fwd")
+        if use_kl:
+            self.epsn.normal_()
+            _lib.check(lib.sln_reparam_fwd(self.mu.data_ptr(), self.logvar.data_ptr(), self.epsn.data_ptr(), O * E, self.z.data_ptr(), st), "reparam_fwd")
+            z = self.z
+        else:
+            z = self.mu
+        _lib.check(lib.sln_vae_decoder_fwd(desc, params, bufs, z.data_ptr(), self.objs.data_ptr(), self.triples.data_ptr(),
+                                           self.attrs.data_ptr(), O, T, self.boxes_pred.data_ptr(), self.angles_pred.data_ptr(),
+                                           self.ws_dec.data_ptr(), self.ws_dec.numel(), st), "decoder_fwd")
+        _lib.check(lib.sln_vae_loss(self.boxes_pred.data_ptr(), self.boxes.data_ptr(), m.box_dim, self.angles_pred.data_ptr(),
+                                    self.angles.data_ptr(), m.Nangle, self.mu.data_ptr() if use_kl else None,
+                                    self.logvar.data_ptr() if use_kl else None, E if use_kl else 0, self.kl_weight if use_kl else 0.0, O,
+                                    self.losses.data_ptr(), self.d_boxes.data_ptr(), self.d_logits.data_ptr(), 1,
+                                    self.d_mu.data_ptr() if use_kl else None, self.d_logvar.data_ptr() if use_kl else None,
+                                    self.loss_scratch.data_ptr(), self.loss_scratch.numel() * 4, st), "vae_loss")
+        _lib.check(lib.sln_vae_decoder_bwd(desc, params, grads, self.d_boxes.data_ptr(), self.d_logits.data_ptr(), 1, self.d_z.data_ptr(),
+                                           O, T, self.ws_dec.data_ptr(), self.ws_dec.numel(), st), "decoder_bwd")
+        if use_kl:
+            _lib.check(lib.sln_reparam_bwd(self.d_z.data_ptr(), self.logvar.data_ptr(), self.epsn.data_ptr(), O * E, self.d_mu.data_ptr(),
+                                           self.d_logvar.data_ptr(), st), "reparam_bwd")
+            d_mu, d_lv = self.d_mu, self.d_logvar
+        else:
+            self.d_logvar.zero_()
+            d_mu, d_lv = self.d_z, self.d_logvar
+        _lib.check(lib.sln_vae_encoder_bwd(desc, params, grads, self.boxes.data_ptr(), d_mu.data_ptr(), d_lv.data_ptr(), O, T,
+                                           self.ws_enc.data_ptr(), self.ws_enc.numel(), st), "encoder_bwd")
+
+    def _opt(self):
+        st = _lib.cur_stream(self.dev)
+        _lib.check(self.lib.sln_adam_step(self.p_arena.data_ptr(), self.sink.flat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                          self.p_arena.numel(), self.lr, self.betas[0], self.betas[1], self.eps, 0.0,
+                                          1.0 / self.world_size, self.step_count.data_ptr(), 1, st), "adam_step")
+
+    def _allreduce(self):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.sink.flat, group=self.pg)
+
+    def capture(self):
+        """Warm up on a side stream, then capture forward+backward (and Adam) into CUDA graphs."""
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._fwd_bwd(); self._allreduce(); self._opt()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        if not self.use_graph:
+            return self
+        self.graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_fb):
+            self._fwd_bwd()
+            if self.world_size == 1:
+                self._opt()
+        if self.world_size > 1:
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt):
+                self._opt()
+        return self
+
+    def load_batch(self, batch):
+        for dst, src in zip(self._static_inputs, batch):
+            dst.copy_(src, non_blocking=True)
+
+    def run(self):
+        if self.graph_fb is not None:
+            self.graph_fb.replay()
+            if self.world_size > 1:
+                self._allreduce()
+                self.graph_opt.replay()
+        else:
+            self._fwd_bwd(); self._allreduce(); self._opt()
+        return self.losses
+
+    def step(self, batch):
+        self.load_batch(batch)
+        return self.run()

@@ -1,0 +1,137 @@
+/*
+ * sln_b200.h — C ABI of the B200-native 3D_SLN hot path (libsln_b200.so).
+ *
+ * The reference (aluo-x/3D_SLN) has no FFI/plugin layer: its hot path is reached through Python nn.Module calls.
+ * The drop-in boundary is therefore the Python class surface (3d_sln_b200/models/*.py mirrors the reference's
+ * models/graph.py, models/Sg2ScVAE_model.py, ...) and THIS header is what those Python classes bind with ctypes.
+ * Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain device pointers + extents; no torch types; every buffer (inputs, outputs, workspace) is caller-owned
+ *   - return 0 on success, negative SLN_E* / on failure; message via sln_last_error() (thread-local)
+ *   - all launches go to `stream` (a cudaStream_t passed as void*); no host synchronisation, no allocation,
+ *     so every call is CUDA-graph capturable
+ *   - all floating point is fp32, row-major; index tensors are int64 exactly as suncg_collate_fn produces them
+ *     (reference data/suncg_dataset.py:295-337)
+ */
+#ifndef SLN_B200_H
+#define SLN_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLN_ABI_VERSION 1
+
+int sln_version(void);
+const char* sln_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------ VAE-graph model
+ * Model description: mirrors the ctor kwargs of Sg2ScVAEModel (reference models/Sg2ScVAE_model.py:7-113,
+ * build_dataset_model.py:40-52). */
+typedef struct sln_vae_desc {
+  int32_t embedding_dim;  /* E (default 64): gconv dim D = 2E, hidden H = 4E, latent Z = E */
+  int32_t n_layers;       /* gconv_num_layers (>= 1) */
+  int32_t recurrent;      /* gconv_mode == 'recurrent': one weight set reused by every layer */
+  int32_t norm;           /* 0 = mlp_normalization 'none', 1 = 'batch' */
+  int32_t training;       /* module.training: BN uses batch statistics and updates running stats */
+  int32_t box_dim;        /* 6 (train_3d) or 4 */
+  int32_t n_angle;        /* Nangle = 24 */
+  int32_t num_objs;       /* rows of obj embedding tables = len(vocab.object_idx_to_name) + 1 */
+  int32_t num_preds;
+  int32_t num_attrs;
+  float bn_eps;           /* 1e-5 */
+  float bn_momentum;      /* 0.1 */
+  int32_t gconv_dim_override;    /* 0, or Din = Dout of a standalone GraphTripleConv (sln_gconv_layer_*) */
+  int32_t gconv_hidden_override; /* 0, or hidden_dim of a standalone GraphTripleConv */
+} sln_vae_desc;
+
+/* Parameter table.  `params[i]` / `grads[i]` are device pointers in this canonical order (grads may be NULL
+ * for forward-only calls; individual entries may be NULL to skip a gradient):
+ *   0 obj_embeddings_ec.weight  1 attr_embedding_ec.weight  2 angle_embeddings.weight  3 pred_embeddings_ec.weight
+ *   4 obj_embeddings_dc.weight  5 attr_embedding_dc.weight  6 pred_embeddings_dc.weight
+ *   then, per Linear block in the order below: weight, bias, and (norm == 1 and the block has a BatchNorm) bn.weight, bn.bias
+ *     box_embeddings
+ *     gconv_net_ec.gconvs[l].{net1.0, net1.<2nd Linear>, net2.0, net2.<2nd Linear>}   l = 0..(recurrent ? 0 : n_layers-1)
+ *     gconv_net_dc.gconvs[l]....                                                        (all four have BN when norm == 1)
+ *     box_mean_var.{0, 2nd}  angle_mean_var.{0, 2nd}          (BN)
+ *     box_mean.0  box_var.0  angle_mean.0  angle_var.0         (no BN: make_mlp(norelu=True), graph.py:22-26)
+ *     box_net.0 (BN)  box_net.<2nd> (no BN)  angle_net.0 (BN)  angle_net.<2nd> (no BN)
+ * `bn_bufs`: for every BatchNorm in the same order: running_mean (float*), running_var (float*),
+ *            num_batches_tracked (int64_t*).  NULL when norm == 0. */
+int sln_vae_num_params(const sln_vae_desc* d);  /* entries of params[] / grads[] */
+int sln_vae_num_bn(const sln_vae_desc* d);      /* BatchNorm count; bn_bufs has 3x this many entries */
+
+/* Workspace holding graph CSR, saved activations, BN statistics and backward scratch.  which: 0 = encoder, 1 = decoder,
+ * 2 = one standalone GraphTripleConv layer. */
+size_t sln_vae_workspace_bytes(const sln_vae_desc* d, int64_t O, int64_t T, int which);
+
+/* Sg2ScVAEModel.encoder (reference Sg2ScVAE_model.py:115-143): objs[O] triples[T,3] boxes[O,box_dim] angles[O]
+ * attributes[O] -> mu[O,E], logvar[O,E].  Saves what encoder_bwd needs in `ws`. */
+int sln_vae_encoder_fwd(const sln_vae_desc* d, const void* const* params, void* const* bn_bufs,
+                        const int64_t* objs, const int64_t* triples, const float* boxes, const int64_t* angles,
+                        const int64_t* attributes, int64_t O, int64_t T, float* mu, float* logvar,
+                        void* ws, size_t ws_bytes, void* stream);
+/* Backward of the encoder: d_mu, d_logvar [O,E] -> parameter gradients ACCUMULATED into grads[] (caller zeroes). */
+int sln_vae_encoder_bwd(const sln_vae_desc* d, const void* const* params, void* const* grads,
+                        const float* boxes, const float* d_mu, const float* d_logvar, int64_t O, int64_t T,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/* Sg2ScVAEModel.decoder (reference Sg2ScVAE_model.py:145-172, decoder_cat=True): z[O,E] objs triples attributes ->
+ * boxes_pred[O,box_dim], angles_pred[O,n_angle] (log-probabilities). */
+int sln_vae_decoder_fwd(const sln_vae_desc* d, const void* const* params, void* const* bn_bufs,
+                        const float* z, const int64_t* objs, const int64_t* triples, const int64_t* attributes,
+                        int64_t O, int64_t T, float* boxes_pred, float* angles_pred,
+                        void* ws, size_t ws_bytes, void* stream);
+/* d_angles is the gradient w.r.t. angles_pred (log-probs) when angles_are_logits == 0, else w.r.t. the pre-softmax
+ * logits (what sln_vae_loss emits).  d_z [O,E] is written (may be NULL). */
+int sln_vae_decoder_bwd(const sln_vae_desc* d, const void* const* params, void* const* grads,
+                        const float* d_boxes, const float* d_angles, int angles_are_logits, float* d_z,
+                        int64_t O, int64_t T, void* ws, size_t ws_bytes, void* stream);
+
+/* GraphTripleConv.forward (reference models/graph.py:57-111), one layer, standalone.
+ * layer_params: W1a,b1a,[g,b] W1b,b1b,[g,b] W2a,b2a,[g,b] W2b,b2b,[g,b]; layer_bn_bufs: 4 x (rm, rv, nbt).
+ * obj_vecs[O,Din] pred_vecs[T,Din] edges[T,2] -> new_obj[O,Dout], new_pred[T,Dout].  Din = Dout = 2E of `d`, H = 4E. */
+int sln_gconv_layer_fwd(const sln_vae_desc* d, const void* const* layer_params, void* const* layer_bn_bufs,
+                        const float* obj_vecs, const float* pred_vecs, const int64_t* edges, int64_t O, int64_t T,
+                        float* new_obj, float* new_pred, void* ws, size_t ws_bytes, void* stream);
+int sln_gconv_layer_bwd(const sln_vae_desc* d, const void* const* layer_params, void* const* layer_grads,
+                        const float* obj_vecs, const float* pred_vecs, const float* d_new_obj, const float* d_new_pred,
+                        int64_t O, int64_t T, float* d_obj, float* d_pred, void* ws, size_t ws_bytes, void* stream);
+
+/* The pooling stage alone (reference graph.py:92-108): edges -> CSR, then
+ * pooled[o] = (sum_{s_t=o} new_s[t] + sum_{o_t=o} new_o[t]) / max(deg(o),1), new_t_vecs[T, 2H+Dout] laid out s|p|o.
+ * Used by the roofline benchmark and the parity tests of the north-star "scatter" kernel. */
+size_t sln_gconv_pool_workspace_bytes(int64_t O, int64_t T);
+int sln_csr_build(const int64_t* edges, int64_t edge_stride, int64_t O, int64_t T, void* ws, size_t ws_bytes, void* stream);
+int sln_gconv_pool_fwd(const float* new_t_vecs, int64_t O, int64_t T, int32_t H, int32_t Dout, float* pooled,
+                       const void* ws, size_t ws_bytes, void* stream);
+/* CSR read-back helpers for tests: copies row_ptr[O+1] / ent[2T] (device pointers inside ws) */
+int sln_csr_pointers(void* ws, int64_t O, int64_t T, const int32_t** row_ptr, const int32_t** ent);
+
+/* z = eps*exp(0.5*logvar)+mu and its backward (reference Sg2ScVAE_model.py:180-183); n = O*E elements. */
+int sln_reparam_fwd(const float* mu, const float* logvar, const float* eps, int64_t n, float* z, void* stream);
+int sln_reparam_bwd(const float* d_z, const float* logvar, const float* eps, int64_t n, float* d_mu, float* d_logvar, void* stream);
+
+/* calculate_model_losses (reference utils.py:12-33): losses[4] = {bbox, angle, KL_weight*KLD, total} on the device and
+ * the gradient seeds of total w.r.t. boxes_pred, angles (the pre-softmax logits when angles_grad_is_logits != 0, else the
+ * log-probabilities angles_pred), mu and logvar (the d_* may be NULL for a loss-only call).
+ * mu == NULL selects use_AE.  scratch: >= 16 + 12*ceil(O/64) bytes, zero-initialised once by the caller. */
+int sln_vae_loss(const float* boxes_pred, const float* boxes_gt, int32_t box_dim, const float* angles_pred,
+                 const int64_t* angles_gt, int32_t n_angle, const float* mu, const float* logvar, int32_t Z,
+                 float kl_weight, int64_t O, float* losses, float* d_boxes, float* d_angles, int32_t angles_grad_is_logits,
+                 float* d_mu, float* d_logvar, void* scratch, size_t scratch_bytes, void* stream);
+
+/* torch.optim.Adam step (reference train.py:15,82-84) over one flat fp32 arena.  *step is a device int64; when
+ * advance_step != 0 it is incremented first, so the launch is identical every iteration (graph-safe); pass 0 for the
+ * 2nd..nth arena of the same optimizer step.  grad_scale multiplies g (1/world_size for gradient averaging). */
+int sln_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, float grad_scale, int64_t* step, int32_t advance_step,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLN_B200_H */

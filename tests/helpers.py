@@ -1,0 +1,66 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import importlib
+import json
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+syn = importlib.import_module("3d_sln_b200.data.synthetic")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+    inp = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("in.")}
+    f32 = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("f32.")}
+    f64 = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("f64.")}
+    return meta, sd, inp, f32, f64
+
+
+def our_model(E=64, layers=5, norm="batch", mode="feedforward", use_AE=False, seed=42, device=None):
+    Model = importlib.import_module("3d_sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
+    torch.manual_seed(seed)
+    m = Model(syn.default_vocab(), embedding_dim=E, batch_size=128, train_3d=True, decoder_cat=True, gconv_mode=mode,
+              gconv_num_layers=layers, mlp_normalization=norm, vec_noise_dim=0, layout_noise_dim=32, use_AE=use_AE)
+    return m.to(device) if device is not None else m
+
+
+def max_norm_err(a, b):
+    """max|a-b| / max(max|b|, tiny)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def check_close(name, new, truth64, ref32=None, tol=1e-4, slack=3.0, abs_floor=0.0):
+    """err(new, fp64 truth) <= max(tol, slack * err(reference fp32, fp64 truth)) in max-norm (SURVEY App. F rule 1).
+
+    Tensors whose true value is identically ~0 (e.g. Linear biases feeding a training-mode BatchNorm) are compared
+    absolutely against the reference's own fp32 noise."""
+    new, truth64 = new.detach().double().cpu(), truth64.detach().double().cpu()
+    assert new.shape == truth64.shape, (name, new.shape, truth64.shape)
+    scale = truth64.abs().max().item()
+    noise = (ref32.detach().double().cpu() - truth64).abs().max().item() if ref32 is not None else 0.0
+    err = (new - truth64).abs().max().item()
+    bound = max(tol * scale, slack * noise, abs_floor)
+    assert err <= bound, "%s: max|err|=%.3e > bound %.3e (scale %.3e, ref fp32 noise %.3e)" % (name, err, bound, scale, noise)
+    return err / max(scale, 1e-30)
+
+
+def with_eps(eps):
+    """Context manager injecting a fixed N(0,1) sample into torch.randn_like (the model keeps torch's RNG call)."""
+    import contextlib
+
+    @contextlib.contextmanager
+    def cm():
+        orig = torch.randn_like
+        torch.randn_like = lambda t, *a, **k: eps.to(device=t.device, dtype=t.dtype)
+        try:
+            yield
+        finally:
+            torch.randn_like = orig
+    return cm()

@@ -1,0 +1,71 @@
+"""CPU-side checks of the drop-in boundary: the library builds for sm_100a, loads, and exports every declared symbol."""
+import ctypes
+import importlib
+
+import pytest
+import torch
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    _lib = importlib.import_module("3d_sln_b200._lib")
+    path = _lib.build()
+    lib = ctypes.CDLL(path)
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 15
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, "symbols declared in include/sln_b200.h but not exported: %s" % missing
+    unbound = [s for s in declared if s not in _lib.SIGNATURES]
+    assert not unbound, "symbols without a ctypes signature: %s" % unbound
+
+
+def test_version_and_error_string():
+    _lib = importlib.import_module("3d_sln_b200._lib")
+    lib = _lib.load()
+    assert lib.sln_version() == 1
+    # argument validation happens on the host before any launch: no GPU needed
+    d = _lib.VaeDesc(embedding_dim=6, n_layers=5, recurrent=0, norm=1, training=1, box_dim=6, n_angle=24, num_objs=33, num_preds=16,
+                     num_attrs=5, bn_eps=1e-5, bn_momentum=0.1, gconv_dim_override=0, gconv_hidden_override=0)
+    assert lib.sln_vae_num_params(d) == -1
+    assert b"multiple of 4" in lib.sln_last_error()
+
+
+def test_parameter_table_matches_module_tree():
+    from helpers import our_model
+    _lib = importlib.import_module("3d_sln_b200._lib")
+    lib = _lib.load()
+    for norm, mode, layers in (("batch", "feedforward", 5), ("none", "feedforward", 5), ("batch", "recurrent", 3)):
+        m = our_model(E=64, layers=layers, norm=norm, mode=mode)
+        ps, bufs, enc, dec = m._param_list()
+        assert lib.sln_vae_num_params(m._desc()) == len(ps)
+        assert lib.sln_vae_num_bn(m._desc()) * 3 == len(bufs)
+        assert sorted(enc + dec) == list(range(len(ps)))
+        assert {id(p) for p in ps} == {id(p) for p in m.parameters()}
+        assert lib.sln_vae_workspace_bytes(m._desc(), 2048, 3968, 0) > 0
+
+
+def test_cpu_tensors_fail_loudly():
+    from helpers import our_model, syn
+    m = our_model(E=8, layers=1)
+    objs, triples, boxes, angles, attrs = syn.fixture_graph()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(objs, triples, boxes, angles, attrs, None)
+    graph = importlib.import_module("3d_sln_b200.models.graph")
+    g = graph.GraphTripleConv(16, hidden_dim=32)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        g(torch.zeros(4, 16), torch.zeros(3, 16), torch.zeros(3, 2, dtype=torch.long))
+
+
+def test_state_dict_keys_and_init_match_reference_when_available():
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    from helpers import our_model, syn
+    Ref = ref_shim.vae_model_class()
+    for norm in ("batch", "none"):
+        torch.manual_seed(42)
+        r = Ref(syn.default_vocab(), embedding_dim=64, batch_size=128, train_3d=True, decoder_cat=True, gconv_mode='feedforward',
+                gconv_num_layers=5, mlp_normalization=norm, vec_noise_dim=0, layout_noise_dim=32, use_AE=False)
+        o = our_model(E=64, layers=5, norm=norm)
+        a, b = r.state_dict(), o.state_dict()
+        assert list(a.keys()) == list(b.keys())
+        assert all(torch.equal(a[k], b[k]) for k in a)
