@@ -14,7 +14,7 @@ _CSRC = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libsln_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
 
-SOURCES = ["vae_engine.cu", "raster.cu", "spade.cu"]
+SOURCES = ["runtime.cu", "vae_engine.cu", "raster.cu", "spade.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -76,6 +76,9 @@ _DESC = ctypes.POINTER(VaeDesc)
 SIGNATURES = {
     "sln_version": (ctypes.c_int, []),
     "sln_last_error": (ctypes.c_char_p, []),
+    "sln_launch_count": (_I64, []),
+    "sln_prof_enable": (ctypes.c_int, [ctypes.c_int]),
+    "sln_prof_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64)]),
     "sln_vae_num_params": (ctypes.c_int, [_DESC]),
     "sln_vae_num_bn": (ctypes.c_int, [_DESC]),
     "sln_vae_workspace_bytes": (_SZ, [_DESC, _I64, _I64, ctypes.c_int]),

@@ -46,7 +46,21 @@ const char* get_error();
     if (_r != SLN_OK) return _r; \
   } while (0)
 
+// Launch accounting + optional per-class CUDA-event profiler (runtime.cu).  Both are host-side only.
+void count_launch();
+enum ProfClass { PROF_GEMM_FWD = 0, PROF_GEMM_BWD_X = 1, PROF_GEMM_BWD_W = 2, PROF_POOL = 3, PROF_PREP = 4, PROF_MISC = 5,
+                 PROF_RASTER_FWD = 6, PROF_RASTER_BWD = 7, PROF_SPADE_CONV = 8, PROF_SPADE_MISC = 9, PROF_NUM = 10 };
+bool prof_enabled();
+void prof_begin(cudaStream_t st, int cls, double work);
+void prof_end(cudaStream_t st);
+struct ProfScope {  // wraps one launch (or a short launch group) in an event pair when profiling is on
+  cudaStream_t st; bool on;
+  ProfScope(cudaStream_t s, int cls, double work) : st(s), on(prof_enabled()) { if (on) prof_begin(st, cls, work); }
+  ~ProfScope() { if (on) prof_end(st); }
+};
+
 inline int check_launch(const char* what) {
+  count_launch();
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     (void)cudaGetLastError();

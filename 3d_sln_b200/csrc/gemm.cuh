@@ -530,8 +530,9 @@ inline int max_row_tiles(int M) { return ceil_div(M, 64); }
 
 template <bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
 int launch_gemm(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, bool allow_split,
-                const char* what) {
+                const char* what, int prof_cls) {
   if (M <= 0 || N <= 0) return SLN_OK;
+  ProfScope prof(st, prof_cls, 2.0 * (double)M * (double)N * (double)K);
   TileChoice c = pick_tile(M, N, K, allow_split);
   dim3 grid(ceil_div(N, c.bn), ceil_div(M, c.bm), c.splits);
   if (c.bm == 128 && c.bn == 128)

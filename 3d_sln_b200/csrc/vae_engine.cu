@@ -11,15 +11,6 @@
 
 namespace sln {
 
-static thread_local char g_err[512] = "";
-void set_error(const char* fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(g_err, sizeof(g_err), fmt, ap);
-  va_end(ap);
-}
-const char* get_error() { return g_err; }
-
 namespace {
 
 constexpr int kMaxLayers = 32;
@@ -161,7 +152,7 @@ void plan_graph(Arena& ar, int O, int T, Graph* g, int** deg, int** err) {
   g->O = O; g->T = T;
   g->s_idx = ar.take<int>(T); g->p_idx = ar.take<int>(T); g->o_idx = ar.take<int>(T);
   g->row_ptr = ar.take<int>(O + 1); g->ent = ar.take<int>((size_t)2 * T);
-  g->inv_cnt = ar.take<float>(O); g->cursor = ar.take<int>(O);
+  g->cnt = ar.take<float>(O); g->cursor = ar.take<int>(O);
   *deg = ar.take<int>(O); *err = ar.take<int>(1);
 }
 
@@ -233,6 +224,9 @@ void make_plan(const Dims& dm, int O, int T, int which, void* ws, NetPlan* p) {
 }
 
 // ---------------------------------------------------------------- building blocks
+// algorithmic bytes of the avg-pool gather-reduce: read new_s,new_o (2*T*H fp32) + CSR (2T entries + O+1 offsets + O counts),
+// write pooled (O*H fp32)   
+double pool_bytes(int O, int T, int H) { return 4.0 * (2.0 * T * H + 2.0 * T + 2.0 * O + 1.0 + (double)O * H); }
 int norm_mode(const Ctx& c, const Blk& b) { return !b.has_bn ? NORM_NONE : (c.dm.training ? NORM_BN_TRAIN : NORM_BN_EVAL); }
 
 MatView block_out(const Blk& b, const BlkState& s) {
@@ -259,7 +253,7 @@ int block_fwd(const Ctx& c, const AOp& A, int M, const Blk& b, BlkState& s, floa
     k_bn_eval_prep<<<ceil_div(b.lin.out, 128), 128, 0, c.st>>>(b.gamma, b.beta, b.rm, b.rv, c.dm.eps, b.lin.out, s.mean, s.rstd, s.scale, s.shift);
     SLN_TRY(check_launch("bn_eval_prep"));
   }
-  return launch_gemm<true, true>(c.st, A, weight_view(b.lin), epi, M, b.lin.out, b.lin.in, false, "linear_fwd");
+  return launch_gemm<true, true>(c.st, A, weight_view(b.lin), epi, M, b.lin.out, b.lin.in, false, "linear_fwd", PROF_GEMM_FWD);
 }
 
 DyView blk_dy(const Ctx& c, const Blk& b, const BlkState& s) {
@@ -287,13 +281,13 @@ template <class XOp>
 int bwd_w(const Ctx& c, const DyView& dy, const XOp& X, const Lin& lin, int M) {
   if (!lin.dW) return SLN_OK;
   EpiAtomic epi{lin.dW, lin.in};
-  return launch_gemm<false, false>(c.st, dy, X, epi, lin.out, lin.in, M, true, "linear_bwd_w");
+  return launch_gemm<false, false>(c.st, dy, X, epi, lin.out, lin.in, M, true, "linear_bwd_w", PROF_GEMM_BWD_W);
 }
 // dX[M,in] = dy W
 int bwd_x_plain(const Ctx& c, const DyView& dy, const Lin& lin, int M, float* dX, int ldx) {
   EpiStore epi; memset(&epi, 0, sizeof(epi));
   epi.C = dX; epi.ldc = ldx;
-  return launch_gemm<true, false>(c.st, dy, weight_view(lin), epi, M, lin.in, lin.out, false, "linear_bwd_x");
+  return launch_gemm<true, false>(c.st, dy, weight_view(lin), epi, M, lin.in, lin.out, false, "linear_bwd_x", PROF_GEMM_BWD_X);
 }
 // prev.g = relu_mask(prev) ? (dy W + add) : 0, with the BN-backward reduction of `prev` fused in the epilogue.
 int bwd_x_masked(const Ctx& c, const DyView& dy, const Lin& lin, int M, const Blk& pb, BlkState& ps, const float* add, int ldadd) {
@@ -303,7 +297,7 @@ int bwd_x_masked(const Ctx& c, const DyView& dy, const Lin& lin, int M, const Bl
   if (pb.has_bn) { epi.scale = ps.scale; epi.shift = ps.shift; epi.mean = ps.mean; epi.rstd = ps.rstd; }
   epi.fin = blk_fin(c, pb, ps);
   SLN_CHECK_ARG(lin.in == pb.lin.out, "internal: masked backward expects matching widths (%d vs %d)", lin.in, pb.lin.out);
-  return launch_gemm<true, false>(c.st, dy, weight_view(lin), epi, M, lin.in, lin.out, false, "linear_bwd_x_masked");
+  return launch_gemm<true, false>(c.st, dy, weight_view(lin), epi, M, lin.in, lin.out, false, "linear_bwd_x_masked", PROF_GEMM_BWD_X);
 }
 // bias gradient of a Linear whose dy is given directly: db += column sums
 int bwd_bias_plain(const Ctx& c, const float* dy, int ld, int M, const Lin& lin) {
@@ -322,7 +316,7 @@ int graph_prep(const Ctx& c, NetPlan& p, const int64_t* triples_or_edges, int st
     k_split_triples<<<ceil_div(g.T, 256), 256, 0, c.st>>>((const long long*)triples_or_edges, g.T, g.O, g.s_idx, g.p_idx, g.o_idx, p.deg, p.err);
     SLN_TRY(check_launch("split_triples"));
   }
-  k_scan_deg<<<1, 1024, 0, c.st>>>(p.deg, g.O, g.row_ptr, g.inv_cnt);
+  k_scan_deg<<<1, 1024, 0, c.st>>>(p.deg, g.O, g.row_ptr, g.cnt);
   SLN_TRY(check_launch("scan_deg"));
   if (g.T > 0) {
     k_fill_csr<<<ceil_div(g.T, 256), 256, 0, c.st>>>(g.s_idx, g.o_idx, g.T, g.row_ptr, g.cursor, g.ent);
@@ -351,7 +345,7 @@ int graph_prep_edges(cudaStream_t st, Graph& g, int* deg, int* err, const int64_
     k_split_edges<<<ceil_div(g.T, 256), 256, 0, st>>>((const long long*)edges, g.T, g.O, g.s_idx, g.o_idx, deg, err);
     SLN_TRY(check_launch("split_edges"));
   }
-  k_scan_deg<<<1, 1024, 0, st>>>(deg, g.O, g.row_ptr, g.inv_cnt);
+  k_scan_deg<<<1, 1024, 0, st>>>(deg, g.O, g.row_ptr, g.cnt);
   SLN_TRY(check_launch("scan_deg"));
   if (g.T > 0) {
     k_fill_csr<<<ceil_div(g.T, 256), 256, 0, st>>>(g.s_idx, g.o_idx, g.T, g.row_ptr, g.cursor, g.ent);
@@ -384,7 +378,8 @@ int gconv_fwd(const Ctx& c, const Graph& g, const Blk* blk, BlkState* st, float*
   MatView a2 = block_out(blk[1], st[1]);
   if (O > 0) {
     int threads = min(256, max(32, ceil_div(H / 4, 32) * 32));
-    k_pool_fwd<<<O, threads, 0, c.st>>>(a2, g.row_ptr, g.ent, g.inv_cnt, O, H, D, pooled);
+    ProfScope prof(c.st, PROF_POOL, pool_bytes(O, T, H));
+    k_pool_fwd<<<O, threads, 0, c.st>>>(a2, g.row_ptr, g.ent, g.cnt, O, H, D, pooled);
     SLN_TRY(check_launch("pool_fwd"));
   }
   SLN_TRY(block_fwd(c, make_view(pooled, H, O, H), O, blk[2], st[2]));
@@ -409,7 +404,7 @@ int gconv_bwd(const Ctx& c, const Graph& g, const Blk* blk, BlkState* st, const 
   SLN_TRY(bwd_w(c, dy3, make_view(pooled, H, O, H), blk[2].lin, O));
   SLN_TRY(bwd_x_plain(c, dy3, blk[2].lin, O, dpooled, H));
   // pooling backward + BN-backward reduction of net1's second Linear
-  PoolBwdSrc src{dpooled, g.inv_cnt, g.s_idx, g.o_idx, dpred_next, ld_dpred, H, D};
+  PoolBwdSrc src{dpooled, g.cnt, g.s_idx, g.o_idx, dpred_next, ld_dpred, H, D};
   SLN_TRY(launch_prep(c.st, src, blk_act(blk[1], st[1]), st[1].g, 2 * H + D, blk_fin(c, blk[1], st[1]), T, 2 * H + D, "pool_bwd_prep"));
   // net1, second Linear
   DyView dy2 = blk_dy(c, blk[1], st[1]);
@@ -493,9 +488,6 @@ int check_dims(int64_t O, int64_t T) {
 using namespace sln;
 
 extern "C" {
-
-int sln_version(void) { return SLN_ABI_VERSION; }
-const char* sln_last_error(void) { return get_error(); }
 
 int sln_vae_num_params(const sln_vae_desc* d) { Dims dm; if (make_dims(d, &dm)) return -1; return count_params(dm); }
 int sln_vae_num_bn(const sln_vae_desc* d) { Dims dm; if (make_dims(d, &dm)) return -1; return count_bn(dm); }
@@ -776,7 +768,8 @@ int sln_gconv_pool_fwd(const float* new_t_vecs, int64_t O, int64_t T, int32_t H,
   plan_graph(ar, (int)O, (int)T, &g, &deg, &err);
   MatView a2 = make_view(new_t_vecs, 2 * H + Dout, (int)T, 2 * H + Dout);
   int threads = min(256, max(32, ceil_div(H / 4, 32) * 32));
-  k_pool_fwd<<<(int)O, threads, 0, (cudaStream_t)stream>>>(a2, g.row_ptr, g.ent, g.inv_cnt, (int)O, H, Dout, pooled);
+  ProfScope prof((cudaStream_t)stream, PROF_POOL, pool_bytes((int)O, (int)T, H));
+  k_pool_fwd<<<(int)O, threads, 0, (cudaStream_t)stream>>>(a2, g.row_ptr, g.ent, g.cnt, (int)O, H, Dout, pooled);
   return check_launch("pool_fwd");
 }
 

@@ -15,7 +15,7 @@ struct Graph {
   int* o_idx;    // [T]
   int* row_ptr;  // [O+1]  CSR over nodes; entries = triples touching the node as subject (side 0) or object (side 1)
   int* ent;      // [2T]   (side << 30) | t, sorted ascending inside each row (= reference scatter_add order)
-  float* inv_cnt;  // [O]  1 / max(deg,1)
+  float* cnt;  // [O]  max(deg,1) as float (reference graph.py:102-108 divides by the clamped count)
   int* cursor;     // [O]  scratch
 };
 
@@ -31,7 +31,7 @@ __global__ void k_split_triples(const long long* __restrict__ triples, int T, in
 }
 
 // single-CTA exclusive scan (O is at most a few 10^5; runs once per batch)
-__global__ void k_scan_deg(const int* __restrict__ deg, int O, int* row_ptr, float* inv_cnt) {
+__global__ void k_scan_deg(const int* __restrict__ deg, int O, int* row_ptr, float* cnt) {
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -56,7 +56,7 @@ __global__ void k_scan_deg(const int* __restrict__ deg, int O, int* row_ptr, flo
     int carry = carry_s;
     if (i < O) {
       row_ptr[i] = carry + warp_off + x - v;
-      inv_cnt[i] = 1.f / (float)max(v, 1);
+      cnt[i] = (float)max(v, 1);
     }
     __syncthreads();
     if (threadIdx.x == 0) carry_s = carry + warp_tot[nw - 1];
@@ -137,13 +137,13 @@ __global__ void k_embed_bwd(const float* __restrict__ a, int lda, const float* _
 }
 
 // ================================================================ avg pooling  (reference graph.py:92-108)
-// pooled[o, c] = inv_cnt[o] * ( sum_{t: s_t = o} a2[t, c] + sum_{t: o_t = o} a2[t, H + D + c] ),  a2 = relu(bn(y2)) lazily.
+// pooled[o, c] = (1 / cnt[o]) * ( sum_{t: s_t = o} a2[t, c] + sum_{t: o_t = o} a2[t, H + D + c] ),  a2 = relu(bn(y2)) lazily.
 // One CTA per node; threads own float4 columns; rows are read as contiguous 4*H-byte segments (coalesced).
 __global__ void k_pool_fwd(const MatView a2, const int* __restrict__ row_ptr, const int* __restrict__ ent,
-                           const float* __restrict__ inv_cnt, int O, int H, int D, float* pooled) {
+                           const float* __restrict__ cnt, int O, int H, int D, float* pooled) {
   int o = blockIdx.x;
   int b = __ldg(row_ptr + o), e = __ldg(row_ptr + o + 1);
-  float ic = __ldg(inv_cnt + o);
+  float ic = __ldg(cnt + o);  // true division below: bit-identical to the reference's pooled / counts
   for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = b; k < e; ++k) {
@@ -153,7 +153,7 @@ __global__ void k_pool_fwd(const MatView a2, const int* __restrict__ row_ptr, co
       float4 v = a2.ld4(t, off + c);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    acc.x *= ic; acc.y *= ic; acc.z *= ic; acc.w *= ic;
+    acc.x = __fdiv_rn(acc.x, ic); acc.y = __fdiv_rn(acc.y, ic); acc.z = __fdiv_rn(acc.z, ic); acc.w = __fdiv_rn(acc.w, ic);
     float* dst = pooled + (size_t)o * H + c;
     if (c + 3 < H) *reinterpret_cast<float4*>(dst) = acc;
     else { dst[0] = acc.x; if (c + 1 < H) dst[1] = acc.y; if (c + 2 < H) dst[2] = acc.z; }
@@ -165,16 +165,16 @@ __global__ void k_pool_fwd(const MatView a2, const int* __restrict__ row_ptr, co
 // rather than produced by a contraction epilogue.
 struct PoolBwdSrc {  // gradient w.r.t. a2 = relu(bn(y2)) [T, 2H+D] from d pooled [O,H] and d new_pred [T,D]
   const float* dpooled;  // [O,H]
-  const float* inv_cnt;
+  const float* cnt;
   const int* s_idx;
   const int* o_idx;
   const float* dpred;  // [T, ldd] slice or null
   int ldd, H, D;
   __device__ __forceinline__ float at(int t, int c) const {
-    if (c < H) { int s = __ldg(s_idx + t); return __ldg(dpooled + (size_t)s * H + c) * __ldg(inv_cnt + s); }
+    if (c < H) { int s = __ldg(s_idx + t); return __fdiv_rn(__ldg(dpooled + (size_t)s * H + c), __ldg(cnt + s)); }
     if (c < H + D) return dpred ? __ldg(dpred + (size_t)t * ldd + (c - H)) : 0.f;
     int o = __ldg(o_idx + t);
-    return __ldg(dpooled + (size_t)o * H + (c - H - D)) * __ldg(inv_cnt + o);
+    return __fdiv_rn(__ldg(dpooled + (size_t)o * H + (c - H - D)), __ldg(cnt + o));
   }
 };
 struct NodeGatherSrc {  // gradient w.r.t. obj_vecs [O,D] from d cat [T,3D]: transpose of the s/o gathers (graph.py:78-79)
@@ -271,6 +271,7 @@ int launch_prep(cudaStream_t st, const Src& src, const ActInfo& act, float* G, i
   int rows = max(64, ceil_div(M, want_tiles));
   rows = ceil_div(rows, 4) * 4;
   dim3 grid(col_blocks, ceil_div(M, rows));
+  ProfScope prof(st, PROF_PREP, 12.0 * (double)M * (double)N);  // read src + y, write G
   k_prep<Src><<<grid, dim3(128, 4), 0, st>>>(src, act, G, ldg, fin, M, N, rows);
   return check_launch(what);
 }

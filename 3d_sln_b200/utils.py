@@ -186,7 +186,7 @@ class VAETrainStep(object):
     """
 
     def __init__(self, model, O, T, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, kl_weight=0.1, use_graph=True, process_group=None,
-                 world_size=1):
+                 world_size=1, sample_eps=True):
         self.lib = _lib.load()
         self.model = model
         dev = next(model.parameters()).device
@@ -195,6 +195,7 @@ class VAETrainStep(object):
         self.dev, self.O, self.T = dev, O, T
         self.kl_weight, self.lr, self.betas, self.eps = kl_weight, lr, betas, eps
         self.world_size, self.pg = world_size, process_group
+        self.sample_eps = sample_eps   # False: the caller writes the N(0,1) draw into self.epsn before run() (parity tests)
         E, BD, NA = model.embedding_dim, model.box_dim, model.Nangle
         model._tables()
         cache = model._cache
@@ -251,7 +252,8 @@ class VAETrainStep(object):
                                            self.angles.data_ptr(), self.attrs.data_ptr(), O, T, self.mu.data_ptr(), self.logvar.data_ptr(),
                                            self.ws_enc.data_ptr(), self.ws_enc.numel(), st), "encoder_fwd")
         if use_kl:
-            self.epsn.normal_()
+            if self.sample_eps:
+                self.epsn.normal_()
             _lib.check(lib.sln_reparam_fwd(self.mu.data_ptr(), self.logvar.data_ptr(), self.epsn.data_ptr(), O * E, self.z.data_ptr(), st), "reparam_fwd")
             z = self.z
         else:

@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract of the 3D_SLN B200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload vae|render|spade] [--impl reference]
+
+Default workload = BASELINE.json configs[1]: the VAE-graph train step (reference train.py:69-84: forward, losses, backward,
+Adam) on synthetic SUNCG-shaped scene graphs, batch 64 x 32 nodes per GPU (O=2048, T=3968), E=64, BatchNorm MLPs, fp32.
+One "step" = one train step over one batch.  N>1 (torchrun, one rank per GPU): every rank steps its own 64 scenes and the
+flat gradient arena is all-reduced over NCCL (weak scaling; BatchNorm statistics stay per rank = DDP semantics).
+
+Printed JSON (rank 0, one line):
+  value        scene-graphs/s, inputs resident in HBM, CUDA-event time of K steps, max over ranks
+  e2e          same metric through the public API (VAETrainStep.step(host batch) + loss read-back) with pinned-host inputs
+  roofline     dominant kernel class, timed live with CUDA events around every launch of an un-graphed step
+  cpu_baseline the oracle port (oracle/vae_oracle.py, plain torch CPU ops restating the reference) on this box's host cores
+  --impl reference : that CPU path alone, on the same config/metric (the reference itself is Python and cannot travel to
+                     the GPU box: /root/reference only exists in the build container).
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SCENES_PER_GPU = 64
+NODES_PER_SCENE = 32
+FP32_SIMT_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 148 SMs x 128 FMA lanes x 2 flop x max SM clock (nominal)
+PROF_CLASSES = ["gemm_fwd", "gemm_bwd_x", "gemm_bwd_w", "pool", "prep", "misc", "raster_fwd", "raster_bwd", "spade_conv", "spade_misc"]
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ================================================================================================ CPU reference arm / baseline
+def cpu_vae_steps(n_scenes, steps, warmup, budget_s):
+    """The reference train-step body (train.py:70-84) restated in oracle/vae_oracle.py, fp32, all host threads.
+    Returns (scene-graphs/s, seconds per step, scenes per step actually used, threads)."""
+    from oracle import vae_oracle as vo
+    syn = importlib.import_module("3d_sln_b200.data.synthetic")
+    Model = importlib.import_module("3d_sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(42)
+    m = Model(syn.default_vocab(), embedding_dim=64, batch_size=128, train_3d=True, decoder_cat=True, gconv_mode='feedforward',
+              gconv_num_layers=5, mlp_normalization='batch', vec_noise_dim=0, layout_noise_dim=32, use_AE=False)
+    sd = vo.leaf_state(m.state_dict(), torch.float32)
+
+    def make(n):
+        _, objs, boxes, triples, angles, attrs, _, _ = syn.synthetic_batch(n, NODES_PER_SCENE, seed=42)
+        return (objs, triples, boxes, angles, attrs)
+
+    batch = make(n_scenes)
+    opt = {}
+    gen = torch.Generator().manual_seed(0)
+    t0 = time.perf_counter()
+    vo.train_step(sd, batch, torch.randn(batch[0].size(0), 64, generator=gen), opt, 1)
+    first = time.perf_counter() - t0
+    per_step_budget = budget_s / max(steps + warmup, 1)
+    used = n_scenes
+    if first > per_step_budget and n_scenes > 8:        # bounded sample: fewer scenes per step, same per-scene shape
+        used = max(8, int(n_scenes * per_step_budget / first))
+        batch = make(used)
+    it = 1
+    for _ in range(max(warmup - 1, 0)):
+        it += 1
+        vo.train_step(sd, batch, torch.randn(batch[0].size(0), 64, generator=gen), opt, it)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        it += 1
+        vo.train_step(sd, batch, torch.randn(batch[0].size(0), 64, generator=gen), opt, it)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return used / dt, dt, used, threads
+
+
+def run_reference(args):
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return
+    n = max(args.gpus, 1)
+    if args.workload != "vae":
+        mod = importlib.import_module("bench_%s" % args.workload)
+        print(json.dumps(mod.run_reference(args)), flush=True)
+        return
+    scenes = SCENES_PER_GPU * n
+    val, dt, used, threads = cpu_vae_steps(scenes, args.steps, args.warmup, budget_s=150.0)
+    sample = "%d scenes x %d nodes per step (%s of the %d-scene workload), %d steps, fp32 torch CPU ops" % (
+        used, NODES_PER_SCENE, "all" if used == scenes else "a bounded sample", scenes, args.steps)
+    line = {
+        "impl": "reference", "metric": "scene-graphs/sec VAE train step (batch64, 32obj)", "value": val, "unit": "scene-graphs/s",
+        "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * scenes / used, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": vae_config(n),
+        "cpu_baseline": {"value": val, "unit": "scene-graphs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "scene-graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def vae_config(n):
+    return {"workload": "BASELINE configs[1]: VAE-graph train step, %d scenes x %d nodes per GPU (O=%d, T=%d per GPU), embedding_dim=64, "
+                        "5+5 GraphTripleConv layers, mlp_normalization=batch, Adam lr 1e-4" % (
+                            SCENES_PER_GPU, NODES_PER_SCENE, SCENES_PER_GPU * NODES_PER_SCENE, SCENES_PER_GPU * (NODES_PER_SCENE - 1) * 2),
+            "global_batch_scenes": SCENES_PER_GPU * n, "parallelism": "dp%d (scene-sharded, NCCL all-reduce of one flat 15.5 MB gradient arena; "
+                                                                     "per-rank BatchNorm statistics)" % n,
+            "l2": "L2 flushed (256 MiB write) before every timed step"}
+
+
+# ================================================================================================ VAE train step on the GPU
+def run_vae(args):
+    rank, local_rank, world = dist_env()
+    n = max(args.gpus, 1)
+    if world != n and world > 1:
+        n = world
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    _lib = importlib.import_module("3d_sln_b200._lib")
+    lib = _lib.load()
+    syn = importlib.import_module("3d_sln_b200.data.synthetic")
+    Model = importlib.import_module("3d_sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
+    sutils = importlib.import_module("3d_sln_b200.utils")
+
+    torch.manual_seed(42)   # reference options/options.py:59 — identical initial weights on every rank
+    model = Model(syn.default_vocab(), embedding_dim=64, batch_size=128, train_3d=True, decoder_cat=True, gconv_mode='feedforward',
+                  gconv_num_layers=5, mlp_normalization='batch', vec_noise_dim=0, layout_noise_dim=32, use_AE=False).float().to(dev).train()
+    _, objs, boxes, triples, angles, attrs, _, _ = syn.synthetic_batch(SCENES_PER_GPU, NODES_PER_SCENE, seed=42 + rank)
+    host = [t.pin_memory() for t in (objs, triples, boxes, angles, attrs)]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    O, T = objs.size(0), triples.size(0)
+    step = sutils.VAETrainStep(model, O, T, lr=1e-4, kl_weight=0.1, use_graph=True, process_group=pg, world_size=world)
+    step.load_batch(host)
+    n0 = lib.sln_launch_count()
+    step._fwd_bwd(); step._allreduce(); step._opt()
+    launches_per_step = int(lib.sln_launch_count() - n0)
+    step.capture()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    losses_host = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step.step(host)
+    barrier()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    # ---- value: device-resident inputs, CUDA events around each step, L2 flushed between steps
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        step.run()
+        b.record()
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # ---- e2e: public API with pinned-host inputs: H2D of the batch, the step, D2H of the losses, every step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step.step(host)
+        losses_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    final_losses = losses_host.tolist()
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = t.tolist()
+    # ---- roofline: one un-graphed step with an event pair around every launch of the library
+    prof = None
+    if rank == 0:
+        barrier_local = lambda: torch.cuda.synchronize(dev)   # noqa: E731
+        rows = {}
+        reps = 3
+        lib.sln_prof_enable(1)
+        for _ in range(reps):
+            flush.zero_()
+            step._fwd_bwd(); step._opt()
+        barrier_local()
+        total_ms = 0.0
+        for ci, cname in enumerate(PROF_CLASSES):
+            ms, work, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+            _lib.check(lib.sln_prof_read(ci, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(cnt)), "prof_read")
+            if cnt.value:
+                rows[cname] = dict(ms=ms.value / reps, work=work.value / reps, launches=cnt.value // reps)
+                total_ms += ms.value / reps
+        lib.sln_prof_enable(0)
+        prof = dict(rows=rows, total_ms=total_ms)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return None
+    peaks = measured_peaks()
+    scenes = SCENES_PER_GPU * n
+    ms_per_step = dev_ms / args.steps
+    value = scenes / (ms_per_step * 1e-3)
+    e2e = scenes * args.steps / e2e_s
+    gemm = {k: v for k, v in prof["rows"].items() if k.startswith("gemm")}
+    g_ms = sum(v["ms"] for v in gemm.values()); g_fl = sum(v["work"] for v in gemm.values()); g_n = sum(v["launches"] for v in gemm.values())
+    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_kernel (fp32 contraction of the graph-conv MLPs, fwd + bwd-data + bwd-weight)",
+        "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
+        "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a step)",
+        "algorithmic_flops_per_launch": g_fl / max(g_n, 1), "launches_per_step": g_n, "avg_launch_us": g_ms * 1e3 / max(g_n, 1),
+        "share_of_step": g_ms / prof["total_ms"] if prof["total_ms"] else None,
+        "note": "the contraction runs on the FP32 FMA pipe (parity contract is fp32, SURVEY App. F); against the nominal FP32-SIMT peak "
+                "%.1f TFLOP/s it is %.3f" % (FP32_SIMT_PEAK_TFLOPS, achieved / FP32_SIMT_PEAK_TFLOPS),
+    }
+    pool = prof["rows"].get("pool")
+    roofline_scatter = None
+    if pool:
+        gbs = pool["work"] / (pool["ms"] * 1e-3) / 1e9
+        roofline_scatter = {"bound": "hbm", "kernel": "k_pool_fwd (scatter_add+count+divide as a CSR gather-reduce)", "achieved": gbs,
+                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                            "algorithmic_bytes_per_launch": pool["work"] / pool["launches"], "avg_launch_us": pool["ms"] * 1e3 / pool["launches"],
+                            "note": "10.3 MB per launch at this config: below launch latency; see profiles/ for the large-batch sweep"}
+    cpu = None
+    if n == 1 and not args.no_cpu_baseline:
+        val, dt, used, threads = cpu_vae_steps(SCENES_PER_GPU, steps=8, warmup=2, budget_s=25.0)
+        cpu = {"value": val, "unit": "scene-graphs/s", "cores": threads, "kind": "port",
+               "sample": "%d scenes x %d nodes per step, 8 timed steps, fp32 torch CPU ops (oracle/vae_oracle.py train_step)" % (used, NODES_PER_SCENE)}
+    line = {
+        "metric": "scene-graphs/sec VAE train step (batch64, 32obj)", "value": value, "unit": "scene-graphs/s", "n_gpus": n,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": vae_config(n),
+        "e2e": {"value": e2e, "unit": "scene-graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
+        "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+        "roofline": roofline, "roofline_scatter": roofline_scatter, "cpu_baseline": cpu, "clocks": clocks,
+        "kernel_classes_ms": {k: round(v["ms"], 4) for k, v in prof["rows"].items()},
+        "final_losses": {"bbox": final_losses[0], "angle": final_losses[1], "kld_weighted": final_losses[2], "total": final_losses[3]},
+    }
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="vae", choices=["vae", "render", "spade"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    if args.workload == "vae":
+        line = run_vae(args)
+    else:
+        line = importlib.import_module("bench_%s" % args.workload).run(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

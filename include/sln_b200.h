@@ -28,6 +28,16 @@ extern "C" {
 int sln_version(void);
 const char* sln_last_error(void);
 
+/* Launch accounting and per-kernel-class timing (used by bench.py; the reference only has the unused wall-clock helper
+ * utils.py:127-137 `timeit`).  sln_launch_count(): kernels launched by this library since load.  With profiling enabled
+ * (never during CUDA-graph capture) every launch is bracketed by CUDA events on its stream; sln_prof_read() sums, for one
+ * class, the device milliseconds, the algorithmic work (FLOPs for contractions, bytes for the rest) and the launch count
+ * since the last sln_prof_enable() call (which also clears the records).
+ * classes: 0 gemm_fwd 1 gemm_bwd_x 2 gemm_bwd_w 3 pool 4 prep 5 misc 6 raster_fwd 7 raster_bwd 8 spade_conv 9 spade_misc */
+int64_t sln_launch_count(void);
+int sln_prof_enable(int on);
+int sln_prof_read(int cls, double* ms, double* work, int64_t* launches);
+
 /* ------------------------------------------------------------------------------------------------ VAE-graph model
  * Model description: mirrors the ctor kwargs of Sg2ScVAEModel (reference models/Sg2ScVAE_model.py:7-113,
  * build_dataset_model.py:40-52). */

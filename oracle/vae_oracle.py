@@ -199,4 +199,4 @@ def train_step(sd, batch, eps, opt_state, step, num_layers=5, kl_weight=0.1, lr=
         adam_step(ps, gs, opt_state['m'], opt_state['v'], step, lr)
         for k, v in stats.items():
             sd[k] = v
-    return float(total), {k: float(v) for k, v in parts.items()}
+    return float(total.detach()), {k: float(v.detach()) for k, v in parts.items()}

@@ -1,0 +1,310 @@
+"""GPU parity tests of the VAE-graph hot path: the CUDA kernels (through the C ABI / the drop-in modules) against the CPU
+oracle (oracle/vae_oracle.py, pinned to the reference by tests/test_oracle_vae.py) and the committed golden vectors.
+
+Tolerance: err(new, fp64 truth) <= max(1e-4 * scale, 3 * err(reference fp32, fp64 truth)) in max-norm;
+index buffers (CSR) are compared bit-exactly.
+"""
+import ctypes
+import importlib
+import json
+import os
+
+import pytest
+import torch
+
+from helpers import GOLD, check_close, load_golden, our_model, syn, with_eps
+from oracle import vae_oracle as vo
+
+pytestmark = pytest.mark.gpu
+
+_lib = importlib.import_module("3d_sln_b200._lib")
+graph = importlib.import_module("3d_sln_b200.models.graph")
+sutils = importlib.import_module("3d_sln_b200.utils")
+
+DEV = "cuda:0"
+
+
+def _rand_edges(O, T, seed, hub=True):
+    g = torch.Generator().manual_seed(seed)
+    e = torch.randint(0, O, (T, 2), generator=g)
+    if hub and T > 8:
+        e[: T // 4, 1] = O - 1          # a high in-degree node (the room node of a scene)
+        e[T // 4: T // 4 + 3, 0] = e[T // 4: T // 4 + 3, 1]   # a few self loops
+    return e
+
+
+# ------------------------------------------------------------------------------------------- CSR + pooling (graph.py:92-108)
+@pytest.mark.parametrize("O,T,H,D", [(7, 0, 8, 4), (1, 5, 16, 8), (37, 91, 32, 16), (2048, 3968, 256, 128), (513, 4001, 36, 20)])
+def test_csr_is_bit_exact_and_pool_matches_reference_order(O, T, H, D):
+    lib = _lib.load()
+    edges = _rand_edges(O, T, seed=O + T)
+    if O > 4 and T > 0:
+        edges[edges == 2] = 3            # node 2 is isolated: pooled row must be exactly 0 (count clamps to 1)
+    ws_bytes = lib.sln_gconv_pool_workspace_bytes(O, T)
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=DEV)
+    ed = edges.to(DEV)
+    st = _lib.cur_stream(torch.device(DEV))
+    _lib.check(lib.sln_csr_build(ed.data_ptr(), 2, O, T, ws.data_ptr(), ws_bytes, st), "csr_build")
+    rp, en = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(lib.sln_csr_pointers(ws.data_ptr(), O, T, ctypes.byref(rp), ctypes.byref(en)), "csr_pointers")
+    torch.cuda.synchronize()
+    base = ws.data_ptr()
+    row_ptr = ws[rp.value - base: rp.value - base + 4 * (O + 1)].view(torch.int32).cpu()
+    ent = ws[en.value - base: en.value - base + 8 * T].view(torch.int32).cpu() if T else torch.zeros(0, dtype=torch.int32)
+    # oracle CSR: for each node, subject-side triples ascending, then object-side triples ascending (scatter_add order)
+    want_rows = [[] for _ in range(O)]
+    for t in range(T):
+        want_rows[int(edges[t, 0])].append(t)
+    for t in range(T):
+        want_rows[int(edges[t, 1])].append((1 << 30) | t)
+    want_ptr = [0]
+    for r in want_rows:
+        want_ptr.append(want_ptr[-1] + len(r))
+    assert row_ptr.tolist() == want_ptr
+    assert ent.tolist() == [x for r in want_rows for x in r]
+    # pooling: same summation order and a true division => bit-identical to the reference's CPU scatter_add / counts
+    g = torch.Generator().manual_seed(1)
+    tv = torch.randn(T, 2 * H + D, generator=g)
+    pooled = torch.empty(O, H, device=DEV)
+    tvd = tv.to(DEV) if T else torch.zeros(1, device=DEV)
+    _lib.check(lib.sln_gconv_pool_fwd(tvd.data_ptr(), O, T, H, D, pooled.data_ptr(), ws.data_ptr(), ws_bytes, st), "pool_fwd")
+    want = torch.zeros(O, H)
+    if T:
+        want = want.index_add(0, edges[:, 0], tv[:, :H]).index_add(0, edges[:, 1], tv[:, H + D:])
+    cnt = torch.zeros(O).index_add(0, edges[:, 0], torch.ones(T)).index_add(0, edges[:, 1], torch.ones(T)).clamp(min=1)
+    want = want / cnt[:, None]
+    assert torch.equal(pooled.cpu(), want)
+
+
+# ------------------------------------------------------------------------------------------- one GraphTripleConv layer
+def _layer_sd(layer, prefix="g"):
+    return {prefix + "." + k: v for k, v in layer.state_dict().items()}
+
+
+@pytest.mark.parametrize("norm,training", [("none", True), ("batch", True), ("batch", False)])
+@pytest.mark.parametrize("O,T,D,H", [(19, 45, 16, 32), (300, 777, 128, 256), (64, 130, 20, 44)])
+def test_gconv_layer_forward_backward_vs_oracle(norm, training, O, T, D, H):
+    torch.manual_seed(3)
+    layer = graph.GraphTripleConv(D, hidden_dim=H, mlp_normalization=norm)
+    if norm == "batch":
+        for m in layer.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+                m.weight.data.uniform_(0.5, 1.5)
+                m.bias.data.normal_(0, 0.2)
+    layer.train(training)
+    sd0 = {k: v.clone() for k, v in _layer_sd(layer).items()}
+    obj = torch.randn(O, D)
+    pred = torch.randn(T, D)
+    edges = _rand_edges(O, T, seed=5)
+    gO, gP = torch.randn(O, D), torch.randn(T, D)
+
+    def run_oracle(dtype):
+        sd = vo.leaf_state(sd0, dtype)
+        o = obj.to(dtype).requires_grad_(True)
+        p = pred.to(dtype).requires_grad_(True)
+        stats = {}
+        no, np_ = vo.gconv_layer(sd, "g", o, p, edges, training, stats)
+        (no * gO.to(dtype)).sum().backward(retain_graph=True)
+        (np_ * gP.to(dtype)).sum().backward()
+        out = {"new_obj": no, "new_pred": np_, "d_obj": o.grad, "d_pred": p.grad}
+        out.update({"grad." + k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items() if v.is_floating_point() and v.requires_grad})
+        out.update({"after." + k: v for k, v in stats.items()})
+        return {k: v.detach() for k, v in out.items()}
+
+    r64, r32 = run_oracle(torch.float64), run_oracle(torch.float32)
+    layer = layer.to(DEV)
+    o = obj.to(DEV).requires_grad_(True)
+    p = pred.to(DEV).requires_grad_(True)
+    no, np_ = layer(o, p, edges.to(DEV))
+    ((no * gO.to(DEV)).sum() + (np_ * gP.to(DEV)).sum()).backward()
+    got = {"new_obj": no, "new_pred": np_, "d_obj": o.grad, "d_pred": p.grad}
+    got.update({"grad.g." + k: v.grad for k, v in layer.named_parameters()})
+    if training and norm == "batch":
+        got.update({"after.g." + k: v for k, v in layer.state_dict().items() if "running" in k or "num_batches" in k})
+    for k, v in got.items():
+        assert v is not None, k
+        check_close(k, v, r64[k], r32[k], tol=1e-4, abs_floor=2e-5 if k.endswith("bias") else 0.0)
+
+
+# ------------------------------------------------------------------------------------------- whole model vs golden vectors
+CASES = ["vae_small_batch_train", "vae_small_batch_eval", "vae_small_none", "vae_small_recurrent"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_model_matches_reference_golden(name):
+    meta, sd0, inp, f32, f64 = load_golden(name)
+    m = our_model(E=meta["E"], layers=meta["layers"], norm=meta["norm"], mode=meta["mode"])
+    m.load_state_dict(sd0)
+    m = m.to(DEV).train(meta["training"])
+    dev = {k: v.to(DEV) for k, v in inp.items()}
+    with with_eps(inp["eps"]):
+        mu, lv, bp, ap = m(dev["objs"], dev["triples"], dev["boxes"], dev["angles"], dev["attrs"], None)
+    import types
+    total, parts = sutils.calculate_model_losses(types.SimpleNamespace(use_AE=False), m, dev["boxes"], bp, dev["angles"], ap, mu=mu,
+                                                 logvar=lv, KL_weight=meta["kl_weight"])
+    m.zero_grad()
+    total.backward()
+    for k, v in (("mu", mu), ("logvar", lv), ("boxes_pred", bp), ("angles_pred", ap), ("total", total)):
+        check_close(k, v, f64[k], f32[k], tol=1e-4)
+    for k, v in parts.items():
+        assert abs(v - float(f64["loss_" + k])) <= 1e-4 * max(abs(float(f64["loss_" + k])), 1e-3), k
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        check_close("grad." + k, p.grad, f64["grad." + k], f32["grad." + k], tol=1e-4, abs_floor=1e-6)
+    after = {k: v for k, v in m.state_dict().items() if "running" in k or "num_batches" in k}
+    for k, v in after.items():
+        check_close("after." + k, v, f64["after." + k], f32["after." + k], tol=1e-4)
+
+
+def test_known_answer_appendix_d_on_gpu():
+    """the reference's embedded 5-object fixture through seed-42 E=64 weights (config 1's graph)."""
+    with open(os.path.join(GOLD, "vae_kat.json")) as f:
+        kat = json.load(f)
+    objs, triples, boxes, angles, attrs = [t.to(DEV) for t in syn.fixture_graph()]
+    for key, want in kat.items():
+        norm, mode = key.split("/")
+        m = our_model(E=64, layers=5, norm=norm, use_AE=True).to(DEV).train(mode == "train")
+        with torch.no_grad():
+            mu, lv, bp, ap = m(objs, triples, boxes, angles, attrs, None)
+        loose = norm == "batch" and mode == "train"     # 6-row BatchNorm amplifies fp32 rounding (App. F)
+        assert abs(mu.sum().item() - want["mu_sum"]) < (2e-3 if loose else 1e-4) * abs(want["mu_sum"]) + 1e-3
+        assert abs(lv.sum().item() - want["logvar_sum"]) < (2e-2 if loose else 1e-4) * abs(want["logvar_sum"]) + 1e-3
+        assert abs(bp.sum().item() - want["boxes_sum"]) < (5e-2 if loose else 1e-3)
+        assert abs(ap.sum().item() - want["angles_sum"]) < (2e-3 if loose else 1e-4) * abs(want["angles_sum"])
+        if not loose:
+            assert ap.argmax(1).tolist() == want["argmax"]
+            assert (bp.cpu() - torch.tensor(want["boxes_pred"])).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- config 2 at full size
+def _config2(B=64, nodes=32, seed=42):
+    _, objs, boxes, triples, angles, attrs, _, _ = syn.synthetic_batch(B, nodes, seed=seed)
+    return objs, triples, boxes, angles, attrs
+
+
+@pytest.mark.parametrize("norm", ["batch", "none"])
+def test_config2_train_step_math_vs_oracle(norm):
+    """BASELINE.json configs[1]: B=64 x 32 nodes (O=2048, T=3968), E=64, train mode — outputs, losses, every gradient."""
+    import types
+    batch = _config2()
+    m = our_model(E=64, layers=5, norm=norm)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    eps = torch.randn(2048, 64, generator=torch.Generator().manual_seed(11))
+
+    def run_oracle(dtype):
+        sd = vo.leaf_state(sd0, dtype)
+        objs, triples, boxes, angles, attrs = batch
+        stats = {}
+        mu, lv, bp, ap = vo.forward(sd, objs, triples, boxes.to(dtype), angles, attrs, eps.to(dtype), 5, True, False, stats)
+        total, parts = vo.losses(boxes.to(dtype), bp, angles, ap, mu, lv, 0.1)
+        total.backward()
+        out = {"mu": mu, "logvar": lv, "boxes_pred": bp, "angles_pred": ap, "total": total}
+        out.update({"grad." + k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items() if v.is_floating_point() and v.requires_grad})
+        out.update({"after." + k: v for k, v in stats.items()})
+        return {k: v.detach() for k, v in out.items()}
+
+    r64, r32 = run_oracle(torch.float64), run_oracle(torch.float32)
+    m = m.to(DEV).train()
+    objs, triples, boxes, angles, attrs = [t.to(DEV) for t in batch]
+    with with_eps(eps):
+        mu, lv, bp, ap = m(objs, triples, boxes, angles, attrs, None)
+    total, parts = sutils.calculate_model_losses(types.SimpleNamespace(use_AE=False), m, boxes, bp, angles, ap, mu=mu, logvar=lv, KL_weight=0.1)
+    m.zero_grad()
+    total.backward()
+    for k, v in (("mu", mu), ("logvar", lv), ("boxes_pred", bp), ("angles_pred", ap), ("total", total)):
+        check_close(k, v, r64[k], r32[k], tol=1e-4)
+    worst = 0.0
+    for k, p in m.named_parameters():
+        worst = max(worst, check_close("grad." + k, p.grad, r64["grad." + k], r32["grad." + k], tol=1e-4, abs_floor=1e-6))
+    if norm == "batch":
+        for k, v in m.state_dict().items():
+            if "running" in k or "num_batches" in k:
+                check_close("after." + k, v, r64["after." + k], r32["after." + k], tol=1e-4)
+
+
+def test_scene_permutation_equivariance_is_bit_exact():
+    """Size-independent property at full size: scenes are independent without BatchNorm (block-diagonal graph,
+    suncg_dataset.py:318-325), so permuting the scenes of a batch permutes the per-scene outputs bit-for-bit."""
+    B, n = 64, 32
+    objs, triples, boxes, angles, attrs = _config2(B, n)
+    m = our_model(E=64, layers=5, norm="none", use_AE=True).to(DEV).eval()
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+    tps = triples.view(B, -1, 3)
+    tp = tps[perm].clone()
+    shift = (torch.arange(B) - perm)[:, None] * n
+    tp[:, :, 0] += shift
+    tp[:, :, 2] += shift
+    pb = (objs.view(B, n)[perm].reshape(-1), tp.reshape(-1, 3), boxes.view(B, n, 6)[perm].reshape(-1, 6),
+          angles.view(B, n)[perm].reshape(-1), attrs.view(B, n)[perm].reshape(-1))
+    with torch.no_grad():
+        a = m(*[t.to(DEV) for t in (objs, triples, boxes, angles, attrs)], None)
+        b = m(*[t.to(DEV) for t in pb], None)
+    for x, y in zip(a, b):
+        assert torch.equal(x.view(B, n, -1)[perm], y.view(B, n, -1))
+
+
+def test_forward_is_deterministic_and_independent_of_batch_padding():
+    """A scene evaluated alone equals the same scene evaluated inside a batch (eval-mode BN folds to an affine)."""
+    B, n = 8, 32
+    objs, triples, boxes, angles, attrs = _config2(B, n, seed=9)
+    m = our_model(E=64, layers=5, norm="batch", use_AE=True).to(DEV).eval()
+    with torch.no_grad():
+        full = m(*[t.to(DEV) for t in (objs, triples, boxes, angles, attrs)], None)
+        again = m(*[t.to(DEV) for t in (objs, triples, boxes, angles, attrs)], None)
+        k = 62
+        one = m(objs[:n].to(DEV), triples[:k].to(DEV), boxes[:n].to(DEV), angles[:n].to(DEV), attrs[:n].to(DEV), None)
+    for x, y, z in zip(full, again, one):
+        assert torch.equal(x, y)
+        assert torch.equal(x[:n], z)
+
+
+# ------------------------------------------------------------------------------------------- fused train step (CUDA graph)
+@pytest.mark.parametrize("norm", ["none", "batch"])
+def test_graph_train_step_tracks_oracle_trajectory(norm):
+    B, n, E, L = 6, 8, 16, 3
+    _, objs, boxes, triples, angles, attrs, _, _ = syn.synthetic_batch(B, n, seed=4)
+    batch = (objs, triples, boxes, angles, attrs)
+    m = our_model(E=E, layers=L, norm=norm)
+    sd = vo.leaf_state(m.state_dict(), torch.float64)
+    m = m.to(DEV).train()
+    step = sutils.VAETrainStep(m, objs.size(0), triples.size(0), lr=1e-3, kl_weight=0.1, use_graph=True, sample_eps=False)
+    gen = torch.Generator().manual_seed(21)
+    eps_list = [torch.randn(objs.size(0), E, generator=gen) for _ in range(4)]
+    step.capture()
+    # capture() ran warm-up steps that moved the parameters: restart both sides from the oracle's initial state
+    with torch.no_grad():
+        for k, p in m.state_dict().items():
+            p.copy_(sd[k].detach().to(p.dtype))
+    step.m.zero_(); step.v.zero_(); step.step_count.zero_()
+    opt_state = {}
+    for it, eps in enumerate(eps_list):
+        want_total, want_parts = vo.train_step(sd, batch, eps.double(), opt_state, it + 1, num_layers=L, kl_weight=0.1, lr=1e-3)
+        step.load_batch([t.to(DEV) for t in batch])
+        step.epsn.copy_(eps)          # sample_eps=False: the caller supplies the N(0,1) draw
+        losses = step.run().tolist()
+        assert abs(losses[3] - want_total) <= 2e-4 * abs(want_total), (it, losses, want_total)
+        assert abs(losses[0] - want_parts["bbox_pred"]) <= 2e-4 * abs(want_parts["bbox_pred"]) + 1e-6
+        assert abs(losses[1] - want_parts["angle_pred"]) <= 2e-4 * abs(want_parts["angle_pred"]) + 1e-6
+        assert abs(losses[2] - want_parts["KLD_Gauss"]) <= 2e-4 * abs(want_parts["KLD_Gauss"]) + 1e-6
+    if norm == "none":   # without BN every gradient is well-conditioned: parameters follow the fp64 trajectory
+        for k, p in m.named_parameters():
+            d = (p.detach().cpu().double() - sd[k].detach()).abs().max().item()
+            assert d <= 2e-4 * max(sd[k].detach().abs().max().item(), 1.0) + 5e-4, (k, d)
+
+
+def test_fused_adam_matches_torch_adam():
+    torch.manual_seed(0)
+    ps = [torch.randn(s, device=DEV, requires_grad=True) for s in ((5, 3), (7,), (130, 9), (1,))]
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    a = sutils.FusedAdam(ps, lr=1e-2)
+    b = torch.optim.Adam(qs, lr=1e-2)
+    for it in range(5):
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(q)
+            q.grad = g.clone()
+            p.grad = g.clone()
+        a.step(); b.step()
+    for p, q in zip(ps, qs):
+        assert (p - q).abs().max().item() < 1e-6
