@@ -92,6 +92,18 @@ SIGNATURES = {
     "sln_csr_build": (ctypes.c_int, [_P, _I64, _I64, _I64, _P, _SZ, _P]),
     "sln_gconv_pool_fwd": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     "sln_csr_pointers": (ctypes.c_int, [_P, _I64, _I64, ctypes.POINTER(_P), ctypes.POINTER(_P)]),
+    "sln_set_engine": (ctypes.c_int, [ctypes.c_int]),
+    "sln_contract": (ctypes.c_int, [_P, _I64, _I32, _P, _I64, _I32, _P, _I64, _I64, _I64, _I64, _I32, _I32, _P]),
+    "sln_raster_workspace_bytes": (_SZ, [_I64, _I64, _I32]),
+    "sln_raster_setup": (ctypes.c_int, [_P, _I64, _P, _I64, _I32, _P, _P, _P, _F, _I32, _P, _SZ, _P]),
+    "sln_raster_face_arrays": (ctypes.c_int, [_P, _I64, _I64, _I32, ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(_P)]),
+    "sln_raster_forward": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _F, _F, _P, _P, _P, _P]),
+    "sln_raster_texture_sample": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _P, _I32, _F, _P, _P, _P, _P, _P]),
+    "sln_raster_backward_rgb": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
+    "sln_raster_backward_depth": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "sln_raster_vertex_grad": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _I32, _P, _P, _P, _F, _P, _P, _P, _P]),
+    "sln_scene_classes_fwd": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _I32, _F, _P, _P, _P, _P, _I32, _P, _P, _P]),
+    "sln_scene_classes_bwd": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _F, _P, _P, _I32, _P, _P, _P, _P]),
     "sln_reparam_fwd": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P]),
     "sln_reparam_bwd": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P, _P]),
     "sln_vae_loss": (ctypes.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P, _I32, _F, _I64, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P]),
@@ -128,6 +140,9 @@ def load():
             fn.argtypes = args
         if lib.sln_version() != 1:
             raise RuntimeError("3d_sln_b200: ABI version mismatch (library %d, binding 1)" % lib.sln_version())
+        eng = os.environ.get("SLN_ENGINE")
+        if eng in ("0", "1"):      # 0 = FP32 SIMT tiles, 1 = tcgen05 3xTF32 tiles (default) for the MLP contractions
+            lib.sln_set_engine(int(eng))
         _lib = lib
         return lib
 

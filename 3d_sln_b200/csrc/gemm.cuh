@@ -31,6 +31,26 @@ struct MatView {
     if (relu) v = fmaxf(v, 0.f);
     return v;
   }
+  // bounds-checked single element in storage coordinates
+  __device__ __forceinline__ float at_t(int r, int c) const { return (r < rows && c < cols) ? at(r, c) : 0.f; }
+  // Two-phase access used by the tensor-core loader (requires vec): fetch4 issues the raw 16-byte load unconditionally
+  // from a clamped address (so that all loads of a chunk can be in flight together), finish4 applies the lazy transform.
+  struct Tok { int r; };
+  __device__ __forceinline__ Tok token(int r) const { return Tok{r}; }
+  __device__ __forceinline__ void fetch4(const Tok& t, int c, float4& a, float4& b) const {
+    const bool ok = t.r < rows && c < cols;
+    a = ldg4(p + (ok ? (size_t)t.r * ld + c : 0));
+  }
+  __device__ __forceinline__ float4 finish4(const Tok& t, int c, float4 v, float4) const {
+    if (!(t.r < rows && c < cols)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale) {
+      float4 s = ldg4(scale + c), h = ldg4(shift + c);
+      v.x = fmaf(v.x, s.x, h.x); v.y = fmaf(v.y, s.y, h.y); v.z = fmaf(v.z, s.z, h.z); v.w = fmaf(v.w, s.w, h.w);
+    }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    return v;
+  }
+  bool vec_ok() const { return vec != 0; }
   // 4 consecutive columns starting at c (c % 4 == 0); zero outside the matrix.
   __device__ __forceinline__ float4 ld4(int r, int c) const {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -74,6 +94,35 @@ struct GatherCat {
     if (c < 2 * D) return pred.ld4(t, c - D);
     return obj.ld4(__ldg(o_idx + t), c - 2 * D);
   }
+  __device__ __forceinline__ float at_t(int t, int c) const {
+    if (t >= rows || c >= cols) return 0.f;
+    if (c < D) return obj.at(__ldg(s_idx + t), c);
+    if (c < 2 * D) return pred.at(t, c - D);
+    return obj.at(__ldg(o_idx + t), c - 2 * D);
+  }
+  struct Tok { int t, s, o; };   // the gather indices of a triple are fetched once per row, not once per K chunk
+  __device__ __forceinline__ Tok token(int t) const {
+    const bool ok = t < rows;
+    return Tok{t, ok ? __ldg(s_idx + t) : 0, ok ? __ldg(o_idx + t) : 0};
+  }
+  __device__ __forceinline__ void fetch4(const Tok& k, int c, float4& a, float4& b) const {
+    const bool ok = k.t < rows && c < cols;
+    const float* src = obj.p;
+    if (ok) src = c < D ? obj.p + (size_t)k.s * obj.ld + c : (c < 2 * D ? pred.p + (size_t)k.t * pred.ld + (c - D) : obj.p + (size_t)k.o * obj.ld + (c - 2 * D));
+    a = ldg4(src);
+  }
+  __device__ __forceinline__ float4 finish4(const Tok& k, int c, float4 v, float4) const {
+    if (!(k.t < rows && c < cols)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const MatView& m = (c >= D && c < 2 * D) ? pred : obj;
+    const int cc = c < D ? c : (c < 2 * D ? c - D : c - 2 * D);
+    if (m.scale) {
+      float4 s = ldg4(m.scale + cc), h = ldg4(m.shift + cc);
+      v.x = fmaf(v.x, s.x, h.x); v.y = fmaf(v.y, s.y, h.y); v.z = fmaf(v.z, s.z, h.z); v.w = fmaf(v.w, s.w, h.w);
+    }
+    if (m.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    return v;
+  }
+  bool vec_ok() const { return obj.vec && pred.vec && D % 4 == 0; }
 };
 
 // Virtual [rows, a.cols + b.cols] matrix [ a | b ]  (decoder box_net input: cat([obj_vecs, attr_vecs]),
@@ -86,6 +135,30 @@ struct Concat2 {
     if (c < a.cols) return a.ld4(r, c);
     return b.ld4(r, c - a.cols);
   }
+  __device__ __forceinline__ float at_t(int r, int c) const {
+    if (r >= rows || c >= cols) return 0.f;
+    return c < a.cols ? a.at(r, c) : b.at(r, c - a.cols);
+  }
+  struct Tok { int r; };
+  __device__ __forceinline__ Tok token(int r) const { return Tok{r}; }
+  __device__ __forceinline__ void fetch4(const Tok& t, int c, float4& va, float4& vb) const {
+    const bool ok = t.r < rows && c < cols;
+    const float* src = a.p;
+    if (ok) src = c < a.cols ? a.p + (size_t)t.r * a.ld + c : b.p + (size_t)t.r * b.ld + (c - a.cols);
+    va = ldg4(src);
+  }
+  __device__ __forceinline__ float4 finish4(const Tok& t, int c, float4 v, float4) const {
+    if (!(t.r < rows && c < cols)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const MatView& m = c < a.cols ? a : b;
+    const int cc = c < a.cols ? c : c - a.cols;
+    if (m.scale) {
+      float4 s = ldg4(m.scale + cc), h = ldg4(m.shift + cc);
+      v.x = fmaf(v.x, s.x, h.x); v.y = fmaf(v.y, s.y, h.y); v.z = fmaf(v.z, s.z, h.z); v.w = fmaf(v.w, s.w, h.w);
+    }
+    if (m.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    return v;
+  }
+  bool vec_ok() const { return a.vec && b.vec && a.cols % 4 == 0; }
 };
 
 // Gradient w.r.t. a pre-BN activation, formed on load:  dy = g*p + y*q + r  (per-column p,q,r).
@@ -110,6 +183,28 @@ struct DyView {
     }
     return v;
   }
+  __device__ __forceinline__ float at_t(int i, int c) const { return (i < rows && c < cols) ? at(i, c) : 0.f; }
+  struct Tok { int r; };
+  __device__ __forceinline__ Tok token(int r) const { return Tok{r}; }
+  __device__ __forceinline__ void fetch4(const Tok& t, int c, float4& a, float4& b) const {
+    const bool ok = t.r < rows && c < cols;
+    a = ldg4(g + (ok ? (size_t)t.r * ldg + c : 0));
+    if (q) b = ldg4(y + (ok ? (size_t)t.r * ldy + c : 0));
+  }
+  __device__ __forceinline__ float4 finish4(const Tok& t, int c, float4 v, float4 yy) const {
+    if (!(t.r < rows && c < cols)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p) {
+      float4 pp = ldg4(p + c);
+      v.x *= pp.x; v.y *= pp.y; v.z *= pp.z; v.w *= pp.w;
+      if (q) {
+        float4 qq = ldg4(q + c), rr = ldg4(r + c);
+        v.x += fmaf(yy.x, qq.x, rr.x); v.y += fmaf(yy.y, qq.y, rr.y);
+        v.z += fmaf(yy.z, qq.z, rr.z); v.w += fmaf(yy.w, qq.w, rr.w);
+      }
+    }
+    return v;
+  }
+  bool vec_ok() const { return vec != 0; }
   __device__ __forceinline__ float4 ld4(int i, int c) const {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i >= rows || c >= cols) return v;
@@ -165,12 +260,7 @@ struct BnFwdFin {  // forward: batch statistics -> scale/shift (+ running stats)
   int M;
 };
 
-__device__ __forceinline__ void bn_fwd_finalize(const BnFwdFin& f, int col, int N, int tiles) {
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < tiles; ++b) {
-    s += (double)__ldcg(f.partial + ((size_t)b * 2 + 0) * N + col);
-    q += (double)__ldcg(f.partial + ((size_t)b * 2 + 1) * N + col);
-  }
+__device__ __forceinline__ void bn_fwd_apply(const BnFwdFin& f, int col, double s, double q) {
   double mean = s / f.M;
   double var = q / f.M - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -205,12 +295,7 @@ struct BnBwdFin {  // backward: column sums of g and g*yhat -> (p,q,r) of DyView
   int M;
 };
 
-__device__ __forceinline__ void bn_bwd_finalize(const BnBwdFin& f, int col, int N, int tiles) {
-  double sg = 0.0, sgy = 0.0;
-  for (int b = 0; b < tiles; ++b) {
-    sg += (double)__ldcg(f.partial + ((size_t)b * 2 + 0) * N + col);
-    sgy += (double)__ldcg(f.partial + ((size_t)b * 2 + 1) * N + col);
-  }
+__device__ __forceinline__ void bn_bwd_apply(const BnBwdFin& f, int col, double sg, double sgy) {
   if (f.mode == NORM_NONE) {
     if (f.dbias) f.dbias[col] += (float)sg;
     return;
@@ -232,6 +317,61 @@ __device__ __forceinline__ void bn_bwd_finalize(const BnBwdFin& f, int col, int 
   // dbias is exactly zero under training-mode BN (the mean subtraction removes it); leave the zeroed buffer.
 }
 
+// ---------------------------------------------------------------- column-statistics finalisation
+// Protocol shared by every kernel that produces per-row-tile column partials partial[tile][2][N]:
+// after a CTA has written its partials for the column block blockIdx.x it takes a ticket on counter[blockIdx.x]; the
+// last of the gridDim.y row tiles reduces that block's columns over all tiles (fp64, fixed order -> deterministic) with
+// every thread of the CTA (threads = column x tile-group, independent loads in flight) and applies `fin`.
+// One counter per column block keeps the finalisation parallel across column blocks and off the critical path of the
+// other CTAs (a single "last CTA reduces everything" tail cost ~60 us per Linear at config 2).
+constexpr int kCounterStride = 16;   // counters reserved per BatchNorm layer (>= number of column blocks)
+
+template <int NT, class FinFn>
+__device__ __forceinline__ void finalize_column_block(const float* partial, unsigned* counter, int n0, int ncols, int N, int tid,
+                                                      double* sred, int* s_last, FinFn fin) {
+  const int tiles = gridDim.y;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned ticket = atomicAdd(counter + blockIdx.x, 1u);
+    *s_last = (ticket == (unsigned)tiles - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!*s_last) return;
+  __threadfence();
+  // thread = (column c, tile group g); every launch configuration has NT >= W >= ncols
+  const int W = ncols <= 32 ? 32 : (ncols <= 64 ? 64 : (ncols <= 128 ? 128 : 256));
+  const int G = NT / W;
+  const int c = tid % W, g = tid / W;
+  const bool live = g < G && c < ncols && n0 + c < N;
+  double s = 0.0, q = 0.0;
+  if (live) {
+    const float* p0 = partial + n0 + c;
+    int b = g;
+    for (; b + 3 * G < tiles; b += 4 * G) {   // 8 independent L2 loads in flight per thread
+      float a0 = __ldcg(p0 + ((size_t)b * 2) * N), a1 = __ldcg(p0 + ((size_t)(b + G) * 2) * N);
+      float a2 = __ldcg(p0 + ((size_t)(b + 2 * G) * 2) * N), a3 = __ldcg(p0 + ((size_t)(b + 3 * G) * 2) * N);
+      float c0 = __ldcg(p0 + ((size_t)b * 2 + 1) * N), c1 = __ldcg(p0 + ((size_t)(b + G) * 2 + 1) * N);
+      float c2 = __ldcg(p0 + ((size_t)(b + 2 * G) * 2 + 1) * N), c3 = __ldcg(p0 + ((size_t)(b + 3 * G) * 2 + 1) * N);
+      s += (double)a0; s += (double)a1; s += (double)a2; s += (double)a3;
+      q += (double)c0; q += (double)c1; q += (double)c2; q += (double)c3;
+    }
+    for (; b < tiles; b += G) {
+      s += (double)__ldcg(p0 + ((size_t)b * 2) * N);
+      q += (double)__ldcg(p0 + ((size_t)b * 2 + 1) * N);
+    }
+  }
+  sred[2 * tid] = s;
+  sred[2 * tid + 1] = q;
+  __syncthreads();
+  if (live && g == 0) {
+    double S = 0.0, Q = 0.0;
+    for (int gg = 0; gg < G; ++gg) { S += sred[2 * (gg * W + c)]; Q += sred[2 * (gg * W + c) + 1]; }
+    fin(n0 + c, S, Q);
+  }
+  if (tid == 0) counter[blockIdx.x] = 0u;
+}
+
 // ---------------------------------------------------------------- epilogues
 // Every epilogue sees the 8x8 register micro-tile of one thread: rows i0 + {0..3} and i0 + BM/2 + {0..3},
 // columns j0 + {0..3} and j0 + BN/2 + {0..3}.
@@ -245,11 +385,12 @@ struct TileCoord {
 // block-level: reduce per-thread column partials (s1,s2 over the thread's 8 rows) across the BM/8 thread rows,
 // write them to partial[blockIdx.y][{0,1}][N]; returns true in the last CTA of the grid (all partials visible).
 template <int BM, int BN>
-__device__ __forceinline__ bool column_partials(const TileCoord<BM, BN>& tc, float (&s1)[8], float (&s2)[8],
-                                                float* smem, float* partial, unsigned* counter, int N) {
+__device__ __forceinline__ void column_partials(const TileCoord<BM, BN>& tc, float (&s1)[8], float (&s2)[8],
+                                                float* smem, float* partial, int N) {
   constexpr int TY = BM / 8;
   float* r1 = smem;            // [TY][BN]
   float* r2 = smem + TY * BN;  // [TY][BN]
+  __syncthreads();             // the main loop's tiles are dead
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
     int jl = (b < 4 ? tc.tx * 4 + b : BN / 2 + tc.tx * 4 + (b - 4));
@@ -267,16 +408,6 @@ __device__ __forceinline__ bool column_partials(const TileCoord<BM, BN>& tc, flo
       partial[((size_t)blockIdx.y * 2 + 1) * N + j] = c;
     }
   }
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  if (tc.tid == 0) {
-    unsigned ticket = atomicAdd(counter, 1u);
-    s_last = (ticket == gridDim.x * gridDim.y - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_last) __threadfence();
-  return s_last != 0;
 }
 
 // C = acc + bias (+ BN batch statistics).
@@ -318,11 +449,11 @@ struct EpiStore {
       }
     }
     if (fin.enabled) {
-      bool last = column_partials<BM, BN>(tc, s1, s2, smem, fin.partial, fin.counter, N);
-      if (last) {
-        for (int col = tc.tid; col < N; col += NT) bn_fwd_finalize(fin, col, N, gridDim.y);
-        if (tc.tid == 0) *fin.counter = 0u;
-      }
+      column_partials<BM, BN>(tc, s1, s2, smem, fin.partial, N);
+      __shared__ int s_last;
+      const BnFwdFin& f = fin;
+      finalize_column_block<NT>(fin.partial, fin.counter, tc.n0, BN, N, tc.tid, reinterpret_cast<double*>(smem), &s_last,
+                                [&](int col, double S, double Q) { bn_fwd_apply(f, col, S, Q); });
     }
   }
 };
@@ -365,11 +496,11 @@ struct EpiMaskReduce {
         s2[b] = fmaf(g, yh, s2[b]);
       }
     }
-    bool last = column_partials<BM, BN>(tc, s1, s2, smem, fin.partial, fin.counter, N);
-    if (last) {
-      for (int col = tc.tid; col < N; col += NT) bn_bwd_finalize(fin, col, N, gridDim.y);
-      if (tc.tid == 0) *fin.counter = 0u;
-    }
+    column_partials<BM, BN>(tc, s1, s2, smem, fin.partial, N);
+    __shared__ int s_last;
+    const BnBwdFin& f = fin;
+    finalize_column_block<NT>(fin.partial, fin.counter, tc.n0, BN, N, tc.tid, reinterpret_cast<double*>(smem), &s_last,
+                              [&](int col, double S, double Q) { bn_bwd_apply(f, col, S, Q); });
   }
 };
 

@@ -1,0 +1,615 @@
+// Differentiable mesh rasterizer for the layout-refinement path (reference models/diff_render.py:359-366,398 through the
+// un-vendored `neural_renderer` package; semantics restated in oracle/raster_oracle.c).
+//
+// B200 design (not upstream's one-thread-per-pixel loop over ALL faces / one-thread-per-face serial backward):
+//   forward   k_project -> k_face_setup (per face: back-face test, pixel-space inverse, conservative pixel bounding box)
+//             -> k_raster_tiles: one CTA per 16x16 pixel tile; the face list is streamed in chunks of 256 bounding boxes,
+//             culled against the tile with a block-wide ORDER-PRESERVING ballot compaction, the survivors' records are
+//             staged in shared memory and every pixel thread walks them in ascending face order (strict '<' z-test, so
+//             ties keep the lower face index exactly as upstream).  Work drops from P*F to P*(faces touching the tile).
+//   backward  k_backward_rgb: one WARP per (face, edge, axis) job, lanes stride the edge's d0 range and sweep d1 serially,
+//             warp-shuffle reduction, one RED.ADD per touched gradient slot; k_backward_depth: per covered pixel.
+//   The arithmetic that decides coverage and depth order uses explicit round-to-nearest intrinsics (no FMA contraction)
+//   in the oracle's operation order, so face_index maps are bit-identical to the CPU oracle.
+#include "../../include/sln_b200.h"
+#include "common.cuh"
+
+namespace sln {
+namespace {
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float dvd(float a, float b) { return __fdiv_rn(a, b); }
+
+// ------------------------------------------------------------------------------------------------ projection
+// nr.projection with the README.md:13-18 patch (no lens distortion): see oracle ro_project.
+__global__ void k_project(const float* __restrict__ verts, int V, const float* __restrict__ K, const float* __restrict__ R,
+                          const float* __restrict__ t, float orig_size, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const float eps = 1e-9f;
+  const float half = dvd(orig_size, 2.0f);
+  const float x = verts[3 * i], y = verts[3 * i + 1], z = verts[3 * i + 2];
+  const float xc = add(add(add(mul(x, R[0]), mul(y, R[1])), mul(z, R[2])), t[0]);
+  const float yc = add(add(add(mul(x, R[3]), mul(y, R[4])), mul(z, R[5])), t[1]);
+  const float zc = add(add(add(mul(x, R[6]), mul(y, R[7])), mul(z, R[8])), t[2]);
+  const float x_ = dvd(xc, add(zc, eps)), y_ = dvd(yc, add(zc, eps));
+  float u = add(add(mul(x_, K[0]), mul(y_, K[1])), K[2]);
+  float v = add(add(mul(x_, K[3]), mul(y_, K[4])), K[5]);
+  v = sub(orig_size, v);
+  u = dvd(mul(2.0f, sub(u, half)), orig_size);
+  v = dvd(mul(2.0f, sub(v, half)), orig_size);
+  out[3 * i] = u; out[3 * i + 1] = v; out[3 * i + 2] = zc;
+}
+
+__global__ void k_project_bwd(const float* __restrict__ verts, int V, const float* __restrict__ K, const float* __restrict__ R,
+                              const float* __restrict__ t, float orig_size, const float* __restrict__ grad_out, float* __restrict__ grad_verts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const float eps = 1e-9f;
+  const float x = verts[3 * i], y = verts[3 * i + 1], z = verts[3 * i + 2];
+  const float xc = x * R[0] + y * R[1] + z * R[2] + t[0];
+  const float yc = x * R[3] + y * R[4] + z * R[5] + t[1];
+  const float zc = x * R[6] + y * R[7] + z * R[8] + t[2];
+  const float zi = 1.0f / (zc + eps);
+  const float du = grad_out[3 * i] * (2.0f / orig_size), dv = -grad_out[3 * i + 1] * (2.0f / orig_size);
+  const float dx_ = K[0] * du + K[3] * dv, dy_ = K[1] * du + K[4] * dv;
+  const float dxc = dx_ * zi, dyc = dy_ * zi;
+  const float dzc = grad_out[3 * i + 2] - (dx_ * xc + dy_ * yc) * zi * zi;
+  grad_verts[3 * i] = R[0] * dxc + R[3] * dyc + R[6] * dzc;
+  grad_verts[3 * i + 1] = R[1] * dxc + R[4] * dyc + R[7] * dzc;
+  grad_verts[3 * i + 2] = R[2] * dxc + R[5] * dyc + R[8] * dzc;
+}
+
+// ------------------------------------------------------------------------------------------------ per-face setup
+__device__ __forceinline__ bool backside(const float* f) {
+  return mul(sub(f[7], f[1]), sub(f[3], f[0])) < mul(sub(f[4], f[1]), sub(f[6], f[0]));
+}
+
+// fv [F2,9] (vertices_to_faces with fill_back: face F+f = face f reversed), finv [F2,9], fbox [F2] = pixel bounding box
+// (x0,x1,y0,y1 inclusive, expanded by one pixel so that rounding in the edge functions can never place a covered pixel
+// outside it; x0 > x1 marks a face that can never be drawn: back-facing or off-screen).
+__global__ void k_face_setup(const float* __restrict__ pv, const int* __restrict__ faces, int F, int fill_back, int is,
+                             float* __restrict__ fv, float* __restrict__ finv, int4* __restrict__ fbox) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int F2 = fill_back ? 2 * F : F;
+  if (f >= F2) return;
+  const int src = f < F ? f : f - F;
+  float face[9];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int vi = faces[3 * src + (f < F ? k : 2 - k)];
+    face[3 * k] = pv[3 * vi]; face[3 * k + 1] = pv[3 * vi + 1]; face[3 * k + 2] = pv[3 * vi + 2];
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) fv[9 * (size_t)f + k] = face[k];
+  float inv[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) inv[k] = 0.f;
+  int4 box = make_int4(1, 0, 1, 0);
+  if (!backside(face)) {
+    const float fis = (float)is;
+    float p[3][2];
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+#pragma unroll
+      for (int d = 0; d < 2; ++d) p[n][d] = mul(0.5f, sub(add(mul(face[3 * n + d], fis), fis), 1.0f));
+    inv[0] = sub(p[1][1], p[2][1]); inv[1] = sub(p[2][0], p[1][0]); inv[2] = sub(mul(p[1][0], p[2][1]), mul(p[2][0], p[1][1]));
+    inv[3] = sub(p[2][1], p[0][1]); inv[4] = sub(p[0][0], p[2][0]); inv[5] = sub(mul(p[2][0], p[0][1]), mul(p[0][0], p[2][1]));
+    inv[6] = sub(p[0][1], p[1][1]); inv[7] = sub(p[1][0], p[0][0]); inv[8] = sub(mul(p[0][0], p[1][1]), mul(p[1][0], p[0][1]));
+    const float den = add(add(mul(p[2][0], sub(p[0][1], p[1][1])), mul(p[0][0], sub(p[1][1], p[2][1]))), mul(p[1][0], sub(p[2][1], p[0][1])));
+#pragma unroll
+    for (int k = 0; k < 9; ++k) inv[k] = dvd(inv[k], den);
+    // conservative bounding box in pixel indices: pixel centre xi <-> ndc (2 xi + 1 - is)/is  <=>  xi = p-space coordinate
+    float xmin = fminf(fminf(p[0][0], p[1][0]), p[2][0]), xmax = fmaxf(fmaxf(p[0][0], p[1][0]), p[2][0]);
+    float ymin = fminf(fminf(p[0][1], p[1][1]), p[2][1]), ymax = fmaxf(fmaxf(p[0][1], p[1][1]), p[2][1]);
+    if (xmin == xmin && xmax == xmax && ymin == ymin && ymax == ymax) {   // NaN coordinates never pass the inside test
+      float lim = (float)is + 4.f;
+      int x0 = (int)floorf(fmaxf(xmin, -4.f)) - 1, x1 = (int)ceilf(fminf(xmax, lim)) + 1;
+      int y0 = (int)floorf(fmaxf(ymin, -4.f)) - 1, y1 = (int)ceilf(fminf(ymax, lim)) + 1;
+      x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, is - 1); y1 = min(y1, is - 1);
+      if (x0 <= x1 && y0 <= y1) box = make_int4(x0, x1, y0, y1);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) finv[9 * (size_t)f + k] = inv[k];
+  fbox[f] = box;
+}
+
+// ------------------------------------------------------------------------------------------------ tiled z-buffer
+constexpr int TILE = 16;
+constexpr int CHUNK = 256;   // faces examined per round = threads per CTA
+
+struct FaceRec { float v[9]; float inv[9]; int id; };
+
+__global__ void __launch_bounds__(256) k_raster_tiles(const float* __restrict__ fv, const float* __restrict__ finv, const int4* __restrict__ fbox,
+                                                      int F2, int is, float near, float far, int* __restrict__ face_index_map,
+                                                      float* __restrict__ weight_map, float* __restrict__ depth_map) {
+  __shared__ FaceRec s_rec[CHUNK];
+  __shared__ int s_warp_cnt[8];
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
+  const int xi = tx0 + (tid % TILE), yi = ty0 + (tid / TILE);
+  const bool live = xi < is && yi < is;
+  const float fis = (float)is;
+  const float yp = dvd(sub(add(mul(2.0f, (float)yi), 1.0f), fis), fis);
+  const float xp = dvd(sub(add(mul(2.0f, (float)xi), 1.0f), fis), fis);
+  const float fxi = (float)xi, fyi = (float)yi;
+  float depth_min = far;
+  int face_min = -1;
+  float w0m = 0.f, w1m = 0.f, w2m = 0.f;
+  const int tx1 = min(tx0 + TILE - 1, is - 1), ty1 = min(ty0 + TILE - 1, is - 1);
+
+  for (int base = 0; base < F2; base += CHUNK) {
+    const int f = base + tid;
+    bool hit = false;
+    if (f < F2) {
+      int4 b = __ldg(fbox + f);
+      hit = b.x <= b.y && b.x <= tx1 && b.y >= tx0 && b.z <= ty1 && b.w >= ty0;
+    }
+    // order-preserving compaction: position = (# hits in lower warps) + (# hits in lower lanes)
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) s_warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int off = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) off += (w < warp) ? s_warp_cnt[w] : 0;
+    if (tid == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += s_warp_cnt[w];
+      s_total = tot;
+    }
+    if (hit) {
+      const int pos = off + __popc(m & ((1u << lane) - 1u));
+      FaceRec& r = s_rec[pos];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { r.v[k] = __ldg(fv + 9 * (size_t)f + k); r.inv[k] = __ldg(finv + 9 * (size_t)f + k); }
+      r.id = f;
+    }
+    __syncthreads();
+    const int n = s_total;
+    if (live) {
+      for (int q = 0; q < n; ++q) {
+        const FaceRec& r = s_rec[q];
+        const float* face = r.v;
+        if (mul(sub(yp, face[1]), sub(face[3], face[0])) < mul(sub(xp, face[0]), sub(face[4], face[1])) ||
+            mul(sub(yp, face[4]), sub(face[6], face[3])) < mul(sub(xp, face[3]), sub(face[7], face[4])) ||
+            mul(sub(yp, face[7]), sub(face[0], face[6])) < mul(sub(xp, face[6]), sub(face[1], face[7])))
+          continue;
+        float w[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = add(add(mul(r.inv[3 * k], fxi), mul(r.inv[3 * k + 1], fyi)), r.inv[3 * k + 2]);
+        float wsum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { w[k] = fminf(fmaxf(w[k], 0.f), 1.f); wsum = add(wsum, w[k]); }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = dvd(w[k], wsum);
+        const float zp = dvd(1.0f, add(add(dvd(w[0], face[2]), dvd(w[1], face[5])), dvd(w[2], face[8])));
+        if (zp <= near || far <= zp) continue;
+        if (zp < depth_min) { depth_min = zp; face_min = r.id; w0m = w[0]; w1m = w[1]; w2m = w[2]; }
+      }
+    }
+    __syncthreads();
+  }
+  if (live) {
+    const int pn = yi * is + xi;
+    face_index_map[pn] = face_min;
+    depth_map[pn] = depth_min;
+    weight_map[3 * pn] = w0m; weight_map[3 * pn + 1] = w1m; weight_map[3 * pn + 2] = w2m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ texture sampling
+__global__ void k_texture_sample(const float* __restrict__ fv, const float* __restrict__ textures, const int* __restrict__ face_index_map,
+                                 const float* __restrict__ weight_map, const float* __restrict__ depth_map, int is, int ts, int F_tex,
+                                 float eps, float* __restrict__ rgb_map) {
+  int pn = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pn >= is * is) return;
+  float acc[3] = {0.f, 0.f, 0.f};
+  const int fi = face_index_map[pn];
+  if (fi >= 0) {
+    const float* face = fv + 9 * (size_t)fi;
+    // fill_back: the back copy (fi >= F_tex) samples the front face's texture with the first and last texel axes swapped
+    // (upstream renderer.py: textures.permute(0,1,4,3,2,5))
+    const bool back = fi >= F_tex;
+    const float* tex = textures + (size_t)(back ? fi - F_tex : fi) * ts * ts * ts * 3;
+    const float depth = depth_map[pn];
+    float tif[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float v = mul(mul(weight_map[3 * pn + k], (float)(ts - 1)), dvd(depth, face[3 * k + 2]));
+      v = fmaxf(v, 0.f);
+      v = fminf(v, sub((float)(ts - 1), eps));
+      tif[k] = v;
+    }
+    for (int pnn = 0; pnn < 8; ++pnn) {
+      float w = 1.f;
+      int ti[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int base = (int)tif[k];
+        if (((pnn >> k) % 2) == 0) { w = mul(w, sub(1.f, sub(tif[k], (float)base))); ti[k] = base; }
+        else { w = mul(w, sub(tif[k], (float)base)); ti[k] = base + 1; }
+      }
+      const int isc = back ? (ti[2] * ts + ti[1]) * ts + ti[0] : (ti[0] * ts + ti[1]) * ts + ti[2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc[k] = add(acc[k], mul(w, tex[isc * 3 + k]));
+    }
+  }
+  rgb_map[3 * pn] = acc[0]; rgb_map[3 * pn + 1] = acc[1]; rgb_map[3 * pn + 2] = acc[2];
+}
+
+// ------------------------------------------------------------------------------------------------ backward: rgb (Kato)
+// One warp per (face, edge, axis).  `C` channels per pixel in `img`/`gimg` (3 for an rgb render).  For the fused scene
+// path (class != null) the image is implicit: channel value of class c at a pixel = sval[pixel] if cls[face_index] == c
+// else 0, and the per-class clamp `diff_grad <= 0 -> skip` is applied per class exactly as 32 separate renders would.
+struct RgbBwdArgs {
+  const float* fv; const int* face_index_map; int F2, is; float eps;
+  // explicit image mode
+  const float* img; const float* gimg; int C;
+  // fused class mode
+  const int* face_cls; const float* sval; const float* gcls; int n_cls;   // gcls [n_cls, is, is] in internal orientation
+  float* grad_faces;
+};
+
+__device__ __forceinline__ float pix_diff_grad(const RgbBwdArgs& a, int idx, int idx_ref) {
+  float d = 0.f;
+  if (a.face_cls == nullptr) {
+    for (int k = 0; k < a.C; ++k) d += (a.img[(size_t)a.C * idx + k] - a.img[(size_t)a.C * idx_ref + k]) * a.gimg[(size_t)a.C * idx + k];
+    return d > 0.f ? d : 0.f;
+  }
+  // fused: only the classes of the two pixels' faces have a non-zero image difference; each class is a separate render
+  // (3 identical channels whose gradient is g/3 each), clamped separately
+  const int fa = a.face_index_map[idx], fb = a.face_index_map[idx_ref];
+  const int ca = fa >= 0 ? a.face_cls[fa] : -1, cb = fb >= 0 ? a.face_cls[fb] : -1;
+  const float va = fa >= 0 ? a.sval[idx] : 0.f, vb = fb >= 0 ? a.sval[idx_ref] : 0.f;
+  const size_t P = (size_t)a.is * a.is;
+  float tot = 0.f;
+  if (ca >= 0) {
+    const float g3 = a.gcls[(size_t)ca * P + idx] / 3.f;
+    const float diff = va - (cb == ca ? vb : 0.f);
+    float dg = 0.f;
+    for (int k = 0; k < 3; ++k) dg += diff * g3;
+    if (dg > 0.f) tot += dg;
+  }
+  if (cb >= 0 && cb != ca) {
+    const float g3 = a.gcls[(size_t)cb * P + idx] / 3.f;
+    const float diff = 0.f - vb;
+    float dg = 0.f;
+    for (int k = 0; k < 3; ++k) dg += diff * g3;
+    if (dg > 0.f) tot += dg;
+  }
+  return tot;
+}
+
+__global__ void __launch_bounds__(256) k_backward_rgb(const RgbBwdArgs a) {
+  const int job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (job >= a.F2 * 6) return;
+  const int fn = job / 6, edge = (job % 6) >> 1, axis = job & 1;
+  const float* face = a.fv + 9 * (size_t)fn;
+  if (backside(face)) return;
+  const int is = a.is;
+  const float fis = (float)is;
+  int pi[3];
+  float p[3][2];
+#pragma unroll
+  for (int n = 0; n < 3; ++n) pi[n] = (edge + n) % 3;
+#pragma unroll
+  for (int n = 0; n < 3; ++n)
+#pragma unroll
+    for (int d = 0; d < 2; ++d) p[n][d] = mul(0.5f, sub(add(mul(face[3 * pi[n] + ((d + axis) % 2)], fis), fis), 1.0f));
+  int direction;
+  if (axis == 0) direction = (p[0][0] < p[1][0]) ? -1 : 1;
+  else direction = (p[0][0] < p[1][0]) ? 1 : -1;
+  const int d0_from = (int)fmaxf(ceilf(fminf(p[0][0], p[1][0])), 0.f);
+  const int d0_to = (int)fminf(fmaxf(p[0][0], p[1][0]), fis - 1.f);
+  float g0 = 0.f, g1 = 0.f;   // gradient of vertex pi[0] / pi[1], component (1 - axis)
+  for (int d0 = d0_from + lane; d0 <= d0_to; d0 += 32) {
+    const float fd0 = (float)d0;
+    const float d1_cross = add(mul(dvd(sub(p[1][1], p[0][1]), sub(p[1][0], p[0][0])), sub(fd0, p[0][0])), p[0][1]);
+    const int d1_in = (0 < direction) ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
+    const int d1_out = d1_in + direction;
+    if (d1_in < 0 || is <= d1_in) continue;
+    if (d1_out < 0 || is <= d1_out) continue;
+    const int idx_in = axis == 0 ? d1_in * is + d0 : d0 * is + d1_in;
+    const int idx_out = axis == 0 ? d1_out * is + d0 : d0 * is + d1_out;
+    const bool use0 = p[1][0] != fd0, use1 = p[0][0] != fd0;
+    const float c0 = use0 ? dvd(sub(p[1][0], p[0][0]), sub(p[1][0], fd0)) : 0.f;
+    const float c1 = use1 ? dvd(sub(p[1][0], p[0][0]), sub(fd0, p[0][0])) : 0.f;
+    if (a.face_index_map[idx_in] == fn) {   // out sweep: from the out-pixel to the image border
+      const int d1_limit = (0 < direction) ? is - 1 : 0;
+      const int d1_from = max(min(d1_out, d1_limit), 0), d1_to = min(max(d1_out, d1_limit), is - 1);
+      for (int d1 = d1_from; d1 <= d1_to; ++d1) {
+        const int idx = axis == 0 ? d1 * is + d0 : d0 * is + d1;
+        const float dg = pix_diff_grad(a, idx, idx_in);
+        if (dg <= 0.f) continue;
+        const float t = sub((float)d1, d1_cross);
+        if (use0) { float dist = dvd(mul(mul(c0, t), 2.0f), fis); dist = (0.f < dist) ? dist + a.eps : dist - a.eps; g0 -= dg / dist; }
+        if (use1) { float dist = dvd(mul(mul(c1, t), 2.0f), fis); dist = (0.f < dist) ? dist + a.eps : dist - a.eps; g1 -= dg / dist; }
+      }
+    }
+    {   // in sweep: from the in-pixel to the opposite edge crossing, pixels showing this face
+      float d0_cross2;
+      if (mul(sub(fd0, p[0][0]), sub(fd0, p[2][0])) < 0.f)
+        d0_cross2 = add(mul(dvd(sub(p[2][1], p[0][1]), sub(p[2][0], p[0][0])), sub(fd0, p[0][0])), p[0][1]);
+      else
+        d0_cross2 = add(mul(dvd(sub(p[1][1], p[2][1]), sub(p[1][0], p[2][0])), sub(fd0, p[2][0])), p[2][1]);
+      const int d1_limit = (0 < direction) ? (int)ceilf(d0_cross2) : (int)floorf(d0_cross2);
+      const int d1_from = max(min(d1_in, d1_limit), 0), d1_to = min(max(d1_in, d1_limit), is - 1);
+      for (int d1 = d1_from; d1 <= d1_to; ++d1) {
+        const int idx = axis == 0 ? d1 * is + d0 : d0 * is + d1;
+        if (a.face_index_map[idx] != fn) continue;
+        const float dg = pix_diff_grad(a, idx, idx_out);
+        if (dg <= 0.f) continue;
+        const float t = sub((float)d1, d1_cross);
+        if (use0) { float dist = dvd(mul(mul(c0, t), 2.0f), fis); dist = (0.f < dist) ? dist + a.eps : dist - a.eps; g0 -= dg / dist; }
+        if (use1) { float dist = dvd(mul(mul(c1, t), 2.0f), fis); dist = (0.f < dist) ? dist + a.eps : dist - a.eps; g1 -= dg / dist; }
+      }
+    }
+  }
+  g0 = warp_sum(g0); g1 = warp_sum(g1);
+  if (lane == 0) {
+    if (g0 != 0.f) atomicAdd(a.grad_faces + 9 * (size_t)fn + pi[0] * 3 + (1 - axis), g0);
+    if (g1 != 0.f) atomicAdd(a.grad_faces + 9 * (size_t)fn + pi[1] * 3 + (1 - axis), g1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward: depth
+__global__ void k_backward_depth(const float* __restrict__ fv, const float* __restrict__ finv, const float* __restrict__ depth_map,
+                                 const int* __restrict__ face_index_map, const float* __restrict__ weight_map,
+                                 const float* __restrict__ grad_depth_map, int is, float* grad_faces) {
+  int pn = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pn >= is * is) return;
+  const int fn = face_index_map[pn];
+  if (fn < 0) return;
+  const float g = grad_depth_map[pn];
+  if (g == 0.f) return;
+  const float* face = fv + 9 * (size_t)fn;
+  const float* fi = finv + 9 * (size_t)fn;
+  const float depth = depth_map[pn], depth2 = depth * depth;
+  float* gf = grad_faces + 9 * (size_t)fn;
+  float w[3] = {weight_map[3 * pn], weight_map[3 * pn + 1], weight_map[3 * pn + 2]};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float zk = face[3 * k + 2];
+    atomicAdd(gf + 3 * k + 2, g * w[k] * depth2 / (zk * zk));
+  }
+  float tmp[2] = {0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int l = 0; l < 3; ++l) tmp[k] += -fi[3 * l + k] / face[3 * l + 2];
+  const float fis = (float)is;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int l = 0; l < 2; ++l) atomicAdd(gf + 3 * k + l, -g * tmp[l] * w[k] * depth2 * fis / 2.f);
+}
+
+// grad_fv [F2,9] -> grad_pv [V,3]  (transpose of vertices_to_faces incl. the fill_back copies)
+__global__ void k_faces_to_vertices_bwd(const float* __restrict__ grad_fv, const int* __restrict__ faces, int F, int fill_back, float* grad_pv) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;   // one (face, corner) per thread
+  const int F2 = fill_back ? 2 * F : F;
+  if (e >= F2 * 3) return;
+  const int f = e / 3, k = e % 3;
+  const int src = f < F ? f : f - F;
+  const int vi = faces[3 * src + (f < F ? k : 2 - k)];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float g = grad_fv[9 * (size_t)f + 3 * k + d];
+    if (g != 0.f) atomicAdd(grad_pv + 3 * (size_t)vi + d, g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fused scene passes
+// Per covered pixel: s = what a constant-1 texture samples to (the sum of the 8 trilinear weights, evaluated exactly as
+// k_texture_sample does), so class image c = s where cls[face] == c, else 0 — bit-identical to 32 separate renders.
+__global__ void k_scene_sval(const float* __restrict__ fv, const int* __restrict__ face_index_map, const float* __restrict__ weight_map,
+                             const float* __restrict__ depth_map, int is, int ts, float eps, float* __restrict__ sval) {
+  int pn = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pn >= is * is) return;
+  const int fi = face_index_map[pn];
+  float acc = 0.f;
+  if (fi >= 0) {
+    const float* face = fv + 9 * (size_t)fi;
+    const float depth = depth_map[pn];
+    float tif[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float v = mul(mul(weight_map[3 * pn + k], (float)(ts - 1)), dvd(depth, face[3 * k + 2]));
+      v = fmaxf(v, 0.f);
+      v = fminf(v, sub((float)(ts - 1), eps));
+      tif[k] = v;
+    }
+    for (int pnn = 0; pnn < 8; ++pnn) {
+      float w = 1.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int base = (int)tif[k];
+        if (((pnn >> k) % 2) == 0) w = mul(w, sub(1.f, sub(tif[k], (float)base)));
+        else w = mul(w, sub(tif[k], (float)base));
+      }
+      acc = add(acc, mul(w, 1.0f));
+    }
+  }
+  sval[pn] = acc;
+}
+
+// class images [n_cls, is, is] in OUTPUT orientation (vertically flipped): value = (s+s+s)/3 as torch.sum(images,1)/3
+__global__ void k_scene_class_images(const int* __restrict__ face_index_map, const int* __restrict__ face_cls, const float* __restrict__ sval,
+                                     int is, int n_cls, float* __restrict__ images) {
+  int pn = blockIdx.x * blockDim.x + threadIdx.x;
+  const int P = is * is;
+  if (pn >= P) return;
+  const int yi = pn / is, xi = pn % is;
+  const int fi = face_index_map[pn];
+  const int c = fi >= 0 ? face_cls[fi] : -1;
+  const float s = sval[pn];
+  const float v = dvd(add(add(s, s), s), 3.0f);
+  const size_t o = (size_t)(is - 1 - yi) * is + xi;
+  for (int k = 0; k < n_cls; ++k) images[(size_t)k * P + o] = (k == c) ? v : 0.f;
+}
+
+}  // namespace
+}  // namespace sln
+
+using namespace sln;
+
+// workspace layout (all 256-byte aligned): pv [V,3] | fv [F2,9] | finv [F2,9] | fbox [F2] int4
+namespace {
+struct RasterPlan { float* pv; float* fv; float* finv; int4* fbox; size_t bytes; };
+RasterPlan plan_raster(void* ws, int64_t V, int64_t F2) {
+  Arena ar(ws, (size_t)-1);
+  RasterPlan p;
+  p.pv = ar.take<float>(3 * (size_t)V);
+  p.fv = ar.take<float>(9 * (size_t)F2);
+  p.finv = ar.take<float>(9 * (size_t)F2);
+  p.fbox = ar.take<int4>((size_t)F2);
+  p.bytes = ar.off;
+  return p;
+}
+int check_raster_args(int64_t V, int64_t F, int32_t is) {
+  SLN_CHECK_ARG(V >= 1 && V < (1ll << 28) && F >= 0 && F < (1ll << 27), "vertex/face count out of range");
+  SLN_CHECK_ARG(is >= 1 && is <= 8192, "image_size out of range");
+  return SLN_OK;
+}
+}  // namespace
+
+extern "C" {
+
+size_t sln_raster_workspace_bytes(int64_t V, int64_t F, int32_t fill_back) {
+  return plan_raster(nullptr, V, fill_back ? 2 * F : F).bytes;
+}
+
+int sln_raster_setup(const float* vertices, int64_t V, const int32_t* faces, int64_t F, int32_t fill_back, const float* K, const float* R,
+                     const float* t, float orig_size, int32_t image_size, void* ws, size_t ws_bytes, void* stream) {
+  SLN_TRY(check_raster_args(V, F, image_size));
+  SLN_CHECK_ARG(vertices && (faces || F == 0) && K && R && t && ws, "null pointer");
+  const int64_t F2 = fill_back ? 2 * F : F;
+  RasterPlan p = plan_raster(ws, V, F2);
+  SLN_CHECK_ARG((uintptr_t)ws % 256 == 0 && ws_bytes >= p.bytes, "raster workspace misaligned or too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(st, PROF_RASTER_FWD, 12.0 * V + 12.0 * F + 88.0 * F2);
+  k_project<<<ceil_div((int)V, 256), 256, 0, st>>>(vertices, (int)V, K, R, t, orig_size, p.pv);
+  SLN_TRY(check_launch("project"));
+  if (F2 > 0) {
+    k_face_setup<<<ceil_div((int)F2, 256), 256, 0, st>>>(p.pv, faces, (int)F, fill_back, image_size, p.fv, p.finv, p.fbox);
+    SLN_TRY(check_launch("face_setup"));
+  }
+  return SLN_OK;
+}
+
+int sln_raster_face_arrays(void* ws, int64_t V, int64_t F, int32_t fill_back, const float** proj_vertices, const float** face_vertices,
+                           const float** face_inv) {
+  RasterPlan p = plan_raster(ws, V, fill_back ? 2 * F : F);
+  if (proj_vertices) *proj_vertices = p.pv;
+  if (face_vertices) *face_vertices = p.fv;
+  if (face_inv) *face_inv = p.finv;
+  return SLN_OK;
+}
+
+int sln_raster_forward(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, float near, float far,
+                       int32_t* face_index_map, float* weight_map, float* depth_map, void* stream) {
+  SLN_TRY(check_raster_args(V, F, image_size));
+  SLN_CHECK_ARG(ws && face_index_map && weight_map && depth_map, "null pointer");
+  const int64_t F2 = fill_back ? 2 * F : F;
+  RasterPlan p = plan_raster((void*)ws, V, F2);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles = ceil_div(image_size, TILE);
+  ProfScope prof(st, PROF_RASTER_FWD, 88.0 * F2 + 20.0 * image_size * image_size);
+  k_raster_tiles<<<dim3(tiles, tiles), 256, 0, st>>>(p.fv, p.finv, p.fbox, (int)F2, image_size, near, far, face_index_map, weight_map, depth_map);
+  return check_launch("raster_tiles");
+}
+
+int sln_raster_texture_sample(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, const float* textures,
+                              int32_t texture_size, float eps, const int32_t* face_index_map, const float* weight_map,
+                              const float* depth_map, float* rgb_map, void* stream) {
+  SLN_TRY(check_raster_args(V, F, image_size));
+  SLN_CHECK_ARG(ws && textures && face_index_map && weight_map && depth_map && rgb_map && texture_size >= 2, "bad argument");
+  RasterPlan p = plan_raster((void*)ws, V, fill_back ? 2 * F : F);
+  const int P = image_size * image_size;
+  ProfScope prof((cudaStream_t)stream, PROF_RASTER_FWD, 32.0 * P);
+  k_texture_sample<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(p.fv, textures, face_index_map, weight_map, depth_map, image_size,
+                                                                      texture_size, (int)F, eps, rgb_map);
+  return check_launch("texture_sample");
+}
+
+int sln_raster_backward_rgb(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, float eps,
+                            const int32_t* face_index_map, const float* rgb_map, const float* grad_rgb_map, float* grad_faces, void* stream) {
+  SLN_TRY(check_raster_args(V, F, image_size));
+  SLN_CHECK_ARG(ws && face_index_map && rgb_map && grad_rgb_map && grad_faces, "null pointer");
+  const int64_t F2 = fill_back ? 2 * F : F;
+  if (F2 == 0) return SLN_OK;
+  RasterPlan p = plan_raster((void*)ws, V, F2);
+  RgbBwdArgs a; memset(&a, 0, sizeof(a));
+  a.fv = p.fv; a.face_index_map = face_index_map; a.F2 = (int)F2; a.is = image_size; a.eps = eps;
+  a.img = rgb_map; a.gimg = grad_rgb_map; a.C = 3; a.grad_faces = grad_faces;
+  ProfScope prof((cudaStream_t)stream, PROF_RASTER_BWD, 36.0 * F2 + 28.0 * image_size * image_size);
+  k_backward_rgb<<<ceil_div((int)F2 * 6, 8), 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("backward_rgb");
+}
+
+int sln_raster_backward_depth(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, const int32_t* face_index_map,
+                              const float* weight_map, const float* depth_map, const float* grad_depth_map, float* grad_faces, void* stream) {
+  SLN_TRY(check_raster_args(V, F, image_size));
+  SLN_CHECK_ARG(ws && face_index_map && weight_map && depth_map && grad_depth_map && grad_faces, "null pointer");
+  RasterPlan p = plan_raster((void*)ws, V, fill_back ? 2 * F : F);
+  const int P = image_size * image_size;
+  ProfScope prof((cudaStream_t)stream, PROF_RASTER_BWD, 24.0 * P);
+  k_backward_depth<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(p.fv, p.finv, depth_map, face_index_map, weight_map, grad_depth_map,
+                                                                      image_size, grad_faces);
+  return check_launch("backward_depth");
+}
+
+int sln_raster_vertex_grad(const void* ws, const float* vertices, int64_t V, const int32_t* faces, int64_t F, int32_t fill_back,
+                           const float* K, const float* R, const float* t, float orig_size, const float* grad_faces, float* grad_proj_scratch,
+                           float* grad_vertices, void* stream) {
+  SLN_CHECK_ARG(ws && vertices && (faces || F == 0) && K && R && t && grad_faces && grad_proj_scratch && grad_vertices, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t F2 = fill_back ? 2 * F : F;
+  ProfScope prof(st, PROF_RASTER_BWD, 36.0 * F2 + 36.0 * V);
+  SLN_CUDA_TRY(cudaMemsetAsync(grad_proj_scratch, 0, sizeof(float) * 3 * (size_t)V, st));
+  if (F2 > 0) {
+    k_faces_to_vertices_bwd<<<ceil_div((int)F2 * 3, 256), 256, 0, st>>>(grad_faces, faces, (int)F, fill_back, grad_proj_scratch);
+    SLN_TRY(check_launch("faces_to_vertices_bwd"));
+  }
+  k_project_bwd<<<ceil_div((int)V, 256), 256, 0, st>>>(vertices, (int)V, K, R, t, orig_size, grad_proj_scratch, grad_vertices);
+  return check_launch("project_bwd");
+}
+
+int sln_scene_classes_fwd(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, int32_t texture_size, float eps,
+                          const int32_t* face_index_map, const float* weight_map, const float* depth_map, const int32_t* face_cls,
+                          int32_t n_cls, float* sval, float* class_images, void* stream) {
+  SLN_TRY(check_raster_args(V, F, image_size));
+  SLN_CHECK_ARG(ws && face_index_map && weight_map && depth_map && face_cls && sval && class_images && n_cls >= 1, "bad argument");
+  RasterPlan p = plan_raster((void*)ws, V, fill_back ? 2 * F : F);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = image_size * image_size;
+  ProfScope prof(st, PROF_RASTER_FWD, (28.0 + 4.0 * n_cls) * P);
+  k_scene_sval<<<ceil_div(P, 256), 256, 0, st>>>(p.fv, face_index_map, weight_map, depth_map, image_size, texture_size, eps, sval);
+  SLN_TRY(check_launch("scene_sval"));
+  k_scene_class_images<<<ceil_div(P, 256), 256, 0, st>>>(face_index_map, face_cls, sval, image_size, n_cls, class_images);
+  return check_launch("scene_class_images");
+}
+
+int sln_scene_classes_bwd(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, float eps,
+                          const int32_t* face_index_map, const int32_t* face_cls, int32_t n_cls, const float* sval,
+                          const float* grad_class_images_internal, float* grad_faces, void* stream) {
+  SLN_TRY(check_raster_args(V, F, image_size));
+  SLN_CHECK_ARG(ws && face_index_map && face_cls && sval && grad_class_images_internal && grad_faces, "null pointer");
+  const int64_t F2 = fill_back ? 2 * F : F;
+  if (F2 == 0) return SLN_OK;
+  RasterPlan p = plan_raster((void*)ws, V, F2);
+  RgbBwdArgs a; memset(&a, 0, sizeof(a));
+  a.fv = p.fv; a.face_index_map = face_index_map; a.F2 = (int)F2; a.is = image_size; a.eps = eps;
+  a.face_cls = face_cls; a.sval = sval; a.gcls = grad_class_images_internal; a.n_cls = n_cls; a.grad_faces = grad_faces;
+  ProfScope prof((cudaStream_t)stream, PROF_RASTER_BWD, 36.0 * F2 + (12.0 + 4.0 * n_cls) * image_size * image_size);
+  k_backward_rgb<<<ceil_div((int)F2 * 6, 8), 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("scene_backward_rgb");
+}
+
+}  // extern "C"

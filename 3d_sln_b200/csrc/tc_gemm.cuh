@@ -1,0 +1,525 @@
+// tcgen05 / TMEM contraction core (sm_100a):  C[i,j] = sum_k A(i,k) * B(j,k)  in "3xTF32" arithmetic.
+//
+// Why 3xTF32: the parity contract of this path is fp32 (single-pass TF32 puts boxes_pred 5e-2 off,
+// 3xTF32 stays at the fp32 noise floor).  Every fp32 operand x is split on the fly into hi = tf32(x) and lo = tf32(x - hi)
+// and the tensor core accumulates  lo*hi + hi*lo + hi*hi  in fp32 in TMEM (short chains only, see "Accumulation scheme").
+//
+// Structure of one CTA (256 threads, tile 128 x BN, K consumed in chunks of 32 floats = one 128-byte swizzle row):
+//   all 8 warps are PRODUCERS: they read A/B through the same operand functors as the SIMT kernel (gather+concat,
+//     lazy BatchNorm+ReLU, BN-backward dy, transposed reads ...), split hi/lo in registers and write four K-major
+//     SWIZZLE_128B tiles (A_hi, A_lo, B_hi, B_lo) of a shared-memory stage;
+//   thread 0 is the MMA ISSUER: after the stage is published (fence.proxy.async + CTA barrier) it issues 4 k-slices x 3
+//     tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) into a TMEM accumulator and commits them to the stage's mbarrier, which
+//     hands the stage back to the producers — loads of chunk c+1 overlap the MMAs of chunk c;
+//   EPILOGUE: tcgen05.ld 32x32b (thread = accumulator row, 32 columns at a time) -> epilogue functor (bias / ReLU mask /
+//     BatchNorm column statistics via an in-warp transpose-reduce / split-K RED.ADD).
+// TMA is not used for the operands because every operand needs a per-element transform (gather, BN, hi/lo split) between
+// global memory and the tensor core; the stores are laid out so that each st.shared.v4 phase covers one full 128-byte row.
+#pragma once
+#include "gemm.cuh"
+
+namespace sln {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;            // floats per K chunk: 128 bytes = one SWIZZLE_128B row
+constexpr int THREADS = 256;
+constexpr int STAGES = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::tf32, issued by ONE thread.
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes (rows) x 32 consecutive fp32 columns of the accumulator: thread t gets row (lane quadrant base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
+// [0,14), leading byte offset >> 4 in [16,30) (unused for swizzled K-major, 1), stride byte offset >> 4 in [32,46) =
+// 1024 B between 8-row groups, version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits 4-5 = 1), A/B tf32 (bits 7-9, 10-12 = 2),
+// both K-major (bits 15, 16 = 0), N >> 3 in [17,23), M >> 4 in [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// byte offset of element (row, k) inside a [rows][32-float] SWIZZLE_128B K-major tile whose base is 1024-byte aligned
+__device__ __forceinline__ uint32_t sw128(int row, int k) { return (uint32_t)(row * 128 + ((((k >> 2) ^ (row & 7)) << 4) | ((k & 3) << 2))); }
+
+__device__ __forceinline__ void split_store4(char* hi_tile, char* lo_tile, int row, int k4, float4 v) {
+  float4 h, l;
+  h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+  uint32_t off = sw128(row, k4);
+  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+__device__ __forceinline__ void split_store1(char* hi_tile, char* lo_tile, int row, int k, float v) {
+  float h = tf32_rna(v);
+  uint32_t off = sw128(row, k);
+  *reinterpret_cast<float*>(hi_tile + off) = h;
+  *reinterpret_cast<float*>(lo_tile + off) = v - h;
+}
+
+// Operand loader.  Every access is a float4 of 4 consecutive STORAGE columns of one storage row, fetched through the
+// functor's two-phase API: fetch() issues all raw 16-byte loads of the chunk back to back (nothing depends on them, so
+// they are all in flight together), store() applies the lazy transform, splits hi/lo and writes the swizzled tiles.
+//   RC == true : storage [row][k]: the quad is 4 consecutive k of one tile row; 8 threads cover one 128-byte row chunk
+//                (coalesced), each st.shared.v4 quarter-warp covers one full swizzle row (conflict-free).
+//   RC == false: storage [k][row]: the quad is 4 consecutive tile rows at one k.  A warp works on [16 k] x [32 rows]
+//                patches in 4 rotations j: lane (kk = lane & 3, rq = lane >> 2) reads k = 4*(((rq >> 1) + j) & 3) + kk,
+//                rows 4*rq .. 4*rq+3: 16 full 32-byte sectors per request, and the 4 scalar stores of a quad hit 32
+//                distinct banks ((k/4) ^ (row % 8) takes 8 values x 4 kk).
+template <int ROWS, bool RC, class Op>
+struct Loader {
+  static constexpr int NV = ROWS * BK / 4 / THREADS;   // quads per thread per chunk
+  static_assert(NV >= 1, "tile too small for 256 loader threads");
+  float4 ra[NV], rb[NV];
+  typename Op::Tok tok[NV];
+  __device__ __forceinline__ void init(const Op& op, int row0, int tid) {
+    if (RC) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) tok[i] = op.token(row0 + ((tid + i * THREADS) >> 3));
+    }
+  }
+  __device__ __forceinline__ void coords(int i, int tid, int& row, int& k) const {   // RC == false: tile row of quad elt 0, k
+    const int lane = tid & 31, warp = tid >> 5;
+    const int kk = lane & 3, rq = lane >> 2;
+    const int u = warp + i * (THREADS / 32);
+    const int patch = u >> 2, j = u & 3;
+    const int h = patch & 1, rb_ = patch >> 1;
+    row = rb_ * 32 + rq * 4;
+    k = 16 * h + 4 * (((rq >> 1) + j) & 3) + kk;
+  }
+  __device__ __forceinline__ void fetch(const Op& op, int row0, int k0, int kend, int tid) {
+    if (RC) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int k = k0 + ((tid + i * THREADS) & 7) * 4;
+        op.fetch4(tok[i], k < kend ? k : 0x3fffffff, ra[i], rb[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        int row, k;
+        coords(i, tid, row, k);
+        tok[i] = op.token(k0 + k < kend ? k0 + k : 0x3fffffff);
+        op.fetch4(tok[i], row0 + row, ra[i], rb[i]);
+      }
+    }
+  }
+  // (k0, kend) must be the ones passed to the matching fetch()
+  __device__ __forceinline__ void store(const Op& op, int row0, int k0, int kend, char* hi_tile, char* lo_tile, int tid) const {
+    if (RC) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int f = tid + i * THREADS;
+        const int k = k0 + (f & 7) * 4;
+        float4 v = op.finish4(tok[i], k < kend ? k : 0x3fffffff, ra[i], rb[i]);
+        split_store4(hi_tile, lo_tile, f >> 3, (f & 7) * 4, v);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        int row, k;
+        coords(i, tid, row, k);
+        float4 v = op.finish4(tok[i], row0 + row, ra[i], rb[i]);
+        split_store1(hi_tile, lo_tile, row + 0, k, v.x);
+        split_store1(hi_tile, lo_tile, row + 1, k, v.y);
+        split_store1(hi_tile, lo_tile, row + 2, k, v.z);
+        split_store1(hi_tile, lo_tile, row + 3, k, v.w);
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------- epilogues
+// The accumulator tile is staged through shared memory (row-per-thread float4 writes, conflict-free with a BN+4 row
+// stride) and then processed with lanes along the columns, so every global access of the epilogue is a coalesced float4
+// and BatchNorm column statistics are plain per-thread sums.  apply4() handles 4 consecutive columns j..j+3 (< N, row < M
+// guaranteed by the caller for full quads; `nvalid` = number of valid columns in the quad).
+struct TcEpiStore {   // C = acc + bias (+ BatchNorm batch statistics)       reference graph.py:12-15
+  float* C; int ldc; const float* bias; BnFwdFin fin;
+  static constexpr bool kStats = true;
+  __device__ __forceinline__ bool wants_stats() const { return fin.enabled != 0; }
+  __device__ __forceinline__ void apply4(int i, int j, int nvalid, float4 a, float (&s1)[4], float (&s2)[4]) const {
+    float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e < nvalid) {
+        if (bias) v[e] += __ldg(bias + j + e);
+        s1[e] += v[e];
+        s2[e] = fmaf(v[e], v[e], s2[e]);
+      }
+    }
+    float* dst = C + (size_t)i * ldc + j;
+    if (nvalid == 4 && ((uintptr_t)dst % 16 == 0)) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (e < nvalid) dst[e] = v[e];
+    }
+  }
+  __device__ __forceinline__ void finalize(int col, double S, double Q) const { bn_fwd_apply(fin, col, S, Q); }
+  __device__ __forceinline__ float* partial() const { return fin.partial; }
+  __device__ __forceinline__ unsigned* counter() const { return fin.counter; }
+};
+
+struct TcEpiMaskReduce {   // G = relu_mask(yprev) ? (acc + add) : 0  + BN-backward column sums
+  float* G; int ldg; const float* add; int ldadd; const float* yprev; int ldy;
+  const float* scale; const float* shift; const float* mean; const float* rstd; BnBwdFin fin;
+  static constexpr bool kStats = true;
+  __device__ __forceinline__ bool wants_stats() const { return true; }
+  __device__ __forceinline__ void apply4(int i, int j, int nvalid, float4 a, float (&s1)[4], float (&s2)[4]) const {
+    float d[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (e < nvalid) {
+        const int jj = j + e;
+        float y = __ldg(yprev + (size_t)i * ldy + jj);
+        float pre = scale ? fmaf(y, __ldg(scale + jj), __ldg(shift + jj)) : y;
+        float dd = d[e];
+        if (add) dd += __ldg(add + (size_t)i * ldadd + jj);
+        float g = pre > 0.f ? dd : 0.f;
+        G[(size_t)i * ldg + jj] = g;
+        s1[e] += g;
+        float yh = mean ? (y - __ldg(mean + jj)) * __ldg(rstd + jj) : 0.f;
+        s2[e] = fmaf(g, yh, s2[e]);
+      }
+    }
+  }
+  __device__ __forceinline__ void finalize(int col, double S, double Q) const { bn_bwd_apply(fin, col, S, Q); }
+  __device__ __forceinline__ float* partial() const { return fin.partial; }
+  __device__ __forceinline__ unsigned* counter() const { return fin.counter; }
+};
+
+struct TcEpiAtomic {   // C += acc (split-K weight gradients, RED.ADD)
+  float* C; int ldc;
+  static constexpr bool kStats = false;
+  __device__ __forceinline__ bool wants_stats() const { return false; }
+  __device__ __forceinline__ void apply4(int i, int j, int nvalid, float4 a, float (&s1)[4], float (&s2)[4]) const {
+    float* dst = C + (size_t)i * ldc + j;
+    if (nvalid == 4 && ((uintptr_t)dst % 16 == 0)) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+    } else {
+      float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (e < nvalid) red_add(dst + e, v[e]);
+    }
+  }
+  __device__ __forceinline__ void finalize(int, double, double) const {}
+  __device__ __forceinline__ float* partial() const { return nullptr; }
+  __device__ __forceinline__ unsigned* counter() const { return nullptr; }
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_TILE = BM * 128;   // bytes of one [128][32] fp32 tile
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+  static constexpr int STAT = 2 * 8 * BN * 4;          // per-warp column statistics [2][8 warps][BN]
+  static constexpr int OUT_LD = BN + 4;                // floats per staged accumulator row
+  static_assert(BM * OUT_LD * 4 <= STAGES * STAGE, "accumulator staging must fit the (idle) stage buffers");
+  static constexpr int BYTES = 1024 + STAGES * STAGE + STAT + 128;
+};
+
+// Accumulation scheme.  The tensor core adds into its fp32 accumulator with truncation, so a long dependent chain of
+// accumulator updates drifts (measured: 1.4e-5 relative at K = 3968, 3 updates per 8 k).  Chains are therefore kept short:
+//   * the dominant hi*hi products of a SEGMENT (SEG_CHUNKS chunks = 64 k -> 8 updates) go to one of two ping-pong TMEM
+//     accumulators; when a segment's MMAs retire it is drained with tcgen05.ld and added — round-to-nearest — into fp32
+//     registers while the next segment's MMAs run into the other buffer;
+//   * the two cross terms lo*hi + hi*lo (2^-11 of the magnitude) accumulate over the whole K range in a third TMEM
+//     accumulator, where truncation is harmless, and are added once at the end.
+// TMEM columns: [0,BN) acc0, [BN,2BN) acc1, [2BN,3BN) cross terms.
+constexpr int SEG_CHUNKS = 2;
+
+// grid = (ceil(N/BN), ceil(M/128), splits); each z-slice reduces k in [z*kchunk, (z+1)*kchunk), kchunk % 32 == 0.
+template <int BN, bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
+__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const BOp B, const Epi epi, int M, int N, int K, int kchunk) {
+  using L = SmemLayout<BN>;
+  extern __shared__ char smem_raw[];
+  char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
+  float* stat = reinterpret_cast<float*>(smem + STAGES * L::STAGE);        // [2][4][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE + L::STAT);   // [STAGES] stage-free + [2] segment-done
+  uint64_t* segbar = bars + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(segbar + 2);
+  int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+  const int nchunks = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
+  constexpr uint32_t TMEM_COLS = (3 * BN <= 128) ? 128 : ((3 * BN <= 256) ? 256 : 512);
+  static_assert(3 * BN <= 512, "three accumulators must fit the 512 TMEM columns");
+
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (tid == 32) {
+#pragma unroll
+    for (int s = 0; s < STAGES + 2; ++s) mbar_init(bars + s, 1);
+    fence_barrier_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  const int quad = warp & 3, half = warp >> 2;          // TMEM lane quadrant (fixed by warp id % 4), column half
+  // BN >= 64: warps 0-3 own the left half of the columns, warps 4-7 the right half; BN = 32: only warps 0-3 hold accumulators
+  constexpr int CH2 = BN >= 64 ? BN / 64 : 1;           // 32-column chunks owned by one thread
+  const bool has_acc = BN >= 64 || half == 0;
+  const int col_off = BN >= 64 ? half * (BN / 2) : 0;
+  const uint32_t tmem_mine = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_off;
+  float racc[CH2][32];
+#pragma unroll
+  for (int j = 0; j < CH2; ++j)
+#pragma unroll
+    for (int e = 0; e < 32; ++e) racc[j][e] = 0.f;
+  auto drain = [&](int seg) {                           // racc += TMEM accumulator of a retired segment
+    mbar_wait(segbar + (seg & 1), (uint32_t)((seg >> 1) & 1));
+    tc_fence_after();
+    if (has_acc) {
+#pragma unroll
+      for (int j = 0; j < CH2; ++j) {
+        float v[32];
+        tmem_ld32(tmem_mine + (uint32_t)((seg & 1) * BN + j * 32), v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) racc[j][e] += v[e];
+      }
+    }
+    tc_fence_before();
+  };
+
+  Loader<BM, A_RC, AOp> la;
+  Loader<BN, B_RC, BOp> lb;
+  la.init(A, m0, tid);
+  lb.init(B, n0, tid);
+  if (nchunks > 0) {
+    la.fetch(A, m0, kbeg, kend, tid);
+    lb.fetch(B, n0, kbeg, kend, tid);
+  }
+  constexpr uint32_t idesc = make_idesc(BN);
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c % STAGES, use = c / STAGES;
+    const int seg = c / SEG_CHUNKS;
+    const bool seg_first = (c % SEG_CHUNKS) == 0, seg_last = (c % SEG_CHUNKS) == SEG_CHUNKS - 1 || c == nchunks - 1;
+    char* st = smem + s * L::STAGE;
+    if (use > 0) mbar_wait(bars + s, (use - 1) & 1);   // the MMAs that read this stage have retired
+    la.store(A, m0, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
+    lb.store(B, n0, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
+    if (c + 1 < nchunks) {                              // next chunk's global loads fly during the MMAs
+      la.fetch(A, m0, kbeg + (c + 1) * BK, kend, tid);
+      lb.fetch(B, n0, kbeg + (c + 1) * BK, kend, tid);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + L::A_TILE, b_hi = a_hi + 2 * L::A_TILE, b_lo = b_hi + L::B_TILE;
+      const uint32_t d_main = tmem_acc + (uint32_t)((seg & 1) * BN), d_cross = tmem_acc + (uint32_t)(2 * BN);
+#pragma unroll
+      for (int k = 0; k < BK / 8; ++k) {               // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
+        const uint32_t o = k * 32;
+        mma_tf32(d_cross, make_desc(a_lo + o), make_desc(b_hi + o), idesc, (c > 0 || k > 0) ? 1u : 0u);
+        mma_tf32(d_cross, make_desc(a_hi + o), make_desc(b_lo + o), idesc, 1u);
+        mma_tf32(d_main, make_desc(a_hi + o), make_desc(b_hi + o), idesc, (!seg_first || k > 0) ? 1u : 0u);
+      }
+      mma_commit(bars + s);
+      if (seg_last) mma_commit(segbar + (seg & 1));
+    }
+    // Drain the previous segment while this chunk's MMAs run.  The buffer it frees is next written two chunks from now,
+    // after two more CTA barriers, so every warp's tcgen05.ld has completed (fence::before_thread_sync in drain()).
+    if (seg_first && seg > 0) drain(seg - 1);
+  }
+  if (nchunks > 0) {
+    const int last_seg = (nchunks - 1) / SEG_CHUNKS;
+    drain(last_seg);                                     // also guarantees every cross-term MMA has retired
+    if (has_acc) {
+#pragma unroll
+      for (int j = 0; j < CH2; ++j) {
+        float v[32];
+        tmem_ld32(tmem_mine + (uint32_t)(2 * BN + j * 32), v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) racc[j][e] += v[e];
+      }
+    }
+  }
+  // ---- epilogue: stage the tile in shared memory (the stage buffers are idle: every MMA has retired) ...
+  float* outs = reinterpret_cast<float*>(smem);
+  if (has_acc) {
+    const int r = quad * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < CH2; ++j)
+#pragma unroll
+      for (int e = 0; e < 32; e += 4)
+        *reinterpret_cast<float4*>(outs + (size_t)r * L::OUT_LD + col_off + j * 32 + e) =
+            make_float4(racc[j][e], racc[j][e + 1], racc[j][e + 2], racc[j][e + 3]);
+  }
+  __syncthreads();
+  // ... then lanes run along the columns: LPR lanes cover one row (4 columns each), a warp covers 32/LPR rows per pass
+  const bool stats = Epi::kStats && epi.wants_stats();
+  constexpr int LPR = BN / 4, RPP = 32 / LPR;           // BN = 128: 32 lanes per row, 1 row per pass
+  const int cq = lane % LPR, rsub = lane / LPR;
+  const int jcol = n0 + cq * 4;
+  const int nvalid = min(4, max(0, N - jcol));
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (nvalid > 0) {
+    for (int r = warp * RPP + rsub; r < BM; r += 8 * RPP) {
+      if (m0 + r >= M) break;
+      float4 a = *reinterpret_cast<const float4*>(outs + (size_t)r * L::OUT_LD + cq * 4);
+      epi.apply4(m0 + r, jcol, nvalid, a, s1, s2);
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {                       // fold the RPP row sub-groups of the warp (fixed order)
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) { s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o); s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o); }
+    }
+    if (rsub == 0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { stat[(0 * 8 + warp) * BN + cq * 4 + e] = s1[e]; stat[(1 * 8 + warp) * BN + cq * 4 + e] = s2[e]; }
+    }
+    __syncthreads();
+    float* partial = epi.partial();
+    for (int j = tid; j < BN; j += THREADS) {
+      if (n0 + j < N) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { a += stat[(0 * 8 + w) * BN + j]; b += stat[(1 * 8 + w) * BN + j]; }
+        partial[((size_t)blockIdx.y * 2 + 0) * N + n0 + j] = a;
+        partial[((size_t)blockIdx.y * 2 + 1) * N + n0 + j] = b;
+      }
+    }
+    // (finalize_column_block starts with a CTA barrier, after which the staging area is reused as fp64 scratch)
+    finalize_column_block<THREADS>(partial, epi.counter(), n0, BN, N, tid, reinterpret_cast<double*>(smem), s_last,
+                                   [&](int col, double S, double Q) { epi.finalize(col, S, Q); });
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_acc, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------- host side
+struct TcChoice { int bn, splits, kchunk; };
+
+inline TcChoice pick_tc(int M, int N, int K, bool allow_split) {
+  const int bns[3] = {128, 64, 32};
+  double best = 1e300;
+  TcChoice c{32, 1, K};
+  for (int t = 0; t < 3; ++t) {
+    const int bn = bns[t];
+    if (bn > 32 && N <= bn / 2) continue;           // do not pad N by more than 2x
+    int tiles = ceil_div(M, BM) * ceil_div(N, bn);
+    int splits = 1;
+    if (allow_split) {
+      splits = tiles >= kNumSMs ? 1 : ceil_div(kNumSMs, tiles);
+      int max_splits = ceil_div(K, 256);
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+    }
+    int kchunk = ceil_div(ceil_div(K, splits), BK) * BK;
+    splits = ceil_div(K, kchunk);
+    int ctas = tiles * splits;
+    int waves = ceil_div(ctas, kNumSMs);            // one CTA per SM (register bound)
+    // cycles per CTA ~ chunks x (one memory round trip + smem fill of 128 + BN rows) + prologue + epilogue (~ BN)
+    double per_cta = (double)ceil_div(kchunk, BK) * (600.0 + 2.0 * (BM + bn)) + 3000.0 + 20.0 * bn;
+    double cost = waves * per_cta;
+    if (cost < best) { best = cost; c = TcChoice{bn, splits, kchunk}; }
+  }
+  return c;
+}
+
+// shapes the tensor-core path accepts; everything else (tiny heads, K = 6 box embedding) stays on the SIMT kernel
+inline bool tc_eligible(int M, int N, int K) { return M >= 64 && N >= 32 && K >= 32; }
+
+template <int BN, bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
+int launch_tc_bn(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, const TcChoice& c) {
+  auto kern = tc_gemm_kernel<BN, A_RC, B_RC, AOp, BOp, Epi>;
+  constexpr int bytes = SmemLayout<BN>::BYTES;
+  static bool configured = false;   // per template instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(tc_gemm, %d B smem) failed: %s", bytes, cudaGetErrorString(e)); return SLN_ECUDA; }
+    configured = true;
+  }
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), c.splits);
+  kern<<<grid, THREADS, bytes, st>>>(A, B, epi, M, N, K, c.kchunk);
+  return SLN_OK;
+}
+
+template <bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
+int launch_tc(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, bool allow_split, const char* what,
+              int prof_cls) {
+  if (M <= 0 || N <= 0) return SLN_OK;
+  ProfScope prof(st, prof_cls, 2.0 * (double)M * (double)N * (double)K);
+  TcChoice c = pick_tc(M, N, K, allow_split);
+  int rc;
+  if (c.bn == 128) rc = launch_tc_bn<128, A_RC, B_RC>(st, A, B, epi, M, N, K, c);
+  else if (c.bn == 64) rc = launch_tc_bn<64, A_RC, B_RC>(st, A, B, epi, M, N, K, c);
+  else rc = launch_tc_bn<32, A_RC, B_RC>(st, A, B, epi, M, N, K, c);
+  if (rc != SLN_OK) return rc;
+  return check_launch(what);
+}
+
+}  // namespace tc
+}  // namespace sln

@@ -8,10 +8,15 @@
 
 #include "../../include/sln_b200.h"
 #include "vae_kernels.cuh"
+#include "tc_gemm.cuh"
 
 namespace sln {
 
 namespace {
+
+// contraction engine of the MLP stage: 1 = tcgen05 3xTF32 tiles (default), 0 = FP32 SIMT tiles (A/B checks, odd shapes)
+int g_engine = 1;
+inline bool use_tc(int M, int N, int K) { return g_engine == 1 && tc::tc_eligible(M, N, K); }
 
 constexpr int kMaxLayers = 32;
 
@@ -144,7 +149,7 @@ void plan_state(Arena& ar, CounterPool& cp, int M, int out, BlkState* s) {
   s->mean = ar.take<float>(out); s->rstd = ar.take<float>(out); s->scale = ar.take<float>(out); s->shift = ar.take<float>(out);
   s->p = ar.take<float>(out); s->q = ar.take<float>(out); s->r = ar.take<float>(out);
   s->partial = ar.take<float>((size_t)2 * max_row_tiles(M) * out);
-  s->counter = cp.base + cp.n; cp.n++;
+  s->counter = cp.base + (size_t)cp.n * kCounterStride; cp.n++;
   s->g = nullptr;
 }
 
@@ -185,7 +190,7 @@ struct NetPlan {
   size_t bytes;
 };
 
-constexpr int kCounterCap = 4 * kMaxLayers + 16;
+constexpr int kCounterCap = (4 * kMaxLayers + 16) * kCounterStride;
 
 // which: 0 encoder, 1 decoder, 2 single standalone layer
 void make_plan(const Dims& dm, int O, int T, int which, void* ws, NetPlan* p) {
@@ -253,6 +258,10 @@ int block_fwd(const Ctx& c, const AOp& A, int M, const Blk& b, BlkState& s, floa
     k_bn_eval_prep<<<ceil_div(b.lin.out, 128), 128, 0, c.st>>>(b.gamma, b.beta, b.rm, b.rv, c.dm.eps, b.lin.out, s.mean, s.rstd, s.scale, s.shift);
     SLN_TRY(check_launch("bn_eval_prep"));
   }
+  if (use_tc(M, b.lin.out, b.lin.in) && A.vec_ok() && weight_view(b.lin).vec_ok()) {
+    tc::TcEpiStore te{epi.C, epi.ldc, epi.bias, epi.fin};
+    return tc::launch_tc<true, true>(c.st, A, weight_view(b.lin), te, M, b.lin.out, b.lin.in, false, "linear_fwd_tc", PROF_GEMM_FWD);
+  }
   return launch_gemm<true, true>(c.st, A, weight_view(b.lin), epi, M, b.lin.out, b.lin.in, false, "linear_fwd", PROF_GEMM_FWD);
 }
 
@@ -280,6 +289,10 @@ ActInfo blk_act(const Blk& b, const BlkState& s) {
 template <class XOp>
 int bwd_w(const Ctx& c, const DyView& dy, const XOp& X, const Lin& lin, int M) {
   if (!lin.dW) return SLN_OK;
+  if (use_tc(lin.out, lin.in, M) && dy.vec_ok() && X.vec_ok()) {
+    tc::TcEpiAtomic te{lin.dW, lin.in};
+    return tc::launch_tc<false, false>(c.st, dy, X, te, lin.out, lin.in, M, true, "linear_bwd_w_tc", PROF_GEMM_BWD_W);
+  }
   EpiAtomic epi{lin.dW, lin.in};
   return launch_gemm<false, false>(c.st, dy, X, epi, lin.out, lin.in, M, true, "linear_bwd_w", PROF_GEMM_BWD_W);
 }
@@ -287,6 +300,10 @@ int bwd_w(const Ctx& c, const DyView& dy, const XOp& X, const Lin& lin, int M) {
 int bwd_x_plain(const Ctx& c, const DyView& dy, const Lin& lin, int M, float* dX, int ldx) {
   EpiStore epi; memset(&epi, 0, sizeof(epi));
   epi.C = dX; epi.ldc = ldx;
+  if (use_tc(M, lin.in, lin.out) && dy.vec_ok() && weight_view(lin).vec_ok()) {
+    tc::TcEpiStore te{dX, ldx, nullptr, epi.fin};
+    return tc::launch_tc<true, false>(c.st, dy, weight_view(lin), te, M, lin.in, lin.out, false, "linear_bwd_x_tc", PROF_GEMM_BWD_X);
+  }
   return launch_gemm<true, false>(c.st, dy, weight_view(lin), epi, M, lin.in, lin.out, false, "linear_bwd_x", PROF_GEMM_BWD_X);
 }
 // prev.g = relu_mask(prev) ? (dy W + add) : 0, with the BN-backward reduction of `prev` fused in the epilogue.
@@ -297,13 +314,16 @@ int bwd_x_masked(const Ctx& c, const DyView& dy, const Lin& lin, int M, const Bl
   if (pb.has_bn) { epi.scale = ps.scale; epi.shift = ps.shift; epi.mean = ps.mean; epi.rstd = ps.rstd; }
   epi.fin = blk_fin(c, pb, ps);
   SLN_CHECK_ARG(lin.in == pb.lin.out, "internal: masked backward expects matching widths (%d vs %d)", lin.in, pb.lin.out);
+  if (use_tc(M, lin.in, lin.out) && dy.vec_ok() && weight_view(lin).vec_ok()) {
+    tc::TcEpiMaskReduce te{epi.G, epi.ldg, epi.add, epi.ldadd, epi.yprev, epi.ldy, epi.scale, epi.shift, epi.mean, epi.rstd, epi.fin};
+    return tc::launch_tc<true, false>(c.st, dy, weight_view(lin), te, M, lin.in, lin.out, false, "linear_bwd_x_masked_tc", PROF_GEMM_BWD_X);
+  }
   return launch_gemm<true, false>(c.st, dy, weight_view(lin), epi, M, lin.in, lin.out, false, "linear_bwd_x_masked", PROF_GEMM_BWD_X);
 }
 // bias gradient of a Linear whose dy is given directly: db += column sums
 int bwd_bias_plain(const Ctx& c, const float* dy, int ld, int M, const Lin& lin) {
   if (!lin.db) return SLN_OK;
-  k_embed_bwd<<<1, 128, 0, c.st>>>(dy, ld, nullptr, 0, nullptr, M, lin.out, lin.db, lin.out);
-  return check_launch("bias_grad");
+  return launch_embed_bwd(c.st, dy, ld, nullptr, 0, nullptr, M, lin.out, lin.db, 1);
 }
 
 int graph_prep(const Ctx& c, NetPlan& p, const int64_t* triples_or_edges, int stride3) {
@@ -363,9 +383,7 @@ int gather_rows(const Ctx& c, const float* table, int ldt, const int* idx, int n
   return check_launch("gather_rows");
 }
 int embed_bwd(const Ctx& c, const float* a, int lda, const float* b, int ldb, const int* idx, int n, int width, float* tg, int rows) {
-  if (!tg || n <= 0) return SLN_OK;
-  k_embed_bwd<<<rows, 128, 0, c.st>>>(a, lda, b, ldb, idx, n, width, tg, width);
-  return check_launch("embed_bwd");
+  return launch_embed_bwd(c.st, a, lda, b, ldb, idx, n, width, tg, rows);
 }
 
 // ---------------------------------------------------------------- one GraphTripleConv layer
@@ -377,7 +395,7 @@ int gconv_fwd(const Ctx& c, const Graph& g, const Blk* blk, BlkState* st, float*
   SLN_TRY(block_fwd(c, block_out(blk[0], st[0]), T, blk[1], st[1]));
   MatView a2 = block_out(blk[1], st[1]);
   if (O > 0) {
-    int threads = min(256, max(32, ceil_div(H / 4, 32) * 32));
+    int threads = pool_threads(H);
     ProfScope prof(c.st, PROF_POOL, pool_bytes(O, T, H));
     k_pool_fwd<<<O, threads, 0, c.st>>>(a2, g.row_ptr, g.ent, g.cnt, O, H, D, pooled);
     SLN_TRY(check_launch("pool_fwd"));
@@ -767,10 +785,47 @@ int sln_gconv_pool_fwd(const float* new_t_vecs, int64_t O, int64_t T, int32_t H,
   Graph g; int *deg, *err;
   plan_graph(ar, (int)O, (int)T, &g, &deg, &err);
   MatView a2 = make_view(new_t_vecs, 2 * H + Dout, (int)T, 2 * H + Dout);
-  int threads = min(256, max(32, ceil_div(H / 4, 32) * 32));
+  int threads = pool_threads(H);
   ProfScope prof((cudaStream_t)stream, PROF_POOL, pool_bytes((int)O, (int)T, H));
   k_pool_fwd<<<(int)O, threads, 0, (cudaStream_t)stream>>>(a2, g.row_ptr, g.ent, g.cnt, (int)O, H, Dout, pooled);
   return check_launch("pool_fwd");
+}
+
+// ---------------------------------------------------------------- contraction primitive (tests / roofline sweeps)
+int sln_set_engine(int engine) {
+  int prev = g_engine;
+  if (engine == 0 || engine == 1) g_engine = engine;
+  return prev;
+}
+
+int sln_contract(const float* A, int64_t lda, int32_t a_rc, const float* B, int64_t ldb, int32_t b_rc, float* C, int64_t ldc, int64_t M,
+                 int64_t N, int64_t K, int32_t accumulate, int32_t engine, void* stream) {
+  SLN_CHECK_ARG(A && B && C && M >= 0 && N >= 0 && K >= 0 && M < (1ll << 30) && N < (1ll << 30) && K < (1ll << 30), "bad argument");
+  SLN_CHECK_ARG(engine == 0 || engine == 1, "engine must be 0 (fp32 SIMT) or 1 (tcgen05 3xTF32)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int m = (int)M, n = (int)N, k = (int)K;
+  MatView a = a_rc ? make_view(A, (int)lda, m, k) : make_view(A, (int)lda, k, m);
+  MatView b = b_rc ? make_view(B, (int)ldb, n, k) : make_view(B, (int)ldb, k, n);
+  const bool tcp = engine == 1;
+  if (tcp) SLN_CHECK_ARG(tc::tc_eligible(m, n, k) && a.vec_ok() && b.vec_ok(),
+                         "tcgen05 engine needs M >= 64, N >= 32, K >= 32, 16-byte aligned operands and leading dimensions % 4 == 0");
+#define SLN_DISPATCH(ARC, BRC)                                                                                                   \
+  do {                                                                                                                           \
+    if (accumulate) {                                                                                                            \
+      if (tcp) { tc::TcEpiAtomic e{C, (int)ldc}; return tc::launch_tc<ARC, BRC>(st, a, b, e, m, n, k, true, "contract_tc", PROF_MISC); } \
+      EpiAtomic e{C, (int)ldc}; return launch_gemm<ARC, BRC>(st, a, b, e, m, n, k, true, "contract", PROF_MISC);                 \
+    } else {                                                                                                                     \
+      EpiStore e; memset(&e, 0, sizeof(e)); e.C = C; e.ldc = (int)ldc;                                                           \
+      if (tcp) { tc::TcEpiStore te{C, (int)ldc, nullptr, e.fin}; return tc::launch_tc<ARC, BRC>(st, a, b, te, m, n, k, false, "contract_tc", PROF_MISC); } \
+      return launch_gemm<ARC, BRC>(st, a, b, e, m, n, k, false, "contract", PROF_MISC);                                          \
+    }                                                                                                                            \
+  } while (0)
+  if (a_rc && b_rc) SLN_DISPATCH(true, true);
+  else if (a_rc && !b_rc) SLN_DISPATCH(true, false);
+  else if (!a_rc && b_rc) SLN_DISPATCH(false, true);
+  else SLN_DISPATCH(false, false);
+#undef SLN_DISPATCH
+  return SLN_OK;
 }
 
 // ---------------------------------------------------------------- reparameterisation, losses, Adam

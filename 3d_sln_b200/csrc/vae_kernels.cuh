@@ -115,25 +115,50 @@ __global__ void k_small_linear(const float* __restrict__ x, int n, int kin, cons
   }
 }
 
-// table_grad[r, c] += sum_{i: idx[i]==r} ( a[i, c] (+ b[i, c]) ); idx == null -> single row 0 (column sum).
-// One CTA per table row (tables have <= 33 rows); threads own columns and walk the index list in order, so the
-// summation order is fixed (deterministic, no atomics).  The match test is warp-uniform.
-__global__ void k_embed_bwd(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb, const int* __restrict__ idx,
-                            int n, int width, float* table_grad, int ldt) {
+// table_grad[r, c] += sum_{i: idx[i]==r} ( a[i, c] (+ b[i, c]) ); idx == null -> single row 0 (column sum: Linear bias grads).
+// grid (table rows, index splits, column blocks of 128); the 8 warps of a CTA walk interleaved entries of their index
+// range (the match test is warp-uniform, the row read a coalesced 128..512-byte segment), reduce through shared memory in
+// a fixed order and add the CTA's partial with one RED.ADD per column.
+__global__ void __launch_bounds__(256) k_embed_bwd(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                                   const int* __restrict__ idx, int n, int width, float* table_grad, int ldt, int per_cta) {
   const int r = blockIdx.x;
-  for (int c = threadIdx.x; c < width; c += blockDim.x) {
-    float acc = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < n; ++i) {
-      int id = idx ? __ldg(idx + i) : r;
-      if (id == r) {
+  const int i0 = blockIdx.y * per_cta, i1 = min(n, i0 + per_cta);
+  const int c0 = blockIdx.z * 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = i0 + warp; i < i1; i += 8) {
+    int id = idx ? __ldg(idx + i) : r;
+    if (id != r) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = c0 + lane + 32 * j;
+      if (c < width) {
         float v = __ldg(a + (size_t)i * lda + c);
         if (b) v += __ldg(b + (size_t)i * ldb + c);
-        acc += v;
+        acc[j] += v;
       }
     }
-    table_grad[(size_t)r * ldt + c] += acc;
   }
+  __shared__ float red[8][128];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[warp][lane + 32 * j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 128 && c0 + threadIdx.x < width) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    if (s != 0.f) red_add(table_grad + (size_t)r * ldt + c0 + threadIdx.x, s);
+  }
+}
+inline int launch_embed_bwd(cudaStream_t st, const float* a, int lda, const float* b, int ldb, const int* idx, int n, int width,
+                            float* table_grad, int rows) {
+  if (!table_grad || n <= 0 || width <= 0) return SLN_OK;
+  int splits = max(1, min(ceil_div(n, 64), (2 * kNumSMs) / max(rows, 1)));
+  int per_cta = ceil_div(n, splits);
+  splits = ceil_div(n, per_cta);
+  dim3 grid(rows, splits, ceil_div(width, 128));
+  k_embed_bwd<<<grid, 256, 0, st>>>(a, lda, b, ldb, idx, n, width, table_grad, width, per_cta);
+  return check_launch("embed_bwd");
 }
 
 // ================================================================ avg pooling  (reference graph.py:92-108)
@@ -144,21 +169,53 @@ __global__ void k_pool_fwd(const MatView a2, const int* __restrict__ row_ptr, co
   int o = blockIdx.x;
   int b = __ldg(row_ptr + o), e = __ldg(row_ptr + o + 1);
   float ic = __ldg(cnt + o);  // true division below: bit-identical to the reference's pooled / counts
-  for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k = b; k < e; ++k) {
-      int en = __ldg(ent + k);
-      int t = en & ((1 << 30) - 1);
-      int off = (en >> 30) ? (H + D) : 0;
-      float4 v = a2.ld4(t, off + c);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  __shared__ int s_ent[256];
+  float4 acc[2];
+  acc[0] = acc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // entries are staged through shared memory so that the row reads (the long-latency part) do not depend on a global
+  // index load: 8 independent row reads are in flight per thread, summed in CSR order (= the reference's scatter order)
+  for (int base = b; base < e; base += 256) {
+    int m = min(256, e - base);
+    __syncthreads();
+    for (int k = threadIdx.x; k < m; k += blockDim.x) s_ent[k] = __ldg(ent + base + k);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      int c = (threadIdx.x + j * blockDim.x) * 4;
+      if (c >= H) break;
+      float4 a = acc[j];
+      int k = 0;
+      for (; k + 8 <= m; k += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          int en = s_ent[k + u];
+          v[u] = a2.ld4(en & ((1 << 30) - 1), ((en >> 30) ? (H + D) : 0) + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+      }
+      for (; k < m; ++k) {
+        int en = s_ent[k];
+        float4 v = a2.ld4(en & ((1 << 30) - 1), ((en >> 30) ? (H + D) : 0) + c);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      acc[j] = a;
     }
-    acc.x = __fdiv_rn(acc.x, ic); acc.y = __fdiv_rn(acc.y, ic); acc.z = __fdiv_rn(acc.z, ic); acc.w = __fdiv_rn(acc.w, ic);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    int c = (threadIdx.x + j * blockDim.x) * 4;
+    if (c >= H) break;
+    float4 a = acc[j];
+    a.x = __fdiv_rn(a.x, ic); a.y = __fdiv_rn(a.y, ic); a.z = __fdiv_rn(a.z, ic); a.w = __fdiv_rn(a.w, ic);
     float* dst = pooled + (size_t)o * H + c;
-    if (c + 3 < H) *reinterpret_cast<float4*>(dst) = acc;
-    else { dst[0] = acc.x; if (c + 1 < H) dst[1] = acc.y; if (c + 2 < H) dst[2] = acc.z; }
+    if (c + 3 < H) *reinterpret_cast<float4*>(dst) = a;
+    else { dst[0] = a.x; if (c + 1 < H) dst[1] = a.y; if (c + 2 < H) dst[2] = a.z; }
   }
 }
+// threads per CTA for k_pool_fwd: one float4 column group per thread, two when H > 1024
+inline int pool_threads(int H) { int t = ceil_div(ceil_div(H, 4), 32) * 32; if (t > 256) t = ceil_div(ceil_div(H, 8), 32) * 32; return max(32, min(t, 1024)); }
 
 // ================================================================ backward "prep" passes
 // G[i,j] = mask(y[i,j]) ? src(i,j) : 0 and the BN-backward column sums, for gradients that are assembled by a gather
@@ -246,19 +303,10 @@ __global__ void __launch_bounds__(512) k_prep(const Src src, const ActInfo act, 
     fin.partial[((size_t)blockIdx.y * 2 + 0) * N + j] = a;
     fin.partial[((size_t)blockIdx.y * 2 + 1) * N + j] = c;
   }
-  __threadfence();
-  __syncthreads();
   const int tid = threadIdx.y * 128 + threadIdx.x;
-  if (tid == 0) {
-    unsigned ticket = atomicAdd(fin.counter, 1u);
-    s_last = (ticket == gridDim.x * gridDim.y - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    for (int col = tid; col < N; col += 512) bn_bwd_finalize(fin, col, N, gridDim.y);
-    if (tid == 0) *fin.counter = 0u;
-  }
+  __shared__ double sred[2 * 512];
+  finalize_column_block<512>(fin.partial, fin.counter, blockIdx.x * 128, 128, N, tid, sred, &s_last,
+                             [&](int col, double S, double Q) { bn_bwd_apply(fin, col, S, Q); });
 }
 
 template <class Src>

@@ -1,0 +1,185 @@
+"""Drop-in for the hot part of the reference's ``models/diff_render.py``: ``get_cam_mat`` (:13-46) and ``mesh_render_func``
+(:48-435) with the same signatures and return values.
+
+What differs from the reference, by design:
+  * the SUNCG mesh retrieval (`suncg_retrieve`, `load_suncg_obj`, models/misc.py — needs the SUNCG dataset, pywavefront,
+    pymesh) is replaced by a resident ``MeshLibrary`` of synthetic meshes (data/synthetic_meshes.py); set another provider
+    with ``set_mesh_library``.  Meshes stay on the device (the reference re-uploads every mesh on every call, misc.py:118);
+  * the per-object Python loop of 4x4 transforms (:76-159) is one batched tensor expression per scene;
+  * depth + the 32 per-class mask renders (:366-431, 33 renderer calls on identical geometry) come from ONE rasterization
+    (neural_renderer.render_scene_classes) and the per-class loop of the compositing is vectorised over classes.
+The result tensor has the reference's layout: [1, 1 + 40 + (n_classes - 3), 256, 256] = depth | one-hot(40) | depth planes.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import neural_renderer as nr
+from ..data.synthetic import OBJECT_NAMES
+from ..data.synthetic_meshes import MeshLibrary, room_shell
+
+nyu_class = ['wall', 'floor', 'cabinet', 'bed', 'chair', 'sofa', 'table', 'door', 'window', 'bookshelf', 'picture', 'counter', 'blinds',
+             'desk', 'shelves', 'curtain', 'dresser', 'pillow', 'mirror', 'floor mat', 'clothes', 'ceiling', 'books', 'refridgerator',
+             'television', 'paper', 'towel', 'shower curtain', 'box', 'whiteboard', 'person', 'night stand', 'toilet', 'sink', 'lamp',
+             'bathtub', 'bag', 'otherstructure', 'otherfurniture', 'otherprop']
+inter_out = 512
+final_out = 256
+object_idx_to_name = list(OBJECT_NAMES)
+SKIPPED_TYPES = ["wall", "ceiling", "floor", "person", "door", "window", "curtain", "blinds"]   # reference :88
+
+_LIBRARY = None
+
+
+def set_mesh_library(lib):
+    global _LIBRARY
+    _LIBRARY = lib
+
+
+def mesh_library(device):
+    global _LIBRARY
+    if _LIBRARY is None:
+        _LIBRARY = MeshLibrary()
+    return _LIBRARY.to(device)
+
+
+def desired_classes():
+    """Class order of the mask renders (reference :65-69,372-374): sorted(31 types + ceiling, floor, wall), wall first."""
+    names = sorted(set(object_idx_to_name[1:] + ['ceiling', 'floor', 'wall']))
+    names.remove("wall")
+    names.insert(0, "wall")
+    return names
+
+
+def get_cam_mat(boxes):
+    """K [1,3,3], R [1,3,3], t [1,1,3] on the device of ``boxes`` (reference :13-46)."""
+    dev = boxes[-1].device
+    theta_rot = -0.4
+    fl_pix = 400
+    int_mat = torch.tensor([[fl_pix * inter_out / 1024, 0, inter_out / 2.0], [0, fl_pix * inter_out / 1024, inter_out / 2.0],
+                            [0, 0, 1.0]], dtype=torch.float32)[None]
+    rot_w2c = torch.from_numpy(np.array([[1, 0, 0], [0, np.cos(theta_rot), np.sin(theta_rot)],
+                                         [0, -np.sin(theta_rot), np.cos(theta_rot)]], dtype="float32"))
+    room = boxes[-1].detach().float().cpu()
+    cam = torch.zeros(3, 1)
+    cam[0, 0] = room[3] / 2.0
+    cam[1, 0] = room[4] / 2.0 + min(0.1, abs(float(room[4]) / 2.0))
+    cam[2, 0] = room[5]
+    t_w2c = torch.matmul(rot_w2c, -cam)
+    cam2cv = torch.tensor([[1, 0, 0], [0, -1, 0], [0, 0, -1]], dtype=torch.float)
+    R = torch.matmul(cam2cv, rot_w2c)
+    t = torch.matmul(cam2cv, t_w2c)
+    return int_mat.to(dev), R.reshape(1, 3, 3).to(dev), t.reshape(1, 1, 3).to(dev)
+
+
+def assemble_scene(boxes, angles, objs, library):
+    """Per-object similarity transforms (reference :76-159) for all objects at once.
+
+    boxes: sequence of [6] tensors (objects normalised to the room; last row = room), angles: sequence of scalars (0..24),
+    objs: class ids.  Returns vertices [1,V,3] (differentiable w.r.t. boxes and angles), faces [1,F,3] int32, face_cls [F]
+    int32 (index into desired_classes()), valid object indices and their sizes."""
+    dev = boxes[-1].device
+    names = desired_classes()
+    room = boxes[-1][3:]
+    verts, faces, cls, kept, sizes = [], [], [], [], []
+    off = 0
+    for i in range(len(boxes) - 1):
+        mtype = object_idx_to_name[int(objs[i])]
+        if mtype in SKIPPED_TYPES:
+            continue
+        kept.append(i)
+    if kept:
+        B = torch.stack([boxes[i] for i in kept])                       # [n,6]
+        A = torch.stack([torch.as_tensor(angles[i], device=dev, dtype=torch.float32).reshape(()) for i in kept])
+        bmin, bmax = B[:, :3] * room, B[:, 3:] * room
+        center, size = (bmax + bmin) / 2, bmax - bmin
+        models = [library.get(object_idx_to_name[int(objs[i])]) for i in kept]
+        msize = torch.stack([m["size"] for m in models])
+        mcent = torch.stack([m["center"] for m in models])
+        scale = (size / msize).min(dim=1).values                          # :106
+        theta = -A * (2 * math.pi / 24)
+        c, s = torch.cos(theta), torch.sin(theta)
+        zero, one = torch.zeros_like(c), torch.ones_like(c)
+        rot = torch.stack([torch.stack([c, zero, s], -1), torch.stack([zero, one, zero], -1), torch.stack([-s, zero, c], -1)], 1)   # :107-113
+        trans = center - scale[:, None] * torch.einsum("nij,nj->ni", rot, mcent)                                                  # :115
+        for j, m in enumerate(models):
+            v = scale[j] * torch.matmul(m["vertices"], rot[j].t()) + trans[j]
+            verts.append(v)
+            faces.append(m["faces"] + off)
+            cls.append(torch.full((m["faces"].size(0),), names.index(object_idx_to_name[int(objs[kept[j]])]), dtype=torch.int32, device=dev))
+            off += v.size(0)
+            sizes.append(size[j])
+    shell = room_shell(boxes[-1][3:].detach().cpu())
+    for name in ("wall", "floor", "ceiling"):
+        v, f = shell[name]
+        verts.append(v.to(dev)); faces.append(f.to(dev) + off)
+        cls.append(torch.full((f.size(0),), names.index(name), dtype=torch.int32, device=dev))
+        off += v.size(0)
+    vertices = torch.cat(verts)[None]
+    face_buf = torch.cat(faces).to(torch.int32)[None]
+    return vertices, face_buf, torch.cat(cls), kept, sizes
+
+
+def cull_faces(vertices, face_buf, face_cls, R, t, eps=0.06):
+    """Drop faces with any vertex closer than eps in front of the camera plane (reference :345-356)."""
+    vc = torch.matmul(vertices, R.transpose(1, 2)) + t
+    z = vc[0, :, 2]
+    fz = z[face_buf[0].long()]
+    valid = ~(fz < eps).any(dim=1)
+    return face_buf[:, valid, :].detach(), face_cls[valid]
+
+
+def composite(depth_data, images, names):
+    """Reference :366-434 vectorised over the classes.  depth_data [1,H,W], images [C,H,W] (class order `names`)."""
+    depth_data = torch.where(depth_data > 15, torch.full_like(depth_data, -1.0), depth_data)           # :367
+    C = images.size(0)
+    hard = images.detach() > 0.1                                                                        # :401
+    cnt = hard.sum(dim=(1, 2))
+    sums = (depth_data * hard).sum(dim=(1, 2))
+    mean = sums / cnt                                                                                   # nan where the class is absent
+    wall = names.index("wall")
+    wall_depth = torch.where(hard[wall], depth_data[0], torch.full_like(depth_data[0], -float("inf")))
+    wall_max = wall_depth.max().detach()
+    wall_max = torch.where(cnt[wall] > 0, wall_max, torch.full_like(wall_max, 10.0))                    # :408-410
+    mean = torch.where(cnt > 0, mean, wall_max.expand_as(mean))                                         # :411-419
+    planes = torch.where(hard, depth_data / wall_max, (mean / wall_max)[:, None, None].expand(-1, *depth_data.shape[1:]))   # :420-421
+    keep = [i for i, n in enumerate(names) if n not in ("wall", "floor", "ceiling")]                    # :422-425
+    one_hot = torch.zeros(41, *depth_data.shape[1:], device=depth_data.device, dtype=depth_data.dtype)
+    index = torch.tensor([nyu_class.index(n.replace("_", " ")) + 1 for n in names], device=depth_data.device)
+    one_hot = one_hot.index_copy(0, index, images)                                                      # :429-431
+    return torch.cat((depth_data, one_hot[1:], planes[keep]), dim=0)[None]                              # :433-434
+
+
+def mesh_render_func(boxes, angles, objs, model_ids_old=None, obj_size_target=None):
+    """Same contract as the reference: -> (final [1,70,256,256], model_ids_return, obj_size_return, size_loss)."""
+    dev = boxes[-1].device
+    if dev.type != "cuda":
+        raise RuntimeError("3d_sln_b200 mesh_render_func runs on CUDA only (no CPU fallback)")
+    boxes = list(boxes)
+    model_ids_return, obj_size_return = {}, []
+    size_loss = 0.0
+    old_wall = boxes[-1].clone()
+    if model_ids_old is not None:
+        boxes[-1] = torch.from_numpy(model_ids_old["box_info"]).float().to(dev)     # :56-57
+    else:
+        model_ids_return["box_info"] = boxes[-1].detach().cpu().numpy()            # :60
+    lib = mesh_library(dev)
+    vertices, face_buf, face_cls, kept, sizes = assemble_scene(boxes, angles, objs, lib)
+    for j, i in enumerate(kept):
+        if model_ids_old is None:
+            model_ids_return[i] = object_idx_to_name[int(objs[i])]
+        if obj_size_target is not None:
+            size_loss = size_loss + nn.functional.mse_loss(sizes[j], torch.from_numpy(obj_size_target[j]).float().to(dev))   # :98
+        else:
+            obj_size_return.append(sizes[j].detach().cpu().numpy())
+    if obj_size_target is not None:
+        size_loss = size_loss + nn.functional.mse_loss(old_wall, torch.from_numpy(obj_size_target[-1]).float().to(dev))      # :164
+    else:
+        obj_size_return.append(boxes[-1].detach().cpu().numpy())
+    K, R, t = get_cam_mat(boxes)
+    face_buf, face_cls = cull_faces(vertices, face_buf, face_cls, R, t)
+    names = desired_classes()
+    depth, images = nr.render_scene_classes(vertices, face_buf, face_cls, len(names), K, R, t, image_size=final_out, orig_size=inter_out,
+                                            near=0.001)
+    return composite(depth, images, names), model_ids_return, obj_size_return, size_loss

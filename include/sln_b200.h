@@ -121,6 +121,16 @@ int sln_gconv_pool_fwd(const float* new_t_vecs, int64_t O, int64_t T, int32_t H,
 /* CSR read-back helpers for tests: copies row_ptr[O+1] / ent[2T] (device pointers inside ws) */
 int sln_csr_pointers(void* ws, int64_t O, int64_t T, const int32_t** row_ptr, const int32_t** ent);
 
+/* The contraction primitive under every Linear of the MLP stage (reference graph.py:12 nn.Linear -> aten::addmm / mm):
+ *   C[i,j] (+)= sum_k A(i,k) * B(j,k),   i < M, j < N, k < K
+ * a_rc != 0: A stored [M][K] row-major with leading dimension lda, else stored [K][M] (the transposed reads of the backward
+ * passes); same for B.  accumulate != 0: C += (split-K, RED.ADD) else C = .  engine 1 = tcgen05 3xTF32 tiles (fp32-level
+ * accuracy: hi/lo TF32 split, fp32 accumulation in TMEM), engine 0 = FP32 SIMT tiles.  sln_set_engine selects the engine
+ * used inside the sln_vae_* and sln_gconv_* entry points (default 1) and returns the previous setting. */
+int sln_set_engine(int engine);
+int sln_contract(const float* A, int64_t lda, int32_t a_rc, const float* B, int64_t ldb, int32_t b_rc, float* C, int64_t ldc,
+                 int64_t M, int64_t N, int64_t K, int32_t accumulate, int32_t engine, void* stream);
+
 /* z = eps*exp(0.5*logvar)+mu and its backward (reference Sg2ScVAE_model.py:180-183); n = O*E elements. */
 int sln_reparam_fwd(const float* mu, const float* logvar, const float* eps, int64_t n, float* z, void* stream);
 int sln_reparam_bwd(const float* d_z, const float* logvar, const float* eps, int64_t n, float* d_mu, float* d_logvar, void* stream);
@@ -140,6 +150,53 @@ int sln_vae_loss(const float* boxes_pred, const float* boxes_gt, int32_t box_dim
 int sln_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, float grad_scale, int64_t* step, int32_t advance_step,
                   void* stream);
+
+/* ------------------------------------------------------------------------------------------------ mesh rasterizer
+ * Replaces what the reference reaches through the un-vendored `neural_renderer` package: nr.Renderer(camera_mode=
+ * 'projection', image_size, K, R, t, anti_aliasing=False, orig_size, near, ...) called with mode='depth' and mode='rgb'
+ * (reference models/diff_render.py:359-366,398; package semantics in SURVEY.md App. C / oracle/raster_oracle.c).
+ * All maps are in the renderer's INTERNAL orientation (row yi = bottom-up); the Python Renderer flips rows on output as
+ * upstream's rasterize.py does.  fill_back doubles the face list: face F+f is face f with reversed winding.
+ *
+ * sln_raster_setup       vertices [V,3] (world), faces [F,3] int32, K [9], R [9], t [3] (device) -> workspace:
+ *                        projected vertices [V,3] (nr.projection, distortion-free per README.md:13-18), per-face vertex
+ *                        array [F2,3,3] (nr.vertices_to_faces), pixel-space inverse [F2,9], pixel bounding boxes.
+ * sln_raster_forward     z-buffer: face_index_map [is,is] int32 (-1 = background; ties keep the lower face index),
+ *                        weight_map [is,is,3], depth_map [is,is] (far on empty pixels); near/far per call because upstream's
+ *                        depth pass uses the rasterizer defaults (0.1, 100) while the rgb pass uses the constructor's near.
+ * sln_raster_texture_sample  trilinear face-texture sampling, textures [F,ts,ts,ts,3] -> rgb_map [is,is,3] (background 0).
+ * sln_raster_backward_rgb    Kato's gradient of the rgb image w.r.t. the face vertices' x,y: grad_faces [F2,9] += (caller zeroes).
+ * sln_raster_backward_depth  gradient of depth_map w.r.t. face vertices: grad_faces [F2,9] +=.
+ * sln_raster_vertex_grad     grad_faces [F2,9] -> grad w.r.t. the world vertices [V,3] (transpose of vertices_to_faces, then
+ *                            the projection's Jacobian); grad_proj_scratch [V,3] is caller-owned scratch.
+ * sln_scene_classes_fwd/bwd  the 32 per-class mask renders of mesh_render_func (diff_render.py:381-431) from ONE rasterization:
+ *                            class image c = what a 0/1 texture of class c renders to (torch.sum(images,1)/3), written in OUTPUT
+ *                            orientation [n_cls,is,is]; the backward applies Kato's per-render clamp per class. */
+size_t sln_raster_workspace_bytes(int64_t V, int64_t F, int32_t fill_back);
+int sln_raster_setup(const float* vertices, int64_t V, const int32_t* faces, int64_t F, int32_t fill_back, const float* K,
+                     const float* R, const float* t, float orig_size, int32_t image_size, void* ws, size_t ws_bytes, void* stream);
+int sln_raster_face_arrays(void* ws, int64_t V, int64_t F, int32_t fill_back, const float** proj_vertices,
+                           const float** face_vertices, const float** face_inv);
+int sln_raster_forward(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, float near, float far,
+                       int32_t* face_index_map, float* weight_map, float* depth_map, void* stream);
+int sln_raster_texture_sample(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, const float* textures,
+                              int32_t texture_size, float eps, const int32_t* face_index_map, const float* weight_map,
+                              const float* depth_map, float* rgb_map, void* stream);
+int sln_raster_backward_rgb(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, float eps,
+                            const int32_t* face_index_map, const float* rgb_map, const float* grad_rgb_map, float* grad_faces,
+                            void* stream);
+int sln_raster_backward_depth(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size,
+                              const int32_t* face_index_map, const float* weight_map, const float* depth_map,
+                              const float* grad_depth_map, float* grad_faces, void* stream);
+int sln_raster_vertex_grad(const void* ws, const float* vertices, int64_t V, const int32_t* faces, int64_t F, int32_t fill_back,
+                           const float* K, const float* R, const float* t, float orig_size, const float* grad_faces,
+                           float* grad_proj_scratch, float* grad_vertices, void* stream);
+int sln_scene_classes_fwd(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, int32_t texture_size, float eps,
+                          const int32_t* face_index_map, const float* weight_map, const float* depth_map, const int32_t* face_cls,
+                          int32_t n_cls, float* sval, float* class_images, void* stream);
+int sln_scene_classes_bwd(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, float eps,
+                          const int32_t* face_index_map, const int32_t* face_cls, int32_t n_cls, const float* sval,
+                          const float* grad_class_images_internal, float* grad_faces, void* stream);
 
 #ifdef __cplusplus
 }

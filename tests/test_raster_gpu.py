@@ -1,0 +1,187 @@
+"""GPU parity tests of the rasterizer (csrc/raster.cu through the C ABI and the nr.Renderer drop-in) against the CPU oracle
+(oracle/raster_oracle.c).  Index buffers and everything that decides coverage/depth order are compared BIT-EXACTLY;
+gradients (different but fixed-precision summation order, atomics) to 1e-4 of the tensor's max-norm."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import raster_oracle as ro
+from test_oracle_raster import scene
+
+pytestmark = pytest.mark.gpu
+nr = importlib.import_module("3d_sln_b200.neural_renderer")
+dr = importlib.import_module("3d_sln_b200.models.diff_render")
+meshes = importlib.import_module("3d_sln_b200.data.synthetic_meshes")
+DEV = "cuda:0"
+
+
+def _dev(verts, faces, K, R, t):
+    return (torch.from_numpy(verts).to(DEV)[None], torch.from_numpy(faces).to(DEV)[None], torch.from_numpy(np.asarray(K)).to(DEV)[None],
+            torch.from_numpy(np.asarray(R)).to(DEV)[None], torch.from_numpy(np.asarray(t)).to(DEV).view(1, 1, 3))
+
+
+def _raster(verts, faces, K, R, t, n):
+    v, f, Kd, Rd, td = _dev(verts, faces, K, R, t)
+    return nr._Raster(v[0].contiguous(), f[0].contiguous().int(), Kd.reshape(-1).contiguous(), Rd.reshape(-1).contiguous(),
+                      td.reshape(-1).contiguous(), 512, n, True)
+
+
+def maxnorm(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.mark.parametrize("n_obj,nu,nv,n", [(4, 2, 3, 64), (10, 6, 7, 256), (3, 1, 1, 37)])
+def test_forward_maps_are_bit_exact(n_obj, nu, nv, n):
+    verts, faces, K, R, t = scene(n_obj, seed=7, nu=nu, nv=nv)
+    r = _raster(verts, faces, K, R, t, n)
+    pv, fv, finv = [x.cpu().numpy() for x in r.face_arrays()]
+    pv_o = ro.project(verts, K, R, t, 512)
+    fv_o = ro.gather_faces(pv_o, faces, True)
+    assert np.array_equal(pv, pv_o) and np.array_equal(fv, fv_o)
+    for near in (0.1, 0.001):
+        want = ro.face_index_map(fv_o, n, near, 100.0)
+        assert np.array_equal(finv, want["face_inv"])
+        fi, w, d = [x.cpu().numpy() for x in r.forward(near, 100.0)]
+        assert np.array_equal(fi, want["face_index"])           # triangle index buffer: bit-exact
+        assert np.array_equal(d, want["depth"]) and np.array_equal(w, want["weight"])
+        assert (fi >= 0).mean() > 0.3
+
+
+def test_texture_sampling_matches_oracle():
+    verts, faces, K, R, t = scene(4, seed=2)
+    n = 96
+    r = _raster(verts, faces, K, R, t, n)
+    fv_o = ro.gather_faces(ro.project(verts, K, R, t, 512), faces, True)
+    maps = ro.face_index_map(fv_o, n, 0.001, 100.0)
+    fi, w, d = r.forward(0.001, 100.0)
+    for ts in (2, 4):
+        tex = np.random.RandomState(ts).rand(len(faces), ts, ts, ts, 3).astype(np.float32)
+        tex2 = np.concatenate([tex, np.ascontiguousarray(tex.transpose(0, 3, 2, 1, 4))])
+        want = ro.texture_sampling(fv_o, tex2, maps, ts)
+        rgb = torch.empty(n, n, 3, device=DEV)
+        lib = r.lib
+        L = importlib.import_module("3d_sln_b200._lib")
+        td = torch.from_numpy(tex).to(DEV)
+        L.check(lib.sln_raster_texture_sample(r.ws.data_ptr(), r.V, r.F, 1, n, td.data_ptr(), ts, 1e-3, fi.data_ptr(), w.data_ptr(),
+                                              d.data_ptr(), rgb.data_ptr(), L.cur_stream(torch.device(DEV))), "tex")
+        assert np.array_equal(rgb.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("n_obj,nu,nv,n", [(4, 2, 3, 64), (10, 6, 7, 256)])
+def test_renderer_module_forward_backward_vs_oracle(n_obj, nu, nv, n):
+    verts, faces, K, R, t = scene(n_obj, seed=11, nu=nu, nv=nv)
+    v, f, Kd, Rd, td = _dev(verts, faces, K, R, t)
+    orc = ro.RendererOracle(n, K, R, t, 512)
+    ren = nr.Renderer(camera_mode='projection', image_size=n, K=Kd, R=Rd, t=td, anti_aliasing=False, orig_size=512, near=0.001,
+                      light_intensity_ambient=1.0, light_intensity_directional=0.0)
+    rng = np.random.RandomState(0)
+    # ---- depth
+    vd = v.clone().requires_grad_(True)
+    depth = ren(vd, f, None, mode='depth')
+    want, ctx = orc.depth(verts, faces)
+    assert depth.shape == (1, n, n) and np.array_equal(depth[0].detach().cpu().numpy(), want)
+    G = (rng.randn(n, n).astype(np.float32)) * (want < 50)
+    depth.backward(torch.from_numpy(G).to(DEV)[None])
+    gwant = orc.depth_bwd(verts, faces, ctx, G)
+    assert maxnorm(vd.grad[0].cpu().numpy(), gwant) < 1e-4
+    # ---- rgb with a 0/1 class-style texture and with a random texture
+    for kind in ("mask", "random"):
+        if kind == "mask":
+            tex = np.zeros((len(faces), 2, 2, 2, 3), np.float32); tex[: len(faces) // 2] = 1.0
+        else:
+            tex = rng.rand(len(faces), 2, 2, 2, 3).astype(np.float32)
+        vr = v.clone().requires_grad_(True)
+        img = ren(vr, f, torch.from_numpy(tex).to(DEV)[None], mode='rgb')
+        want, ctx = orc.rgb(verts, faces, tex)
+        assert img.shape == (1, 3, n, n) and np.array_equal(img[0].detach().cpu().numpy(), want)
+        G = rng.randn(3, n, n).astype(np.float32)
+        img.backward(torch.from_numpy(G).to(DEV)[None])
+        gwant = orc.rgb_bwd(verts, faces, ctx, G)
+        assert np.abs(gwant).max() > 0
+        assert maxnorm(vr.grad[0].cpu().numpy(), gwant) < 1e-4
+
+
+def test_fused_scene_equals_separate_class_renders():
+    """depth + 5 class images from one rasterization == what per-class renderer(mode='rgb') calls give (diff_render.py:381-431),
+    forward bit-exact, backward equal to the sum of the separate backward passes."""
+    verts, faces, K, R, t = scene(6, seed=4, nu=3, nv=3)
+    n, C = 128, 5
+    v, f, Kd, Rd, td = _dev(verts, faces, K, R, t)
+    cls = torch.from_numpy((np.arange(len(faces)) * C // len(faces)).astype(np.int32)).to(DEV)
+    ren = nr.Renderer(camera_mode='projection', image_size=n, K=Kd, R=Rd, t=td, anti_aliasing=False, orig_size=512, near=0.001,
+                      light_intensity_ambient=1.0, light_intensity_directional=0.0)
+    rng = np.random.RandomState(1)
+    Gd = torch.from_numpy(rng.randn(1, n, n).astype(np.float32)).to(DEV)
+    Gi = torch.from_numpy(rng.randn(C, n, n).astype(np.float32)).to(DEV)
+    vf = v.clone().requires_grad_(True)
+    depth, images = nr.render_scene_classes(vf, f, cls, C, Kd, Rd, td, image_size=n, orig_size=512, near=0.001)
+    ((depth * Gd * (depth < 50)).sum() + (images * Gi).sum()).backward()
+    vs = v.clone().requires_grad_(True)
+    d2 = ren(vs, f, None, mode='depth')
+    loss = (d2 * Gd * (d2 < 50)).sum()
+    assert torch.equal(depth, d2)
+    for c in range(C):
+        tex = torch.zeros(1, len(faces), 2, 2, 2, 3, device=DEV)
+        tex[:, cls == c] = 1.0
+        img = torch.sum(ren(vs, f, tex, mode='rgb'), dim=1)[0] / 3.0
+        assert torch.equal(images[c], img)
+        loss = loss + (img * Gi[c]).sum()
+    loss.backward()
+    assert vs.grad.abs().max() > 0
+    assert maxnorm(vf.grad.cpu().numpy(), vs.grad.cpu().numpy()) < 1e-4
+
+
+def test_edge_cases_empty_and_degenerate():
+    verts, faces, K, R, t = scene(2, seed=1)
+    v, f, Kd, Rd, td = _dev(verts, faces, K, R, t)
+    ren = nr.Renderer(camera_mode='projection', image_size=32, K=Kd, R=Rd, t=td, anti_aliasing=False, orig_size=512, near=0.001,
+                      light_intensity_ambient=1.0, light_intensity_directional=0.0)
+    empty = torch.zeros(1, 0, 3, dtype=torch.int32, device=DEV)
+    d = ren(v, empty, None, mode='depth')
+    assert (d == 100.0).all()                                  # no faces: far everywhere
+    deg = torch.zeros(1, 4, 3, dtype=torch.int32, device=DEV)  # zero-area faces (all corners = vertex 0)
+    d = ren(v, deg, None, mode='depth')
+    assert torch.isfinite(d).all() and (d == 100.0).all()
+    behind = v.clone(); behind[..., 2] += 100.0                # everything behind the camera / beyond far
+    d = ren(behind, f, None, mode='depth')
+    assert torch.isfinite(d).all()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ren(v.cpu(), f.cpu(), None, mode='depth')
+    with pytest.raises(NotImplementedError):
+        nr.Renderer(camera_mode='look_at', anti_aliasing=False)
+
+
+def test_mesh_render_func_contract_and_gradients():
+    boxes, angles, objs = meshes.synthetic_layout(10, seed=13)
+    boxes = boxes.to(DEV)
+    b = [boxes[i].clone().requires_grad_(i < 10) for i in range(11)]
+    a = [angles[i].to(DEV).clone().requires_grad_(i < 10) for i in range(11)]
+    final, ids, sizes, size_loss = dr.mesh_render_func(b, a, objs.tolist())
+    names = dr.desired_classes()
+    assert final.shape == (1, 1 + 40 + len(names) - 3, 256, 256) == (1, 70, 256, 256)
+    assert "box_info" in ids and len(sizes) == 11 and size_loss == 0.0
+    # compositing == the oracle's restatement of diff_render.py:366-434 on the same depth / class images
+    v, fb, cls, kept, _ = dr.assemble_scene(b, a, objs.tolist(), dr.mesh_library(torch.device(DEV)))
+    assert v.shape[1] > 3000 and fb.shape[1] == 10 * 504 + 160
+    K, R, t = dr.get_cam_mat(b)
+    Ko, Ro, to = ro.get_cam_mat(boxes[-1].cpu())
+    assert np.allclose(K[0].cpu().numpy(), Ko) and np.allclose(R[0].cpu().numpy(), Ro, atol=1e-7) and np.allclose(t.view(3).cpu().numpy(), to, atol=1e-6)
+    fb2, cls2 = dr.cull_faces(v, fb, cls, R, t)
+    depth, images = nr.render_scene_classes(v, fb2, cls2, len(names), K, R, t)
+    want = ro.composite(depth.detach().cpu(), [images[c].detach().cpu()[None] for c in range(len(names))], names)
+    assert maxnorm(final.detach().cpu().numpy(), want.numpy()) < 1e-5
+    present = [names.index(n) for n in ("wall", "floor", "bed", "chair")]
+    assert all(images[c].sum() > 0 for c in present)
+    # gradients reach the layout parameters through the rasterizer
+    target = final.detach().roll(3, dims=3)
+    loss = (final[:, :1] - target[:, :1]).abs().mean() * 100 + ((final[:, 1:41] - target[:, 1:41]) ** 2).mean() * 100
+    loss.backward()
+    gb = torch.stack([x.grad for x in b[:10]])
+    ga = torch.stack([x.grad for x in a[:10]])
+    assert torch.isfinite(gb).all() and torch.isfinite(ga).all() and gb.abs().sum() > 0 and ga.abs().sum() > 0
+    # second call with cached ids / size targets (refinement iterations k > 0, test_render_refine.py:324)
+    final2, _, _, size_loss2 = dr.mesh_render_func([x.detach() for x in b], [x.detach() for x in a], objs.tolist(), ids, sizes)
+    assert torch.equal(final2, final.detach()) and float(size_loss2) < 1e-10
