@@ -36,20 +36,46 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def _obj_stale(obj, src):
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    deps = [src, os.path.join(INCLUDE_DIR, "sln_b200.h")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
 def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into libsln_b200.so (nvcc cross-compiles without a GPU)."""
+    """Compile every CUDA source for sm_100a into libsln_b200.so (nvcc cross-compiles without a GPU).  Each translation
+    unit is compiled to an object file in parallel (build/ is git-ignored), then linked."""
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("3d_sln_b200: nvcc not found and %s is missing/stale; cannot build the CUDA library" % LIB_PATH)
+    objdir = os.path.join(_PKG_DIR, "build")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+    jobs = []
+    for src in _sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if force or _obj_stale(obj, src):
+            cmd = [nvcc] + cflags + ["-I", INCLUDE_DIR, "-c", "-o", obj, src]
+            jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    errs = []
+    for cmd, pr in jobs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            errs.append("%s\n%s" % (" ".join(cmd), err[-8000:]))
+        elif verbose:
+            print(err)
+    if errs:
+        raise RuntimeError("3d_sln_b200: nvcc failed\n" + "\n".join(errs))
+    objs = [os.path.join(objdir, os.path.basename(s)[:-3] + ".o") for s in _sources()]
     tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [nvcc] + [f for f in NVCC_FLAGS] + ["-I", INCLUDE_DIR, "-o", tmp] + _sources()
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("3d_sln_b200: nvcc failed\n%s\n%s" % (" ".join(cmd), res.stderr[-8000:]))
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("3d_sln_b200: link failed\n%s\n%s" % (" ".join(cmd), res.stderr[-8000:]))
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

@@ -33,16 +33,14 @@ struct MatView {
   }
   // bounds-checked single element in storage coordinates
   __device__ __forceinline__ float at_t(int r, int c) const { return (r < rows && c < cols) ? at(r, c) : 0.f; }
-  // Two-phase access used by the tensor-core loader (requires vec): fetch4 issues the raw 16-byte load unconditionally
-  // from a clamped address (so that all loads of a chunk can be in flight together), finish4 applies the lazy transform.
-  struct Tok { int r; };
-  __device__ __forceinline__ Tok token(int r) const { return Tok{r}; }
-  __device__ __forceinline__ void fetch4(const Tok& t, int c, float4& a, float4& b) const {
-    const bool ok = t.r < rows && c < cols;
-    a = ldg4(p + (ok ? (size_t)t.r * ld + c : 0));
-  }
+  // Two-phase access used by the tensor-core loader (requires vec): fetch4 issues the raw 16-byte load, finish4 applies
+  // the lazy transform.  Neither checks bounds: token() clamps the row and the caller clamps the column with clampc(), so
+  // padded tile rows/columns read valid (finite) memory whose products are never stored; the caller zeroes K padding.
+  struct Tok { const float* rp; };
+  __device__ __forceinline__ Tok token(int r) const { return Tok{p + (size_t)min(r, rows - 1) * ld}; }
+  __device__ __forceinline__ int clampc(int c) const { return min(c, cols - 4); }
+  __device__ __forceinline__ void fetch4(const Tok& t, int c, float4& a, float4& b) const { a = ldg4(t.rp + c); }
   __device__ __forceinline__ float4 finish4(const Tok& t, int c, float4 v, float4) const {
-    if (!(t.r < rows && c < cols)) return make_float4(0.f, 0.f, 0.f, 0.f);
     if (scale) {
       float4 s = ldg4(scale + c), h = ldg4(shift + c);
       v.x = fmaf(v.x, s.x, h.x); v.y = fmaf(v.y, s.y, h.y); v.z = fmaf(v.z, s.z, h.z); v.w = fmaf(v.w, s.w, h.w);
@@ -100,19 +98,16 @@ struct GatherCat {
     if (c < 2 * D) return pred.at(t, c - D);
     return obj.at(__ldg(o_idx + t), c - 2 * D);
   }
-  struct Tok { int t, s, o; };   // the gather indices of a triple are fetched once per row, not once per K chunk
+  struct Tok { const float* sp; const float* pp; const float* op; };   // the three source rows of a triple, resolved once per row
   __device__ __forceinline__ Tok token(int t) const {
-    const bool ok = t < rows;
-    return Tok{t, ok ? __ldg(s_idx + t) : 0, ok ? __ldg(o_idx + t) : 0};
+    t = min(t, rows - 1);
+    return Tok{obj.p + (size_t)__ldg(s_idx + t) * obj.ld, pred.p + (size_t)t * pred.ld, obj.p + (size_t)__ldg(o_idx + t) * obj.ld};
   }
+  __device__ __forceinline__ int clampc(int c) const { return min(c, cols - 4); }
   __device__ __forceinline__ void fetch4(const Tok& k, int c, float4& a, float4& b) const {
-    const bool ok = k.t < rows && c < cols;
-    const float* src = obj.p;
-    if (ok) src = c < D ? obj.p + (size_t)k.s * obj.ld + c : (c < 2 * D ? pred.p + (size_t)k.t * pred.ld + (c - D) : obj.p + (size_t)k.o * obj.ld + (c - 2 * D));
-    a = ldg4(src);
+    a = ldg4(c < D ? k.sp + c : (c < 2 * D ? k.pp + (c - D) : k.op + (c - 2 * D)));
   }
   __device__ __forceinline__ float4 finish4(const Tok& k, int c, float4 v, float4) const {
-    if (!(k.t < rows && c < cols)) return make_float4(0.f, 0.f, 0.f, 0.f);
     const MatView& m = (c >= D && c < 2 * D) ? pred : obj;
     const int cc = c < D ? c : (c < 2 * D ? c - D : c - 2 * D);
     if (m.scale) {
@@ -139,16 +134,16 @@ struct Concat2 {
     if (r >= rows || c >= cols) return 0.f;
     return c < a.cols ? a.at(r, c) : b.at(r, c - a.cols);
   }
-  struct Tok { int r; };
-  __device__ __forceinline__ Tok token(int r) const { return Tok{r}; }
+  struct Tok { const float* ap; const float* bp; };
+  __device__ __forceinline__ Tok token(int r) const {
+    r = min(r, rows - 1);
+    return Tok{a.p + (size_t)r * a.ld, b.p + (size_t)r * b.ld};
+  }
+  __device__ __forceinline__ int clampc(int c) const { return min(c, cols - 4); }
   __device__ __forceinline__ void fetch4(const Tok& t, int c, float4& va, float4& vb) const {
-    const bool ok = t.r < rows && c < cols;
-    const float* src = a.p;
-    if (ok) src = c < a.cols ? a.p + (size_t)t.r * a.ld + c : b.p + (size_t)t.r * b.ld + (c - a.cols);
-    va = ldg4(src);
+    va = ldg4(c < a.cols ? t.ap + c : t.bp + (c - a.cols));
   }
   __device__ __forceinline__ float4 finish4(const Tok& t, int c, float4 v, float4) const {
-    if (!(t.r < rows && c < cols)) return make_float4(0.f, 0.f, 0.f, 0.f);
     const MatView& m = c < a.cols ? a : b;
     const int cc = c < a.cols ? c : c - a.cols;
     if (m.scale) {
@@ -184,15 +179,17 @@ struct DyView {
     return v;
   }
   __device__ __forceinline__ float at_t(int i, int c) const { return (i < rows && c < cols) ? at(i, c) : 0.f; }
-  struct Tok { int r; };
-  __device__ __forceinline__ Tok token(int r) const { return Tok{r}; }
+  struct Tok { const float* gp; const float* yp; };
+  __device__ __forceinline__ Tok token(int r) const {
+    r = min(r, rows - 1);
+    return Tok{g + (size_t)r * ldg, q ? y + (size_t)r * ldy : nullptr};
+  }
+  __device__ __forceinline__ int clampc(int c) const { return min(c, cols - 4); }
   __device__ __forceinline__ void fetch4(const Tok& t, int c, float4& a, float4& b) const {
-    const bool ok = t.r < rows && c < cols;
-    a = ldg4(g + (ok ? (size_t)t.r * ldg + c : 0));
-    if (q) b = ldg4(y + (ok ? (size_t)t.r * ldy + c : 0));
+    a = ldg4(t.gp + c);
+    if (q) b = ldg4(t.yp + c);
   }
   __device__ __forceinline__ float4 finish4(const Tok& t, int c, float4 v, float4 yy) const {
-    if (!(t.r < rows && c < cols)) return make_float4(0.f, 0.f, 0.f, 0.f);
     if (p) {
       float4 pp = ldg4(p + c);
       v.x *= pp.x; v.y *= pp.y; v.z *= pp.z; v.w *= pp.w;
@@ -657,7 +654,7 @@ inline TileChoice pick_tile(int M, int N, int K, bool allow_split) {
   return c;
 }
 
-inline int max_row_tiles(int M) { return ceil_div(M, 64); }
+inline int max_row_tiles(int M) { return ceil_div(M, 16); }
 
 template <bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
 int launch_gemm(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, bool allow_split,

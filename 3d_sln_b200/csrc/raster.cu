@@ -269,14 +269,14 @@ __device__ __forceinline__ float pix_diff_grad(const RgbBwdArgs& a, int idx, int
   const size_t P = (size_t)a.is * a.is;
   float tot = 0.f;
   if (ca >= 0) {
-    const float g3 = a.gcls[(size_t)ca * P + idx] / 3.f;
+    const float g3 = a.gcls[(size_t)ca * P + idx] * (1.0f / 3.0f);
     const float diff = va - (cb == ca ? vb : 0.f);
     float dg = 0.f;
     for (int k = 0; k < 3; ++k) dg += diff * g3;
     if (dg > 0.f) tot += dg;
   }
   if (cb >= 0 && cb != ca) {
-    const float g3 = a.gcls[(size_t)cb * P + idx] / 3.f;
+    const float g3 = a.gcls[(size_t)cb * P + idx] * (1.0f / 3.0f);
     const float diff = 0.f - vb;
     float dg = 0.f;
     for (int k = 0; k < 3; ++k) dg += diff * g3;
@@ -439,7 +439,7 @@ __global__ void k_scene_sval(const float* __restrict__ fv, const int* __restrict
   sval[pn] = acc;
 }
 
-// class images [n_cls, is, is] in OUTPUT orientation (vertically flipped): value = (s+s+s)/3 as torch.sum(images,1)/3
+// class images [n_cls, is, is] in OUTPUT orientation (vertically flipped): value = (s+s+s)*(1/3) as torch.sum(images,1)/3.0 on CUDA
 __global__ void k_scene_class_images(const int* __restrict__ face_index_map, const int* __restrict__ face_cls, const float* __restrict__ sval,
                                      int is, int n_cls, float* __restrict__ images) {
   int pn = blockIdx.x * blockDim.x + threadIdx.x;
@@ -449,7 +449,9 @@ __global__ void k_scene_class_images(const int* __restrict__ face_index_map, con
   const int fi = face_index_map[pn];
   const int c = fi >= 0 ? face_cls[fi] : -1;
   const float s = sval[pn];
-  const float v = dvd(add(add(s, s), s), 3.0f);
+  // torch evaluates `tensor / 3.0` on CUDA as a multiplication by the fp32 reciprocal (ATen div_true_kernel_cuda with a
+  // CPU-scalar divisor), and the reference's renderer only exists on CUDA, so that is the arithmetic to reproduce
+  const float v = mul(add(add(s, s), s), 1.0f / 3.0f);
   const size_t o = (size_t)(is - 1 - yi) * is + xi;
   for (int k = 0; k < n_cls; ++k) images[(size_t)k * P + o] = (k == c) ? v : 0.f;
 }

@@ -4,15 +4,14 @@
 // 3xTF32 stays at the fp32 noise floor).  Every fp32 operand x is split on the fly into hi = tf32(x) and lo = tf32(x - hi)
 // and the tensor core accumulates  lo*hi + hi*lo + hi*hi  in fp32 in TMEM (short chains only, see "Accumulation scheme").
 //
-// Structure of one CTA (256 threads, tile 128 x BN, K consumed in chunks of 32 floats = one 128-byte swizzle row):
-//   all 8 warps are PRODUCERS: they read A/B through the same operand functors as the SIMT kernel (gather+concat,
-//     lazy BatchNorm+ReLU, BN-backward dy, transposed reads ...), split hi/lo in registers and write four K-major
-//     SWIZZLE_128B tiles (A_hi, A_lo, B_hi, B_lo) of a shared-memory stage;
-//   thread 0 is the MMA ISSUER: after the stage is published (fence.proxy.async + CTA barrier) it issues 4 k-slices x 3
-//     tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) into a TMEM accumulator and commits them to the stage's mbarrier, which
-//     hands the stage back to the producers — loads of chunk c+1 overlap the MMAs of chunk c;
-//   EPILOGUE: tcgen05.ld 32x32b (thread = accumulator row, 32 columns at a time) -> epilogue functor (bias / ReLU mask /
-//     BatchNorm column statistics via an in-warp transpose-reduce / split-K RED.ADD).
+// Structure of one CTA (288 threads, tile 128 x BN, K consumed in chunks of 32 floats = one 128-byte swizzle row):
+//   8 PRODUCER warps read A/B through the same operand functors as the SIMT kernel (gather+concat, lazy BatchNorm+ReLU,
+//     BN-backward dy, transposed reads ...), split hi/lo in registers and write four K-major SWIZZLE_128B tiles
+//     (A_hi, A_lo, B_hi, B_lo) of a shared-memory stage, then publish it (fence.proxy.async + mbarrier arrive);
+//   a ninth warp is the MMA ISSUER: per stage 4 k-slices x 3 tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) into TMEM
+//     accumulators, tcgen05.commit hands the stage back.  A ring of 3-4 stages decouples the two sides;
+//   EPILOGUE (the producer warps): tcgen05.ld 32x32b (thread = accumulator row, 32 columns at a time) -> staging in shared
+//     memory -> epilogue functor with lanes along the columns (bias / ReLU mask / BatchNorm column statistics / RED.ADD).
 // TMA is not used for the operands because every operand needs a per-element transform (gather, BN, hi/lo split) between
 // global memory and the tensor core; the stores are laid out so that each st.shared.v4 phase covers one full 128-byte row.
 #pragma once
@@ -23,8 +22,10 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 32;            // floats per K chunk: 128 bytes = one SWIZZLE_128B row
-constexpr int THREADS = 256;
-constexpr int STAGES = 2;
+constexpr int PROD_WARPS = 8;               // producer / epilogue warps
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int MMA_WARP = PROD_WARPS;        // the ninth warp issues the tcgen05.mma stream
+constexpr int THREADS = PROD_THREADS + 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -99,96 +100,115 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// hi = x rounded to TF32 (10 explicit mantissa bits), round-to-nearest with ties away from zero in the magnitude: an integer
+// add + mask on the bit pattern (two full-rate ALU ops; identical to cvt.rna.tf32.f32 for finite x, Inf stays Inf)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 // byte offset of element (row, k) inside a [rows][32-float] SWIZZLE_128B K-major tile whose base is 1024-byte aligned
 __device__ __forceinline__ uint32_t sw128(int row, int k) { return (uint32_t)(row * 128 + ((((k >> 2) ^ (row & 7)) << 4) | ((k & 3) << 2))); }
-
-__device__ __forceinline__ void split_store4(char* hi_tile, char* lo_tile, int row, int k4, float4 v) {
-  float4 h, l;
-  h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-  uint32_t off = sw128(row, k4);
-  *reinterpret_cast<float4*>(hi_tile + off) = h;
-  *reinterpret_cast<float4*>(lo_tile + off) = l;
+__device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ void split_store1(char* hi_tile, char* lo_tile, int row, int k, float v) {
-  float h = tf32_rna(v);
-  uint32_t off = sw128(row, k);
-  *reinterpret_cast<float*>(hi_tile + off) = h;
-  *reinterpret_cast<float*>(lo_tile + off) = v - h;
+__device__ __forceinline__ void sts1(uint32_t addr, float a) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory"); }
+
+__device__ __forceinline__ void split_store4(uint32_t hi_addr, uint32_t lo_addr, float4 v) {
+  const float hx = tf32_hi(v.x), hy = tf32_hi(v.y), hz = tf32_hi(v.z), hw = tf32_hi(v.w);
+  sts4(hi_addr, hx, hy, hz, hw);
+  sts4(lo_addr, v.x - hx, v.y - hy, v.z - hz, v.w - hw);
+}
+__device__ __forceinline__ void split_store1(uint32_t hi_addr, uint32_t lo_addr, float v) {
+  const float h = tf32_hi(v);
+  sts1(hi_addr, h);
+  sts1(lo_addr, v - h);
 }
 
 // Operand loader.  Every access is a float4 of 4 consecutive STORAGE columns of one storage row, fetched through the
 // functor's two-phase API: fetch() issues all raw 16-byte loads of the chunk back to back (nothing depends on them, so
 // they are all in flight together), store() applies the lazy transform, splits hi/lo and writes the swizzled tiles.
-//   RC == true : storage [row][k]: the quad is 4 consecutive k of one tile row; 8 threads cover one 128-byte row chunk
-//                (coalesced), each st.shared.v4 quarter-warp covers one full swizzle row (conflict-free).
+// Everything that does not change from chunk to chunk (row pointers, shared-memory offsets) is computed once in init().
+//   RC == true : storage [row][k]: thread (tid >> 3, tid & 7) owns the k-quad tid & 7 of tile rows (tid >> 3) + 32 i;
+//                8 threads cover one 128-byte row chunk (coalesced), each st.shared.v4 quarter-warp covers one full
+//                swizzle row (conflict-free).
 //   RC == false: storage [k][row]: the quad is 4 consecutive tile rows at one k.  A warp works on [16 k] x [32 rows]
 //                patches in 4 rotations j: lane (kk = lane & 3, rq = lane >> 2) reads k = 4*(((rq >> 1) + j) & 3) + kk,
 //                rows 4*rq .. 4*rq+3: 16 full 32-byte sectors per request, and the 4 scalar stores of a quad hit 32
 //                distinct banks ((k/4) ^ (row % 8) takes 8 values x 4 kk).
+// Bounds: tile rows beyond the operand are clamped by the functor (their products are never stored); only the K padding of
+// the last chunk (CHECK == true) is zeroed.
 template <int ROWS, bool RC, class Op>
 struct Loader {
-  static constexpr int NV = ROWS * BK / 4 / THREADS;   // quads per thread per chunk
+  static constexpr int NV = ROWS * BK / 4 / PROD_THREADS;   // quads per thread per chunk
   static_assert(NV >= 1, "tile too small for 256 loader threads");
   float4 ra[NV], rb[NV];
   typename Op::Tok tok[NV];
-  __device__ __forceinline__ void init(const Op& op, int row0, int tid) {
-    if (RC) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) tok[i] = op.token(row0 + ((tid + i * THREADS) >> 3));
-    }
-  }
+  int col[NV];          // RC == false: clamped storage column of the quad
+  uint32_t soff[NV];    // RC == false: byte offset of (row, k) in the tile;  RC == true: soff[0] only
   __device__ __forceinline__ void coords(int i, int tid, int& row, int& k) const {   // RC == false: tile row of quad elt 0, k
     const int lane = tid & 31, warp = tid >> 5;
     const int kk = lane & 3, rq = lane >> 2;
-    const int u = warp + i * (THREADS / 32);
+    const int u = warp + i * (PROD_THREADS / 32);
     const int patch = u >> 2, j = u & 3;
     const int h = patch & 1, rb_ = patch >> 1;
     row = rb_ * 32 + rq * 4;
     k = 16 * h + 4 * (((rq >> 1) + j) & 3) + kk;
   }
-  __device__ __forceinline__ void fetch(const Op& op, int row0, int k0, int kend, int tid) {
+  __device__ __forceinline__ void init(const Op& op, int row0, int tid) {
     if (RC) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int k = k0 + ((tid + i * THREADS) & 7) * 4;
-        op.fetch4(tok[i], k < kend ? k : 0x3fffffff, ra[i], rb[i]);
-      }
+      for (int i = 0; i < NV; ++i) tok[i] = op.token(row0 + (tid >> 3) + 32 * i);
+      soff[0] = sw128(tid >> 3, (tid & 7) * 4);
     } else {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         int row, k;
         coords(i, tid, row, k);
-        tok[i] = op.token(k0 + k < kend ? k0 + k : 0x3fffffff);
-        op.fetch4(tok[i], row0 + row, ra[i], rb[i]);
+        col[i] = op.clampc(row0 + row);
+        soff[i] = (uint32_t)(row * 128 + ((k & 3) << 2)) | ((uint32_t)(k >> 2) << 24) | ((uint32_t)(row & 7) << 28);
       }
     }
   }
-  // (k0, kend) must be the ones passed to the matching fetch()
-  __device__ __forceinline__ void store(const Op& op, int row0, int k0, int kend, char* hi_tile, char* lo_tile, int tid) const {
+  template <bool CHECK>
+  __device__ __forceinline__ void fetch(const Op& op, int k0, int kend, int tid) {
     if (RC) {
+      int k = k0 + (tid & 7) * 4;
+      if (CHECK) k = min(k, kend - 4);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) op.fetch4(tok[i], k, ra[i], rb[i]);
+    } else {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        const int f = tid + i * THREADS;
-        const int k = k0 + (f & 7) * 4;
-        float4 v = op.finish4(tok[i], k < kend ? k : 0x3fffffff, ra[i], rb[i]);
-        split_store4(hi_tile, lo_tile, f >> 3, (f & 7) * 4, v);
+        int k = k0 + (int)((soff[i] >> 24) & 15) * 4 + (int)((soff[i] >> 2) & 3);
+        if (CHECK) k = min(k, kend - 1);
+        tok[i] = op.token(k);
+        op.fetch4(tok[i], col[i], ra[i], rb[i]);
+      }
+    }
+  }
+  // (k0, kend, CHECK) must be the ones passed to the matching fetch()
+  template <bool CHECK>
+  __device__ __forceinline__ void store(const Op& op, int k0, int kend, uint32_t hi_tile, uint32_t lo_tile, int tid) const {
+    if (RC) {
+      const int k = k0 + (tid & 7) * 4;
+      const bool valid = !CHECK || k < kend;
+      const int kc = CHECK ? min(k, kend - 4) : k;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float4 v = op.finish4(tok[i], kc, ra[i], rb[i]);
+        if (CHECK && !valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        split_store4(hi_tile + soff[0] + i * 4096, lo_tile + soff[0] + i * 4096, v);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        int row, k;
-        coords(i, tid, row, k);
-        float4 v = op.finish4(tok[i], row0 + row, ra[i], rb[i]);
-        split_store1(hi_tile, lo_tile, row + 0, k, v.x);
-        split_store1(hi_tile, lo_tile, row + 1, k, v.y);
-        split_store1(hi_tile, lo_tile, row + 2, k, v.z);
-        split_store1(hi_tile, lo_tile, row + 3, k, v.w);
+        const uint32_t kq = (soff[i] >> 24) & 15, r7 = soff[i] >> 28, base = soff[i] & 0xffffffu;
+        float4 v = op.finish4(tok[i], col[i], ra[i], rb[i]);
+        if (CHECK) {
+          const int k = k0 + (int)kq * 4 + (int)((soff[i] >> 2) & 3);
+          if (k >= kend) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        split_store1(hi_tile + base + (((kq ^ (r7 + 0)) & 7) << 4), lo_tile + base + (((kq ^ (r7 + 0)) & 7) << 4), v.x);
+        split_store1(hi_tile + base + 128 + (((kq ^ (r7 + 1)) & 7) << 4), lo_tile + base + 128 + (((kq ^ (r7 + 1)) & 7) << 4), v.y);
+        split_store1(hi_tile + base + 256 + (((kq ^ (r7 + 2)) & 7) << 4), lo_tile + base + 256 + (((kq ^ (r7 + 2)) & 7) << 4), v.z);
+        split_store1(hi_tile + base + 384 + (((kq ^ (r7 + 3)) & 7) << 4), lo_tile + base + 384 + (((kq ^ (r7 + 3)) & 7) << 4), v.w);
       }
     }
   }
@@ -277,56 +297,87 @@ struct SmemLayout {
   static constexpr int A_TILE = BM * 128;   // bytes of one [128][32] fp32 tile
   static constexpr int B_TILE = BN * 128;
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+  static constexpr int STAGES = BN >= 128 ? 3 : 4;     // 192 KB / 192 KB / 160 KB of operand ring
+  static constexpr int PF = BN >= 128 ? 1 : 2;         // chunks prefetched into registers per producer thread (register budget)
   static constexpr int STAT = 2 * 8 * BN * 4;          // per-warp column statistics [2][8 warps][BN]
   static constexpr int OUT_LD = BN + 4;                // floats per staged accumulator row
   static_assert(BM * OUT_LD * 4 <= STAGES * STAGE, "accumulator staging must fit the (idle) stage buffers");
-  static constexpr int BYTES = 1024 + STAGES * STAGE + STAT + 128;
+  static constexpr int NBARS = 2 * STAGES + 4;         // full[S] empty[S] segfull[2] accempty[2]
+  static constexpr int BYTES = 1024 + STAGES * STAGE + STAT + NBARS * 8 + 64;
 };
 
-// Accumulation scheme.  The tensor core adds into its fp32 accumulator with truncation, so a long dependent chain of
-// accumulator updates drifts (measured: 1.4e-5 relative at K = 3968, 3 updates per 8 k).  Chains are therefore kept short:
-//   * the dominant hi*hi products of a SEGMENT (SEG_CHUNKS chunks = 64 k -> 8 updates) go to one of two ping-pong TMEM
-//     accumulators; when a segment's MMAs retire it is drained with tcgen05.ld and added — round-to-nearest — into fp32
-//     registers while the next segment's MMAs run into the other buffer;
-//   * the two cross terms lo*hi + hi*lo (2^-11 of the magnitude) accumulate over the whole K range in a third TMEM
-//     accumulator, where truncation is harmless, and are added once at the end.
-// TMEM columns: [0,BN) acc0, [BN,2BN) acc1, [2BN,3BN) cross terms.
-constexpr int SEG_CHUNKS = 2;
+// Accumulation scheme.
+//   * Dependent tcgen05.mma instructions (same TMEM accumulator) serialise on the accumulate latency (~170 cycles measured),
+//     far above the 16-64 cycle occupancy of a 128 x BN x 8 TF32 instruction.  The three products of the 3xTF32 scheme are
+//     therefore kept in SEPARATE accumulators and each of them alternates between an even and an odd k-slice accumulator
+//     (BN <= 64; BN = 128 is occupancy-bound with four chains): 4-6 independent MMA chains per CTA.
+//   * The tensor core adds into its fp32 accumulator with truncation, so a long dependent chain of accumulator updates
+//     drifts (measured: 1.4e-5 relative after 1488 updates).  Chains are bounded by draining all accumulators into fp32
+//     registers (round-to-nearest adds) every SEG_CHUNKS chunks = 640 k (40 updates per chain, < 1e-6); every contraction
+//     of the VAE path at the default sizes (K <= 640 per CTA, split-K above that) is a single segment.
+// TMEM columns: NM main regions, then NC regions for lo*hi, then NC regions for hi*lo, BN columns each.
+constexpr int SEG_CHUNKS = 20;
 
+// tuning aid: SM-clock timestamps of CTA (0,0,0) at the phase boundaries of the last tc_gemm launch (sln_debug_tc_trace)
+__device__ long long g_tc_trace[16];
+#define TC_TRACE(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid & 31) == 0 && (tid == 0 || tid == MMA_WARP * 32)) g_tc_trace[(slot) + (tid ? 8 : 0)] = clock64(); } while (0)
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One CTA = 8 producer/epilogue warps + 1 MMA warp, decoupled by mbarriers (no CTA-wide barrier in the main loop):
+//   producers   wait empty[s] -> transform + hi/lo split + st.shared of chunk c (fetched PF chunks earlier into registers)
+//               -> issue the global loads of chunk c+PF -> fence.proxy.async -> one arrive per warp on full[s];
+//   MMA warp    (one lane) wait full[s] -> 12 tcgen05.mma.kind::tf32 -> tcgen05.commit -> empty[s]  (-> segfull at segment ends);
+//   the ring of STAGES stages lets the producers run ahead of the tensor core, so global-load latency is hidden behind
+//   the MMAs of the previous chunks instead of being exposed once per chunk.
 // grid = (ceil(N/BN), ceil(M/128), splits); each z-slice reduces k in [z*kchunk, (z+1)*kchunk), kchunk % 32 == 0.
 template <int BN, bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const BOp B, const Epi epi, int M, int N, int K, int kchunk) {
   using L = SmemLayout<BN>;
+  constexpr int S = L::STAGES, PF = L::PF;
   extern __shared__ char smem_raw[];
   char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
-  float* stat = reinterpret_cast<float*>(smem + STAGES * L::STAGE);        // [2][4][BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE + L::STAT);   // [STAGES] stage-free + [2] segment-done
-  uint64_t* segbar = bars + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(segbar + 2);
+  float* stat = reinterpret_cast<float*>(smem + S * L::STAGE);             // [2][8][BN]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * L::STAGE + L::STAT);
+  uint64_t* empty = full + S;
+  uint64_t* segfull = empty + S;
+  uint64_t* accempty = segfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
   int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
   const int nchunks = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
-  constexpr uint32_t TMEM_COLS = (3 * BN <= 128) ? 128 : ((3 * BN <= 256) ? 256 : 512);
-  static_assert(3 * BN <= 512, "three accumulators must fit the 512 TMEM columns");
+  TC_TRACE(0);
+  constexpr int NM = 2;                       // hi*hi chains (even / odd k-slices)
+  constexpr int NC = BN >= 128 ? 1 : 2;       // chains per cross term
+  constexpr int NREG = NM + 2 * NC;
+  constexpr uint32_t TMEM_COLS = (NREG * BN <= 128) ? 128 : ((NREG * BN <= 256) ? 256 : 512);
+  static_assert(NREG * BN <= 512, "the accumulators must fit the 512 TMEM columns");
 
-  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
-  if (tid == 32) {
+  if (warp == MMA_WARP) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES + 2; ++s) mbar_init(bars + s, 1);
-    fence_barrier_init();
+      for (int s = 0; s < S; ++s) { mbar_init(full + s, PROD_WARPS); mbar_init(empty + s, 1); }
+      mbar_init(segfull, 1); mbar_init(segfull + 1, 1);
+      mbar_init(accempty, PROD_WARPS); mbar_init(accempty + 1, PROD_WARPS);
+      fence_barrier_init();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  TC_TRACE(1);
 
-  const int quad = warp & 3, half = warp >> 2;          // TMEM lane quadrant (fixed by warp id % 4), column half
+  const int quad = warp & 3, half = (warp >> 2) & 1;    // TMEM lane quadrant (fixed by warp id % 4), column half
   // BN >= 64: warps 0-3 own the left half of the columns, warps 4-7 the right half; BN = 32: only warps 0-3 hold accumulators
   constexpr int CH2 = BN >= 64 ? BN / 64 : 1;           // 32-column chunks owned by one thread
-  const bool has_acc = BN >= 64 || half == 0;
+  const bool has_acc = warp < PROD_WARPS && (BN >= 64 || half == 0);
   const int col_off = BN >= 64 ? half * (BN / 2) : 0;
   const uint32_t tmem_mine = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_off;
   float racc[CH2][32];
@@ -334,75 +385,108 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   for (int j = 0; j < CH2; ++j)
 #pragma unroll
     for (int e = 0; e < 32; ++e) racc[j][e] = 0.f;
-  auto drain = [&](int seg) {                           // racc += TMEM accumulator of a retired segment
-    mbar_wait(segbar + (seg & 1), (uint32_t)((seg >> 1) & 1));
-    tc_fence_after();
-    if (has_acc) {
-#pragma unroll
-      for (int j = 0; j < CH2; ++j) {
-        float v[32];
-        tmem_ld32(tmem_mine + (uint32_t)((seg & 1) * BN + j * 32), v);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) racc[j][e] += v[e];
-      }
-    }
-    tc_fence_before();
-  };
 
-  Loader<BM, A_RC, AOp> la;
-  Loader<BN, B_RC, BOp> lb;
-  la.init(A, m0, tid);
-  lb.init(B, n0, tid);
-  if (nchunks > 0) {
-    la.fetch(A, m0, kbeg, kend, tid);
-    lb.fetch(B, n0, kbeg, kend, tid);
-  }
-  constexpr uint32_t idesc = make_idesc(BN);
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c % STAGES, use = c / STAGES;
-    const int seg = c / SEG_CHUNKS;
-    const bool seg_first = (c % SEG_CHUNKS) == 0, seg_last = (c % SEG_CHUNKS) == SEG_CHUNKS - 1 || c == nchunks - 1;
-    char* st = smem + s * L::STAGE;
-    if (use > 0) mbar_wait(bars + s, (use - 1) & 1);   // the MMAs that read this stage have retired
-    la.store(A, m0, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
-    lb.store(B, n0, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
-    if (c + 1 < nchunks) {                              // next chunk's global loads fly during the MMAs
-      la.fetch(A, m0, kbeg + (c + 1) * BK, kend, tid);
-      lb.fetch(B, n0, kbeg + (c + 1) * BK, kend, tid);
+  if (warp == MMA_WARP) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % S, use = c / S;
+        const int seg = c / SEG_CHUNKS;
+        const bool seg_first = (c % SEG_CHUNKS) == 0, seg_last = (c % SEG_CHUNKS) == SEG_CHUNKS - 1 || c == nchunks - 1;
+        if (seg_first && seg > 0) {                       // the producers have drained the accumulators of the previous segment
+          mbar_wait(accempty, (uint32_t)((seg - 1) & 1));
+          tc_fence_after();
+        }
+        mbar_wait(full + s, (uint32_t)(use & 1));
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * L::STAGE), a_lo = a_hi + L::A_TILE, b_hi = a_hi + 2 * L::A_TILE, b_lo = b_hi + L::B_TILE;
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {               // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
+          const uint32_t o = k * 32;
+          const uint32_t d_c1 = tmem_acc + (uint32_t)((NM + (k % NC)) * BN), d_c2 = tmem_acc + (uint32_t)((NM + NC + (k % NC)) * BN);
+          const uint32_t d_main = tmem_acc + (uint32_t)((k % NM) * BN);
+          mma_tf32(d_c1, make_desc(a_lo + o), make_desc(b_hi + o), idesc, (!seg_first || k >= NC) ? 1u : 0u);
+          mma_tf32(d_c2, make_desc(a_hi + o), make_desc(b_lo + o), idesc, (!seg_first || k >= NC) ? 1u : 0u);
+          mma_tf32(d_main, make_desc(a_hi + o), make_desc(b_hi + o), idesc, (!seg_first || k >= NM) ? 1u : 0u);
+        }
+        mma_commit(empty + s);                             // stage s may be overwritten once these MMAs retire
+        if (seg_last) mma_commit(segfull);
+        if (c == 0) TC_TRACE(2);
+      }
+      TC_TRACE(3);
     }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ producers (and owners of the register accumulators)
+    auto drain = [&](int seg) {                           // racc += every TMEM accumulator of a retired segment
+      mbar_wait(segfull, (uint32_t)(seg & 1));
       tc_fence_after();
-      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + L::A_TILE, b_hi = a_hi + 2 * L::A_TILE, b_lo = b_hi + L::B_TILE;
-      const uint32_t d_main = tmem_acc + (uint32_t)((seg & 1) * BN), d_cross = tmem_acc + (uint32_t)(2 * BN);
+      if (has_acc) {
 #pragma unroll
-      for (int k = 0; k < BK / 8; ++k) {               // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
-        const uint32_t o = k * 32;
-        mma_tf32(d_cross, make_desc(a_lo + o), make_desc(b_hi + o), idesc, (c > 0 || k > 0) ? 1u : 0u);
-        mma_tf32(d_cross, make_desc(a_hi + o), make_desc(b_lo + o), idesc, 1u);
-        mma_tf32(d_main, make_desc(a_hi + o), make_desc(b_hi + o), idesc, (!seg_first || k > 0) ? 1u : 0u);
+        for (int rg = 0; rg < NREG; ++rg) {
+#pragma unroll
+          for (int j = 0; j < CH2; ++j) {
+            float v[32];
+            tmem_ld32(tmem_mine + (uint32_t)(rg * BN + j * 32), v);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) racc[j][e] += v[e];
+          }
+        }
       }
-      mma_commit(bars + s);
-      if (seg_last) mma_commit(segbar + (seg & 1));
-    }
-    // Drain the previous segment while this chunk's MMAs run.  The buffer it frees is next written two chunks from now,
-    // after two more CTA barriers, so every warp's tcgen05.ld has completed (fence::before_thread_sync in drain()).
-    if (seg_first && seg > 0) drain(seg - 1);
-  }
-  if (nchunks > 0) {
-    const int last_seg = (nchunks - 1) / SEG_CHUNKS;
-    drain(last_seg);                                     // also guarantees every cross-term MMA has retired
-    if (has_acc) {
-#pragma unroll
-      for (int j = 0; j < CH2; ++j) {
-        float v[32];
-        tmem_ld32(tmem_mine + (uint32_t)(2 * BN + j * 32), v);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) racc[j][e] += v[e];
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accempty);
+    };
+    // PF register buffers per operand, named (not arrays) so that they stay in registers
+    Loader<BM, A_RC, AOp> la0, la1;
+    Loader<BN, B_RC, BOp> lb0, lb1;
+    const bool tail = ((kend - kbeg) & (BK - 1)) != 0;     // only the last chunk can have K padding
+    const uint32_t sbase = smem_u32(smem);
+    auto fetch = [&](auto& LA, auto& LB, int c) {
+      if (tail && c == nchunks - 1) {
+        LA.template fetch<true>(A, kbeg + c * BK, kend, tid);
+        LB.template fetch<true>(B, kbeg + c * BK, kend, tid);
+      } else {
+        LA.template fetch<false>(A, kbeg + c * BK, kend, tid);
+        LB.template fetch<false>(B, kbeg + c * BK, kend, tid);
       }
+    };
+    auto produce = [&](auto& LA, auto& LB, int c) {
+      const int s = c % S, use = c / S;
+      const uint32_t st = sbase + s * L::STAGE;
+      if (use > 0) mbar_wait(empty + s, (uint32_t)((use - 1) & 1));   // the MMAs that read this stage have retired
+      if (tail && c == nchunks - 1) {
+        LA.template store<true>(A, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
+        LB.template store<true>(B, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
+      } else {
+        LA.template store<false>(A, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
+        LB.template store<false>(B, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
+      }
+      if (c + PF < nchunks) fetch(LA, LB, c + PF);        // refill the register buffer: these loads fly during the next PF chunks
+      fence_async_smem();                                 // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + s);
+      const int seg = c / SEG_CHUNKS;
+      if ((c % SEG_CHUNKS) == 0 && seg > 0) drain(seg - 1);
+    };
+    la0.init(A, m0, tid);
+    lb0.init(B, n0, tid);
+    if (nchunks > 0) fetch(la0, lb0, 0);
+    if (PF == 2) {
+      la1.init(A, m0, tid);
+      lb1.init(B, n0, tid);
+      if (nchunks > 1) fetch(la1, lb1, 1);
     }
+    TC_TRACE(2);
+    for (int c = 0; c < nchunks; c += PF) {
+      produce(la0, lb0, c);
+      if (c == 0) TC_TRACE(3);
+      if (PF == 2 && c + 1 < nchunks) produce(la1, lb1, c + 1);
+    }
+    if (nchunks > 0) drain((nchunks - 1) / SEG_CHUNKS);
   }
+  TC_TRACE(4);
   // ---- epilogue: stage the tile in shared memory (the stage buffers are idle: every MMA has retired) ...
   float* outs = reinterpret_cast<float*>(smem);
   if (has_acc) {
@@ -422,22 +506,25 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   const int jcol = n0 + cq * 4;
   const int nvalid = min(4, max(0, N - jcol));
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-  if (nvalid > 0) {
-    for (int r = warp * RPP + rsub; r < BM; r += 8 * RPP) {
+  if (nvalid > 0 && warp < PROD_WARPS) {
+    for (int r = warp * RPP + rsub; r < BM; r += PROD_WARPS * RPP) {
       if (m0 + r >= M) break;
       float4 a = *reinterpret_cast<const float4*>(outs + (size_t)r * L::OUT_LD + cq * 4);
       epi.apply4(m0 + r, jcol, nvalid, a, s1, s2);
     }
   }
+  TC_TRACE(5);
   if (stats) {
+    if (warp < PROD_WARPS) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {                       // fold the RPP row sub-groups of the warp (fixed order)
+      for (int e = 0; e < 4; ++e) {                       // fold the RPP row sub-groups of the warp (fixed order)
 #pragma unroll
-      for (int o = LPR; o < 32; o <<= 1) { s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o); s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o); }
-    }
-    if (rsub == 0) {
+        for (int o = LPR; o < 32; o <<= 1) { s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o); s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o); }
+      }
+      if (rsub == 0) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { stat[(0 * 8 + warp) * BN + cq * 4 + e] = s1[e]; stat[(1 * 8 + warp) * BN + cq * 4 + e] = s2[e]; }
+        for (int e = 0; e < 4; ++e) { stat[(0 * 8 + warp) * BN + cq * 4 + e] = s1[e]; stat[(1 * 8 + warp) * BN + cq * 4 + e] = s2[e]; }
+      }
     }
     __syncthreads();
     float* partial = epi.partial();
@@ -452,11 +539,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
     }
     // (finalize_column_block starts with a CTA barrier, after which the staging area is reused as fp64 scratch)
     finalize_column_block<THREADS>(partial, epi.counter(), n0, BN, N, tid, reinterpret_cast<double*>(smem), s_last,
-                                   [&](int col, double S, double Q) { epi.finalize(col, S, Q); });
+                                   [&](int col, double S_, double Q_) { epi.finalize(col, S_, Q_); });
   }
+  TC_TRACE(6);
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_acc, TMEM_COLS);
+  if (warp == MMA_WARP) tmem_dealloc(tmem_acc, TMEM_COLS);
+  TC_TRACE(7);
 }
 
 // ---------------------------------------------------------------- host side
@@ -480,17 +569,20 @@ inline TcChoice pick_tc(int M, int N, int K, bool allow_split) {
     int kchunk = ceil_div(ceil_div(K, splits), BK) * BK;
     splits = ceil_div(K, kchunk);
     int ctas = tiles * splits;
-    int waves = ceil_div(ctas, kNumSMs);            // one CTA per SM (register bound)
-    // cycles per CTA ~ chunks x (one memory round trip + smem fill of 128 + BN rows) + prologue + epilogue (~ BN)
-    double per_cta = (double)ceil_div(kchunk, BK) * (600.0 + 2.0 * (BM + bn)) + 3000.0 + 20.0 * bn;
+    int waves = ceil_div(ctas, kNumSMs);            // one CTA per SM (shared-memory bound)
+    // cycles per CTA ~ prologue (TMEM alloc, first loads) + chunks x max(MMA time, producer time) + epilogue:
+    //   12 MMAs of 128 x bn x 8 per chunk at 128*bn/256 cycles each; producers move (128 + bn) x 32 floats per chunk
+    double t_mma = 12.0 * (bn / 2 < 32 ? 32 : bn / 2), t_prod = 1.6 * (BM + bn);
+    double per_cta = 2500.0 + (double)ceil_div(kchunk, BK) * (t_mma > t_prod ? t_mma : t_prod) + 1500.0 + 14.0 * bn;
     double cost = waves * per_cta;
     if (cost < best) { best = cost; c = TcChoice{bn, splits, kchunk}; }
   }
   return c;
 }
 
-// shapes the tensor-core path accepts; everything else (tiny heads, K = 6 box embedding) stays on the SIMT kernel
-inline bool tc_eligible(int M, int N, int K) { return M >= 64 && N >= 32 && K >= 32; }
+// shapes the tensor-core path accepts; everything else (tiny heads, K = 6 box embedding) stays on the SIMT kernels
+// (independent of M, so that a scene evaluated alone and inside a batch takes the same arithmetic path)
+inline bool tc_eligible(int M, int N, int K) { return M >= 1 && N >= 32 && K >= 32; }
 
 template <int BN, bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
 int launch_tc_bn(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, const TcChoice& c) {

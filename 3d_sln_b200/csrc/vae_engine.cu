@@ -5,6 +5,9 @@
 // Reference being replaced: models/graph.py:57-143 (GraphTripleConv[Net]), models/Sg2ScVAE_model.py:115-188
 // (encoder / decoder / forward), utils.py:12-33 (losses), train.py:82-84 (Adam).
 #include <stdarg.h>
+#include <stdlib.h>
+
+#include <unordered_map>
 
 #include "../../include/sln_b200.h"
 #include "vae_kernels.cuh"
@@ -16,7 +19,16 @@ namespace {
 
 // contraction engine of the MLP stage: 1 = tcgen05 3xTF32 tiles (default), 0 = FP32 SIMT tiles (A/B checks, odd shapes)
 int g_engine = 1;
-inline bool use_tc(int M, int N, int K) { return g_engine == 1 && tc::tc_eligible(M, N, K); }
+// debug knob: sln_set_engine(16 | mask) keeps tcgen05 only for the call sites in `mask` (1 fwd, 2 bwd_w, 4 bwd_x_plain, 8 bwd_x_masked)
+int g_tc_mask = 15;
+enum { SITE_FWD = 1, SITE_BWD_W = 2, SITE_BWD_X = 4, SITE_BWD_XM = 8 };
+// debug knob (env SLN_SKINNY, default 7): narrow-head kernels per call site (1 fwd, 2 bwd_w, 4 bwd_x)
+int g_skinny = -1;
+inline bool use_skinny(int site) {
+  if (g_skinny < 0) { const char* e = getenv("SLN_SKINNY"); g_skinny = e ? atoi(e) : 7; }
+  return (g_skinny & site) != 0;
+}
+inline bool use_tc(int M, int N, int K, int site) { return g_engine == 1 && (g_tc_mask & site) && tc::tc_eligible(M, N, K); }
 
 constexpr int kMaxLayers = 32;
 
@@ -53,10 +65,86 @@ struct Model {
   Blk bmv[2], amv[2], box_mean, box_var, angle_mean, angle_var, box_net[2], angle_net[2];
 };
 
+// Weight-gradient contractions (dW = dy^T X) only feed the optimizer, so they leave the dependency chain of the backward
+// pass: they are forked onto a side stream (event record / wait, capturable in a CUDA graph as a parallel branch) and run
+// concurrently with the data-gradient chain, filling the SMs that the 62..128-CTA grids of the chain leave idle.
+// Hazards: a dW kernel READS a masked-gradient buffer `g` that a later chain kernel overwrites (the g buffers are shared
+// by all layers), so every chain kernel that writes such a buffer first waits for the last side-stream reader of it.
+struct Side {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[64];
+  int next = 0;
+  bool ready = false, active = false;
+  std::unordered_map<const void*, cudaEvent_t> readers;
+  cudaEvent_t take() { cudaEvent_t e = ev[next]; next = (next + 1) % 64; return e; }
+};
+thread_local Side g_side;
+int g_side_enabled = -1;
+
 struct Ctx {
   cudaStream_t st;
   Dims dm;
+  bool side = false;   // weight gradients go to the side stream during this call
 };
+
+// Decide whether this call uses the side stream (creating it on first use; never created while the caller is capturing).
+void side_begin(Ctx& c) {
+  c.side = false;
+  if (g_side_enabled < 0) { const char* e = getenv("SLN_SIDE_STREAM"); g_side_enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!g_side_enabled) return;
+  Side& sd = g_side;
+  if (!sd.ready) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(c.st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { (void)cudaGetLastError(); return; }
+    if (cudaStreamCreateWithFlags(&sd.st, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    for (int i = 0; i < 64; ++i)
+      if (cudaEventCreateWithFlags(&sd.ev[i], cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    sd.ready = true;
+  }
+  sd.readers.clear();
+  sd.active = false;
+  c.side = true;
+}
+// stream for a weight-gradient launch that reads buffer `g`: forks from the chain (everything issued so far is visible)
+cudaStream_t side_fork(const Ctx& c) {
+  if (!c.side) return c.st;
+  Side& sd = g_side;
+  cudaEvent_t e = sd.take();
+  cudaEventRecord(e, c.st);
+  cudaStreamWaitEvent(sd.st, e, 0);
+  sd.active = true;
+  return sd.st;
+}
+void side_read_done(const Ctx& c, const void* g) {
+  if (!c.side) return;
+  Side& sd = g_side;
+  cudaEvent_t e = sd.take();
+  cudaEventRecord(e, sd.st);
+  sd.readers[g] = e;
+}
+// the chain is about to overwrite buffer `g`
+void side_before_write(const Ctx& c, const void* g) {
+  if (!c.side || g == nullptr) return;
+  Side& sd = g_side;
+  auto it = sd.readers.find(g);
+  if (it == sd.readers.end()) return;
+  cudaStreamWaitEvent(c.st, it->second, 0);
+  sd.readers.erase(it);
+}
+// join: every weight gradient of this call is complete before anything the caller enqueues next
+int side_end(Ctx& c) {
+  if (!c.side) return SLN_OK;
+  Side& sd = g_side;
+  if (sd.active) {
+    cudaEvent_t e = sd.take();
+    SLN_CUDA_TRY(cudaEventRecord(e, sd.st));
+    SLN_CUDA_TRY(cudaStreamWaitEvent(c.st, e, 0));
+  }
+  sd.readers.clear();
+  sd.active = false;
+  c.side = false;
+  return SLN_OK;
+}
 
 int make_dims(const sln_vae_desc* d, Dims* o) {
   SLN_CHECK_ARG(d != nullptr, "null model descriptor");
@@ -258,7 +346,9 @@ int block_fwd(const Ctx& c, const AOp& A, int M, const Blk& b, BlkState& s, floa
     k_bn_eval_prep<<<ceil_div(b.lin.out, 128), 128, 0, c.st>>>(b.gamma, b.beta, b.rm, b.rv, c.dm.eps, b.lin.out, s.mean, s.rstd, s.scale, s.shift);
     SLN_TRY(check_launch("bn_eval_prep"));
   }
-  if (use_tc(M, b.lin.out, b.lin.in) && A.vec_ok() && weight_view(b.lin).vec_ok()) {
+  if (use_skinny(1) && mode == NORM_NONE && b.lin.out <= 32 && b.lin.in <= 1024)   // narrow heads: latency problems, not contractions
+    return launch_skinny_fwd(c.st, A, b.lin.W, b.lin.b, M, b.lin.out, b.lin.in, epi.C, epi.ldc);
+  if (use_tc(M, b.lin.out, b.lin.in, SITE_FWD) && A.vec_ok() && weight_view(b.lin).vec_ok()) {
     tc::TcEpiStore te{epi.C, epi.ldc, epi.bias, epi.fin};
     return tc::launch_tc<true, true>(c.st, A, weight_view(b.lin), te, M, b.lin.out, b.lin.in, false, "linear_fwd_tc", PROF_GEMM_FWD);
   }
@@ -285,22 +375,39 @@ ActInfo blk_act(const Blk& b, const BlkState& s) {
   return a;
 }
 
-// dW[out,in] += dy^T X     (split along the sample dimension, RED.ADD)
+// dW[out,in] += dy^T X     (split along the sample dimension, RED.ADD); runs on the side stream (see Side)
+// head_bias: also reduce the Linear bias gradient (layers without a following activation: their bias gradient is not
+// produced by a BatchNorm-backward finalisation)
 template <class XOp>
-int bwd_w(const Ctx& c, const DyView& dy, const XOp& X, const Lin& lin, int M) {
-  if (!lin.dW) return SLN_OK;
-  if (use_tc(lin.out, lin.in, M) && dy.vec_ok() && X.vec_ok()) {
+int bwd_w(const Ctx& c, const DyView& dy, const XOp& X, const Lin& lin, int M, bool head_bias = false) {
+  if (!lin.dW) return head_bias && lin.db ? launch_embed_bwd(c.st, dy.g, dy.ldg, nullptr, 0, nullptr, M, lin.out, lin.db, 1) : SLN_OK;
+  const bool skinny = use_skinny(2) && lin.out <= 32 && dy.p == nullptr;   // narrow layer with a plain gradient [M, out]
+  if (head_bias && !skinny && lin.db) SLN_TRY(launch_embed_bwd(c.st, dy.g, dy.ldg, nullptr, 0, nullptr, M, lin.out, lin.db, 1));
+  cudaStream_t st = side_fork(c);
+  int rc;
+  if (skinny) {
+    rc = launch_skinny_bwd_w(st, dy.g, dy.ldg, lin.out, X, M, lin.in, lin.dW, lin.in, false, head_bias ? lin.db : nullptr);
+  } else if (use_tc(lin.out, lin.in, M, SITE_BWD_W) && dy.vec_ok() && X.vec_ok()) {
     tc::TcEpiAtomic te{lin.dW, lin.in};
-    return tc::launch_tc<false, false>(c.st, dy, X, te, lin.out, lin.in, M, true, "linear_bwd_w_tc", PROF_GEMM_BWD_W);
+    rc = tc::launch_tc<false, false>(st, dy, X, te, lin.out, lin.in, M, true, "linear_bwd_w_tc", PROF_GEMM_BWD_W);
+  } else {
+    EpiAtomic epi{lin.dW, lin.in};
+    rc = launch_gemm<false, false>(st, dy, X, epi, lin.out, lin.in, M, true, "linear_bwd_w", PROF_GEMM_BWD_W);
   }
-  EpiAtomic epi{lin.dW, lin.in};
-  return launch_gemm<false, false>(c.st, dy, X, epi, lin.out, lin.in, M, true, "linear_bwd_w", PROF_GEMM_BWD_W);
+  side_read_done(c, dy.g);
+  return rc;
 }
 // dX[M,in] = dy W
 int bwd_x_plain(const Ctx& c, const DyView& dy, const Lin& lin, int M, float* dX, int ldx) {
+  if (use_skinny(4) && lin.out <= 32 && dy.p == nullptr) {
+    SmallKSrc src{dy.g, dy.ldg, lin.out, lin.W, lin.in, nullptr, 0};
+    ActInfo none; memset(&none, 0, sizeof(none));
+    BnBwdFin nofin; memset(&nofin, 0, sizeof(nofin));
+    return launch_prep(c.st, src, none, dX, ldx, nofin, M, lin.in, "skinny_bwd_x");
+  }
   EpiStore epi; memset(&epi, 0, sizeof(epi));
   epi.C = dX; epi.ldc = ldx;
-  if (use_tc(M, lin.in, lin.out) && dy.vec_ok() && weight_view(lin).vec_ok()) {
+  if (use_tc(M, lin.in, lin.out, SITE_BWD_X) && dy.vec_ok() && weight_view(lin).vec_ok()) {
     tc::TcEpiStore te{dX, ldx, nullptr, epi.fin};
     return tc::launch_tc<true, false>(c.st, dy, weight_view(lin), te, M, lin.in, lin.out, false, "linear_bwd_x_tc", PROF_GEMM_BWD_X);
   }
@@ -314,16 +421,16 @@ int bwd_x_masked(const Ctx& c, const DyView& dy, const Lin& lin, int M, const Bl
   if (pb.has_bn) { epi.scale = ps.scale; epi.shift = ps.shift; epi.mean = ps.mean; epi.rstd = ps.rstd; }
   epi.fin = blk_fin(c, pb, ps);
   SLN_CHECK_ARG(lin.in == pb.lin.out, "internal: masked backward expects matching widths (%d vs %d)", lin.in, pb.lin.out);
-  if (use_tc(M, lin.in, lin.out) && dy.vec_ok() && weight_view(lin).vec_ok()) {
+  side_before_write(c, ps.g);
+  if (use_skinny(4) && lin.out <= 32 && dy.p == nullptr) {
+    SmallKSrc src{dy.g, dy.ldg, lin.out, lin.W, lin.in, add, ldadd};
+    return launch_prep(c.st, src, blk_act(pb, ps), ps.g, pb.lin.out, epi.fin, M, lin.in, "skinny_bwd_x_masked");
+  }
+  if (use_tc(M, lin.in, lin.out, SITE_BWD_XM) && dy.vec_ok() && weight_view(lin).vec_ok()) {
     tc::TcEpiMaskReduce te{epi.G, epi.ldg, epi.add, epi.ldadd, epi.yprev, epi.ldy, epi.scale, epi.shift, epi.mean, epi.rstd, epi.fin};
     return tc::launch_tc<true, false>(c.st, dy, weight_view(lin), te, M, lin.in, lin.out, false, "linear_bwd_x_masked_tc", PROF_GEMM_BWD_X);
   }
   return launch_gemm<true, false>(c.st, dy, weight_view(lin), epi, M, lin.in, lin.out, false, "linear_bwd_x_masked", PROF_GEMM_BWD_X);
-}
-// bias gradient of a Linear whose dy is given directly: db += column sums
-int bwd_bias_plain(const Ctx& c, const float* dy, int ld, int M, const Lin& lin) {
-  if (!lin.db) return SLN_OK;
-  return launch_embed_bwd(c.st, dy, ld, nullptr, 0, nullptr, M, lin.out, lin.db, 1);
 }
 
 int graph_prep(const Ctx& c, NetPlan& p, const int64_t* triples_or_edges, int stride3) {
@@ -423,6 +530,7 @@ int gconv_bwd(const Ctx& c, const Graph& g, const Blk* blk, BlkState* st, const 
   SLN_TRY(bwd_x_plain(c, dy3, blk[2].lin, O, dpooled, H));
   // pooling backward + BN-backward reduction of net1's second Linear
   PoolBwdSrc src{dpooled, g.cnt, g.s_idx, g.o_idx, dpred_next, ld_dpred, H, D};
+  side_before_write(c, st[1].g);
   SLN_TRY(launch_prep(c.st, src, blk_act(blk[1], st[1]), st[1].g, 2 * H + D, blk_fin(c, blk[1], st[1]), T, 2 * H + D, "pool_bwd_prep"));
   // net1, second Linear
   DyView dy2 = blk_dy(c, blk[1], st[1]);
@@ -441,6 +549,7 @@ int gconv_bwd(const Ctx& c, const Graph& g, const Blk* blk, BlkState* st, const 
 int node_gather(const Ctx& c, const Graph& g, const float* dcat, const Blk* pblk, BlkState* pst, float* plain_out) {
   const int D = c.dm.D;
   NodeGatherSrc src{dcat, 3 * D, D, g.row_ptr, g.ent};
+  if (pblk) side_before_write(c, pst->g);
   if (pblk) return launch_prep(c.st, src, blk_act(*pblk, *pst), pst->g, D, blk_fin(c, *pblk, *pst), g.O, D, "node_gather_prep");
   ActInfo none; memset(&none, 0, sizeof(none));
   BnBwdFin nofin; memset(&nofin, 0, sizeof(nofin));
@@ -570,14 +679,15 @@ int sln_vae_encoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_TRY(parse_model(dm, params, grads, nullptr, &m));
   make_plan(dm, O, T, 0, ws, &p);
   SLN_TRY(check_ws(p, ws, ws_bytes));
+  side_begin(c);
   const int L = dm.L;
   MatView obj_f = block_out(m.enc[L - 1][3], p.st[L - 1][3]);
   MatView hb = block_out(m.bmv[1], p.bmv[1]), ha = block_out(m.amv[1], p.amv[1]);
   MatView hb1 = block_out(m.bmv[0], p.bmv[0]), ha1 = block_out(m.amv[0], p.amv[0]);
   // --- box branch
   DyView dmu_b = make_dy(d_mu, dm.Z, O, dm.box_w), dlv_b = make_dy(d_logvar, dm.Z, O, dm.box_w);
-  SLN_TRY(bwd_w(c, dmu_b, hb, m.box_mean.lin, O)); SLN_TRY(bwd_bias_plain(c, d_mu, dm.Z, O, m.box_mean.lin));
-  SLN_TRY(bwd_w(c, dlv_b, hb, m.box_var.lin, O)); SLN_TRY(bwd_bias_plain(c, d_logvar, dm.Z, O, m.box_var.lin));
+  SLN_TRY(bwd_w(c, dmu_b, hb, m.box_mean.lin, O, true));
+  SLN_TRY(bwd_w(c, dlv_b, hb, m.box_var.lin, O, true));
   SLN_TRY(bwd_x_plain(c, dmu_b, m.box_mean.lin, O, p.tmpA, dm.D));
   SLN_TRY(bwd_x_masked(c, dlv_b, m.box_var.lin, O, m.bmv[1], p.bmv[1], p.tmpA, dm.D));
   DyView dyb2 = blk_dy(c, m.bmv[1], p.bmv[1]);
@@ -588,8 +698,8 @@ int sln_vae_encoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_TRY(bwd_x_plain(c, dyb1, m.bmv[0].lin, O, p.tmpB, dm.D));
   // --- angle branch
   DyView dmu_a = make_dy(d_mu + dm.box_w, dm.Z, O, dm.ang_w), dlv_a = make_dy(d_logvar + dm.box_w, dm.Z, O, dm.ang_w);
-  SLN_TRY(bwd_w(c, dmu_a, ha, m.angle_mean.lin, O)); SLN_TRY(bwd_bias_plain(c, d_mu + dm.box_w, dm.Z, O, m.angle_mean.lin));
-  SLN_TRY(bwd_w(c, dlv_a, ha, m.angle_var.lin, O)); SLN_TRY(bwd_bias_plain(c, d_logvar + dm.box_w, dm.Z, O, m.angle_var.lin));
+  SLN_TRY(bwd_w(c, dmu_a, ha, m.angle_mean.lin, O, true));
+  SLN_TRY(bwd_w(c, dlv_a, ha, m.angle_var.lin, O, true));
   SLN_TRY(bwd_x_plain(c, dmu_a, m.angle_mean.lin, O, p.tmpA, dm.D));
   SLN_TRY(bwd_x_masked(c, dlv_a, m.angle_var.lin, O, m.amv[1], p.amv[1], p.tmpA, dm.D));
   DyView dya2 = blk_dy(c, m.amv[1], p.amv[1]);
@@ -607,13 +717,15 @@ int sln_vae_encoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_TRY(embed_bwd(c, p.dobj0 + dm.obj_w, dm.D, nullptr, 0, p.attrs32, O, dm.attr_w, m.demb[1], d->num_attrs));
   {
     const int off = dm.obj_w + dm.attr_w;
-    DyView dyb = make_dy(p.dobj0 + off, dm.D, O, dm.box_w);
-    SLN_TRY(bwd_w(c, dyb, make_view(boxes, dm.box_dim, O, dm.box_dim), m.box_emb.lin, O));
-    SLN_TRY(bwd_bias_plain(c, p.dobj0 + off, dm.D, O, m.box_emb.lin));
+    // dW [box_w, box_dim] = dy^T boxes: the SMALL side is the input (6), so boxes play the role of the narrow operand
+    if (m.box_emb.lin.dW)
+      SLN_TRY(launch_skinny_bwd_w(c.st, boxes, dm.box_dim, dm.box_dim, make_view(p.dobj0 + off, dm.D, O, dm.box_w), O, dm.box_w,
+                                  m.box_emb.lin.dW, dm.box_dim, true, nullptr));
+    if (m.box_emb.lin.db) SLN_TRY(launch_embed_bwd(c.st, p.dobj0 + off, dm.D, nullptr, 0, nullptr, O, dm.box_w, m.box_emb.lin.db, 1));
   }
   SLN_TRY(embed_bwd(c, p.dobj0 + dm.obj_w + dm.attr_w + dm.box_w, dm.D, nullptr, 0, p.angles32, O, dm.ang_w, m.demb[2], d->n_angle));
   SLN_TRY(embed_bwd(c, dpred0, ldp, nullptr, 0, p.g.p_idx, T, dm.D, m.demb[3], d->num_preds));
-  return SLN_OK;
+  return side_end(c);
 }
 
 int sln_vae_decoder_fwd(const sln_vae_desc* d, const void* const* params, void* const* bn_bufs, const float* z, const int64_t* objs,
@@ -661,6 +773,7 @@ int sln_vae_decoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_TRY(parse_model(dm, params, grads, nullptr, &m));
   make_plan(dm, O, T, 1, ws, &p);
   SLN_TRY(check_ws(p, ws, ws_bytes));
+  side_begin(c);
   const int L = dm.L;
   MatView obj_f = block_out(m.dec[L - 1][3], p.st[L - 1][3]);
   const float* dlogits = d_angles;
@@ -671,13 +784,11 @@ int sln_vae_decoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   }
   // angle_net
   DyView dyl = make_dy(dlogits, dm.n_angle, O, dm.n_angle);
-  SLN_TRY(bwd_w(c, dyl, block_out(m.angle_net[0], p.angle_net0), m.angle_net[1].lin, O));
-  SLN_TRY(bwd_bias_plain(c, dlogits, dm.n_angle, O, m.angle_net[1].lin));
+  SLN_TRY(bwd_w(c, dyl, block_out(m.angle_net[0], p.angle_net0), m.angle_net[1].lin, O, true));
   SLN_TRY(bwd_x_masked(c, dyl, m.angle_net[1].lin, O, m.angle_net[0], p.angle_net0, nullptr, 0));
   // box_net
   DyView dyb = make_dy(d_boxes, dm.box_dim, O, dm.box_dim);
-  SLN_TRY(bwd_w(c, dyb, block_out(m.box_net[0], p.box_net0), m.box_net[1].lin, O));
-  SLN_TRY(bwd_bias_plain(c, d_boxes, dm.box_dim, O, m.box_net[1].lin));
+  SLN_TRY(bwd_w(c, dyb, block_out(m.box_net[0], p.box_net0), m.box_net[1].lin, O, true));
   SLN_TRY(bwd_x_masked(c, dyb, m.box_net[1].lin, O, m.box_net[0], p.box_net0, nullptr, 0));
   DyView dyb0 = blk_dy(c, m.box_net[0], p.box_net0);
   Concat2 cat{obj_f, make_view(p.obj0 + dm.obj_w, dm.D, O, dm.attr_w), O, dm.D + dm.attr_w};
@@ -695,7 +806,7 @@ int sln_vae_decoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_TRY(embed_bwd(c, p.dobj0 + dm.obj_w, dm.D, p.tmpC + dm.D, ldc, p.attrs32, O, dm.attr_w, m.demb[5], d->num_attrs));
   SLN_TRY(embed_bwd(c, dpred0, ldp, nullptr, 0, p.g.p_idx, T, dm.D, m.demb[6], d->num_preds));
   if (d_z) SLN_TRY(gather_rows(c, p.dobj0 + dm.obj_w + dm.attr_w, dm.D, nullptr, O, dm.Z, d_z, dm.Z, 0));
-  return SLN_OK;
+  return side_end(c);
 }
 
 // ---------------------------------------------------------------- standalone GraphTripleConv layer
@@ -742,15 +853,17 @@ int sln_gconv_layer_bwd(const sln_vae_desc* d, const void* const* layer_params, 
   SLN_TRY(parse_layer(dm, layer_params, layer_grads, nullptr, blk));
   make_plan(dm, O, T, 2, ws, &p);
   SLN_TRY(check_ws(p, ws, ws_bytes));
+  side_begin(c);
   // masked gradient of the node output + BN-backward reduction of net2's last Linear
   PlainSrc src{d_new_obj, dm.D};
+  side_before_write(c, p.st[0][3].g);
   SLN_TRY(launch_prep(c.st, src, blk_act(blk[3], p.st[0][3]), p.st[0][3].g, dm.D, blk_fin(c, blk[3], p.st[0][3]), O, dm.D, "out_prep"));
   float* dcat = p.sc.dcat[0];
   SLN_TRY(gconv_bwd(c, p.g, blk, p.st[0], p.pooled[0], p.sc.dpooled, make_view(obj_vecs, dm.D, O, dm.D), make_view(pred_vecs, dm.D, T, dm.D),
                     d_new_pred, dm.D, dcat));
   SLN_TRY(node_gather(c, p.g, dcat, nullptr, nullptr, d_obj));
   if (d_pred && T > 0) SLN_TRY(gather_rows(c, dcat + dm.D, 3 * dm.D, nullptr, T, dm.D, d_pred, dm.D, 0));
-  return SLN_OK;
+  return side_end(c);
 }
 
 // ---------------------------------------------------------------- pooling stage alone
@@ -794,7 +907,8 @@ int sln_gconv_pool_fwd(const float* new_t_vecs, int64_t O, int64_t T, int32_t H,
 // ---------------------------------------------------------------- contraction primitive (tests / roofline sweeps)
 int sln_set_engine(int engine) {
   int prev = g_engine;
-  if (engine == 0 || engine == 1) g_engine = engine;
+  if (engine == 0 || engine == 1) { g_engine = engine; g_tc_mask = 15; }
+  else if (engine >= 16 && engine < 32) { g_engine = 1; g_tc_mask = engine & 15; }
   return prev;
 }
 
@@ -825,6 +939,13 @@ int sln_contract(const float* A, int64_t lda, int32_t a_rc, const float* B, int6
   else if (!a_rc && b_rc) SLN_DISPATCH(false, true);
   else SLN_DISPATCH(false, false);
 #undef SLN_DISPATCH
+  return SLN_OK;
+}
+
+// tuning aid (not part of the public header): SM-clock trace of the last tcgen05 contraction launched by sln_contract
+int sln_debug_tc_trace(long long* out16) {
+  SLN_CUDA_TRY(cudaDeviceSynchronize());
+  SLN_CUDA_TRY(cudaMemcpyFromSymbol(out16, tc::g_tc_trace, sizeof(long long) * 16));
   return SLN_OK;
 }
 

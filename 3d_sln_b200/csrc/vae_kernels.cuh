@@ -313,15 +313,133 @@ template <class Src>
 int launch_prep(cudaStream_t st, const Src& src, const ActInfo& act, float* G, int ldg, const BnBwdFin& fin, int M, int N,
                 const char* what) {
   if (M <= 0 || N <= 0) return SLN_OK;
-  // aim for ~2 waves of CTAs; partial buffer is sized for max_row_tiles(M) = ceil(M/64) tiles
+  // aim for ~2 waves of CTAs; partial buffer is sized for max_row_tiles(M) = ceil(M/16) tiles
   int col_blocks = ceil_div(N, 128);
   int want_tiles = max(1, (2 * kNumSMs) / col_blocks);
-  int rows = max(64, ceil_div(M, want_tiles));
+  int rows = max(16, ceil_div(M, want_tiles));
   rows = ceil_div(rows, 4) * 4;
   dim3 grid(col_blocks, ceil_div(M, rows));
   ProfScope prof(st, PROF_PREP, 12.0 * (double)M * (double)N);  // read src + y, write G
   k_prep<Src><<<grid, dim3(128, 4), 0, st>>>(src, act, G, ldg, fin, M, N, rows);
   return check_launch(what);
+}
+
+// ================================================================ skinny Linear layers (heads: N or K <= 32)
+// The output / input heads of the model (box_net.1: 256 -> 6, angle_net.1: 256 -> 24, angle_mean/var: 128 -> 16,
+// box_embeddings: 6 -> 48; reference Sg2ScVAE_model.py:61-104) are far too narrow for 128-wide contraction tiles: they
+// are latency problems.  Three small kernels cover them.
+//
+// forward: out[i, j] = bias[j] + sum_k A(i,k) W[j,k], N <= 32.  W^T is staged in shared memory ([k][32], conflict-free),
+// one warp per row (lane = output column), the row of A is read as broadcast float4s through the lazy-BN/ReLU view.
+template <class AOp>
+__global__ void __launch_bounds__(256) k_skinny_fwd(const AOp A, const float* __restrict__ W, const float* __restrict__ bias, int M, int N, int K,
+                                                    float* out, int ldo) {
+  extern __shared__ float s_wt[];   // [K][32]
+  for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
+    int j = e / K, k = e - j * K;
+    s_wt[k * 32 + j] = __ldg(W + e);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float b = (bias && lane < N) ? __ldg(bias + lane) : 0.f;
+  for (int i = blockIdx.x * 8 + warp; i < M; i += gridDim.x * 8) {
+    float acc0 = b, acc1 = 0.f;
+    int k = 0;
+    for (; k + 8 <= K; k += 8) {
+      float4 a = A.ld4(i, k), c = A.ld4(i, k + 4);
+      acc0 = fmaf(a.x, s_wt[(k + 0) * 32 + lane], acc0); acc1 = fmaf(a.y, s_wt[(k + 1) * 32 + lane], acc1);
+      acc0 = fmaf(a.z, s_wt[(k + 2) * 32 + lane], acc0); acc1 = fmaf(a.w, s_wt[(k + 3) * 32 + lane], acc1);
+      acc0 = fmaf(c.x, s_wt[(k + 4) * 32 + lane], acc0); acc1 = fmaf(c.y, s_wt[(k + 5) * 32 + lane], acc1);
+      acc0 = fmaf(c.z, s_wt[(k + 6) * 32 + lane], acc0); acc1 = fmaf(c.w, s_wt[(k + 7) * 32 + lane], acc1);
+    }
+    for (; k < K; ++k) acc0 = fmaf(A.at_t(i, k), s_wt[k * 32 + lane], acc0);
+    if (lane < N) out[(size_t)i * ldo + lane] = acc0 + acc1;
+  }
+}
+template <class AOp>
+int launch_skinny_fwd(cudaStream_t st, const AOp& A, const float* W, const float* bias, int M, int N, int K, float* out, int ldo) {
+  if (M <= 0) return SLN_OK;
+  size_t smem = (size_t)K * 32 * sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(k_skinny_fwd<AOp>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_skinny_fwd) failed: %s", cudaGetErrorString(e)); return SLN_ECUDA; }
+      configured = true;
+    }
+  }
+  ProfScope prof(st, PROF_GEMM_FWD, 2.0 * (double)M * N * K);
+  k_skinny_fwd<AOp><<<min(ceil_div(M, 8), 2 * kNumSMs), 256, smem, st>>>(A, W, bias, M, N, K, out, ldo);
+  return check_launch("skinny_fwd");
+}
+
+// backward-data with a tiny reduction: src(i, j) = sum_{k < Kt} dy[i, k] W[k, j] (+ add[i, j]), used as a k_prep source so
+// that the ReLU mask and the BatchNorm-backward column sums of the producing layer are fused exactly as in the contraction
+// epilogue.  dy [M, Kt] plain (a loss gradient), W [Kt, N] = the Linear weight [out, in].
+struct SmallKSrc {
+  const float* dy; int lddy; int Kt;
+  const float* W; int ldw;
+  const float* add; int ldadd;
+  __device__ __forceinline__ float at(int i, int j) const {
+    float acc = add ? __ldg(add + (size_t)i * ldadd + j) : 0.f;
+    for (int k = 0; k < Kt; ++k) acc = fmaf(__ldg(dy + (size_t)i * lddy + k), __ldg(W + (size_t)k * ldw + j), acc);
+    return acc;
+  }
+};
+
+// backward-weight with a tiny output dimension:  C[p, q] += sum_i P[i, p] * Q(i, q),  p < KP <= 32 (P plain, e.g. a loss
+// gradient), q < NQ (Q through a lazy view).  Written to Cout[p * ldc + q], or transposed (Cout[q * ldc + p]) for the
+// box-embedding weight whose SMALL side is the input.  db (optional) += column sums of P (the Linear bias gradient).
+// grid (ceil(NQ/128), row splits), 128 threads = 128 columns q; P rows are staged in shared memory per 32-row slab.
+template <int KP, class QOp>
+__global__ void __launch_bounds__(128) k_skinny_bwd_w(const float* __restrict__ P, int ldp, int kp, const QOp Q, int M, int NQ, float* C, int ldc,
+                                                      int transposed, float* db, int rows_per_cta) {
+  __shared__ float s_p[32][KP];
+  const int q = blockIdx.x * 128 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float acc[KP];
+#pragma unroll
+  for (int e = 0; e < KP; ++e) acc[e] = 0.f;
+  float bsum = 0.f;   // thread t < kp of column block 0 accumulates the bias gradient of output t
+  for (int base = r0; base < r1; base += 32) {
+    const int nr = min(32, r1 - base);
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * KP; e += 128) {
+      int r = e / KP, c = e - r * KP;
+      s_p[r][c] = (r < nr && c < kp) ? __ldg(P + (size_t)(base + r) * ldp + c) : 0.f;
+    }
+    __syncthreads();
+    if (q < NQ) {
+      for (int r = 0; r < nr; ++r) {
+        const float x = Q.at_t(base + r, q);
+#pragma unroll
+        for (int e = 0; e < KP; ++e) acc[e] = fmaf(s_p[r][e], x, acc[e]);
+      }
+    }
+    if (db && blockIdx.x == 0 && threadIdx.x < kp)
+      for (int r = 0; r < nr; ++r) bsum += s_p[r][threadIdx.x];
+  }
+  if (q < NQ) {
+#pragma unroll
+    for (int e = 0; e < KP; ++e)
+      if (e < kp) red_add(transposed ? C + (size_t)q * ldc + e : C + (size_t)e * ldc + q, acc[e]);
+  }
+  if (db && blockIdx.x == 0 && threadIdx.x < kp) red_add(db + threadIdx.x, bsum);
+}
+template <class QOp>
+int launch_skinny_bwd_w(cudaStream_t st, const float* P, int ldp, int kp, const QOp& Q, int M, int NQ, float* C, int ldc, bool transposed,
+                        float* db) {
+  if (M <= 0 || (!C && !db)) return SLN_OK;
+  if (kp > 32) { set_error("internal: skinny backward-weight needs <= 32 small-side columns (got %d)", kp); return SLN_EINVAL; }
+  const int col_blocks = ceil_div(NQ, 128);
+  int splits = max(1, min(ceil_div(M, 32), (2 * kNumSMs) / col_blocks));
+  int rows = ceil_div(ceil_div(M, splits), 32) * 32;
+  dim3 grid(col_blocks, ceil_div(M, rows));
+  ProfScope prof(st, PROF_GEMM_BWD_W, 2.0 * (double)M * kp * NQ);
+  if (kp <= 8) k_skinny_bwd_w<8, QOp><<<grid, 128, 0, st>>>(P, ldp, kp, Q, M, NQ, C, ldc, transposed ? 1 : 0, db, rows);
+  else if (kp <= 16) k_skinny_bwd_w<16, QOp><<<grid, 128, 0, st>>>(P, ldp, kp, Q, M, NQ, C, ldc, transposed ? 1 : 0, db, rows);
+  else k_skinny_bwd_w<32, QOp><<<grid, 128, 0, st>>>(P, ldp, kp, Q, M, NQ, C, ldc, transposed ? 1 : 0, db, rows);
+  return check_launch("skinny_bwd_w");
 }
 
 // scale/shift (+mean/rstd) of an eval-mode BatchNorm from its running statistics

@@ -137,7 +137,9 @@ def composite(depth_data, images, names):
     hard = images.detach() > 0.1                                                                        # :401
     cnt = hard.sum(dim=(1, 2))
     sums = (depth_data * hard).sum(dim=(1, 2))
-    mean = sums / cnt                                                                                   # nan where the class is absent
+    # the reference's torch.mean over an empty selection is nan and is then replaced by wall_max (:411-419); dividing by
+    # max(cnt, 1) gives the same forward value after the replacement without a 0/0 in the backward pass
+    mean = sums / cnt.clamp(min=1)
     wall = names.index("wall")
     wall_depth = torch.where(hard[wall], depth_data[0], torch.full_like(depth_data[0], -float("inf")))
     wall_max = wall_depth.max().detach()
