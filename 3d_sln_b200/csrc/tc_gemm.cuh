@@ -88,16 +88,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in
-// [0,14), leading byte offset >> 4 in [16,30) (unused for swizzled K-major, 1), stride byte offset >> 4 in [32,46) =
-// 1024 B between 8-row groups, version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in [0,14), leading byte
+// offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+//   K-major tile  [rows][32 floats]: canonical ((8,n),2):((8,SBO),1) in 16-byte units — 8-row groups 1024 B apart (SBO), LBO unused;
+//                 one MMA (K = 8) reads 32 bytes of every row: the k-slice advances the start address by 32 B.
+//   MN-major tile [32 k][rows]:      TF32 MN-major operands must use SWIZZLE_128B_BASE32B (layout type 1): canonical
+//                 ((8,n),(4,k)):((1,LBO),(8,SBO)) — a 512-byte atom holds 4 k-rows of 32 consecutive rows (128 B each) and the
+//                 32-byte chunk index (address bits 5-6) is XORed with k mod 4 (bits 7-8).  Here the 8 k-atoms of a 32-row column
+//                 block are contiguous (SBO = 512 B) and column blocks follow each other (LBO = 4096 B); one MMA (K = 8) reads
+//                 two k-atoms: the k-slice advances the start address by 1024 B.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
+template <bool RC>
+__device__ __forceinline__ uint64_t make_desc_t(uint32_t tile, int kslice) {
+  return RC ? make_desc(tile + kslice * 32) : make_desc_mn(tile + kslice * 1024);
+}
 // tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits 4-5 = 1), A/B tf32 (bits 7-9, 10-12 = 2),
-// both K-major (bits 15, 16 = 0), N >> 3 in [17,23), M >> 4 in [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// a_major bit 15 / b_major bit 16 (0 = K-major, 1 = MN-major), N >> 3 in [17,23), M >> 4 in [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
 }
 
 // hi = x rounded to TF32 (10 explicit mantissa bits), round-to-nearest with ties away from zero in the magnitude: an integer
@@ -125,13 +139,12 @@ __device__ __forceinline__ void split_store1(uint32_t hi_addr, uint32_t lo_addr,
 // functor's two-phase API: fetch() issues all raw 16-byte loads of the chunk back to back (nothing depends on them, so
 // they are all in flight together), store() applies the lazy transform, splits hi/lo and writes the swizzled tiles.
 // Everything that does not change from chunk to chunk (row pointers, shared-memory offsets) is computed once in init().
-//   RC == true : storage [row][k]: thread (tid >> 3, tid & 7) owns the k-quad tid & 7 of tile rows (tid >> 3) + 32 i;
-//                8 threads cover one 128-byte row chunk (coalesced), each st.shared.v4 quarter-warp covers one full
-//                swizzle row (conflict-free).
-//   RC == false: storage [k][row]: the quad is 4 consecutive tile rows at one k.  A warp works on [16 k] x [32 rows]
-//                patches in 4 rotations j: lane (kk = lane & 3, rq = lane >> 2) reads k = 4*(((rq >> 1) + j) & 3) + kk,
-//                rows 4*rq .. 4*rq+3: 16 full 32-byte sectors per request, and the 4 scalar stores of a quad hit 32
-//                distinct banks ((k/4) ^ (row % 8) takes 8 values x 4 kk).
+//   RC == true : storage [row][k] -> K-major tile.  Thread (tid >> 3, tid & 7) owns the k-quad tid & 7 of tile rows
+//                (tid >> 3) + 32 i; 8 threads cover one 128-byte row chunk (coalesced), each st.shared.v4 quarter-warp
+//                covers one full swizzle row (conflict-free).
+//   RC == false: storage [k][row] -> MN-major tile (the tensor core transposes, not the loader).  Thread (tid >> 3, tid & 7)
+//                owns, at k-row tid >> 3, the 4 consecutive tile rows 32 i + 4 (tid & 7): again 8 threads read one 128-byte
+//                segment of a storage row and write one full 128-byte swizzle row.
 // Bounds: tile rows beyond the operand are clamped by the functor (their products are never stored); only the K padding of
 // the last chunk (CHECK == true) is zeroed.
 template <int ROWS, bool RC, class Op>
@@ -139,31 +152,18 @@ struct Loader {
   static constexpr int NV = ROWS * BK / 4 / PROD_THREADS;   // quads per thread per chunk
   static_assert(NV >= 1, "tile too small for 256 loader threads");
   float4 ra[NV], rb[NV];
-  typename Op::Tok tok[NV];
-  int col[NV];          // RC == false: clamped storage column of the quad
-  uint32_t soff[NV];    // RC == false: byte offset of (row, k) in the tile;  RC == true: soff[0] only
-  __device__ __forceinline__ void coords(int i, int tid, int& row, int& k) const {   // RC == false: tile row of quad elt 0, k
-    const int lane = tid & 31, warp = tid >> 5;
-    const int kk = lane & 3, rq = lane >> 2;
-    const int u = warp + i * (PROD_THREADS / 32);
-    const int patch = u >> 2, j = u & 3;
-    const int h = patch & 1, rb_ = patch >> 1;
-    row = rb_ * 32 + rq * 4;
-    k = 16 * h + 4 * (((rq >> 1) + j) & 3) + kk;
-  }
+  typename Op::Tok tok[RC ? NV : 1];   // RC: one token per owned tile row (fixed); !RC: the token of this chunk's k-row
+  int col[RC ? 1 : NV];                // !RC: clamped storage column of quad i
+  uint32_t soff;                       // byte offset of quad 0 inside the tile (quad i: + 4096 i)
   __device__ __forceinline__ void init(const Op& op, int row0, int tid) {
+    if (RC) soff = sw128(tid >> 3, (tid & 7) * 4);                                   // K-major SWIZZLE_128B: (row, k-quad)
+    else soff = (uint32_t)((tid >> 3) * 128 + (((((tid & 7) >> 1) ^ ((tid >> 3) & 3)) << 5) | ((tid & 1) << 4)));   // MN-major 128B_BASE32B: (k-row, row-quad)
     if (RC) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) tok[i] = op.token(row0 + (tid >> 3) + 32 * i);
-      soff[0] = sw128(tid >> 3, (tid & 7) * 4);
     } else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        int row, k;
-        coords(i, tid, row, k);
-        col[i] = op.clampc(row0 + row);
-        soff[i] = (uint32_t)(row * 128 + ((k & 3) << 2)) | ((uint32_t)(k >> 2) << 24) | ((uint32_t)(row & 7) << 28);
-      }
+      for (int i = 0; i < NV; ++i) col[i] = op.clampc(row0 + 32 * i + 4 * (tid & 7));
     }
   }
   template <bool CHECK>
@@ -174,13 +174,11 @@ struct Loader {
 #pragma unroll
       for (int i = 0; i < NV; ++i) op.fetch4(tok[i], k, ra[i], rb[i]);
     } else {
+      int k = k0 + (tid >> 3);
+      if (CHECK) k = min(k, kend - 1);
+      tok[0] = op.token(k);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        int k = k0 + (int)((soff[i] >> 24) & 15) * 4 + (int)((soff[i] >> 2) & 3);
-        if (CHECK) k = min(k, kend - 1);
-        tok[i] = op.token(k);
-        op.fetch4(tok[i], col[i], ra[i], rb[i]);
-      }
+      for (int i = 0; i < NV; ++i) op.fetch4(tok[0], col[i], ra[i], rb[i]);
     }
   }
   // (k0, kend, CHECK) must be the ones passed to the matching fetch()
@@ -194,21 +192,15 @@ struct Loader {
       for (int i = 0; i < NV; ++i) {
         float4 v = op.finish4(tok[i], kc, ra[i], rb[i]);
         if (CHECK && !valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
-        split_store4(hi_tile + soff[0] + i * 4096, lo_tile + soff[0] + i * 4096, v);
+        split_store4(hi_tile + soff + i * 4096, lo_tile + soff + i * 4096, v);
       }
     } else {
+      const bool valid = !CHECK || (k0 + (tid >> 3)) < kend;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        const uint32_t kq = (soff[i] >> 24) & 15, r7 = soff[i] >> 28, base = soff[i] & 0xffffffu;
-        float4 v = op.finish4(tok[i], col[i], ra[i], rb[i]);
-        if (CHECK) {
-          const int k = k0 + (int)kq * 4 + (int)((soff[i] >> 2) & 3);
-          if (k >= kend) v = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        split_store1(hi_tile + base + (((kq ^ (r7 + 0)) & 7) << 4), lo_tile + base + (((kq ^ (r7 + 0)) & 7) << 4), v.x);
-        split_store1(hi_tile + base + 128 + (((kq ^ (r7 + 1)) & 7) << 4), lo_tile + base + 128 + (((kq ^ (r7 + 1)) & 7) << 4), v.y);
-        split_store1(hi_tile + base + 256 + (((kq ^ (r7 + 2)) & 7) << 4), lo_tile + base + 256 + (((kq ^ (r7 + 2)) & 7) << 4), v.z);
-        split_store1(hi_tile + base + 384 + (((kq ^ (r7 + 3)) & 7) << 4), lo_tile + base + 384 + (((kq ^ (r7 + 3)) & 7) << 4), v.w);
+        float4 v = op.finish4(tok[0], col[i], ra[i], rb[i]);
+        if (CHECK && !valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        split_store4(hi_tile + soff + i * 4096, lo_tile + soff + i * 4096, v);
       }
     }
   }
@@ -389,7 +381,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
+      constexpr uint32_t idesc = make_idesc(BN, !A_RC, !B_RC);
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % S, use = c / S;
         const int seg = c / SEG_CHUNKS;
@@ -402,13 +394,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + s * L::STAGE), a_lo = a_hi + L::A_TILE, b_hi = a_hi + 2 * L::A_TILE, b_lo = b_hi + L::B_TILE;
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {               // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
-          const uint32_t o = k * 32;
+        for (int k = 0; k < BK / 8; ++k) {               // UMMA_K = 8 tf32: one 32-byte slice of every K-major row / one MN-major k-atom
           const uint32_t d_c1 = tmem_acc + (uint32_t)((NM + (k % NC)) * BN), d_c2 = tmem_acc + (uint32_t)((NM + NC + (k % NC)) * BN);
           const uint32_t d_main = tmem_acc + (uint32_t)((k % NM) * BN);
-          mma_tf32(d_c1, make_desc(a_lo + o), make_desc(b_hi + o), idesc, (!seg_first || k >= NC) ? 1u : 0u);
-          mma_tf32(d_c2, make_desc(a_hi + o), make_desc(b_lo + o), idesc, (!seg_first || k >= NC) ? 1u : 0u);
-          mma_tf32(d_main, make_desc(a_hi + o), make_desc(b_hi + o), idesc, (!seg_first || k >= NM) ? 1u : 0u);
+          mma_tf32(d_c1, make_desc_t<A_RC>(a_lo, k), make_desc_t<B_RC>(b_hi, k), idesc, (!seg_first || k >= NC) ? 1u : 0u);
+          mma_tf32(d_c2, make_desc_t<A_RC>(a_hi, k), make_desc_t<B_RC>(b_lo, k), idesc, (!seg_first || k >= NC) ? 1u : 0u);
+          mma_tf32(d_main, make_desc_t<A_RC>(a_hi, k), make_desc_t<B_RC>(b_hi, k), idesc, (!seg_first || k >= NM) ? 1u : 0u);
         }
         mma_commit(empty + s);                             // stage s may be overwritten once these MMAs retire
         if (seg_last) mma_commit(segfull);

@@ -1,0 +1,197 @@
+"""bench.py --workload render : BASELINE.json configs[2] — layout refinement through the differentiable renderer.
+
+One "step" = one refinement iteration of one scene (10 objects x 504 triangles + 160-triangle room shell = 5200 triangles,
+10400 with fill_back, 256x256): mesh_render_func forward (projection, z-buffer, 32 class masks + 29 depth planes -> [1,70,256,256]),
+the reference's multi-scale loss against a fixed target, backward to the boxes / angles, Adam.  metric = diff-render iters/s.
+The path does not shard (one scene = one sequential optimisation chain): --gpus N runs N independent replicas.
+"""
+import importlib
+import json
+import os
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+METRIC = "diff-render iters/sec 256^2 5k-tri"
+
+
+def _config(n):
+    return {"workload": "BASELINE configs[2]: scene_refine, 10 objects, 5200 triangles (10400 with fill_back), 256x256, Adam lr 2e-4 over boxes+angles, "
+                        "one rasterization per iteration (depth + 32 class masks + 29 depth planes -> [1,70,256,256])",
+            "replicas": n, "parallelism": "replicas only (one scene is one sequential chain)",
+            "l2": "working set (maps 4 MB + faces 1 MB) is far below L2; an L2 flush (256 MiB write) precedes every timed iteration of `value`"}
+
+
+def _scene(dev, seed=13):
+    meshes = importlib.import_module("3d_sln_b200.data.synthetic_meshes")
+    boxes, angles, objs = meshes.synthetic_layout(10, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    start = boxes.clone()
+    shift = (torch.rand(10, 3, generator=g) - 0.5) * 0.06          # perturbed start: the refinement has something to do
+    start[:10, :3] += shift; start[:10, 3:] += shift
+    a0 = (angles.clone() + torch.cat([torch.randn(10, generator=g) * 0.5, torch.zeros(1)])).clamp(0, 23.9)
+    return boxes.to(dev), angles.to(dev), objs, start.to(dev), a0.to(dev)
+
+
+def run(args):
+    import bench as B
+    rank, local_rank, world = B.dist_env()
+    n = max(args.gpus, 1)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    _lib = importlib.import_module("3d_sln_b200._lib")
+    lib = _lib.load()
+    refine = importlib.import_module("3d_sln_b200.models.refine")
+    dr = importlib.import_module("3d_sln_b200.models.diff_render")
+    boxes, angles, objs, start, a0 = _scene(dev, seed=13 + rank)
+    objs_l = objs.tolist()
+    with torch.no_grad():
+        target, model_ids, sizes, _ = dr.mesh_render_func([boxes[i] for i in range(11)], [angles[i] for i in range(11)], objs_l)
+    t_depth, t_labels = refine.refine_targets(target)
+    b = start.clone().requires_grad_(True)
+    a = a0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([b, a], lr=2e-4)
+    room, a_room = boxes[-1].detach(), angles[-1:].detach().float()
+
+    def iteration(bsrc, asrc):
+        bb = torch.cat([bsrc[:-1], room[None]], 0); bb.register_hook(refine.fix_grad)
+        aa = torch.cat([asrc[:-1], a_room], 0); aa.register_hook(refine.quad_grad)
+        image, _, _, size_loss = dr.mesh_render_func([bb[i] for i in range(11)], [aa[i] for i in range(11)], objs_l, model_ids, sizes)
+        loss = refine.refine_loss(image, t_depth, t_labels, size_loss)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    n0 = lib.sln_launch_count()
+    first = float(iteration(b, a).detach())
+    launches_per_iter = int(lib.sln_launch_count() - n0)
+    for _ in range(max(args.warmup, 3)):
+        iteration(b, a)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    barrier()
+    sampler = B.ClockSampler(local_rank).start() if rank == 0 else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for e0, e1 in evs:
+        flush.zero_()
+        e0.record()
+        loss = iteration(b, a)
+        e1.record()
+    barrier()
+    dev_ms = sum(x.elapsed_time(y) for x, y in evs)
+    loss_after_value_loop = float(loss.detach())
+    # e2e: the layout comes from pinned host memory every iteration and the loss goes back to the host
+    hb, ha = start.detach().cpu().pin_memory(), a0.detach().cpu().pin_memory()
+    loss_host = torch.empty(1).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        with torch.no_grad():
+            b.copy_(hb, non_blocking=True); a.copy_(ha, non_blocking=True)
+        loss = iteration(b, a)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    # roofline of the dominant kernel class (rasterizer forward): event pair around every library launch
+    prof = {}
+    if rank == 0:
+        import ctypes
+        lib.sln_prof_enable(1)
+        reps = 5
+        for _ in range(reps):
+            iteration(b, a)
+        torch.cuda.synchronize(dev)
+        for ci, cname in enumerate(B.PROF_CLASSES):
+            ms, work, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+            _lib.check(lib.sln_prof_read(ci, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(cnt)), "prof_read")
+            if cnt.value:
+                prof[cname] = dict(ms=ms.value / reps, work=work.value / reps, launches=cnt.value // reps)
+        lib.sln_prof_enable(0)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = t.tolist()
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    peaks = B.measured_peaks()
+    ms_per_step = dev_ms / args.steps
+    fwd, bwd = prof.get("raster_fwd"), prof.get("raster_bwd")
+    roofline = None
+    if fwd:
+        gbs = fwd["work"] / (fwd["ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "raster_fwd class (k_project, k_face_setup, k_raster_tiles, k_scene_sval, k_scene_class_images)",
+                    "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                    "algorithmic_bytes_per_iter": fwd["work"], "launches_per_iter": fwd["launches"], "ms_per_iter": fwd["ms"],
+                    "peak_source": peaks["source"],
+                    "note": "a 256x256 scene moves ~5 MB: the rasterizer is latency/launch-bound, not HBM-bound (SURVEY 8d); backward class: %s" % (
+                        json.dumps(bwd) if bwd else "n/a")}
+    cpu = None
+    if n == 1 and not args.no_cpu_baseline:
+        cpu = cpu_render_baseline(budget_s=25.0)
+    return {
+        "metric": METRIC, "value": n * 1e3 / ms_per_step, "unit": "iters/s", "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": _config(n), "e2e": {"value": n * args.steps / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": 11 * 6 * 4 + 11 * 4, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches_per_iter * args.steps, "launches_per_step": launches_per_iter, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "kernel_classes_ms": {k: round(v["ms"], 4) for k, v in prof.items()}, "first_loss": first, "loss_after_timed_iters": loss_after_value_loop,
+    }
+
+
+def cpu_render_baseline(budget_s=25.0):
+    """The reference's iteration on the CPU restatement of neural_renderer (oracle/raster_oracle.c, single thread): 1 depth render +
+    32 per-class rgb renders, forward and backward, on identical geometry (diff_render.py:366-431).  Bounded sample: the depth
+    pass and as many class passes as fit the budget are timed and the iteration is extrapolated to 1 + 32 passes."""
+    import numpy as np
+    from oracle import raster_oracle as ro
+    dr = importlib.import_module("3d_sln_b200.models.diff_render")
+    meshes = importlib.import_module("3d_sln_b200.data.synthetic_meshes")
+    boxes, angles, objs = meshes.synthetic_layout(10, seed=13)
+    lib = meshes.MeshLibrary()
+    v, fb, cls, kept, _ = dr.assemble_scene([boxes[i] for i in range(11)], [angles[i] for i in range(11)], objs.tolist(), lib)
+    K, R, t = dr.get_cam_mat([boxes[i] for i in range(11)])
+    fb2, cls2 = dr.cull_faces(v, fb, cls, R, t)
+    verts, faces = v[0].numpy().astype(np.float32), fb2[0].numpy().astype(np.int32)
+    orc = ro.RendererOracle(256, K[0].numpy(), R[0].numpy(), t.view(3).numpy(), 512)
+    rng = np.random.RandomState(0)
+    t0 = time.perf_counter()
+    d, ctx = orc.depth(verts, faces)
+    orc.depth_bwd(verts, faces, ctx, rng.randn(256, 256).astype(np.float32))
+    t_depth = time.perf_counter() - t0
+    t_cls, n_cls = 0.0, 0
+    while n_cls < 32 and (t_depth + t_cls) < budget_s and (n_cls < 1 or t_cls / n_cls * (n_cls + 1) + t_depth < budget_s):
+        tex = np.zeros((len(faces), 2, 2, 2, 3), np.float32)
+        tex[cls2.numpy() == n_cls] = 1.0
+        t0 = time.perf_counter()
+        img, ctx = orc.rgb(verts, faces, tex)
+        orc.rgb_bwd(verts, faces, ctx, rng.randn(3, 256, 256).astype(np.float32))
+        t_cls += time.perf_counter() - t0
+        n_cls += 1
+    per_iter = t_depth + 32 * (t_cls / max(n_cls, 1))
+    return {"value": 1.0 / per_iter, "unit": "iters/s", "cores": 1, "kind": "port",
+            "sample": "1 depth pass + %d of the 32 class passes (forward + backward, %d faces with fill_back, 256x256) timed in %.1f s and extrapolated to "
+                      "1 + 32 passes; CPU restatement of neural_renderer (the reference has no CPU renderer)" % (n_cls, 2 * len(faces), t_depth + t_cls)}
+
+
+def run_reference(args):
+    cpu = cpu_render_baseline(budget_s=60.0)
+    n = max(args.gpus, 1)
+    return {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "iters/s", "n_gpus": n, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / cpu["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": _config(n), "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
