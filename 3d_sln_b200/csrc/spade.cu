@@ -1,0 +1,467 @@
+// SPADEGenerator4 inference path (reference models/SPADE_related.py:70-85,128-149,1404-1605; eval mode, batch-sharded).
+//
+// Activations are NHWC fp32 so that every convolution is an implicit GEMM  out[pixel, cout] = sum_k A(pixel, k) W[cout, k]
+// with k = (ky, kx, cin) and cin contiguous: the A operand is the `Im2col` functor below (reflection padding is index
+// arithmetic in its row token — no padded copy), the B operand the re-packed weight matrix, and the
+// contraction runs on the tcgen05 3xTF32 engine of tc_gemm.cuh (fp32-level accuracy: SURVEY App. F shows single-pass
+// TF32/BF16 miss the 1e-4 contract by 40-300x).  The gamma and beta convolutions of a SPADE4 are ONE contraction over
+// interleaved weight rows whose epilogue (TcEpiSpade) computes lrelu(x_hat * (1 + gamma) + beta) directly: gamma and beta
+// never reach HBM (they are 61 % of the generator's FLOPs and would be 2 x C x H x W floats per SPADE4 otherwise).
+#include "../../include/sln_b200.h"
+#include "gemm.cuh"
+#include "tc_gemm.cuh"
+
+namespace sln {
+namespace {
+
+__device__ __forceinline__ int reflect(int v, int n) { return v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v); }
+
+// Virtual [B*H*W, ks*ks*C] matrix over an NHWC tensor: row = output pixel, column k = (ky*ks + kx)*C + c, reading the
+// input at the REFLECTED position (y + ky - ks/2, x + kx - ks/2)   (nn.ReflectionPad2d(1) + Conv2d(k=3, padding=0)), or the
+// pixel itself for ks == 1.  Optional lazy ReLU on load.
+struct Im2col {
+  const float* p;
+  int H, W, C, ks, rows, cols, relu, vec;
+  __device__ __forceinline__ float elem(int r, int k) const {
+    const int tap = ks == 3 ? k / C : 0, c = k - tap * C;
+    const int ky = ks == 3 ? tap / 3 : 1, kx = ks == 3 ? tap - 3 * (tap / 3) : 1;
+    const int hw = H * W, b = r / hw, rem = r - b * hw, y = rem / W, x = rem - y * W;
+    const int yy = ks == 3 ? reflect(y + ky - 1, H) : y, xx = ks == 3 ? reflect(x + kx - 1, W) : x;
+    float v = __ldg(p + ((size_t)b * hw + (size_t)yy * W + xx) * C + c);
+    return relu ? fmaxf(v, 0.f) : v;
+  }
+  __device__ __forceinline__ float at_t(int r, int k) const { return (r < rows && k < cols) ? elem(r, k) : 0.f; }
+  __device__ __forceinline__ float4 ld4(int r, int k) const {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= rows || k >= cols) return v;
+    if (vec) {   // C % 4 == 0: the quad stays inside one tap
+      const int tap = ks == 3 ? k / C : 0, c = k - tap * C;
+      const int ky = ks == 3 ? tap / 3 : 1, kx = ks == 3 ? tap - 3 * (tap / 3) : 1;
+      const int hw = H * W, b = r / hw, rem = r - b * hw, y = rem / W, x = rem - y * W;
+      const int yy = ks == 3 ? reflect(y + ky - 1, H) : y, xx = ks == 3 ? reflect(x + kx - 1, W) : x;
+      v = ldg4(p + ((size_t)b * hw + (size_t)yy * W + xx) * C + c);
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    } else {
+      v.x = elem(r, k);
+      if (k + 1 < cols) v.y = elem(r, k + 1);
+      if (k + 2 < cols) v.z = elem(r, k + 2);
+      if (k + 3 < cols) v.w = elem(r, k + 3);
+    }
+    return v;
+  }
+  // two-phase API of the tensor-core loader: the token holds the image base and the three reflected row / column offsets
+  struct Tok { const float* base; int y0, y1, y2, x0, x1, x2; };
+  __device__ __forceinline__ Tok token(int r) const {
+    r = min(r, rows - 1);
+    const int hw = H * W, b = r / hw, rem = r - b * hw, y = rem / W, x = rem - y * W;
+    Tok t;
+    t.base = p + (size_t)b * hw * C;
+    if (ks == 3) {
+      t.y0 = reflect(y - 1, H) * W; t.y1 = y * W; t.y2 = reflect(y + 1, H) * W;
+      t.x0 = reflect(x - 1, W); t.x1 = x; t.x2 = reflect(x + 1, W);
+    } else {
+      t.y0 = t.y1 = t.y2 = y * W; t.x0 = t.x1 = t.x2 = x;
+    }
+    return t;
+  }
+  __device__ __forceinline__ int clampc(int c) const { return min(c, cols - 4); }
+  __device__ __forceinline__ void fetch4(const Tok& t, int k, float4& a, float4&) const {
+    const int tap = ks == 3 ? k / C : 0, c = k - tap * C;
+    const int ky = ks == 3 ? tap / 3 : 1, kx = ks == 3 ? tap - 3 * (tap / 3) : 1;
+    const int yo = ky == 0 ? t.y0 : (ky == 1 ? t.y1 : t.y2), xo = kx == 0 ? t.x0 : (kx == 1 ? t.x1 : t.x2);
+    a = ldg4(t.base + (size_t)(yo + xo) * C + c);
+  }
+  __device__ __forceinline__ float4 finish4(const Tok&, int, float4 v, float4) const {
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    return v;
+  }
+  bool vec_ok() const { return vec != 0; }
+};
+
+Im2col make_im2col(const float* p, int B, int H, int W, int C, int ks, int relu) {
+  Im2col a;
+  a.p = p; a.H = H; a.W = W; a.C = C; a.ks = ks; a.rows = B * H * W; a.cols = ks * ks * C; a.relu = relu;
+  a.vec = (C % 4 == 0 && (uintptr_t)p % 16 == 0) ? 1 : 0;
+  return a;
+}
+
+// SPADE4 modulation epilogue (reference SPADE_related.py:139-144,1451) fused with the block's leaky_relu (:1490-1491,1504):
+// out[pix, c] = act( (x[pix, c] - mean[b]) * inv[b] * (1 + gamma) + beta ),  gamma/beta = the two halves of the tile + bias.
+struct TcEpiSpade {
+  float* out; const float* x; int C;
+  const float* bias_g; const float* bias_b;
+  const float* mean; const float* inv; int HW; float slope;
+  static constexpr bool kStats = false;
+  static constexpr bool kPaired = true;
+  __device__ __forceinline__ bool wants_stats() const { return false; }
+  __device__ __forceinline__ void apply4(int, int, int, float4, float (&)[4], float (&)[4]) const {}
+  __device__ __forceinline__ void apply_pair(int i, int c, float4 g, float4 b) const {
+    const int bi = i / HW;
+    const float m = __ldg(mean + bi), iv = __ldg(inv + bi);
+    const float4 xv = ldg4(x + (size_t)i * C + c), bg = ldg4(bias_g + c), bb = ldg4(bias_b + c);
+    float4 o;
+    o.x = fmaf((xv.x - m) * iv, 1.f + (g.x + bg.x), b.x + bb.x);
+    o.y = fmaf((xv.y - m) * iv, 1.f + (g.y + bg.y), b.y + bb.y);
+    o.z = fmaf((xv.z - m) * iv, 1.f + (g.z + bg.z), b.z + bb.z);
+    o.w = fmaf((xv.w - m) * iv, 1.f + (g.w + bg.w), b.w + bb.w);
+    o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+    o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+    *reinterpret_cast<float4*>(out + (size_t)i * C + c) = o;
+  }
+  __device__ __forceinline__ void finalize(int, double, double) const {}
+  __device__ __forceinline__ float* partial() const { return nullptr; }
+  __device__ __forceinline__ unsigned* counter() const { return nullptr; }
+};
+
+// direct fallback of the modulation for channel counts the paired tiles cannot hold (2C < 32: reduced test models only)
+__global__ void k_modulate_direct(const Im2col A, const float* __restrict__ Wg, const float* __restrict__ Wb, const float* __restrict__ bg,
+                                  const float* __restrict__ bb, int C, const float* __restrict__ x, const float* __restrict__ mean,
+                                  const float* __restrict__ inv, int HW, float slope, float* out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= A.rows * C) return;
+  const int i = idx / C, c = idx - i * C;
+  float g = __ldg(bg + c), b = __ldg(bb + c);
+  for (int k = 0; k < A.cols; ++k) {
+    const float a = A.at_t(i, k);
+    g = fmaf(a, __ldg(Wg + (size_t)c * A.cols + k), g);
+    b = fmaf(a, __ldg(Wb + (size_t)c * A.cols + k), b);
+  }
+  const int bi = i / HW;
+  float o = fmaf((__ldg(x + idx) - __ldg(mean + bi)) * __ldg(inv + bi), 1.f + g, b);
+  out[idx] = o > 0.f ? o : o * slope;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm2D statistics
+// per sample: mean and 1 / (unbiased std + eps) over C*H*W (reference :139-144).  fp64 accumulation.
+__global__ void __launch_bounds__(256) k_ln_partial(const float* __restrict__ x, long long n, double* acc) {
+  const int b = blockIdx.y;
+  const float* xb = x + (size_t)b * n;
+  double s = 0.0, q = 0.0;
+  const long long n4 = n / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xb) + i);
+    s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+    q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; ++i) { s += xb[i]; q += (double)xb[i] * xb[i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  __shared__ double ss[8], sq[8];
+  if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sq[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S = 0.0, Q = 0.0;
+    for (int w = 0; w < 8; ++w) { S += ss[w]; Q += sq[w]; }
+    atomicAdd(acc + 2 * b, S);
+    atomicAdd(acc + 2 * b + 1, Q);
+  }
+}
+__global__ void k_ln_final(const double* acc, int B, long long n, float eps, float* mean, float* inv) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double m = acc[2 * b] / (double)n;
+  double var = (acc[2 * b + 1] - (double)n * m * m) / (double)(n > 1 ? n - 1 : 1);
+  if (var < 0.0) var = 0.0;
+  mean[b] = (float)m;
+  inv[b] = (float)(1.0 / (sqrt(var) + (double)eps));
+}
+
+// ------------------------------------------------------------------------------------------------ segmentation features
+// SPADE4 part 2 up to the concat (reference :1444-1447): resize the map to (h, w) [bilinear, align_corners=False; or the
+// nearest-neighbour map seg_1 that head_0 receives, :1579], depth channel -> reflect-pad 3x3 conv (1 -> nd) + LeakyReLU(0.01),
+// concatenated with the nc-1 label channels -> NHWC [B, h, w, nd + nc - 1].
+__device__ __forceinline__ float seg_sample(const float* __restrict__ ch, int S, int h, int w, int mode, int y, int x) {
+  if (mode == 1) {   // nearest (torch: min(floor(dst * scale), S - 1), scale = S / size)
+    const int sy = min((int)floorf((float)y * ((float)S / (float)h)), S - 1), sx = min((int)floorf((float)x * ((float)S / (float)w)), S - 1);
+    return __ldg(ch + (size_t)sy * S + sx);
+  }
+  if (h == S && w == S) return __ldg(ch + (size_t)y * S + x);
+  const float fy = fmaxf(((float)S / (float)h) * ((float)y + 0.5f) - 0.5f, 0.f), fx = fmaxf(((float)S / (float)w) * ((float)x + 0.5f) - 0.5f, 0.f);
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < S - 1 ? 1 : 0), x1 = x0 + (x0 < S - 1 ? 1 : 0);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float v00 = __ldg(ch + (size_t)y0 * S + x0), v01 = __ldg(ch + (size_t)y0 * S + x1);
+  const float v10 = __ldg(ch + (size_t)y1 * S + x0), v11 = __ldg(ch + (size_t)y1 * S + x1);
+  return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+}
+__global__ void __launch_bounds__(128) k_seg_features(const float* __restrict__ seg, int B, int nc, int S, int mode, int h, int w,
+                                                      const float* __restrict__ dw, const float* __restrict__ db, int nd, float* out) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= B * h * w) return;
+  const int b = pix / (h * w), rem = pix - b * h * w, y = rem / w, x = rem - y * w;
+  const float* sb = seg + (size_t)b * nc * S * S;
+  float d[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) d[t] = seg_sample(sb, S, h, w, mode, reflect(y + t / 3 - 1, h), reflect(x + t % 3 - 1, w));
+  float* o = out + (size_t)pix * (nd + nc - 1);
+  for (int j = 0; j < nd; ++j) {
+    float acc = __ldg(db + j);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc = fmaf(d[t], __ldg(dw + j * 9 + t), acc);
+    o[j] = acc > 0.f ? acc : acc * 0.01f;
+  }
+  for (int c = 1; c < nc; ++c) o[nd + c - 1] = seg_sample(sb + (size_t)c * S * S, S, h, w, mode, y, x);
+}
+
+// ------------------------------------------------------------------------------------------------ 2x upsampling (NHWC)
+// nn.Upsample(scale_factor=2, mode='nearest' | 'bilinear' [align_corners=False])   (reference :1544-1545)
+__global__ void k_upsample2x(const float* __restrict__ x, int B, int H, int W, int C, int bilinear, float* out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4n = C / 4;
+  const long long total = (long long)B * 2 * H * 2 * W * c4n;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % c4n);
+  long long pix = idx / c4n;
+  const int ox = (int)(pix % (2 * W)); pix /= 2 * W;
+  const int oy = (int)(pix % (2 * H));
+  const int b = (int)(pix / (2 * H));
+  const float* xb = x + (size_t)b * H * W * C + c4 * 4;
+  float4 v;
+  if (!bilinear) {
+    v = ldg4(xb + ((size_t)(oy >> 1) * W + (ox >> 1)) * C);
+  } else {
+    const float fy = fmaxf(0.5f * ((float)oy + 0.5f) - 0.5f, 0.f), fx = fmaxf(0.5f * ((float)ox + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)fy, x0 = (int)fx, y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float4 a = ldg4(xb + ((size_t)y0 * W + x0) * C), bq = ldg4(xb + ((size_t)y0 * W + x1) * C);
+    const float4 c = ldg4(xb + ((size_t)y1 * W + x0) * C), dq = ldg4(xb + ((size_t)y1 * W + x1) * C);
+    v.x = (1.f - ly) * ((1.f - lx) * a.x + lx * bq.x) + ly * ((1.f - lx) * c.x + lx * dq.x);
+    v.y = (1.f - ly) * ((1.f - lx) * a.y + lx * bq.y) + ly * ((1.f - lx) * c.y + lx * dq.y);
+    v.z = (1.f - ly) * ((1.f - lx) * a.z + lx * bq.z) + ly * ((1.f - lx) * c.z + lx * dq.z);
+    v.w = (1.f - ly) * ((1.f - lx) * a.w + lx * bq.w) + ly * ((1.f - lx) * c.w + lx * dq.w);
+  }
+  *reinterpret_cast<float4*>(out + ((size_t)b * 4 * H * W + (size_t)oy * 2 * W + ox) * C + c4 * 4) = v;
+}
+
+// ------------------------------------------------------------------------------------------------ squeeze-excite + residual
+// SEBlock2 (reference :81-85, reduction 8) and the block's residual add (:1493).
+__global__ void __launch_bounds__(256) k_se_pool(const float* __restrict__ dx, int HW, int C, int rows_per, float* partial) {
+  const int b = blockIdx.y, chunk = blockIdx.x, nch = gridDim.x;
+  const int r0 = chunk * rows_per, r1 = min(HW, r0 + rows_per);
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = r0; r < r1; ++r) {
+      const float4 v = ldg4(dx + ((size_t)b * HW + r) * C + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(partial + ((size_t)b * nch + chunk) * C + c) = acc;
+  }
+}
+__global__ void __launch_bounds__(256) k_se_fc(const float* __restrict__ partial, int nch, int HW, int C, const float* __restrict__ W1,
+                                               const float* __restrict__ W2, int Ch, float* svec) {
+  extern __shared__ float sm[];   // pooled [C] | hidden [Ch]
+  float* pooled = sm;
+  float* hidden = sm + C;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < nch; ++k) s += partial[((size_t)b * nch + k) * C + c];
+    pooled[c] = s / (float)HW;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = warp; j < Ch; j += blockDim.x >> 5) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s = fmaf(__ldg(W1 + (size_t)j * C + c), pooled[c], s);
+    s = warp_sum(s);
+    if (lane == 0) hidden[j] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < Ch; ++j) s = fmaf(__ldg(W2 + (size_t)c * Ch + j), hidden[j], s);
+    svec[(size_t)b * C + c] = 1.f / (1.f + expf(-s));
+  }
+}
+__global__ void k_se_apply(const float* __restrict__ dx, const float* __restrict__ xs, const float* __restrict__ svec, long long n4, int HWC4, int C4,
+                           float* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int b = (int)(i / HWC4), c4 = (int)(i % C4);
+  const float4 d = __ldg(reinterpret_cast<const float4*>(dx) + i), s = __ldg(reinterpret_cast<const float4*>(svec) + (size_t)b * C4 + c4);
+  const float4 r = __ldg(reinterpret_cast<const float4*>(xs) + i);
+  reinterpret_cast<float4*>(out)[i] = make_float4(fmaf(d.x, s.x, r.x), fmaf(d.y, s.y, r.y), fmaf(d.z, s.z, r.z), fmaf(d.w, s.w, r.w));
+}
+
+// ------------------------------------------------------------------------------------------------ conv_img + tanh
+// leaky_relu(x, 0.2) -> Conv2d(nf, 3, 5, padding=2 [zeros]) -> tanh (reference :1602-1603); NHWC in, NCHW out.  N = 3 is far
+// too narrow for tensor-core tiles: one thread per pixel, weights in shared memory (broadcast reads).
+template <int MAXC>
+__global__ void __launch_bounds__(128) k_to_rgb(const float* __restrict__ x, int B, int H, int W, int Cin, const float* __restrict__ Wt,
+                                                const float* __restrict__ bias, int Cout, int ks, float slope, float* pre, float* out) {
+  extern __shared__ float s_w[];   // [ks*ks*Cin][MAXC]
+  const int K = ks * ks * Cin;
+  for (int e = threadIdx.x; e < K * MAXC; e += blockDim.x) {
+    const int k = e / MAXC, co = e - k * MAXC;
+    s_w[e] = co < Cout ? __ldg(Wt + (size_t)co * K + k) : 0.f;
+  }
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= B * H * W) return;
+  const int b = pix / (H * W), rem = pix - b * H * W, y = rem / W, xq = rem - y * W;
+  float acc[MAXC];
+#pragma unroll
+  for (int co = 0; co < MAXC; ++co) acc[co] = co < Cout ? __ldg(bias + co) : 0.f;
+  const int pad = ks / 2;
+  for (int ky = 0; ky < ks; ++ky) {
+    const int yy = y + ky - pad;
+    if (yy < 0 || yy >= H) continue;
+    for (int kx = 0; kx < ks; ++kx) {
+      const int xx = xq + kx - pad;
+      if (xx < 0 || xx >= W) continue;
+      const float* src = x + ((size_t)b * H * W + (size_t)yy * W + xx) * Cin;
+      const float* wk = s_w + (size_t)((ky * ks + kx) * Cin) * MAXC;
+      for (int c = 0; c < Cin; c += 4) {
+        float4 v = ldg4(src + c);
+        v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+        v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+#pragma unroll
+        for (int co = 0; co < MAXC; ++co)
+          acc[co] = fmaf(v.x, wk[(c + 0) * MAXC + co], fmaf(v.y, wk[(c + 1) * MAXC + co], fmaf(v.z, wk[(c + 2) * MAXC + co], fmaf(v.w, wk[(c + 3) * MAXC + co], acc[co]))));
+      }
+    }
+  }
+  for (int co = 0; co < Cout; ++co) {
+    const size_t o = ((size_t)b * Cout + co) * H * W + (size_t)y * W + xq;
+    if (pre) pre[o] = acc[co];
+    out[o] = tanhf(acc[co]);
+  }
+}
+
+int check_img(int64_t B, int64_t H, int64_t W, int64_t C) {
+  SLN_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && C >= 1 && B * H * W < (1ll << 31) && B * H * W * C < (1ll << 40), "image extents out of range");
+  return SLN_OK;
+}
+
+}  // namespace
+}  // namespace sln
+
+using namespace sln;
+
+extern "C" {
+
+int sln_spade_conv(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, const float* Wp, const float* bias,
+                   int64_t Cout, float* out, void* stream) {
+  SLN_TRY(check_img(B, H, W, Cin));
+  SLN_CHECK_ARG(x && Wp && out && Cout >= 1, "null pointer");
+  SLN_CHECK_ARG(ks == 1 || ks == 3, "kernel size must be 1 or 3 (reflection-padded)");
+  SLN_CHECK_ARG(ks == 1 || (H >= 2 && W >= 2), "reflection padding needs at least 2 rows and columns");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = (int)(B * H * W), N = (int)Cout, K = (int)(ks * ks * Cin);
+  Im2col A = make_im2col(x, (int)B, (int)H, (int)W, (int)Cin, ks, relu_in);
+  MatView Wv = make_view(Wp, K, N, K);
+  EpiStore epi; memset(&epi, 0, sizeof(epi));
+  epi.C = out; epi.ldc = N; epi.bias = bias;
+  if (tc::tc_eligible(M, N, K) && A.vec_ok() && Wv.vec_ok()) {
+    tc::TcEpiStore te{out, N, bias, epi.fin};
+    return tc::launch_tc<true, true>(st, A, Wv, te, M, N, K, false, "spade_conv_tc", PROF_SPADE_CONV);
+  }
+  return launch_gemm<true, true>(st, A, Wv, epi, M, N, K, false, "spade_conv", PROF_SPADE_CONV);
+}
+
+int sln_spade_modulate(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* bias_g, const float* bias_b,
+                       int64_t C, int32_t pair, const float* x, const float* mean, const float* inv, float slope, float* out, void* stream) {
+  SLN_TRY(check_img(B, H, W, Ca));
+  SLN_CHECK_ARG(actv && Wgb && bias_g && bias_b && x && mean && inv && out, "null pointer");
+  SLN_CHECK_ARG(H >= 2 && W >= 2 && C >= 1 && pair >= 2 && (2 * C) % pair == 0, "bad modulation shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = (int)(B * H * W), N = (int)(2 * C), K = (int)(9 * Ca);
+  Im2col A = make_im2col(actv, (int)B, (int)H, (int)W, (int)Ca, 3, 1);   // ReLU of mlp_shared applied on load
+  MatView Wv = make_view(Wgb, K, N, K);
+  const bool tc_ok = (pair == 32 || pair == 64 || pair == 128) && C % 4 == 0 && A.vec_ok() && Wv.vec_ok() && ((uintptr_t)x % 16 == 0) &&
+                     ((uintptr_t)out % 16 == 0) && ((uintptr_t)bias_g % 16 == 0) && ((uintptr_t)bias_b % 16 == 0);
+  ProfScope prof(st, PROF_SPADE_CONV, 2.0 * (double)M * N * K);
+  if (tc_ok) {
+    TcEpiSpade te{out, x, (int)C, bias_g, bias_b, mean, inv, (int)(H * W), slope};
+    tc::TcChoice ch{pair, 1, ceil_div(K, tc::BK) * tc::BK};
+    int rc;
+    if (pair == 128) rc = tc::launch_tc_bn<128, true, true>(st, A, Wv, te, M, N, K, ch);
+    else if (pair == 64) rc = tc::launch_tc_bn<64, true, true>(st, A, Wv, te, M, N, K, ch);
+    else rc = tc::launch_tc_bn<32, true, true>(st, A, Wv, te, M, N, K, ch);
+    if (rc != SLN_OK) return rc;
+    return check_launch("spade_modulate_tc");
+  }
+  // interleaved weight rows: tile t = [gamma of channels t*half .. | beta of the same]; the direct kernel needs them per channel
+  SLN_CHECK_ARG(pair == 2 * C, "the direct modulation fallback expects a single pair tile (pair == 2C)");
+  const long long total = (long long)M * C;
+  k_modulate_direct<<<(int)ceil_div64(total, 256), 256, 0, st>>>(A, Wgb, Wgb + (size_t)C * K, bias_g, bias_b, (int)C, x, mean, inv, (int)(H * W), slope, out);
+  return check_launch("spade_modulate_direct");
+}
+
+int sln_spade_ln_stats(const float* x, int64_t B, int64_t n_per_sample, float eps, void* scratch, float* mean, float* inv, void* stream) {
+  SLN_CHECK_ARG(x && scratch && mean && inv && B >= 1 && B <= 65535 && n_per_sample >= 1, "bad argument");
+  SLN_CHECK_ARG((uintptr_t)x % 16 == 0 && (uintptr_t)scratch % 8 == 0 && n_per_sample % 4 == 0, "LayerNorm statistics need 16-byte aligned samples");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(st, PROF_SPADE_MISC, 4.0 * (double)B * n_per_sample);
+  SLN_CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * B, st));
+  int chunks = (int)max((int64_t)1, min(ceil_div64(n_per_sample / 4, 256 * 8), (int64_t)(4 * kNumSMs) / B + 1));
+  k_ln_partial<<<dim3(chunks, (unsigned)B), 256, 0, st>>>(x, n_per_sample, (double*)scratch);
+  SLN_TRY(check_launch("ln_partial"));
+  k_ln_final<<<ceil_div((int)B, 128), 128, 0, st>>>((const double*)scratch, (int)B, n_per_sample, eps, mean, inv);
+  return check_launch("ln_final");
+}
+
+int sln_spade_seg_features(const float* seg, int64_t B, int32_t nc, int32_t S, int32_t mode, int64_t h, int64_t w, const float* dw, const float* db,
+                           int32_t nd, float* out, void* stream) {
+  SLN_TRY(check_img(B, h, w, nd + nc - 1));
+  SLN_CHECK_ARG(seg && dw && db && out && nc >= 2 && S >= 1 && (mode == 0 || mode == 1) && h >= 2 && w >= 2 && nd >= 1, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = (int)(B * h * w);
+  ProfScope prof(st, PROF_SPADE_MISC, 4.0 * P * (double)(nd + nc - 1));
+  k_seg_features<<<ceil_div(P, 128), 128, 0, st>>>(seg, (int)B, nc, S, mode, (int)h, (int)w, dw, db, nd, out);
+  return check_launch("seg_features");
+}
+
+int sln_spade_upsample2x(const float* x, int64_t B, int64_t H, int64_t W, int64_t C, int32_t bilinear, float* out, void* stream) {
+  SLN_TRY(check_img(B, 2 * H, 2 * W, C));
+  SLN_CHECK_ARG(x && out && C % 4 == 0, "upsample2x needs C % 4 == 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)B * 4 * H * W * (C / 4);
+  ProfScope prof(st, PROF_SPADE_MISC, 20.0 * (double)total);
+  k_upsample2x<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(x, (int)B, (int)H, (int)W, (int)C, bilinear, out);
+  return check_launch("upsample2x");
+}
+
+int sln_spade_se_residual(const float* dx, const float* xs, int64_t B, int64_t H, int64_t W, int64_t C, const float* W1, const float* W2, int32_t Ch,
+                          void* scratch, size_t scratch_bytes, float* out, void* stream) {
+  SLN_TRY(check_img(B, H, W, C));
+  SLN_CHECK_ARG(dx && xs && W1 && W2 && scratch && out && C % 4 == 0 && Ch >= 1, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = (int)(H * W);
+  int nch = min(HW, 64);
+  int rows_per = ceil_div(HW, nch);
+  nch = ceil_div(HW, rows_per);
+  const size_t need = ((size_t)B * nch * C + (size_t)B * C) * sizeof(float);
+  SLN_CHECK_ARG(scratch_bytes >= need && (uintptr_t)scratch % 16 == 0, "SE scratch too small (%zu < %zu bytes) or misaligned", scratch_bytes, need);
+  float* partial = (float*)scratch;
+  float* svec = partial + (size_t)B * nch * C;
+  ProfScope prof(st, PROF_SPADE_MISC, 16.0 * (double)B * HW * C);
+  k_se_pool<<<dim3(nch, (unsigned)B), 256, 0, st>>>(dx, HW, (int)C, rows_per, partial);
+  SLN_TRY(check_launch("se_pool"));
+  k_se_fc<<<(unsigned)B, 256, (size_t)(C + Ch) * sizeof(float), st>>>(partial, nch, HW, (int)C, W1, W2, Ch, svec);
+  SLN_TRY(check_launch("se_fc"));
+  const long long n4 = (long long)B * HW * (C / 4);
+  k_se_apply<<<(unsigned)ceil_div64(n4, 256), 256, 0, st>>>(dx, xs, svec, n4, HW * (int)(C / 4), (int)(C / 4), out);
+  return check_launch("se_apply");
+}
+
+int sln_spade_to_rgb(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const float* Wt, const float* bias, int32_t Cout, int32_t ks,
+                     float slope, float* pre, float* out, void* stream) {
+  SLN_TRY(check_img(B, H, W, Cin));
+  SLN_CHECK_ARG(x && Wt && bias && out && Cout >= 1 && Cout <= 4 && (ks & 1) && Cin % 4 == 0, "to_rgb supports <= 4 output channels, odd kernels, Cin % 4 == 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)ks * ks * Cin * 4 * sizeof(float);
+  SLN_CHECK_ARG(smem <= 200 * 1024, "to_rgb weights do not fit shared memory");
+  static bool configured = false;
+  if (!configured) {
+    SLN_CUDA_TRY(cudaFuncSetAttribute(k_to_rgb<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  const int P = (int)(B * H * W);
+  ProfScope prof(st, PROF_SPADE_CONV, 2.0 * (double)P * ks * ks * Cin * Cout);
+  k_to_rgb<4><<<ceil_div(P, 128), 128, smem, st>>>(x, (int)B, (int)H, (int)W, (int)Cin, Wt, bias, Cout, ks, slope, pre, out);
+  return check_launch("to_rgb");
+}
+
+}  // extern "C"

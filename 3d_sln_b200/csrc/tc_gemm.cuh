@@ -214,6 +214,7 @@ struct Loader {
 struct TcEpiStore {   // C = acc + bias (+ BatchNorm batch statistics)       reference graph.py:12-15
   float* C; int ldc; const float* bias; BnFwdFin fin;
   static constexpr bool kStats = true;
+  static constexpr bool kPaired = false;
   __device__ __forceinline__ bool wants_stats() const { return fin.enabled != 0; }
   __device__ __forceinline__ void apply4(int i, int j, int nvalid, float4 a, float (&s1)[4], float (&s2)[4]) const {
     float v[4] = {a.x, a.y, a.z, a.w};
@@ -241,6 +242,7 @@ struct TcEpiMaskReduce {   // G = relu_mask(yprev) ? (acc + add) : 0  + BN-backw
   float* G; int ldg; const float* add; int ldadd; const float* yprev; int ldy;
   const float* scale; const float* shift; const float* mean; const float* rstd; BnBwdFin fin;
   static constexpr bool kStats = true;
+  static constexpr bool kPaired = false;
   __device__ __forceinline__ bool wants_stats() const { return true; }
   __device__ __forceinline__ void apply4(int i, int j, int nvalid, float4 a, float (&s1)[4], float (&s2)[4]) const {
     float d[4] = {a.x, a.y, a.z, a.w};
@@ -268,6 +270,7 @@ struct TcEpiMaskReduce {   // G = relu_mask(yprev) ? (acc + add) : 0  + BN-backw
 struct TcEpiAtomic {   // C += acc (split-K weight gradients, RED.ADD)
   float* C; int ldc;
   static constexpr bool kStats = false;
+  static constexpr bool kPaired = false;
   __device__ __forceinline__ bool wants_stats() const { return false; }
   __device__ __forceinline__ void apply4(int i, int j, int nvalid, float4 a, float (&s1)[4], float (&s2)[4]) const {
     float* dst = C + (size_t)i * ldc + j;
@@ -497,7 +500,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   const int jcol = n0 + cq * 4;
   const int nvalid = min(4, max(0, N - jcol));
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-  if (nvalid > 0 && warp < PROD_WARPS) {
+  if constexpr (Epi::kPaired) {
+    // paired tiles: columns [0, BN/2) and [BN/2, BN) of a tile belong to the SAME BN/2 output channels (gamma | beta of a SPADE
+    // modulation); a lane takes 4 channels of one row from both halves
+    constexpr int HB = BN / 2, LPR2 = HB / 4, RPP2 = 32 / LPR2;
+    const int cq2 = lane % LPR2, rsub2 = lane / LPR2;
+    const int ch = n0 / 2 + cq2 * 4;
+    if (warp < PROD_WARPS && 2 * ch < N) {
+      for (int r = warp * RPP2 + rsub2; r < BM; r += PROD_WARPS * RPP2) {
+        if (m0 + r >= M) break;
+        float4 a = *reinterpret_cast<const float4*>(outs + (size_t)r * L::OUT_LD + cq2 * 4);
+        float4 b = *reinterpret_cast<const float4*>(outs + (size_t)r * L::OUT_LD + HB + cq2 * 4);
+        epi.apply_pair(m0 + r, ch, a, b);
+      }
+    }
+  } else if (nvalid > 0 && warp < PROD_WARPS) {
     for (int r = warp * RPP + rsub; r < BM; r += PROD_WARPS * RPP) {
       if (m0 + r >= M) break;
       float4 a = *reinterpret_cast<const float4*>(outs + (size_t)r * L::OUT_LD + cq * 4);

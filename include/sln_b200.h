@@ -198,6 +198,42 @@ int sln_scene_classes_bwd(const void* ws, int64_t V, int64_t F, int32_t fill_bac
                           const int32_t* face_index_map, const int32_t* face_cls, int32_t n_cls, const float* sval,
                           const float* grad_class_images_internal, float* grad_faces, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ SPADE generator
+ * Inference path of SPADEGenerator4 (reference models/SPADE_related.py:1507-1605, instantiated at testing/test_SPADE_shade.py:9).
+ * Activations are NHWC fp32; weights are packed by the caller ONCE per weight version: convolution kernels as
+ * [Cout][ky][kx][Cin], spectral norm folded (W / (u^T W v), eval mode).
+ *
+ * sln_spade_conv        ReflectionPad2d(ks/2) + Conv2d(Cin, Cout, ks, padding=0) (ks = 3; SPADE_related.py:1429-1436,1472-1474) or a
+ *                       1x1 convolution / nn.Linear (ks = 1; conv_s :1476, fc :1521) as an implicit GEMM; relu_in != 0 applies
+ *                       ReLU to the input on load; bias may be NULL.  x [B,H,W,Cin] -> out [B,H,W,Cout].
+ * sln_spade_modulate    the gamma AND beta convolutions of one SPADE4 (:1448-1449) as ONE contraction plus the modulation
+ *                       out = act((x - mean[b]) * inv[b] * (1 + gamma) + beta) (:1451; act = leaky_relu(slope), slope 1 = none):
+ *                       Wgb [2C][9*Ca] holds, per tile of `pair` rows, the gamma rows of pair/2 channels followed by the beta
+ *                       rows of the same channels; gamma / beta are never written to memory.
+ * sln_spade_ln_stats    LayerNorm2D(affine=False) statistics (:139-144): per sample mean and 1/(unbiased std + eps) over
+ *                       n_per_sample = C*H*W values; scratch >= 16*B bytes.
+ * sln_spade_seg_features  SPADE4 part 2 up to the concat (:1444-1447): resize the NCHW map seg [B,nc,S,S] to (h,w) (mode 0 =
+ *                       bilinear align_corners=False, mode 1 = the nearest-neighbour map head_0 receives, :1579), depth channel
+ *                       -> reflect-padded 3x3 conv to nd channels + LeakyReLU(0.01), concatenated with the nc-1 label channels
+ *                       -> NHWC [B,h,w,nd+nc-1].
+ * sln_spade_upsample2x  nn.Upsample(scale_factor=2, nearest | bilinear) (:1544-1545) on NHWC.
+ * sln_spade_se_residual SEBlock2 (:81-85; W1 [Ch][C], W2 [C][Ch], no biases) on dx, then out = xs + dx * s (:1493);
+ *                       scratch >= 4*(B*min(HW,64)*C + B*C) bytes, 16-byte aligned.
+ * sln_spade_to_rgb      leaky_relu(slope) -> Conv2d(Cin, Cout <= 4, ks, zero padding ks/2) -> tanh (:1602-1603); NHWC in, NCHW
+ *                       out; `pre` (optional) receives the pre-tanh values. */
+int sln_spade_conv(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, const float* Wp, const float* bias,
+                   int64_t Cout, float* out, void* stream);
+int sln_spade_modulate(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* bias_g, const float* bias_b,
+                       int64_t C, int32_t pair, const float* x, const float* mean, const float* inv, float slope, float* out, void* stream);
+int sln_spade_ln_stats(const float* x, int64_t B, int64_t n_per_sample, float eps, void* scratch, float* mean, float* inv, void* stream);
+int sln_spade_seg_features(const float* seg, int64_t B, int32_t nc, int32_t S, int32_t mode, int64_t h, int64_t w, const float* dw, const float* db,
+                           int32_t nd, float* out, void* stream);
+int sln_spade_upsample2x(const float* x, int64_t B, int64_t H, int64_t W, int64_t C, int32_t bilinear, float* out, void* stream);
+int sln_spade_se_residual(const float* dx, const float* xs, int64_t B, int64_t H, int64_t W, int64_t C, const float* W1, const float* W2, int32_t Ch,
+                          void* scratch, size_t scratch_bytes, float* out, void* stream);
+int sln_spade_to_rgb(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, const float* Wt, const float* bias, int32_t Cout, int32_t ks,
+                     float slope, float* pre, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
