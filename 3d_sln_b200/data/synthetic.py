@@ -82,3 +82,20 @@ def fixture_graph():
     angles = torch.tensor([0, 18, 6, 12, 12, 0])
     attributes = torch.zeros(6, dtype=torch.long)
     return objs, triples, boxes, angles, attributes
+
+
+def shard_batch(batch, rank, world):
+    """Scene-shard a collated batch (the 8-tuple of synthetic_batch / suncg_collate_fn, data/suncg_dataset.py:295-337) for data
+    parallelism: rank r keeps a contiguous block of scenes; the batched graph is block-diagonal (no edge crosses scenes,
+    :318-325), so the shard is self-contained once node ids are re-based.  -> (objs, triples, boxes, angles, attributes)."""
+    _, objs, boxes, triples, angles, attrs, o2i, t2i = batch
+    n_scenes = int(o2i.max().item()) + 1
+    per = (n_scenes + world - 1) // world
+    lo, hi = rank * per, min(n_scenes, (rank + 1) * per)
+    om = (o2i >= lo) & (o2i < hi)
+    tm = (t2i >= lo) & (t2i < hi)
+    first = int(torch.nonzero(om)[0]) if om.any() else 0
+    tr = triples[tm].clone()
+    tr[:, 0] -= first
+    tr[:, 2] -= first
+    return objs[om], tr, boxes[om], angles[om], attrs[om]
