@@ -15,6 +15,8 @@
 // TMA is not used for the operands because every operand needs a per-element transform (gather, BN, hi/lo split) between
 // global memory and the tensor core; the stores are laid out so that each st.shared.v4 phase covers one full 128-byte row.
 #pragma once
+#include <stdlib.h>
+
 #include "gemm.cuh"
 
 namespace sln {
@@ -347,6 +349,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
   const int nchunks = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
   TC_TRACE(0);
+  // Programmatic dependent launch: let the next kernel of the stream start its prologue (TMEM allocation, barrier set-up) on idle
+  // SMs while this grid runs; that kernel's own griddepcontrol.wait (below) orders its first global read after our last write.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr int NM = 2;                       // hi*hi chains (even / odd k-slices)
   constexpr int NC = BN >= 128 ? 1 : 2;       // chains per cross term
   constexpr int NREG = NM + 2 * NC;
@@ -367,6 +372,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // everything above overlapped the previous kernel's tail; its results are visible from here on
   TC_TRACE(1);
 
   const int quad = warp & 3, half = (warp >> 2) & 1;    // TMEM lane quadrant (fixed by warp id % 4), column half
@@ -557,6 +563,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
 }
 
 // ---------------------------------------------------------------- host side
+inline bool pdl_enabled() {   // env SLN_PDL=0 disables programmatic dependent launch (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SLN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 struct TcChoice { int bn, splits, kchunk; };
 
 inline TcChoice pick_tc(int M, int N, int K, bool allow_split) {
@@ -602,8 +614,20 @@ int launch_tc_bn(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, in
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(tc_gemm, %d B smem) failed: %s", bytes, cudaGetErrorString(e)); return SLN_ECUDA; }
     configured = true;
   }
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM), c.splits);
-  kern<<<grid, THREADS, bytes, st>>>(A, B, epi, M, N, K, c.kchunk);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ceil_div(N, BN), ceil_div(M, BM), c.splits);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int kchunk = c.kchunk;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, A, B, epi, M, N, K, kchunk);
+  if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(tc_gemm) failed: %s", cudaGetErrorString(e)); return SLN_ECUDA; }
   return SLN_OK;
 }
 

@@ -242,7 +242,18 @@ struct NodeGatherSrc {  // gradient w.r.t. obj_vecs [O,D] from d cat [T,3D]: tra
   __device__ __forceinline__ float at(int o, int c) const {
     int b = __ldg(row_ptr + o), e = __ldg(row_ptr + o + 1);
     float acc = 0.f;
-    for (int k = b; k < e; ++k) {
+    int k = b;
+    for (; k + 8 <= e; k += 8) {   // 8 independent (entry -> row) load chains in flight, summed in CSR order
+      int en[8];
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) en[u] = __ldg(ent + k + u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(dcat + (size_t)(en[u] & ((1 << 30) - 1)) * ld + ((en[u] >> 30) ? 2 * D + c : c));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; k < e; ++k) {
       int en = __ldg(ent + k);
       int t = en & ((1 << 30) - 1);
       acc += __ldg(dcat + (size_t)t * ld + ((en >> 30) ? 2 * D + c : c));
@@ -278,16 +289,26 @@ __global__ void __launch_bounds__(512) k_prep(const Src src, const ActInfo act, 
     float sc = 1.f, sh = 0.f, mu = 0.f, rs = 0.f;
     if (act.has_act && act.scale) { sc = __ldg(act.scale + j); sh = __ldg(act.shift + j); }
     if (act.has_act && act.mean) { mu = __ldg(act.mean + j); rs = __ldg(act.rstd + j); }
-    for (int i = r0 + threadIdx.y; i < r1; i += 4) {
-      float d = src.at(i, j);
-      if (act.has_act) {
-        float y = __ldg(act.y + (size_t)i * act.ldy + j);
-        float g = fmaf(y, sc, sh) > 0.f ? d : 0.f;
-        G[(size_t)i * ldg + j] = g;
-        s1 += g;
-        s2 = fmaf(g, (y - mu) * rs, s2);
-      } else {
-        G[(size_t)i * ldg + j] = d;
+    for (int i = r0 + threadIdx.y; i < r1; i += 16) {   // 4 rows per trip: their (dependent) load chains overlap
+      float d[4], y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ii = i + 4 * u;
+        d[u] = ii < r1 ? src.at(ii, j) : 0.f;
+        y[u] = (ii < r1 && act.has_act) ? __ldg(act.y + (size_t)ii * act.ldy + j) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ii = i + 4 * u;
+        if (ii >= r1) break;
+        if (act.has_act) {
+          float g = fmaf(y[u], sc, sh) > 0.f ? d[u] : 0.f;
+          G[(size_t)ii * ldg + j] = g;
+          s1 += g;
+          s2 = fmaf(g, (y[u] - mu) * rs, s2);
+        } else {
+          G[(size_t)ii * ldg + j] = d[u];
+        }
       }
     }
   }
