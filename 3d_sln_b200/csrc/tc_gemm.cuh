@@ -150,11 +150,17 @@ __device__ __forceinline__ void split_store1(uint32_t hi_addr, uint32_t lo_addr,
 // Bounds: tile rows beyond the operand are clamped by the functor (their products are never stored); only the K padding of
 // the last chunk (CHECK == true) is zeroed.
 template <int ROWS, bool RC, class Op>
-struct Loader {
+struct LoaderBuf {   // the registers holding one fetched chunk (PF of these per operand)
   static constexpr int NV = ROWS * BK / 4 / PROD_THREADS;   // quads per thread per chunk
-  static_assert(NV >= 1, "tile too small for 256 loader threads");
   float4 ra[NV], rb[NV];
-  typename Op::Tok tok[RC ? NV : 1];   // RC: one token per owned tile row (fixed); !RC: the token of this chunk's k-row
+  typename Op::Tok ktok;               // RC == false: the token of this chunk's k-row
+};
+template <int ROWS, bool RC, class Op>
+struct Loader {      // per-thread loop invariants, shared by all register buffers
+  static constexpr int NV = ROWS * BK / 4 / PROD_THREADS;
+  static_assert(NV >= 1, "tile too small for 256 loader threads");
+  using Buf = LoaderBuf<ROWS, RC, Op>;
+  typename Op::Tok tok[RC ? NV : 1];   // RC: one token per owned tile row
   int col[RC ? 1 : NV];                // !RC: clamped storage column of quad i
   uint32_t soff;                       // byte offset of quad 0 inside the tile (quad i: + 4096 i)
   __device__ __forceinline__ void init(const Op& op, int row0, int tid) {
@@ -169,30 +175,30 @@ struct Loader {
     }
   }
   template <bool CHECK>
-  __device__ __forceinline__ void fetch(const Op& op, int k0, int kend, int tid) {
+  __device__ __forceinline__ void fetch(const Op& op, Buf& b, int k0, int kend, int tid) const {
     if (RC) {
       int k = k0 + (tid & 7) * 4;
       if (CHECK) k = min(k, kend - 4);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) op.fetch4(tok[i], k, ra[i], rb[i]);
+      for (int i = 0; i < NV; ++i) op.fetch4(tok[i], k, b.ra[i], b.rb[i]);
     } else {
       int k = k0 + (tid >> 3);
       if (CHECK) k = min(k, kend - 1);
-      tok[0] = op.token(k);
+      b.ktok = op.token(k);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) op.fetch4(tok[0], col[i], ra[i], rb[i]);
+      for (int i = 0; i < NV; ++i) op.fetch4(b.ktok, col[i], b.ra[i], b.rb[i]);
     }
   }
   // (k0, kend, CHECK) must be the ones passed to the matching fetch()
   template <bool CHECK>
-  __device__ __forceinline__ void store(const Op& op, int k0, int kend, uint32_t hi_tile, uint32_t lo_tile, int tid) const {
+  __device__ __forceinline__ void store(const Op& op, const Buf& b, int k0, int kend, uint32_t hi_tile, uint32_t lo_tile, int tid) const {
     if (RC) {
       const int k = k0 + (tid & 7) * 4;
       const bool valid = !CHECK || k < kend;
       const int kc = CHECK ? min(k, kend - 4) : k;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        float4 v = op.finish4(tok[i], kc, ra[i], rb[i]);
+        float4 v = op.finish4(tok[i], kc, b.ra[i], b.rb[i]);
         if (CHECK && !valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
         split_store4(hi_tile + soff + i * 4096, lo_tile + soff + i * 4096, v);
       }
@@ -200,7 +206,7 @@ struct Loader {
       const bool valid = !CHECK || (k0 + (tid >> 3)) < kend;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        float4 v = op.finish4(tok[0], col[i], ra[i], rb[i]);
+        float4 v = op.finish4(b.ktok, col[i], b.ra[i], b.rb[i]);
         if (CHECK && !valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
         split_store4(hi_tile + soff + i * 4096, lo_tile + soff + i * 4096, v);
       }
@@ -295,7 +301,6 @@ struct SmemLayout {
   static constexpr int B_TILE = BN * 128;
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
   static constexpr int STAGES = BN >= 128 ? 3 : 4;     // 192 KB / 192 KB / 160 KB of operand ring
-  static constexpr int PF = BN >= 128 ? 1 : 2;         // chunks prefetched into registers per producer thread (register budget)
   static constexpr int STAT = 2 * 8 * BN * 4;          // per-warp column statistics [2][8 warps][BN]
   static constexpr int OUT_LD = BN + 4;                // floats per staged accumulator row
   static_assert(BM * OUT_LD * 4 <= STAGES * STAGE, "accumulator staging must fit the (idle) stage buffers");
@@ -310,14 +315,19 @@ struct SmemLayout {
 //     (BN <= 64; BN = 128 is occupancy-bound with four chains): 4-6 independent MMA chains per CTA.
 //   * The tensor core adds into its fp32 accumulator with truncation, so a long dependent chain of accumulator updates
 //     drifts (measured: 1.4e-5 relative after 1488 updates).  Chains are bounded by draining all accumulators into fp32
-//     registers (round-to-nearest adds) every SEG_CHUNKS chunks = 640 k (40 updates per chain, < 1e-6); every contraction
-//     of the VAE path at the default sizes (K <= 640 per CTA, split-K above that) is a single segment.
+//     registers (round-to-nearest adds) every SEG_CHUNKS chunks = 1280 k (80 updates per chain, < 1e-6).  Contractions whose
+//     K range per CTA fits one segment (every contraction of the VAE path, most convolutions) run the MSEG == false variant:
+//     no in-loop drain, so the register accumulators only exist in the epilogue and two chunks are prefetched per operand.
 // TMEM columns: NM main regions, then NC regions for lo*hi, then NC regions for hi*lo, BN columns each.
-constexpr int SEG_CHUNKS = 20;
+constexpr int SEG_CHUNKS = 40;
 
 // tuning aid: SM-clock timestamps of CTA (0,0,0) at the phase boundaries of the last tc_gemm launch (sln_debug_tc_trace)
 __device__ long long g_tc_trace[16];
+#ifdef SLN_TC_TRACE
 #define TC_TRACE(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid & 31) == 0 && (tid == 0 || tid == MMA_WARP * 32)) g_tc_trace[(slot) + (tid ? 8 : 0)] = clock64(); } while (0)
+#else
+#define TC_TRACE(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -330,10 +340,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 //   the ring of STAGES stages lets the producers run ahead of the tensor core, so global-load latency is hidden behind
 //   the MMAs of the previous chunks instead of being exposed once per chunk.
 // grid = (ceil(N/BN), ceil(M/128), splits); each z-slice reduces k in [z*kchunk, (z+1)*kchunk), kchunk % 32 == 0.
-template <int BN, bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
+template <int BN, bool A_RC, bool B_RC, bool MSEG, class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const BOp B, const Epi epi, int M, int N, int K, int kchunk) {
   using L = SmemLayout<BN>;
-  constexpr int S = L::STAGES, PF = L::PF;
+  constexpr int S = L::STAGES, PF = MSEG ? 1 : 2;   // chunks prefetched into registers per producer thread
   extern __shared__ char smem_raw[];
   char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
   float* stat = reinterpret_cast<float*>(smem + S * L::STAGE);             // [2][8][BN]
@@ -381,11 +391,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   const bool has_acc = warp < PROD_WARPS && (BN >= 64 || half == 0);
   const int col_off = BN >= 64 ? half * (BN / 2) : 0;
   const uint32_t tmem_mine = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_off;
-  float racc[CH2][32];
+  float racc[MSEG ? CH2 : 1][32];      // MSEG: running sum over the drained segments (otherwise the sum is formed in the epilogue)
+  if (MSEG) {
 #pragma unroll
-  for (int j = 0; j < CH2; ++j)
+    for (int j = 0; j < (MSEG ? CH2 : 1); ++j)
 #pragma unroll
-    for (int e = 0; e < 32; ++e) racc[j][e] = 0.f;
+      for (int e = 0; e < 32; ++e) racc[j][e] = 0.f;
+  }
 
   if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
@@ -419,14 +431,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ producers (and owners of the register accumulators)
-    auto drain = [&](int seg) {                           // racc += every TMEM accumulator of a retired segment
+    auto drain = [&](int seg) {                           // MSEG only: racc += every TMEM accumulator of a retired segment
       mbar_wait(segfull, (uint32_t)(seg & 1));
       tc_fence_after();
-      if (has_acc) {
+      if (MSEG && has_acc) {
 #pragma unroll
         for (int rg = 0; rg < NREG; ++rg) {
 #pragma unroll
-          for (int j = 0; j < CH2; ++j) {
+          for (int j = 0; j < (MSEG ? CH2 : 1); ++j) {
             float v[32];
             tmem_ld32(tmem_mine + (uint32_t)(rg * BN + j * 32), v);
 #pragma unroll
@@ -438,53 +450,55 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
       __syncwarp();
       if (lane == 0) mbar_arrive(accempty);
     };
-    // PF register buffers per operand, named (not arrays) so that they stay in registers
-    Loader<BM, A_RC, AOp> la0, la1;
-    Loader<BN, B_RC, BOp> lb0, lb1;
+    // loop invariants once per operand; PF register buffers (named, not arrays, so that they stay in registers)
+    Loader<BM, A_RC, AOp> la;
+    Loader<BN, B_RC, BOp> lb;
+    typename Loader<BM, A_RC, AOp>::Buf a0, a1;
+    typename Loader<BN, B_RC, BOp>::Buf b0, b1;
     const bool tail = ((kend - kbeg) & (BK - 1)) != 0;     // only the last chunk can have K padding
     const uint32_t sbase = smem_u32(smem);
-    auto fetch = [&](auto& LA, auto& LB, int c) {
+    auto fetch = [&](auto& BA, auto& BB, int c) {
       if (tail && c == nchunks - 1) {
-        LA.template fetch<true>(A, kbeg + c * BK, kend, tid);
-        LB.template fetch<true>(B, kbeg + c * BK, kend, tid);
+        la.template fetch<true>(A, BA, kbeg + c * BK, kend, tid);
+        lb.template fetch<true>(B, BB, kbeg + c * BK, kend, tid);
       } else {
-        LA.template fetch<false>(A, kbeg + c * BK, kend, tid);
-        LB.template fetch<false>(B, kbeg + c * BK, kend, tid);
+        la.template fetch<false>(A, BA, kbeg + c * BK, kend, tid);
+        lb.template fetch<false>(B, BB, kbeg + c * BK, kend, tid);
       }
     };
-    auto produce = [&](auto& LA, auto& LB, int c) {
+    auto produce = [&](auto& BA, auto& BB, int c) {
       const int s = c % S, use = c / S;
       const uint32_t st = sbase + s * L::STAGE;
       if (use > 0) mbar_wait(empty + s, (uint32_t)((use - 1) & 1));   // the MMAs that read this stage have retired
       if (tail && c == nchunks - 1) {
-        LA.template store<true>(A, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
-        LB.template store<true>(B, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
+        la.template store<true>(A, BA, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
+        lb.template store<true>(B, BB, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
       } else {
-        LA.template store<false>(A, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
-        LB.template store<false>(B, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
+        la.template store<false>(A, BA, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
+        lb.template store<false>(B, BB, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
       }
-      if (c + PF < nchunks) fetch(LA, LB, c + PF);        // refill the register buffer: these loads fly during the next PF chunks
+      if (c + PF < nchunks) fetch(BA, BB, c + PF);        // refill the register buffer: these loads fly during the next PF chunks
       fence_async_smem();                                 // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(full + s);
-      const int seg = c / SEG_CHUNKS;
-      if ((c % SEG_CHUNKS) == 0 && seg > 0) drain(seg - 1);
+      if (MSEG) {
+        const int seg = c / SEG_CHUNKS;
+        if ((c % SEG_CHUNKS) == 0 && seg > 0) drain(seg - 1);
+      }
     };
-    la0.init(A, m0, tid);
-    lb0.init(B, n0, tid);
-    if (nchunks > 0) fetch(la0, lb0, 0);
-    if (PF == 2) {
-      la1.init(A, m0, tid);
-      lb1.init(B, n0, tid);
-      if (nchunks > 1) fetch(la1, lb1, 1);
-    }
-    TC_TRACE(2);
+    la.init(A, m0, tid);
+    lb.init(B, n0, tid);
+    if (nchunks > 0) fetch(a0, b0, 0);
+    if (PF == 2 && nchunks > 1) fetch(a1, b1, 1);
     for (int c = 0; c < nchunks; c += PF) {
-      produce(la0, lb0, c);
-      if (c == 0) TC_TRACE(3);
-      if (PF == 2 && c + 1 < nchunks) produce(la1, lb1, c + 1);
+      produce(a0, b0, c);
+      if (PF == 2 && c + 1 < nchunks) produce(a1, b1, c + 1);
     }
-    if (nchunks > 0) drain((nchunks - 1) / SEG_CHUNKS);
+    if (MSEG && nchunks > 0) drain((nchunks - 1) / SEG_CHUNKS);
+    if (!MSEG && nchunks > 0) {                           // single segment: every MMA has retired when segfull completes
+      mbar_wait(segfull, 0u);
+      tc_fence_after();
+    }
   }
   TC_TRACE(4);
   // ---- epilogue: stage the tile in shared memory (the stage buffers are idle: every MMA has retired) ...
@@ -492,11 +506,28 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   if (has_acc) {
     const int r = quad * 32 + lane;
 #pragma unroll
-    for (int j = 0; j < CH2; ++j)
+    for (int j = 0; j < CH2; ++j) {
+      float acc[32];
+      if (MSEG) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = racc[MSEG ? j : 0][e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+        if (nchunks > 0) {
+#pragma unroll
+          for (int rg = 0; rg < NREG; ++rg) {
+            float v[32];
+            tmem_ld32(tmem_mine + (uint32_t)(rg * BN + j * 32), v);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[e] += v[e];
+          }
+        }
+      }
 #pragma unroll
       for (int e = 0; e < 32; e += 4)
-        *reinterpret_cast<float4*>(outs + (size_t)r * L::OUT_LD + col_off + j * 32 + e) =
-            make_float4(racc[j][e], racc[j][e + 1], racc[j][e + 2], racc[j][e + 3]);
+        *reinterpret_cast<float4*>(outs + (size_t)r * L::OUT_LD + col_off + j * 32 + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+    }
   }
   __syncthreads();
   // ... then lanes run along the columns: LPR lanes cover one row (4 columns each), a warp covers 32/LPR rows per pass
@@ -604,9 +635,9 @@ inline TcChoice pick_tc(int M, int N, int K, bool allow_split) {
 // (independent of M, so that a scene evaluated alone and inside a batch takes the same arithmetic path)
 inline bool tc_eligible(int M, int N, int K) { return M >= 1 && N >= 32 && K >= 32; }
 
-template <int BN, bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
-int launch_tc_bn(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, const TcChoice& c) {
-  auto kern = tc_gemm_kernel<BN, A_RC, B_RC, AOp, BOp, Epi>;
+template <int BN, bool A_RC, bool B_RC, bool MSEG, class AOp, class BOp, class Epi>
+int launch_tc_bn_seg(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, const TcChoice& c) {
+  auto kern = tc_gemm_kernel<BN, A_RC, B_RC, MSEG, AOp, BOp, Epi>;
   constexpr int bytes = SmemLayout<BN>::BYTES;
   static bool configured = false;   // per template instantiation
   if (!configured) {
@@ -629,6 +660,13 @@ int launch_tc_bn(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, in
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, A, B, epi, M, N, K, kchunk);
   if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(tc_gemm) failed: %s", cudaGetErrorString(e)); return SLN_ECUDA; }
   return SLN_OK;
+}
+
+template <int BN, bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
+int launch_tc_bn(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, const TcChoice& c) {
+  // K ranges that fit one accumulation segment take the variant without in-loop drains (deeper register prefetch)
+  if (ceil_div(c.kchunk < K ? c.kchunk : K, BK) > SEG_CHUNKS) return launch_tc_bn_seg<BN, A_RC, B_RC, true>(st, A, B, epi, M, N, K, c);
+  return launch_tc_bn_seg<BN, A_RC, B_RC, false>(st, A, B, epi, M, N, K, c);
 }
 
 template <bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
