@@ -130,8 +130,10 @@ def cull_faces(vertices, face_buf, face_cls, R, t, eps=0.06):
     return face_buf[:, valid, :].detach(), face_cls[valid]
 
 
-def composite(depth_data, images, names):
-    """Reference :366-434 vectorised over the classes.  depth_data [1,H,W], images [C,H,W] (class order `names`)."""
+def composite(depth_data, images, names, index=None, keep=None):
+    """Reference :366-434 vectorised over the classes.  depth_data [1,H,W], images [C,H,W] (class order `names`).
+    index / keep: optional precomputed device tensors (one-hot channel of every class; classes that get a depth plane), so that
+    the call contains no host->device transfer (CUDA-graph capture)."""
     depth_data = torch.where(depth_data > 15, torch.full_like(depth_data, -1.0), depth_data)           # :367
     C = images.size(0)
     hard = images.detach() > 0.1                                                                        # :401
@@ -146,11 +148,13 @@ def composite(depth_data, images, names):
     wall_max = torch.where(cnt[wall] > 0, wall_max, torch.full_like(wall_max, 10.0))                    # :408-410
     mean = torch.where(cnt > 0, mean, wall_max.expand_as(mean))                                         # :411-419
     planes = torch.where(hard, depth_data / wall_max, (mean / wall_max)[:, None, None].expand(-1, *depth_data.shape[1:]))   # :420-421
-    keep = [i for i, n in enumerate(names) if n not in ("wall", "floor", "ceiling")]                    # :422-425
+    if keep is None:
+        keep = torch.tensor([i for i, n in enumerate(names) if n not in ("wall", "floor", "ceiling")], device=depth_data.device)   # :422-425
     one_hot = torch.zeros(41, *depth_data.shape[1:], device=depth_data.device, dtype=depth_data.dtype)
-    index = torch.tensor([nyu_class.index(n.replace("_", " ")) + 1 for n in names], device=depth_data.device)
+    if index is None:
+        index = torch.tensor([nyu_class.index(n.replace("_", " ")) + 1 for n in names], device=depth_data.device)
     one_hot = one_hot.index_copy(0, index, images)                                                      # :429-431
-    return torch.cat((depth_data, one_hot[1:], planes[keep]), dim=0)[None]                              # :433-434
+    return torch.cat((depth_data, one_hot[1:], planes.index_select(0, keep)), dim=0)[None]              # :433-434
 
 
 def mesh_render_func(boxes, angles, objs, model_ids_old=None, obj_size_target=None):
@@ -185,3 +189,82 @@ def mesh_render_func(boxes, angles, objs, model_ids_old=None, obj_size_target=No
     depth, images = nr.render_scene_classes(vertices, face_buf, face_cls, len(names), K, R, t, image_size=final_out, orig_size=inter_out,
                                             near=0.001)
     return composite(depth, images, names), model_ids_return, obj_size_return, size_loss
+
+
+# ------------------------------------------------------------------------------------------------ static-scene fast path
+class SceneStatic(object):
+    """Everything of a scene that does not change during layout refinement (object classes, retrieved meshes, room box, camera):
+    built once, then ``render_static`` is pure device-tensor arithmetic on the layout — no Python per-object loop, no host
+    synchronisation, fixed shapes — so a whole refinement iteration can be captured in a CUDA graph (``RefineStep``)."""
+
+    def __init__(self, objs, room_box, library, device):
+        dev = torch.device(device)
+        names = desired_classes()
+        self.dev, self.names = dev, names
+        self.objs = [int(o) for o in objs]
+        self.kept = [i for i in range(len(self.objs) - 1) if object_idx_to_name[self.objs[i]] not in SKIPPED_TYPES]
+        models = [library.get(object_idx_to_name[self.objs[i]]) for i in self.kept]
+        self.n_kept = len(self.kept)
+        self.kept_idx = torch.tensor(self.kept, dtype=torch.long, device=dev)
+        faces, cls, off = [], [], 0
+        mv, vobj = [], []
+        for j, m in enumerate(models):
+            nv = m["vertices"].size(0)
+            mv.append(m["vertices"].to(dev)); vobj.append(torch.full((nv,), j, dtype=torch.long, device=dev))
+            faces.append(m["faces"].to(dev) + off)
+            cls.append(torch.full((m["faces"].size(0),), names.index(object_idx_to_name[self.objs[self.kept[j]]]), dtype=torch.int32, device=dev))
+            off += nv
+        self.mv = torch.cat(mv) if mv else torch.zeros(0, 3, device=dev)
+        self.vobj = torch.cat(vobj) if vobj else torch.zeros(0, dtype=torch.long, device=dev)
+        self.msize = torch.stack([m["size"].to(dev) for m in models]) if models else torch.zeros(0, 3, device=dev)
+        self.mcent = torch.stack([m["center"].to(dev) for m in models]) if models else torch.zeros(0, 3, device=dev)
+        room_box = room_box.detach().float().cpu()
+        shell = room_shell(room_box[3:])
+        sv = []
+        for name in ("wall", "floor", "ceiling"):
+            v, f = shell[name]
+            sv.append(v.to(dev)); faces.append(f.to(dev) + off)
+            cls.append(torch.full((f.size(0),), names.index(name), dtype=torch.int32, device=dev))
+            off += v.size(0)
+        self.shell_v = torch.cat(sv)
+        self.faces = torch.cat(faces).to(torch.int32)[None].contiguous()
+        self.face_cls = torch.cat(cls).contiguous()
+        self.room = room_box.to(dev)
+        K, R, t = get_cam_mat([self.room])
+        self.K, self.R, self.t = K, R, t
+        self.index = torch.tensor([nyu_class.index(n.replace("_", " ")) + 1 for n in names], device=dev)
+        self.keep = torch.tensor([i for i, n in enumerate(names) if n not in ("wall", "floor", "ceiling")], device=dev)
+        self.wall = names.index("wall")
+
+    def vertices(self, boxes, angles):
+        """[1, V, 3] world-space vertices, differentiable w.r.t. boxes [n+1, 6] and angles [n+1] (reference diff_render.py:76-159)."""
+        room = self.room[3:]
+        B = boxes.index_select(0, self.kept_idx)
+        A = angles.index_select(0, self.kept_idx).float()
+        bmin, bmax = B[:, :3] * room, B[:, 3:] * room
+        center, size = (bmax + bmin) / 2, bmax - bmin
+        scale = (size / self.msize).min(dim=1).values
+        theta = -A * (2 * math.pi / 24)
+        c, s = torch.cos(theta), torch.sin(theta)
+        zero, one = torch.zeros_like(c), torch.ones_like(c)
+        rot = torch.stack([torch.stack([c, zero, s], -1), torch.stack([zero, one, zero], -1), torch.stack([-s, zero, c], -1)], 1)
+        trans = center - scale[:, None] * torch.einsum("nij,nj->ni", rot, self.mcent)
+        v = scale[self.vobj, None] * torch.einsum("vij,vj->vi", rot[self.vobj], self.mv) + trans[self.vobj]
+        return torch.cat([v, self.shell_v])[None], size
+
+    def culled_faces(self, vertices, eps=0.06):
+        """Reference :345-356 without a dynamic shape: a face with any vertex closer than eps keeps its slot but collapses to a
+        zero-area triangle (vertex 0 three times), which the rasterizer never draws."""
+        vc = torch.matmul(vertices.detach(), self.R.transpose(1, 2)) + self.t
+        fz = vc[0, :, 2][self.faces[0].long()]
+        valid = ~(fz < eps).any(dim=1)
+        return torch.where(valid[None, :, None], self.faces, torch.zeros_like(self.faces))
+
+
+def render_static(static, boxes, angles):
+    """final [1, 70, 256, 256] of the scene described by `static` at layout (boxes, angles): tensor ops + one rasterization."""
+    vertices, size = static.vertices(boxes, angles)
+    faces = static.culled_faces(vertices)
+    depth, images = nr.render_scene_classes(vertices, faces, static.face_cls, len(static.names), static.K, static.R, static.t,
+                                            image_size=final_out, orig_size=inter_out, near=0.001)
+    return composite(depth, images, static.names, static.index, static.keep), size

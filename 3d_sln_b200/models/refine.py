@@ -9,7 +9,6 @@ small torch ops on [1,70,256,256] tensors, exactly the ops the reference uses.
 import torch
 import torch.nn.functional as F
 
-from .diff_render import mesh_render_func
 
 PSP_SIZES = (32, 48, 64, 96)
 
@@ -72,38 +71,97 @@ def refine_loss(iter_image, target_depth, target_labels, size_loss=None):
     return loss
 
 
-def scene_refine(boxes, angles, objs, target_boxes=None, target_angles=None, n_iters=200, lr=2e-4, optimizer="adam", callback=None):
-    """Refine the layout of ONE scene by gradient descent through the differentiable renderer.
+def scene_refine(boxes, angles, objs, target_boxes=None, target_angles=None, n_iters=200, lr=2e-4, use_graph=True, callback=None):
+    """Refine the layout of ONE scene by gradient descent through the differentiable renderer (BASELINE.json configs[2]).
 
     boxes [n+1, 6] (objects normalised to the room, last row = room box), angles [n+1] (0..24, float), objs [n+1] class ids,
-    all on the CUDA device.  The target image is the render of (target_boxes, target_angles) (default: the initial layout
-    shifted — callers normally pass the ground-truth layout).  Returns (boxes, angles, losses list).
-    Reference loop: testing/test_render_refine.py:279-359 (there the optimised variable is the VAE latent z and the optimiser
-    is a re-created SGD; BASELINE.json asks for Adam over the layout)."""
+    on the CUDA device.  The target image is the render of (target_boxes, target_angles).  Returns (boxes, angles, losses).
+    Reference loop: testing/test_render_refine.py:279-359 (there the optimised variable is the VAE latent z that decodes to the
+    layout and the optimiser is a re-created SGD; BASELINE.json asks for Adam over the layout itself).  With use_graph the whole
+    iteration (render, multi-scale loss, backward, Adam) is one CUDA-graph replay (RefineStep)."""
     if boxes.device.type != "cuda":
         raise RuntimeError("scene_refine runs on CUDA only (no CPU fallback)")
-    objs_l = [int(o) for o in objs]
     tb = boxes if target_boxes is None else target_boxes
     ta = angles if target_angles is None else target_angles
-    with torch.no_grad():
-        target, model_ids, sizes, _ = mesh_render_func([tb[i] for i in range(tb.size(0))], [ta[i] for i in range(ta.size(0))], objs_l)
-    t_depth, t_labels = refine_targets(target)
-    b = boxes.detach().clone().requires_grad_(True)
-    a = angles.detach().clone().float().requires_grad_(True)
-    opt = torch.optim.Adam([b, a], lr=lr) if optimizer == "adam" else torch.optim.SGD([b, a], lr=lr, nesterov=True, momentum=0.1)
+    step = RefineStep(boxes, angles, objs, tb, ta, lr=lr, use_graph=use_graph)
     losses = []
-    room = boxes[-1].detach()
     for k in range(n_iters):
-        bb = torch.cat([b[:-1], room[None]], 0)                 # boxes_pred[-1] = boxes_gt[-1] (:291)
-        bb.register_hook(fix_grad)
-        aa = torch.cat([a[:-1], angles[-1:].detach().float()], 0)
-        aa.register_hook(quad_grad)
-        image, _, _, size_loss = mesh_render_func([bb[i] for i in range(bb.size(0))], [aa[i] for i in range(aa.size(0))], objs_l, model_ids, sizes)
-        loss = refine_loss(image, t_depth, t_labels, size_loss)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        losses.append(loss.detach())
+        loss = step.step()
+        losses.append(loss.detach().clone())
         if callback is not None:
-            callback(k, loss, image)
-    return b.detach(), a.detach(), losses
+            callback(k, loss, step)
+    return step.b.detach().clone(), step.a.detach().clone(), losses
+
+
+class RefineStep(object):
+    """One refinement iteration (render -> multi-scale loss -> backward -> Adam) of a fixed scene as a replayable CUDA graph.
+
+    The layout (boxes [n+1,6], angles [n+1]) lives in static device tensors that the graph updates in place; ``step()`` replays
+    the graph and returns the (device) loss of that iteration.  Same arithmetic as ``scene_refine`` — the graph removes the
+    ~600 kernel-launch / Python overheads per iteration that otherwise dominate (the rasterizer itself takes < 1 ms)."""
+
+    def __init__(self, boxes, angles, objs, target_boxes, target_angles, lr=2e-4, use_graph=True, library=None):
+        from . import diff_render as dr
+        dev = boxes.device
+        if dev.type != "cuda":
+            raise RuntimeError("RefineStep runs on CUDA only (no CPU fallback)")
+        lib = library if library is not None else dr.mesh_library(dev)
+        self.static = dr.SceneStatic(objs, boxes[-1], lib, dev)
+        with torch.no_grad():
+            target, tsize = dr.render_static(self.static, target_boxes.to(dev), target_angles.to(dev).float())
+        self.t_depth, self.t_labels = refine_targets(target)
+        self.size_target = tsize.detach()
+        self.room_row = boxes[-1:].detach().clone()
+        self.angle_room = angles[-1:].detach().float().clone()
+        self.b = boxes.detach().clone().requires_grad_(True)
+        self.a = angles.detach().float().clone().requires_grad_(True)
+        self.opt = torch.optim.Adam([self.b, self.a], lr=lr, capturable=True)
+        self.loss = torch.zeros((), device=dev)
+        self.graph = None
+        self._dr = dr
+        if use_graph:
+            self.capture()
+
+    def _iteration(self):
+        bb = torch.cat([self.b[:-1], self.room_row], 0)
+        bb.register_hook(fix_grad)
+        aa = torch.cat([self.a[:-1], self.angle_room], 0)
+        aa.register_hook(quad_grad)
+        image, size = self._dr.render_static(self.static, bb, aa)
+        size_loss = ((size - self.size_target) ** 2).mean(dim=1).sum()        # :98: sum over objects of mse(size, size of the first render)
+        loss = refine_loss(image, self.t_depth, self.t_labels, size_loss)
+        self.opt.zero_grad(set_to_none=False)
+        loss.backward()
+        self.opt.step()
+        self.loss.copy_(loss.detach())
+
+    def capture(self):
+        s = torch.cuda.Stream(self.b.device)
+        s.wait_stream(torch.cuda.current_stream(self.b.device))
+        b0, a0 = self.b.detach().clone(), self.a.detach().clone()
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._iteration()
+        torch.cuda.current_stream(self.b.device).wait_stream(s)
+        torch.cuda.synchronize(self.b.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._iteration()
+        self.reset(b0, a0)
+        return self
+
+    def reset(self, boxes, angles):
+        """Restart from a layout (also clears the Adam moments)."""
+        with torch.no_grad():
+            self.b.copy_(boxes); self.a.copy_(angles.float())
+            for st in self.opt.state.values():
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        v.zero_()
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._iteration()
+        return self.loss

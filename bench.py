@@ -330,6 +330,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="vae", choices=["vae", "render", "spade"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="render workload: run the refinement iteration eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

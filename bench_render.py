@@ -49,23 +49,10 @@ def run(args):
     dr = importlib.import_module("3d_sln_b200.models.diff_render")
     boxes, angles, objs, start, a0 = _scene(dev, seed=13 + rank)
     objs_l = objs.tolist()
-    with torch.no_grad():
-        target, model_ids, sizes, _ = dr.mesh_render_func([boxes[i] for i in range(11)], [angles[i] for i in range(11)], objs_l)
-    t_depth, t_labels = refine.refine_targets(target)
-    b = start.clone().requires_grad_(True)
-    a = a0.clone().requires_grad_(True)
-    opt = torch.optim.Adam([b, a], lr=2e-4)
-    room, a_room = boxes[-1].detach(), angles[-1:].detach().float()
+    step = refine.RefineStep(start, a0, objs, boxes, angles, lr=2e-4, use_graph=not args.no_graph)
 
-    def iteration(bsrc, asrc):
-        bb = torch.cat([bsrc[:-1], room[None]], 0); bb.register_hook(refine.fix_grad)
-        aa = torch.cat([asrc[:-1], a_room], 0); aa.register_hook(refine.quad_grad)
-        image, _, _, size_loss = dr.mesh_render_func([bb[i] for i in range(11)], [aa[i] for i in range(11)], objs_l, model_ids, sizes)
-        loss = refine.refine_loss(image, t_depth, t_labels, size_loss)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        return loss
+    def iteration(*_):
+        return step.step()
 
     def barrier():
         if world > 1:
@@ -73,11 +60,18 @@ def run(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    b, a = step.b, step.a
+    step.reset(start, a0)
     n0 = lib.sln_launch_count()
-    first = float(iteration(b, a).detach())
+    first = float(iteration().detach())
     launches_per_iter = int(lib.sln_launch_count() - n0)
+    if step.graph is not None:        # a replay does not pass through the host-side launch counter: count an eager iteration instead
+        n0 = lib.sln_launch_count()
+        step._iteration()
+        launches_per_iter = int(lib.sln_launch_count() - n0)
+        step.reset(start, a0)
     for _ in range(max(args.warmup, 3)):
-        iteration(b, a)
+        iteration()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     barrier()
     sampler = B.ClockSampler(local_rank).start() if rank == 0 else None
@@ -86,7 +80,7 @@ def run(args):
     for e0, e1 in evs:
         flush.zero_()
         e0.record()
-        loss = iteration(b, a)
+        loss = iteration()
         e1.record()
     barrier()
     dev_ms = sum(x.elapsed_time(y) for x, y in evs)
@@ -99,7 +93,7 @@ def run(args):
     for _ in range(args.steps):
         with torch.no_grad():
             b.copy_(hb, non_blocking=True); a.copy_(ha, non_blocking=True)
-        loss = iteration(b, a)
+        loss = iteration()
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
     barrier()
@@ -112,7 +106,7 @@ def run(args):
         lib.sln_prof_enable(1)
         reps = 5
         for _ in range(reps):
-            iteration(b, a)
+            step._iteration()      # un-graphed: event pairs around every library launch
         torch.cuda.synchronize(dev)
         for ci, cname in enumerate(B.PROF_CLASSES):
             ms, work, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()

@@ -185,3 +185,24 @@ def test_mesh_render_func_contract_and_gradients():
     # second call with cached ids / size targets (refinement iterations k > 0, test_render_refine.py:324)
     final2, _, _, size_loss2 = dr.mesh_render_func([x.detach() for x in b], [x.detach() for x in a], objs.tolist(), ids, sizes)
     assert torch.equal(final2, final.detach()) and float(size_loss2) < 1e-10
+
+
+def test_static_scene_fast_path_equals_mesh_render_func_and_graph_replays():
+    """SceneStatic/render_static (no per-object Python loop, no host sync, fixed shapes) == mesh_render_func, and RefineStep's CUDA
+    graph replays the same iteration as the eager path (identical losses over several Adam steps)."""
+    refine = importlib.import_module("3d_sln_b200.models.refine")
+    boxes, angles, objs = meshes.synthetic_layout(10, seed=13)
+    boxes, angles = boxes.to(DEV), angles.to(DEV)
+    final, ids, sizes, _ = dr.mesh_render_func([boxes[i] for i in range(11)], [angles[i] for i in range(11)], objs.tolist())
+    static = dr.SceneStatic(objs, boxes[-1], dr.mesh_library(torch.device(DEV)), DEV)
+    fast, size = dr.render_static(static, boxes, angles)
+    assert fast.shape == final.shape
+    assert maxnorm(fast.cpu().numpy(), final.cpu().numpy()) < 1e-5
+    start = boxes.clone(); start[:10, 0] += 0.01; start[:10, 3] += 0.01
+    runs = []
+    for use_graph in (False, True):
+        step = refine.RefineStep(start, angles, objs, boxes, angles, lr=2e-4, use_graph=use_graph)
+        step.reset(start, angles)
+        runs.append([float(step.step()) for _ in range(4)])
+    assert all(np.isfinite(runs[0])) and runs[0][0] > 0
+    assert np.allclose(runs[0], runs[1], rtol=1e-4, atol=1e-6), runs
