@@ -22,6 +22,7 @@ __device__ __forceinline__ int reflect(int v, int n) { return v < 0 ? -v : (v >=
 struct Im2col {
   const float* p;
   int H, W, C, ks, rows, cols, relu, vec;
+  int cshift;   // log2(C) when C is a power of two (the usual case), else -1: k -> (tap, c) without an integer division
   __device__ __forceinline__ float elem(int r, int k) const {
     const int tap = ks == 3 ? k / C : 0, c = k - tap * C;
     const int ky = ks == 3 ? tap / 3 : 1, kx = ks == 3 ? tap - 3 * (tap / 3) : 1;
@@ -66,10 +67,10 @@ struct Im2col {
   }
   __device__ __forceinline__ int clampc(int c) const { return min(c, cols - 4); }
   __device__ __forceinline__ void fetch4(const Tok& t, int k, float4& a, float4&) const {
-    const int tap = ks == 3 ? k / C : 0, c = k - tap * C;
-    const int ky = ks == 3 ? tap / 3 : 1, kx = ks == 3 ? tap - 3 * (tap / 3) : 1;
+    const int tap = ks == 3 ? (cshift >= 0 ? (k >> cshift) : k / C) : 0, c = k - tap * C;
+    const int ky = ks == 3 ? (tap * 11) >> 5 : 1, kx = ks == 3 ? tap - 3 * ky : 1;      // tap / 3 for tap < 9
     const int yo = ky == 0 ? t.y0 : (ky == 1 ? t.y1 : t.y2), xo = kx == 0 ? t.x0 : (kx == 1 ? t.x1 : t.x2);
-    a = ldg4(t.base + (size_t)(yo + xo) * C + c);
+    a = ldg4(t.base + (size_t)(unsigned)((yo + xo) * C + c));
   }
   __device__ __forceinline__ float4 finish4(const Tok&, int, float4 v, float4) const {
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
@@ -82,6 +83,8 @@ Im2col make_im2col(const float* p, int B, int H, int W, int C, int ks, int relu)
   Im2col a;
   a.p = p; a.H = H; a.W = W; a.C = C; a.ks = ks; a.rows = B * H * W; a.cols = ks * ks * C; a.relu = relu;
   a.vec = (C % 4 == 0 && (uintptr_t)p % 16 == 0) ? 1 : 0;
+  a.cshift = -1;
+  for (int sh = 0; sh < 30; ++sh) if ((1 << sh) == C) a.cshift = sh;
   return a;
 }
 
@@ -347,6 +350,7 @@ int sln_spade_conv(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin,
   SLN_CHECK_ARG(x && Wp && out && Cout >= 1, "null pointer");
   SLN_CHECK_ARG(ks == 1 || ks == 3, "kernel size must be 1 or 3 (reflection-padded)");
   SLN_CHECK_ARG(ks == 1 || (H >= 2 && W >= 2), "reflection padding needs at least 2 rows and columns");
+  SLN_CHECK_ARG(H * W * Cin < (1ll << 31), "one image must have fewer than 2^31 elements");
   cudaStream_t st = (cudaStream_t)stream;
   const int M = (int)(B * H * W), N = (int)Cout, K = (int)(ks * ks * Cin);
   Im2col A = make_im2col(x, (int)B, (int)H, (int)W, (int)Cin, ks, relu_in);

@@ -606,9 +606,12 @@ inline TcChoice pick_tc(int M, int N, int K, bool allow_split) {
   const int bns[3] = {128, 64, 32};
   double best = 1e300;
   TcChoice c{32, 1, K};
+  static int forced = -1;                            // env SLN_TC_BN = 32 | 64 | 128 forces the tile width (tuning experiments)
+  if (forced < 0) { const char* e = getenv("SLN_TC_BN"); forced = e ? atoi(e) : 0; }
   for (int t = 0; t < 3; ++t) {
     const int bn = bns[t];
-    if (bn > 32 && N <= bn / 2) continue;           // do not pad N by more than 2x
+    if (forced > 0 && bn != forced) continue;
+    if (forced == 0 && bn > 32 && N <= bn / 2) continue;           // do not pad N by more than 2x
     int tiles = ceil_div(M, BM) * ceil_div(N, bn);
     int splits = 1;
     if (allow_split) {

@@ -356,9 +356,9 @@ template <class AOp>
 __global__ void __launch_bounds__(256) k_skinny_fwd(const AOp A, const float* __restrict__ W, const float* __restrict__ bias, int M, int N, int K,
                                                     float* out, int ldo) {
   extern __shared__ float s_wt[];   // [K][32]
-  for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
-    int j = e / K, k = e - j * K;
-    s_wt[k * 32 + j] = __ldg(W + e);
+  for (int e = threadIdx.x; e < N * K; e += blockDim.x) {   // j fastest: conflict-free shared-memory writes (W is small and L1/L2-resident)
+    int k = e / N, j = e - k * N;
+    s_wt[k * 32 + j] = __ldg(W + (size_t)j * K + k);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -431,10 +431,14 @@ __global__ void __launch_bounds__(128) k_skinny_bwd_w(const float* __restrict__ 
     }
     __syncthreads();
     if (q < NQ) {
-      for (int r = 0; r < nr; ++r) {
-        const float x = Q.at_t(base + r, q);
+      for (int r = 0; r < nr; r += 4) {        // 4 independent loads in flight
+        float x[4];
 #pragma unroll
-        for (int e = 0; e < KP; ++e) acc[e] = fmaf(s_p[r][e], x, acc[e]);
+        for (int u = 0; u < 4; ++u) x[u] = r + u < nr ? Q.at_t(base + r + u, q) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int e = 0; e < KP; ++e) acc[e] = fmaf(s_p[(r + u) & 31][e], x[u], acc[e]);
       }
     }
     if (db && blockIdx.x == 0 && threadIdx.x < kp)

@@ -9,7 +9,7 @@ lib = _lib.load()
 eng = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 dev = torch.device("cuda:0")
 st = _lib.cur_stream(dev)
-shapes = [(3968, 640, 256, 1, 1, 0), (3968, 640, 32, 1, 1, 0), (3968, 640, 128, 1, 1, 0), (3968, 256, 384, 1, 1, 0), (2048, 256, 256, 1, 1, 0), (2048, 128, 256, 1, 1, 0),
+shapes = [(3968, 640, 256, 1, 1, 0), (3968, 384, 256, 1, 0, 0), (2048, 256, 128, 1, 0, 0), (3968, 640, 32, 1, 1, 0), (3968, 640, 128, 1, 1, 0), (3968, 256, 384, 1, 1, 0), (2048, 256, 256, 1, 1, 0), (2048, 128, 256, 1, 1, 0),
           (2048, 128, 32, 1, 1, 0), (128, 128, 32, 1, 1, 0), (128, 128, 256, 1, 1, 0), (3968, 256, 640, 1, 0, 0), (640, 256, 3968, 0, 0, 1), (256, 384, 3968, 0, 0, 1), (256, 256, 2048, 0, 0, 1)]
 for (M, N, K, arc, brc, acc) in shapes:
     A = torch.randn((M, K) if arc else (K, M), device=dev)
