@@ -134,8 +134,10 @@ SIGNATURES = {
     "sln_reparam_bwd": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P, _P]),
     "sln_vae_loss": (ctypes.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P, _I32, _F, _I64, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P]),
     "sln_adam_step": (ctypes.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P, _I32, _P]),
-    "sln_spade_conv": (ctypes.c_int, [_P, _I64, _I64, _I64, _I64, _I32, _I32, _P, _P, _I64, _P, _P]),
-    "sln_spade_modulate": (ctypes.c_int, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _I64, _I32, _P, _P, _P, _F, _P, _P]),
+    "sln_packed_weights_bytes": (_SZ, [_I64, _I64]),
+    "sln_pack_weights": (ctypes.c_int, [_P, _I64, _I64, _P, _P]),
+    "sln_spade_conv": (ctypes.c_int, [_P, _I64, _I64, _I64, _I64, _I32, _I32, _P, _P, _P, _I64, _P, _P]),
+    "sln_spade_modulate": (ctypes.c_int, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _F, _P, _P]),
     "sln_spade_ln_stats": (ctypes.c_int, [_P, _I64, _I64, _F, _P, _P, _P, _P]),
     "sln_spade_seg_features": (ctypes.c_int, [_P, _I64, _I32, _I32, _I32, _I64, _I64, _P, _P, _I32, _P, _P]),
     "sln_spade_upsample2x": (ctypes.c_int, [_P, _I64, _I64, _I64, _I64, _I32, _P, _P]),

@@ -332,6 +332,23 @@ __global__ void __launch_bounds__(128) k_to_rgb(const float* __restrict__ x, int
   }
 }
 
+// W [N][K] row-major -> the pre-split, pre-tiled image described at tc::PackedB (one CTA per 32 x 32 unit)
+__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ Wm, int N, int K, int kchunks, float* out) {
+  const int unit = blockIdx.x, n32 = unit / kchunks, kc = unit - n32 * kchunks;
+  const int r = threadIdx.x >> 3, q = threadIdx.x & 7;
+  const int n = n32 * 32 + r, k = kc * 32 + q * 4;
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) v[e] = (n < N && k + e < K) ? __ldg(Wm + (size_t)n * K + k + e) : 0.f;
+  float h[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = tc::tf32_hi(v[e]);
+  float* u = out + (size_t)unit * tc::PACK_UNIT_FLOATS;
+  const uint32_t off = tc::sw128(r, q * 4) / 4;
+  *reinterpret_cast<float4*>(u + off) = make_float4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<float4*>(u + 1024 + off) = make_float4(v[0] - h[0], v[1] - h[1], v[2] - h[2], v[3] - h[3]);
+}
+
 int check_img(int64_t B, int64_t H, int64_t W, int64_t C) {
   SLN_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && C >= 1 && B * H * W < (1ll << 31) && B * H * W * C < (1ll << 40), "image extents out of range");
   return SLN_OK;
@@ -344,8 +361,20 @@ using namespace sln;
 
 extern "C" {
 
-int sln_spade_conv(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, const float* Wp, const float* bias,
-                   int64_t Cout, float* out, void* stream) {
+size_t sln_packed_weights_bytes(int64_t N, int64_t K) { return (N < 1 || K < 1) ? 0 : tc::packed_weight_floats(N, K) * sizeof(float); }
+
+int sln_pack_weights(const float* Wm, int64_t N, int64_t K, float* out, void* stream) {
+  SLN_CHECK_ARG(Wm && out && N >= 1 && K >= 1 && N < (1ll << 24) && K < (1ll << 24) && (uintptr_t)out % 16 == 0, "bad argument");
+  const int kchunks = (int)ceil_div64(K, 32);
+  const long long units = ceil_div64(N, 128) * 4 * kchunks;
+  SLN_CHECK_ARG(units < (1ll << 31), "weight matrix too large");
+  ProfScope prof((cudaStream_t)stream, PROF_SPADE_MISC, 12.0 * (double)N * K);
+  k_pack_weights<<<(unsigned)units, 256, 0, (cudaStream_t)stream>>>(Wm, (int)N, (int)K, kchunks, out);
+  return check_launch("pack_weights");
+}
+
+int sln_spade_conv(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, const float* Wp, const float* Wpacked,
+                   const float* bias, int64_t Cout, float* out, void* stream) {
   SLN_TRY(check_img(B, H, W, Cin));
   SLN_CHECK_ARG(x && Wp && out && Cout >= 1, "null pointer");
   SLN_CHECK_ARG(ks == 1 || ks == 3, "kernel size must be 1 or 3 (reflection-padded)");
@@ -359,13 +388,19 @@ int sln_spade_conv(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin,
   epi.C = out; epi.ldc = N; epi.bias = bias;
   if (tc::tc_eligible(M, N, K) && A.vec_ok() && Wv.vec_ok()) {
     tc::TcEpiStore te{out, N, bias, epi.fin};
+    if (Wpacked) {   // weights pre-split and pre-tiled once per weight version: their tiles arrive by cp.async.bulk
+      tc::PackedB pb{Wpacked, ceil_div(K, tc::BK)};
+      SLN_CHECK_ARG(pb.vec_ok(), "packed weights must be 16-byte aligned");
+      return tc::launch_tc<true, true>(st, A, pb, te, M, N, K, false, "spade_conv_tc_packed", PROF_SPADE_CONV);
+    }
     return tc::launch_tc<true, true>(st, A, Wv, te, M, N, K, false, "spade_conv_tc", PROF_SPADE_CONV);
   }
   return launch_gemm<true, true>(st, A, Wv, epi, M, N, K, false, "spade_conv", PROF_SPADE_CONV);
 }
 
-int sln_spade_modulate(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* bias_g, const float* bias_b,
-                       int64_t C, int32_t pair, const float* x, const float* mean, const float* inv, float slope, float* out, void* stream) {
+int sln_spade_modulate(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* Wgb_packed, const float* bias_g,
+                       const float* bias_b, int64_t C, int32_t pair, const float* x, const float* mean, const float* inv, float slope, float* out,
+                       void* stream) {
   SLN_TRY(check_img(B, H, W, Ca));
   SLN_CHECK_ARG(actv && Wgb && bias_g && bias_b && x && mean && inv && out, "null pointer");
   SLN_CHECK_ARG(H >= 2 && W >= 2 && C >= 1 && pair >= 2 && (2 * C) % pair == 0, "bad modulation shape");
@@ -380,7 +415,13 @@ int sln_spade_modulate(const float* actv, int64_t B, int64_t H, int64_t W, int64
     TcEpiSpade te{out, x, (int)C, bias_g, bias_b, mean, inv, (int)(H * W), slope};
     tc::TcChoice ch{pair, 1, ceil_div(K, tc::BK) * tc::BK};
     int rc;
-    if (pair == 128) rc = tc::launch_tc_bn<128, true, true>(st, A, Wv, te, M, N, K, ch);
+    if (Wgb_packed) {
+      tc::PackedB pb{Wgb_packed, ceil_div(K, tc::BK)};
+      SLN_CHECK_ARG(pb.vec_ok(), "packed weights must be 16-byte aligned");
+      if (pair == 128) rc = tc::launch_tc_bn<128, true, true>(st, A, pb, te, M, N, K, ch);
+      else if (pair == 64) rc = tc::launch_tc_bn<64, true, true>(st, A, pb, te, M, N, K, ch);
+      else rc = tc::launch_tc_bn<32, true, true>(st, A, pb, te, M, N, K, ch);
+    } else if (pair == 128) rc = tc::launch_tc_bn<128, true, true>(st, A, Wv, te, M, N, K, ch);
     else if (pair == 64) rc = tc::launch_tc_bn<64, true, true>(st, A, Wv, te, M, N, K, ch);
     else rc = tc::launch_tc_bn<32, true, true>(st, A, Wv, te, M, N, K, ch);
     if (rc != SLN_OK) return rc;

@@ -137,6 +137,36 @@ __device__ __forceinline__ void split_store1(uint32_t hi_addr, uint32_t lo_addr,
   sts1(lo_addr, v - h);
 }
 
+// Pre-split, pre-tiled B operand (weights that do not change between launches: convolution kernels at inference, Linear weights
+// between optimizer steps).  sln_pack_weights() writes, for every (32-row group, 32-k chunk) UNIT, the K-major SWIZZLE_128B image of
+// the hi tile (4096 B) followed by the lo tile (4096 B).  The kernel then moves a stage's B tiles with cp.async.bulk (the TMA
+// engine's linear mode, SASS UBLKCP) straight into shared memory — no registers, no producer instructions, completion counted on the
+// stage's `full` mbarrier — instead of loading, splitting and storing them with the producer warps.
+struct PackedB {
+  const float* units;   // [ceil(N/128)*4][ceil(K/32)][2][32][32] floats
+  int kchunks;          // ceil(K/32)
+  // functor API stubs (never called: the kernel takes the bulk-copy path for this type)
+  struct Tok { int unused; };
+  __device__ __forceinline__ Tok token(int) const { return Tok{0}; }
+  __device__ __forceinline__ int clampc(int c) const { return c; }
+  __device__ __forceinline__ void fetch4(const Tok&, int, float4&, float4&) const {}
+  __device__ __forceinline__ float4 finish4(const Tok&, int, float4 v, float4) const { return v; }
+  bool vec_ok() const { return ((uintptr_t)units % 16) == 0; }
+};
+template <class T> struct is_packed { static constexpr bool value = false; };
+template <> struct is_packed<PackedB> { static constexpr bool value = true; };
+constexpr int PACK_UNIT_FLOATS = 2 * 32 * 32;   // hi + lo of a 32 x 32 unit
+inline size_t packed_weight_floats(int64_t N, int64_t K) { return (size_t)(ceil_div64(N, 128) * 4) * (size_t)ceil_div64(K, 32) * PACK_UNIT_FLOATS; }
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+
 // Operand loader.  Every access is a float4 of 4 consecutive STORAGE columns of one storage row, fetched through the
 // functor's two-phase API: fetch() issues all raw 16-byte loads of the chunk back to back (nothing depends on them, so
 // they are all in flight together), store() applies the lazy transform, splits hi/lo and writes the swizzled tiles.
@@ -344,6 +374,7 @@ template <int BN, bool A_RC, bool B_RC, bool MSEG, class AOp, class BOp, class E
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const BOp B, const Epi epi, int M, int N, int K, int kchunk) {
   using L = SmemLayout<BN>;
   constexpr int S = L::STAGES, PF = MSEG ? 1 : 2;   // chunks prefetched into registers per producer thread
+  constexpr bool BP = is_packed<BOp>::value;       // B tiles arrive by cp.async.bulk from a pre-split, pre-tiled image
   extern __shared__ char smem_raw[];
   char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
   float* stat = reinterpret_cast<float*>(smem + S * L::STAGE);             // [2][8][BN]
@@ -372,7 +403,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
     tmem_alloc(tmem_slot, TMEM_COLS);
     if (lane == 0) {
 #pragma unroll
-      for (int s = 0; s < S; ++s) { mbar_init(full + s, PROD_WARPS); mbar_init(empty + s, 1); }
+      for (int s = 0; s < S; ++s) { mbar_init(full + s, PROD_WARPS + (BP ? 1 : 0)); mbar_init(empty + s, 1); }
       mbar_init(segfull, 1); mbar_init(segfull + 1, 1);
       mbar_init(accempty, PROD_WARPS); mbar_init(accempty + 1, PROD_WARPS);
       fence_barrier_init();
@@ -460,22 +491,34 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
     auto fetch = [&](auto& BA, auto& BB, int c) {
       if (tail && c == nchunks - 1) {
         la.template fetch<true>(A, BA, kbeg + c * BK, kend, tid);
-        lb.template fetch<true>(B, BB, kbeg + c * BK, kend, tid);
+        if constexpr (!BP) lb.template fetch<true>(B, BB, kbeg + c * BK, kend, tid);
       } else {
         la.template fetch<false>(A, BA, kbeg + c * BK, kend, tid);
-        lb.template fetch<false>(B, BB, kbeg + c * BK, kend, tid);
+        if constexpr (!BP) lb.template fetch<false>(B, BB, kbeg + c * BK, kend, tid);
       }
     };
     auto produce = [&](auto& BA, auto& BB, int c) {
       const int s = c % S, use = c / S;
       const uint32_t st = sbase + s * L::STAGE;
       if (use > 0) mbar_wait(empty + s, (uint32_t)((use - 1) & 1));   // the MMAs that read this stage have retired
+      if constexpr (BP) {
+        if (tid == 0) {                                   // B_hi | B_lo tiles of this stage: BN/32 units, two 4 KB bulk copies each
+          mbar_expect_tx(full + s, 2 * L::B_TILE);
+          const float* u0 = B.units + ((size_t)(n0 / 32) * B.kchunks + (size_t)(kbeg / BK + c)) * PACK_UNIT_FLOATS;
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j) {
+            const float* u = u0 + (size_t)j * B.kchunks * PACK_UNIT_FLOATS;
+            bulk_g2s(st + 2 * L::A_TILE + j * 4096, u, 4096, full + s);
+            bulk_g2s(st + 2 * L::A_TILE + L::B_TILE + j * 4096, u + 1024, 4096, full + s);
+          }
+        }
+      }
       if (tail && c == nchunks - 1) {
         la.template store<true>(A, BA, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
-        lb.template store<true>(B, BB, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
+        if constexpr (!BP) lb.template store<true>(B, BB, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
       } else {
         la.template store<false>(A, BA, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
-        lb.template store<false>(B, BB, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
+        if constexpr (!BP) lb.template store<false>(B, BB, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
       }
       if (c + PF < nchunks) fetch(BA, BB, c + PF);        // refill the register buffer: these loads fly during the next PF chunks
       fence_async_smem();                                 // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -487,7 +530,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
       }
     };
     la.init(A, m0, tid);
-    lb.init(B, n0, tid);
+    if constexpr (!BP) lb.init(B, n0, tid);
     if (nchunks > 0) fetch(a0, b0, 0);
     if (PF == 2 && nchunks > 1) fetch(a1, b1, 1);
     for (int c = 0; c < nchunks; c += PF) {

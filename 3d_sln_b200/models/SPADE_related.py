@@ -98,6 +98,17 @@ class _Packed(object):
     pass
 
 
+def _pretile(w):
+    """Pre-split (TF32 hi | lo) and pre-tile a packed weight matrix [N, K] on its device for the bulk-copy operand path
+    (sln_pack_weights); None when the matrix is too narrow for the tensor-core path anyway."""
+    if not w.is_cuda or w.size(0) < 32 or w.size(1) < 32:
+        return None
+    lib = _lib.load()
+    out = torch.empty(lib.sln_packed_weights_bytes(w.size(0), w.size(1)) // 4, device=w.device, dtype=torch.float32)
+    _lib.check(lib.sln_pack_weights(w.data_ptr(), w.size(0), w.size(1), out.data_ptr(), _lib.cur_stream(w.device)), "pack_weights")
+    return out
+
+
 class SPADEGenerator4(nn.Module):
     def __init__(self, semantic_nc, target_nc, nz, ngf, norm, crop_size, n_up):
         super().__init__()
@@ -132,12 +143,14 @@ class SPADEGenerator4(nn.Module):
         P.db = sp.mlp_preshared_depth[1].bias.detach().contiguous().float().to(dev)
         P.ws = _pack_conv(sp.mlp_shared[1].weight.detach()).to(dev)
         P.bs = sp.mlp_shared[1].bias.detach().contiguous().float().to(dev)
+        P.ws_t = _pretile(P.ws)
         wg, wb = _pack_conv(sp.mlp_gamma[1].weight.detach()), _pack_conv(sp.mlp_beta[1].weight.detach())
         # one contraction for gamma and beta: output tile of `pair` columns = [gamma of pair/2 channels | beta of the same channels]
         P.pair = min(128, 2 * C)
         half = P.pair // 2
         K = wg.size(1)
         P.wgb = torch.stack([wg.view(C // half, half, K), wb.view(C // half, half, K)], dim=1).reshape(2 * C, K).contiguous().to(dev)
+        P.wgb_t = _pretile(P.wgb)
         P.bg = sp.mlp_gamma[1].bias.detach().contiguous().float().to(dev)
         P.bb = sp.mlp_beta[1].bias.detach().contiguous().float().to(dev)
         P.eps = float(sp.param_free_norm.eps)
@@ -146,11 +159,12 @@ class SPADEGenerator4(nn.Module):
     def _pack_block(self, blk, dev):
         P = _Packed()
         P.fin, P.fout, P.fmiddle, P.learned = blk.fin, blk.fout, blk.fmiddle, blk.learned_shortcut
-        P.w0 = _pack_conv(_sn_weight(blk.conv_0[1])).to(dev); P.b0 = blk.conv_0[1].bias.detach().contiguous().float().to(dev)
-        P.w1 = _pack_conv(_sn_weight(blk.conv_1[1])).to(dev); P.b1 = blk.conv_1[1].bias.detach().contiguous().float().to(dev)
+        P.w0 = _pack_conv(_sn_weight(blk.conv_0[1])).to(dev); P.w0_t = _pretile(P.w0); P.b0 = blk.conv_0[1].bias.detach().contiguous().float().to(dev)
+        P.w1 = _pack_conv(_sn_weight(blk.conv_1[1])).to(dev); P.w1_t = _pretile(P.w1); P.b1 = blk.conv_1[1].bias.detach().contiguous().float().to(dev)
         P.n0, P.n1 = self._pack_spade(blk.norm_0, dev), self._pack_spade(blk.norm_1, dev)
         if blk.learned_shortcut:
             P.ws = _pack_conv(_sn_weight(blk.conv_s)).to(dev)
+            P.ws_t = _pretile(P.ws)
             P.ns = self._pack_spade(blk.norm_s, dev)
         P.se1 = blk.se.fc[0].weight.detach().contiguous().float().to(dev)      # [C/8, C]
         P.se2 = blk.se.fc[2].weight.detach().contiguous().float().to(dev)      # [C, C/8]
@@ -169,6 +183,7 @@ class SPADEGenerator4(nn.Module):
         # fc output (B, C0*sh*sw) is viewed as NCHW (B, C0, sh, sw) by the reference: permute the rows so that it comes out NHWC
         w = self.fc.weight.detach().view(C0, hw, self.nz).permute(1, 0, 2).reshape(C0 * hw, self.nz)
         P.fcw = w.contiguous().float().to(dev)
+        P.fcw_t = _pretile(P.fcw)
         P.fcb = self.fc.bias.detach().view(C0, hw).t().reshape(-1).contiguous().float().to(dev)
         P.blocks = {n: self._pack_block(getattr(self, n), dev) for n in ("head_0", "G_middle_0", "G_middle_1", "up_0", "up_1", "up_2", "up_3")}
         P.wimg = self.conv_img.weight.detach().permute(0, 2, 3, 1).contiguous().float().to(dev)     # [3, 5, 5, nf]
@@ -178,9 +193,10 @@ class SPADEGenerator4(nn.Module):
 
     # ---------------------------------------------------------------------------------------- kernels
     @staticmethod
-    def _conv(lib, st, x, B, H, W, Cin, ks, relu_in, w, b, Cout):
+    def _conv(lib, st, x, B, H, W, Cin, ks, relu_in, w, b, Cout, wt=None):
         out = torch.empty(B, H, W, Cout, device=x.device, dtype=torch.float32)
-        _lib.check(lib.sln_spade_conv(x.data_ptr(), B, H, W, Cin, ks, int(relu_in), w.data_ptr(), _lib.ptr(b), Cout, out.data_ptr(), st), "spade_conv")
+        _lib.check(lib.sln_spade_conv(x.data_ptr(), B, H, W, Cin, ks, int(relu_in), w.data_ptr(), _lib.ptr(wt), _lib.ptr(b), Cout, out.data_ptr(), st),
+                   "spade_conv")
         return out
 
     def _spade(self, lib, st, P, x, seg, seg_mode, B, H, W, slope, scratch):
@@ -192,20 +208,20 @@ class SPADEGenerator4(nn.Module):
         feat = torch.empty(B, H, W, NHIDDEN // 8 + self.semantic_nc - 1, device=dev)
         _lib.check(lib.sln_spade_seg_features(seg.data_ptr(), B, self.semantic_nc, seg.size(2), seg_mode, H, W, P.dw.data_ptr(), P.db.data_ptr(),
                                               NHIDDEN // 8, feat.data_ptr(), st), "seg_features")
-        actv = self._conv(lib, st, feat, B, H, W, feat.size(3), 3, False, P.ws, P.bs, NHIDDEN)      # ReLU applied lazily by the consumer
+        actv = self._conv(lib, st, feat, B, H, W, feat.size(3), 3, False, P.ws, P.bs, NHIDDEN, P.ws_t)      # ReLU applied lazily by the consumer
         out = torch.empty(B, H, W, C, device=dev)
-        _lib.check(lib.sln_spade_modulate(actv.data_ptr(), B, H, W, NHIDDEN, P.wgb.data_ptr(), P.bg.data_ptr(), P.bb.data_ptr(), C, P.pair,
+        _lib.check(lib.sln_spade_modulate(actv.data_ptr(), B, H, W, NHIDDEN, P.wgb.data_ptr(), _lib.ptr(P.wgb_t), P.bg.data_ptr(), P.bb.data_ptr(), C, P.pair,
                                           x.data_ptr(), mean.data_ptr(), inv.data_ptr(), float(slope), out.data_ptr(), st), "spade_modulate")
         return out
 
     def _block(self, lib, st, P, x, seg, seg_mode, B, H, W, scratch):
         """SPADEResnetBlock4.forward (:1487-1495)."""
         if P.learned:
-            xs = self._conv(lib, st, self._spade(lib, st, P.ns, x, seg, seg_mode, B, H, W, 1.0, scratch), B, H, W, P.fin, 1, False, P.ws, None, P.fout)
+            xs = self._conv(lib, st, self._spade(lib, st, P.ns, x, seg, seg_mode, B, H, W, 1.0, scratch), B, H, W, P.fin, 1, False, P.ws, None, P.fout, P.ws_t)
         else:
             xs = x
-        dx = self._conv(lib, st, self._spade(lib, st, P.n0, x, seg, seg_mode, B, H, W, 0.2, scratch), B, H, W, P.fin, 3, False, P.w0, P.b0, P.fmiddle)
-        dx = self._conv(lib, st, self._spade(lib, st, P.n1, dx, seg, seg_mode, B, H, W, 0.2, scratch), B, H, W, P.fmiddle, 3, False, P.w1, P.b1, P.fout)
+        dx = self._conv(lib, st, self._spade(lib, st, P.n0, x, seg, seg_mode, B, H, W, 0.2, scratch), B, H, W, P.fin, 3, False, P.w0, P.b0, P.fmiddle, P.w0_t)
+        dx = self._conv(lib, st, self._spade(lib, st, P.n1, dx, seg, seg_mode, B, H, W, 0.2, scratch), B, H, W, P.fmiddle, 3, False, P.w1, P.b1, P.fout, P.w1_t)
         out = torch.empty(B, H, W, P.fout, device=x.device)
         _lib.check(lib.sln_spade_se_residual(dx.data_ptr(), xs.data_ptr(), B, H, W, P.fout, P.se1.data_ptr(), P.se2.data_ptr(), P.se1.size(0),
                                              scratch.data_ptr(), scratch.numel() * 4, out.data_ptr(), st), "se_residual")
@@ -237,7 +253,7 @@ class SPADEGenerator4(nn.Module):
             nf = self.nf
             scratch = torch.zeros(max(4096, 2 * B * 16 * nf * 64 + 64), device=dev, dtype=torch.float32)
             taps = self.taps
-            x = self._conv(lib, st, z, B, 1, 1, self.nz, 1, False, P.fcw, P.fcb, 16 * nf * self.sh * self.sw).view(B, self.sh, self.sw, 16 * nf)
+            x = self._conv(lib, st, z, B, 1, 1, self.nz, 1, False, P.fcw, P.fcb, 16 * nf * self.sh * self.sw, P.fcw_t).view(B, self.sh, self.sw, 16 * nf)
             H = W = self.sh
 
             def tap(name, t):

@@ -140,6 +140,31 @@ def cpu_vae_steps(n_scenes, steps, warmup, budget_s):
     return used / dt, dt, used, threads
 
 
+def eager_gpu_vae_steps(dev, n_scenes, steps=10, warmup=3):
+    """Baseline only: the oracle's plain-torch restatement of the reference train step (train.py:70-84) run EAGERLY ON THE SAME GPU —
+    the launch-per-aten-op execution the reference itself has after model.cuda() (the reference cannot travel to the GPU box)."""
+    from oracle import vae_oracle as vo
+    syn = importlib.import_module("3d_sln_b200.data.synthetic")
+    Model = importlib.import_module("3d_sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
+    torch.manual_seed(42)
+    m = Model(syn.default_vocab(), embedding_dim=64, batch_size=128, train_3d=True, decoder_cat=True, gconv_mode='feedforward',
+              gconv_num_layers=5, mlp_normalization='batch', vec_noise_dim=0, layout_noise_dim=32, use_AE=False)
+    sd = vo.leaf_state(m.state_dict(), torch.float32, device=dev)
+    _, objs, boxes, triples, angles, attrs, _, _ = syn.synthetic_batch(n_scenes, NODES_PER_SCENE, seed=42)
+    batch = tuple(t.to(dev) for t in (objs, triples, boxes, angles, attrs))
+    opt = {}
+    for it in range(warmup):
+        vo.train_step(sd, batch, torch.randn(batch[0].size(0), 64, device=dev), opt, it + 1)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for it in range(steps):
+        vo.train_step(sd, batch, torch.randn(batch[0].size(0), 64, device=dev), opt, warmup + it + 1)   # returns python floats: syncs like train.py:78
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": n_scenes / dt, "unit": "scene-graphs/s", "ms_per_step": dt * 1e3, "kind": "port, torch eager on the same GPU (fp32, TF32 matmul off)",
+            "sample": "%d scenes x %d nodes, %d timed steps of oracle/vae_oracle.py train_step on cuda" % (n_scenes, NODES_PER_SCENE, steps)}
+
+
 def run_reference(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
@@ -306,13 +331,19 @@ def run_vae(args):
         val, dt, used, threads = cpu_vae_steps(SCENES_PER_GPU, steps=8, warmup=2, budget_s=25.0)
         cpu = {"value": val, "unit": "scene-graphs/s", "cores": threads, "kind": "port",
                "sample": "%d scenes x %d nodes per step, 8 timed steps, fp32 torch CPU ops (oracle/vae_oracle.py train_step)" % (used, NODES_PER_SCENE)}
+    eager = None
+    if n == 1 and not args.no_cpu_baseline:
+        try:
+            eager = eager_gpu_vae_steps(dev, SCENES_PER_GPU)
+        except Exception as e:   # baseline only: never fail the bench line because of it
+            eager = {"unavailable": repr(e)[:200]}
     line = {
         "metric": "scene-graphs/sec VAE train step (batch64, 32obj)", "value": value, "unit": "scene-graphs/s", "n_gpus": n,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": vae_config(n),
         "e2e": {"value": e2e, "unit": "scene-graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-        "roofline": roofline, "roofline_scatter": roofline_scatter, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roofline, "roofline_scatter": roofline_scatter, "cpu_baseline": cpu, "eager_gpu_baseline": eager, "clocks": clocks,
         "kernel_classes_ms": {k: round(v["ms"], 4) for k, v in prof["rows"].items()},
         "final_losses": {"bbox": final_losses[0], "angle": final_losses[1], "kld_weighted": final_losses[2], "total": final_losses[3]},
     }

@@ -221,10 +221,16 @@ int sln_scene_classes_bwd(const void* ws, int64_t V, int64_t F, int32_t fill_bac
  *                       scratch >= 4*(B*min(HW,64)*C + B*C) bytes, 16-byte aligned.
  * sln_spade_to_rgb      leaky_relu(slope) -> Conv2d(Cin, Cout <= 4, ks, zero padding ks/2) -> tanh (:1602-1603); NHWC in, NCHW
  *                       out; `pre` (optional) receives the pre-tanh values. */
-int sln_spade_conv(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, const float* Wp, const float* bias,
-                   int64_t Cout, float* out, void* stream);
-int sln_spade_modulate(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* bias_g, const float* bias_b,
-                       int64_t C, int32_t pair, const float* x, const float* mean, const float* inv, float slope, float* out, void* stream);
+/* sln_pack_weights: optional one-off transform of a weight matrix W [N][K] (row-major) into the pre-split (TF32 hi | lo), pre-tiled
+ * image the contraction kernel can pull into shared memory with cp.async.bulk; pass the result as `Wpacked` / `Wgb_packed` (or NULL:
+ * the weights are then split on the fly).  out: sln_packed_weights_bytes(N, K) bytes, 16-byte aligned. */
+size_t sln_packed_weights_bytes(int64_t N, int64_t K);
+int sln_pack_weights(const float* W, int64_t N, int64_t K, float* out, void* stream);
+int sln_spade_conv(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, const float* Wp, const float* Wpacked,
+                   const float* bias, int64_t Cout, float* out, void* stream);
+int sln_spade_modulate(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* Wgb_packed, const float* bias_g,
+                       const float* bias_b, int64_t C, int32_t pair, const float* x, const float* mean, const float* inv, float slope, float* out,
+                       void* stream);
 int sln_spade_ln_stats(const float* x, int64_t B, int64_t n_per_sample, float eps, void* scratch, float* mean, float* inv, void* stream);
 int sln_spade_seg_features(const float* seg, int64_t B, int32_t nc, int32_t S, int32_t mode, int64_t h, int64_t w, const float* dw, const float* db,
                            int32_t nd, float* out, void* stream);

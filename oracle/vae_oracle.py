@@ -78,9 +78,9 @@ def gconv_layer(sd, prefix, obj_vecs, pred_vecs, edges, training, stats_out=None
     t_in = torch.cat([obj_vecs.index_select(0, s_idx), pred_vecs, obj_vecs.index_select(0, o_idx)], dim=1)   # :78-83
     t_out = mlp(sd, prefix + '.net1', t_in, training, stats_out=stats_out)                                  # :84
     new_s, new_p, new_o = t_out[:, :H], t_out[:, H:H + Dout], t_out[:, H + Dout:2 * H + Dout]                # :88-90
-    pooled = torch.zeros(O, H, dtype=obj_vecs.dtype)
+    pooled = torch.zeros(O, H, dtype=obj_vecs.dtype, device=obj_vecs.device)
     pooled = pooled.index_add(0, s_idx, new_s).index_add(0, o_idx, new_o)                                   # :93-100
-    counts = torch.zeros(O, dtype=obj_vecs.dtype).index_add(0, s_idx, torch.ones_like(s_idx, dtype=obj_vecs.dtype))
+    counts = torch.zeros(O, dtype=obj_vecs.dtype, device=obj_vecs.device).index_add(0, s_idx, torch.ones_like(s_idx, dtype=obj_vecs.dtype))
     counts = counts.index_add(0, o_idx, torch.ones_like(o_idx, dtype=obj_vecs.dtype)).clamp(min=1)          # :102-107
     pooled = pooled / counts[:, None]                                                                       # :108
     return mlp(sd, prefix + '.net2', pooled, training, stats_out=stats_out), new_p                           # :109
@@ -164,11 +164,13 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.9
         p.addcdiv_(m, v.sqrt() / math.sqrt(bc2) + eps, value=-lr / bc1)
 
 
-def leaf_state(state_dict, dtype=torch.float64, requires_grad=True):
-    """Detached copy of a model state_dict as oracle input: float tensors cast to ``dtype`` (parameters become leaves)."""
+def leaf_state(state_dict, dtype=torch.float64, requires_grad=True, device="cpu"):
+    """Detached copy of a model state_dict as oracle input: float tensors cast to ``dtype`` (parameters become leaves).
+    device: "cpu" for the oracle proper; bench.py also runs the same plain-torch restatement on the GPU as the "PyTorch eager on
+    the same B200" baseline (what the reference's train.py would execute after model.cuda())."""
     sd = {}
     for k, v in state_dict.items():
-        v = v.detach().cpu()
+        v = v.detach().to(device)
         if v.is_floating_point():
             v = v.to(dtype).clone()
             if requires_grad and not (k.endswith('running_mean') or k.endswith('running_var')):
