@@ -88,6 +88,7 @@ class VaeDesc(ctypes.Structure):
         ("n_angle", ctypes.c_int32), ("num_objs", ctypes.c_int32), ("num_preds", ctypes.c_int32),
         ("num_attrs", ctypes.c_int32), ("bn_eps", ctypes.c_float), ("bn_momentum", ctypes.c_float),
         ("gconv_dim_override", ctypes.c_int32), ("gconv_hidden_override", ctypes.c_int32),
+        ("packed_weights", ctypes.c_void_p),
     ]
 
 
@@ -107,6 +108,8 @@ SIGNATURES = {
     "sln_prof_read": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_I64)]),
     "sln_vae_num_params": (ctypes.c_int, [_DESC]),
     "sln_vae_num_bn": (ctypes.c_int, [_DESC]),
+    "sln_vae_packed_bytes": (_SZ, [_DESC]),
+    "sln_vae_pack_weights": (ctypes.c_int, [_DESC, _P, _P, _SZ, _P]),
     "sln_vae_workspace_bytes": (_SZ, [_DESC, _I64, _I64, ctypes.c_int]),
     "sln_vae_encoder_fwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "sln_vae_encoder_bwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _I64, _I64, _P, _SZ, _P]),
@@ -173,8 +176,8 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.sln_version() != 1:
-            raise RuntimeError("3d_sln_b200: ABI version mismatch (library %d, binding 1)" % lib.sln_version())
+        if lib.sln_version() != 2:
+            raise RuntimeError("3d_sln_b200: ABI version mismatch (library %d, binding 2)" % lib.sln_version())
         eng = os.environ.get("SLN_ENGINE")
         if eng in ("0", "1"):      # 0 = FP32 SIMT tiles, 1 = tcgen05 3xTF32 tiles (default) for the MLP contractions
             lib.sln_set_engine(int(eng))

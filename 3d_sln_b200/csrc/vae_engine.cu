@@ -7,7 +7,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/sln_b200.h"
 #include "vae_kernels.cuh"
@@ -34,7 +36,10 @@ constexpr int kMaxLayers = 32;
 
 struct Lin {
   const float* W; const float* b; float* dW; float* db; int in, out;
+  const float* pf;   // pre-split, pre-tiled image of W  [out][in]  (forward B operand; tc::PackedB), or null
+  const float* pb;   // ... of W^T [in][out] (backward-data B operand), or null
 };
+struct PackJob { const float* W; float* out; int N, K, ldw, transposed; };
 struct Blk {  // Linear [+ BatchNorm1d] [+ ReLU]   (reference graph.py:10-27)
   Lin lin;
   int has_bn, relu;
@@ -179,10 +184,22 @@ int count_bn(const Dims& dm) { return dm.norm ? (2 * dm.Lw * 4 + 4 + 2) : 0; }
 
 struct TableReader {
   const void* const* params; void* const* grads; void* const* bn; int ip, ib; int norm;
+  float* pack_base = nullptr;             // packed weight images (sln_vae_desc::packed_weights) or null
+  size_t pack_off = 0;                    // floats; advanced even when pack_base is null (size query)
+  std::vector<PackJob>* jobs = nullptr;   // filled by sln_vae_pack_weights
   Blk take(int in, int out, bool with_bn, bool relu) {
     Blk b; memset(&b, 0, sizeof(b));
     b.lin.in = in; b.lin.out = out; b.relu = relu ? 1 : 0;
     b.lin.W = (const float*)params[ip]; b.lin.dW = grads ? (float*)grads[ip] : nullptr; ++ip;
+    if (in >= 32 && out >= 32 && in % 4 == 0) {   // the shapes the tensor-core path accepts (tc_eligible) get packed images
+      const size_t nf = tc::packed_weight_floats(out, in), nb = tc::packed_weight_floats(in, out);
+      if (pack_base) { b.lin.pf = pack_base + pack_off; b.lin.pb = pack_base + pack_off + nf; }
+      if (jobs && pack_base) {
+        jobs->push_back(PackJob{b.lin.W, pack_base + pack_off, out, in, in, 0});
+        jobs->push_back(PackJob{b.lin.W, pack_base + pack_off + nf, in, out, in, 1});
+      }
+      pack_off += nf + nb;
+    }
     b.lin.b = (const float*)params[ip]; b.lin.db = grads ? (float*)grads[ip] : nullptr; ++ip;
     if (with_bn && norm) {
       b.has_bn = 1;
@@ -202,11 +219,13 @@ void take_gconv(TableReader& tr, const Dims& dm, Blk* blk) {
   blk[3] = tr.take(dm.H, dm.D, true, true);
 }
 
-int parse_model(const Dims& dm, const void* const* params, void* const* grads, void* const* bn, Model* m) {
+int parse_model(const Dims& dm, const void* const* params, void* const* grads, void* const* bn, Model* m, const void* packed = nullptr,
+                std::vector<PackJob>* jobs = nullptr, size_t* packed_floats = nullptr) {
   SLN_CHECK_ARG(params != nullptr, "null parameter table");
   memset(m, 0, sizeof(Model));
   for (int i = 0; i < 7; ++i) { m->emb[i] = (const float*)params[i]; m->demb[i] = grads ? (float*)grads[i] : nullptr; }
   TableReader tr{params, grads, bn, 7, 0, dm.norm};
+  tr.pack_base = (float*)packed; tr.jobs = jobs;
   m->box_emb = tr.take(dm.box_dim, dm.box_w, false, false);
   for (int l = 0; l < dm.Lw; ++l) take_gconv(tr, dm, m->enc[l]);
   for (int l = dm.Lw; l < dm.L; ++l) for (int k = 0; k < 4; ++k) m->enc[l][k] = m->enc[0][k];
@@ -225,7 +244,32 @@ int parse_model(const Dims& dm, const void* const* params, void* const* grads, v
   m->angle_net[0] = tr.take(dm.D, dm.H, true, true);
   m->angle_net[1] = tr.take(dm.H, dm.n_angle, false, false);
   if (tr.ip != count_params(dm)) { set_error("internal: parameter table walk mismatch (%d vs %d)", tr.ip, count_params(dm)); return SLN_EINVAL; }
+  if (packed_floats) *packed_floats = tr.pack_off;
   return SLN_OK;
+}
+
+// all weight images of a model in a few launches: the job table travels by value in the kernel parameters (graph-capturable)
+constexpr int kPackJobsPerLaunch = 96;
+struct PackJobs { PackJob job[kPackJobsPerLaunch]; int unit_start[kPackJobsPerLaunch + 1]; int n; };
+__global__ void __launch_bounds__(256) k_pack_jobs(const PackJobs jobs) {
+  int j = 0;
+  while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.unit_start[j + 1]) ++j;
+  const PackJob& jb = jobs.job[j];
+  const int unit = blockIdx.x - jobs.unit_start[j], kchunks = ceil_div(jb.K, 32);
+  const int n32 = unit / kchunks, kc = unit - n32 * kchunks;
+  const int r = threadIdx.x >> 3, q = threadIdx.x & 7;
+  const int n = n32 * 32 + r, k = kc * 32 + q * 4;
+  float v[4], h[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const bool ok = n < jb.N && k + e < jb.K;
+    v[e] = ok ? __ldg(jb.transposed ? jb.W + (size_t)(k + e) * jb.ldw + n : jb.W + (size_t)n * jb.ldw + k + e) : 0.f;
+    h[e] = tc::tf32_hi(v[e]);
+  }
+  float* u = jb.out + (size_t)unit * tc::PACK_UNIT_FLOATS;
+  const uint32_t off = tc::sw128(r, q * 4) / 4;
+  *reinterpret_cast<float4*>(u + off) = make_float4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<float4*>(u + 1024 + off) = make_float4(v[0] - h[0], v[1] - h[1], v[2] - h[2], v[3] - h[3]);
 }
 
 // ---------------------------------------------------------------- workspace plans
@@ -350,6 +394,10 @@ int block_fwd(const Ctx& c, const AOp& A, int M, const Blk& b, BlkState& s, floa
     return launch_skinny_fwd(c.st, A, b.lin.W, b.lin.b, M, b.lin.out, b.lin.in, epi.C, epi.ldc);
   if (use_tc(M, b.lin.out, b.lin.in, SITE_FWD) && A.vec_ok() && weight_view(b.lin).vec_ok()) {
     tc::TcEpiStore te{epi.C, epi.ldc, epi.bias, epi.fin};
+    if (b.lin.pf) {   // pre-split weight image: the B tiles arrive by cp.async.bulk
+      tc::PackedB pb{b.lin.pf, ceil_div(b.lin.in, tc::BK)};
+      return tc::launch_tc<true, true>(c.st, A, pb, te, M, b.lin.out, b.lin.in, false, "linear_fwd_tc_packed", PROF_GEMM_FWD);
+    }
     return tc::launch_tc<true, true>(c.st, A, weight_view(b.lin), te, M, b.lin.out, b.lin.in, false, "linear_fwd_tc", PROF_GEMM_FWD);
   }
   return launch_gemm<true, true>(c.st, A, weight_view(b.lin), epi, M, b.lin.out, b.lin.in, false, "linear_fwd", PROF_GEMM_FWD);
@@ -409,6 +457,10 @@ int bwd_x_plain(const Ctx& c, const DyView& dy, const Lin& lin, int M, float* dX
   epi.C = dX; epi.ldc = ldx;
   if (use_tc(M, lin.in, lin.out, SITE_BWD_X) && dy.vec_ok() && weight_view(lin).vec_ok()) {
     tc::TcEpiStore te{dX, ldx, nullptr, epi.fin};
+    if (lin.pb) {
+      tc::PackedB pb{lin.pb, ceil_div(lin.out, tc::BK)};
+      return tc::launch_tc<true, true>(c.st, dy, pb, te, M, lin.in, lin.out, false, "linear_bwd_x_tc_packed", PROF_GEMM_BWD_X);
+    }
     return tc::launch_tc<true, false>(c.st, dy, weight_view(lin), te, M, lin.in, lin.out, false, "linear_bwd_x_tc", PROF_GEMM_BWD_X);
   }
   return launch_gemm<true, false>(c.st, dy, weight_view(lin), epi, M, lin.in, lin.out, false, "linear_bwd_x", PROF_GEMM_BWD_X);
@@ -428,6 +480,10 @@ int bwd_x_masked(const Ctx& c, const DyView& dy, const Lin& lin, int M, const Bl
   }
   if (use_tc(M, lin.in, lin.out, SITE_BWD_XM) && dy.vec_ok() && weight_view(lin).vec_ok()) {
     tc::TcEpiMaskReduce te{epi.G, epi.ldg, epi.add, epi.ldadd, epi.yprev, epi.ldy, epi.scale, epi.shift, epi.mean, epi.rstd, epi.fin};
+    if (lin.pb) {
+      tc::PackedB pb{lin.pb, ceil_div(lin.out, tc::BK)};
+      return tc::launch_tc<true, true>(c.st, dy, pb, te, M, lin.in, lin.out, false, "linear_bwd_x_masked_tc_packed", PROF_GEMM_BWD_X);
+    }
     return tc::launch_tc<true, false>(c.st, dy, weight_view(lin), te, M, lin.in, lin.out, false, "linear_bwd_x_masked_tc", PROF_GEMM_BWD_X);
   }
   return launch_gemm<true, false>(c.st, dy, weight_view(lin), epi, M, lin.in, lin.out, false, "linear_bwd_x_masked", PROF_GEMM_BWD_X);
@@ -616,6 +672,43 @@ using namespace sln;
 
 extern "C" {
 
+size_t sln_vae_packed_bytes(const sln_vae_desc* d) {
+  Dims dm;
+  if (make_dims(d, &dm)) return 0;
+  std::vector<const void*> fake((size_t)count_params(dm), (const void*)(uintptr_t)256);
+  static thread_local Model m;
+  size_t floats = 0;
+  if (parse_model(dm, fake.data(), nullptr, nullptr, &m, nullptr, nullptr, &floats)) return 0;
+  return floats * sizeof(float);
+}
+
+int sln_vae_pack_weights(const sln_vae_desc* d, const void* const* params, void* packed, size_t packed_bytes, void* stream) {
+  Dims dm;
+  SLN_TRY(make_dims(d, &dm));
+  SLN_CHECK_ARG(params && packed && (uintptr_t)packed % 16 == 0, "null or misaligned pointer");
+  static thread_local Model m;
+  std::vector<PackJob> jobs;
+  size_t floats = 0;
+  SLN_TRY(parse_model(dm, params, nullptr, nullptr, &m, packed, &jobs, &floats));
+  if (packed_bytes < floats * sizeof(float)) { set_error("packed weight buffer too small: %zu < %zu bytes", packed_bytes, floats * sizeof(float)); return SLN_EWORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(st, PROF_MISC, 12.0 * (double)floats);
+  for (size_t j0 = 0; j0 < jobs.size(); j0 += kPackJobsPerLaunch) {
+    PackJobs pj; memset(&pj, 0, sizeof(pj));
+    pj.n = (int)std::min((size_t)kPackJobsPerLaunch, jobs.size() - j0);
+    int units = 0;
+    for (int j = 0; j < pj.n; ++j) {
+      pj.job[j] = jobs[j0 + j];
+      pj.unit_start[j] = units;
+      units += (int)(ceil_div64(pj.job[j].N, 128) * 4 * ceil_div64(pj.job[j].K, 32));
+    }
+    pj.unit_start[pj.n] = units;
+    k_pack_jobs<<<units, 256, 0, st>>>(pj);
+    SLN_TRY(check_launch("pack_weights"));
+  }
+  return SLN_OK;
+}
+
 int sln_vae_num_params(const sln_vae_desc* d) { Dims dm; if (make_dims(d, &dm)) return -1; return count_params(dm); }
 int sln_vae_num_bn(const sln_vae_desc* d) { Dims dm; if (make_dims(d, &dm)) return -1; return count_bn(dm); }
 
@@ -635,7 +728,7 @@ int sln_vae_encoder_fwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_CHECK_ARG(objs && boxes && angles && attributes && mu && logvar && (triples || T64 == 0), "null input/output pointer");
   const Dims& dm = c.dm; const int O = (int)O64, T = (int)T64;
   static thread_local Model m; static thread_local NetPlan p;
-  SLN_TRY(parse_model(dm, params, nullptr, bn_bufs, &m));
+  SLN_TRY(parse_model(dm, params, nullptr, bn_bufs, &m, d->packed_weights));
   make_plan(dm, O, T, 0, ws, &p);
   SLN_TRY(check_ws(p, ws, ws_bytes));
   SLN_CUDA_TRY(cudaMemsetAsync(p.cp.base, 0, sizeof(unsigned) * kCounterCap, c.st));
@@ -676,7 +769,7 @@ int sln_vae_encoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_CHECK_ARG(grads && boxes && d_mu && d_logvar, "null pointer");
   const Dims& dm = c.dm; const int O = (int)O64, T = (int)T64;
   static thread_local Model m; static thread_local NetPlan p;
-  SLN_TRY(parse_model(dm, params, grads, nullptr, &m));
+  SLN_TRY(parse_model(dm, params, grads, nullptr, &m, d->packed_weights));
   make_plan(dm, O, T, 0, ws, &p);
   SLN_TRY(check_ws(p, ws, ws_bytes));
   side_begin(c);
@@ -736,7 +829,7 @@ int sln_vae_decoder_fwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_CHECK_ARG(z && objs && attributes && boxes_pred && angles_pred && (triples || T64 == 0), "null input/output pointer");
   const Dims& dm = c.dm; const int O = (int)O64, T = (int)T64;
   static thread_local Model m; static thread_local NetPlan p;
-  SLN_TRY(parse_model(dm, params, nullptr, bn_bufs, &m));
+  SLN_TRY(parse_model(dm, params, nullptr, bn_bufs, &m, d->packed_weights));
   make_plan(dm, O, T, 1, ws, &p);
   SLN_TRY(check_ws(p, ws, ws_bytes));
   SLN_CUDA_TRY(cudaMemsetAsync(p.cp.base, 0, sizeof(unsigned) * kCounterCap, c.st));
@@ -770,7 +863,7 @@ int sln_vae_decoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_CHECK_ARG(grads && d_boxes && d_angles, "null pointer");
   const Dims& dm = c.dm; const int O = (int)O64, T = (int)T64;
   static thread_local Model m; static thread_local NetPlan p;
-  SLN_TRY(parse_model(dm, params, grads, nullptr, &m));
+  SLN_TRY(parse_model(dm, params, grads, nullptr, &m, d->packed_weights));
   make_plan(dm, O, T, 1, ws, &p);
   SLN_TRY(check_ws(p, ws, ws_bytes));
   side_begin(c);

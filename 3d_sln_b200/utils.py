@@ -186,7 +186,7 @@ class VAETrainStep(object):
     """
 
     def __init__(self, model, O, T, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, kl_weight=0.1, use_graph=True, process_group=None,
-                 world_size=1, sample_eps=True):
+                 world_size=1, sample_eps=True, pack_weights=True):
         self.lib = _lib.load()
         self.model = model
         dev = next(model.parameters()).device
@@ -232,6 +232,9 @@ class VAETrainStep(object):
         self.loss_scratch = _loss_scratch(dev, O)
         self.ws_enc = torch.empty(self.lib.sln_vae_workspace_bytes(model._desc(), O, T, 0), dtype=torch.uint8, device=dev)
         self.ws_dec = torch.empty(self.lib.sln_vae_workspace_bytes(model._desc(), O, T, 1), dtype=torch.uint8, device=dev)
+        # pre-split / pre-tiled weight images, refreshed from the parameter arena at the start of every step (one launch)
+        nbytes = self.lib.sln_vae_packed_bytes(model._desc()) if pack_weights else 0
+        self.packed = torch.empty(max(nbytes // 4, 4), device=dev, dtype=torch.float32) if nbytes else None
         self.launches_per_step = None
         self.graph_fb = None
         self.graph_opt = None
@@ -248,6 +251,9 @@ class VAETrainStep(object):
         E = m.embedding_dim
         use_kl = not m.use_AE
         self.sink.flat.zero_()
+        if self.packed is not None:
+            _lib.check(lib.sln_vae_pack_weights(desc, params, self.packed.data_ptr(), self.packed.numel() * 4, st), "vae_pack_weights")
+            desc.packed_weights = self.packed.data_ptr()
         _lib.check(lib.sln_vae_encoder_fwd(desc, params, bufs, self.objs.data_ptr(), self.triples.data_ptr(), self.boxes.data_ptr(),
                                            self.angles.data_ptr(), self.attrs.data_ptr(), O, T, self.mu.data_ptr(), self.logvar.data_ptr(),
                                            self.ws_enc.data_ptr(), self.ws_enc.numel(), st), "encoder_fwd")

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SLN_ABI_VERSION 1
+#define SLN_ABI_VERSION 2
 
 int sln_version(void);
 const char* sln_last_error(void);
@@ -56,6 +56,9 @@ typedef struct sln_vae_desc {
   float bn_momentum;      /* 0.1 */
   int32_t gconv_dim_override;    /* 0, or Din = Dout of a standalone GraphTripleConv (sln_gconv_layer_*) */
   int32_t gconv_hidden_override; /* 0, or hidden_dim of a standalone GraphTripleConv */
+  const void* packed_weights;    /* NULL, or the buffer sln_vae_pack_weights() filled FROM THE CURRENT PARAMETER VALUES: pre-split
+                                    (TF32 hi | lo), pre-tiled images of every Linear weight, pulled into shared memory by cp.async.bulk
+                                    instead of being split on the fly (forward and backward-data contractions) */
 } sln_vae_desc;
 
 /* Parameter table.  `params[i]` / `grads[i]` are device pointers in this canonical order (grads may be NULL
@@ -72,6 +75,10 @@ typedef struct sln_vae_desc {
  * `bn_bufs`: for every BatchNorm in the same order: running_mean (float*), running_var (float*),
  *            num_batches_tracked (int64_t*).  NULL when norm == 0. */
 int sln_vae_num_params(const sln_vae_desc* d);  /* entries of params[] / grads[] */
+/* Weight images for sln_vae_desc::packed_weights: size of the buffer, and the (graph-capturable) kernel that fills it from params[].
+ * Re-run after every optimizer step; passing a stale buffer computes with stale weights. */
+size_t sln_vae_packed_bytes(const sln_vae_desc* d);
+int sln_vae_pack_weights(const sln_vae_desc* d, const void* const* params, void* packed, size_t packed_bytes, void* stream);
 int sln_vae_num_bn(const sln_vae_desc* d);      /* BatchNorm count; bn_bufs has 3x this many entries */
 
 /* Workspace holding graph CSR, saved activations, BN statistics and backward scratch.  which: 0 = encoder, 1 = decoder,

@@ -21,7 +21,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_version_and_error_string():
     _lib = importlib.import_module("3d_sln_b200._lib")
     lib = _lib.load()
-    assert lib.sln_version() == 1
+    assert lib.sln_version() == 2
     # argument validation happens on the host before any launch: no GPU needed
     d = _lib.VaeDesc(embedding_dim=6, n_layers=5, recurrent=0, norm=1, training=1, box_dim=6, n_angle=24, num_objs=33, num_preds=16,
                      num_attrs=5, bn_eps=1e-5, bn_momentum=0.1, gconv_dim_override=0, gconv_hidden_override=0)
