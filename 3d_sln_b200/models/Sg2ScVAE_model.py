@@ -103,7 +103,9 @@ class _ModelGradSink(object):
         self.params = list(params)
         self.groups = groups
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
+        # every slot starts 16-byte aligned (float4 / red.v4 / tensor-core loader paths need it; an unaligned weight silently
+        # falls back to the scalar FP32 kernel): slots are padded to a multiple of 4 floats, the pads stay zero
+        n = sum((p.numel() + 3) // 4 * 4 for p in self.params)
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.views = [None] * len(self.params)
         self.ranges, off = {}, 0
@@ -114,7 +116,7 @@ class _ModelGradSink(object):
                 k = self.params[i].numel()
                 self.views[i] = self.flat[off:off + k].view_as(self.params[i])
                 self.order.append(i)
-                off += k
+                off += (k + 3) // 4 * 4
             self.ranges[name] = (lo, off)
         assert off == n and all(v is not None for v in self.views)
 

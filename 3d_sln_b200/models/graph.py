@@ -91,12 +91,12 @@ class GradSink:
     def __init__(self, params):
         self.params = list(params)
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
+        n = sum((p.numel() + 3) // 4 * 4 for p in self.params)     # 16-byte aligned slots (vector reductions into dW)
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
         self.views, off = [], 0
         for p in self.params:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+            off += (p.numel() + 3) // 4 * 4
         self.key = tuple(p.data_ptr() for p in self.params)
 
     def matches(self, params):

@@ -202,15 +202,13 @@ class VAETrainStep(object):
         sink = model._grad_sink()
         # flat parameter arena in the gradient arena's order -> one Adam launch, one all-reduce bucket
         n = sink.flat.numel()
-        self.p_arena = torch.empty(n, device=dev, dtype=torch.float32)
-        off = 0
+        self.p_arena = torch.zeros(n, device=dev, dtype=torch.float32)
         with torch.no_grad():
             for i in sink.order:
                 p = cache['params'][i]
-                k = p.numel()
+                k, off = p.numel(), sink.views[i].storage_offset()     # same (16-byte aligned, zero-padded) slots as the gradient arena
                 self.p_arena[off:off + k].copy_(p.data.reshape(-1))
                 p.data = self.p_arena[off:off + k].view_as(p)
-                off += k
         model._cache = None
         model._tables()
         model._sink, model._gtable = sink, None
