@@ -78,11 +78,18 @@ def full_capture(rep, fname, title):
         except ValueError:
             return v
         return "%.2f" % (x * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1.0))
+    def us(r):
+        k = "gpu__time_duration.sum"
+        v, u = g(r, k), rows[1][hdr.index(k)]
+        try:
+            return "%.1f" % (float(v.replace(",", "")) * {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}.get(u, 1.0))
+        except ValueError:
+            return v
     for r in rows[2:]:
         t = re.search(r"tc_gemm_kernel<(.*?)>\(", g(r, "Kernel Name"))
         name = re.sub(r"sln::(tc::)?|\((int|bool)\)|\(anonymous namespace\)::", "", t.group(1)) if t else g(r, "Kernel Name")[:40]
         lines.append("| `%s` | %s | %s | %s | %s | %s | %s | %s | %s |" % (name, g(r, "launch__grid_size"), g(r, "launch__registers_per_thread"),
-                     g(r, "gpu__time_duration.sum"), mb(r, "dram__bytes_read.sum"), mb(r, "dram__bytes_write.sum"), mb(r, "lts__t_bytes.sum"),
+                     us(r), mb(r, "dram__bytes_read.sum"), mb(r, "dram__bytes_write.sum"), mb(r, "lts__t_bytes.sum"),
                      g(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")[:6], g(r, "smsp__issue_active.avg.pct_of_peak_sustained_active")[:6]))
     return "\n".join(lines) + "\n"
 
