@@ -150,9 +150,49 @@ __global__ void __launch_bounds__(256) k_embed_bwd(const float* __restrict__ a, 
     if (s != 0.f) red_add(table_grad + (size_t)r * ldt + c0 + threadIdx.x, s);
   }
 }
+// Small tables (the four embedding tables: <= 33 rows, <= 128 columns): every warp accumulates its entries into a private copy of the
+// table in shared memory (fixed order inside a warp), the copies are summed in warp order and the CTA adds one partial per element.
+__global__ void __launch_bounds__(256) k_embed_bwd_tab(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                                       const int* __restrict__ idx, int n, int width, int rows, float* table_grad, int per_warp) {
+  extern __shared__ float tab[];   // [8][rows * width]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sz = rows * width;
+  for (int e = threadIdx.x; e < 8 * sz; e += 256) tab[e] = 0.f;
+  __syncthreads();
+  float* mine = tab + warp * sz;
+  const int i0 = (blockIdx.x * 8 + warp) * per_warp, i1 = min(n, i0 + per_warp);
+  for (int i = i0; i < i1; ++i) {
+    const int id = __ldg(idx + i);
+    for (int c = lane; c < width; c += 32) {
+      float v = __ldg(a + (size_t)i * lda + c);
+      if (b) v += __ldg(b + (size_t)i * ldb + c);
+      mine[id * width + c] += v;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < sz; e += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += tab[w * sz + e];
+    if (s != 0.f) red_add(table_grad + e, s);
+  }
+}
 inline int launch_embed_bwd(cudaStream_t st, const float* a, int lda, const float* b, int ldb, const int* idx, int n, int width,
                             float* table_grad, int rows) {
   if (!table_grad || n <= 0 || width <= 0) return SLN_OK;
+  if (idx && (size_t)rows * width * 8 * sizeof(float) <= 64 * 1024) {
+    const int per_warp = 16;
+    const size_t smem = (size_t)rows * width * 8 * sizeof(float);
+    if (smem > 48 * 1024) {
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_embed_bwd_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_embed_bwd_tab) failed: %s", cudaGetErrorString(e)); return SLN_ECUDA; }
+        configured = true;
+      }
+    }
+    k_embed_bwd_tab<<<ceil_div(n, 8 * per_warp), 256, smem, st>>>(a, lda, b, ldb, idx, n, width, rows, table_grad, per_warp);
+    return check_launch("embed_bwd_tab");
+  }
   int splits = max(1, min(ceil_div(n, 64), (2 * kNumSMs) / max(rows, 1)));
   int per_cta = ceil_div(n, splits);
   splits = ceil_div(n, per_cta);
@@ -166,6 +206,7 @@ inline int launch_embed_bwd(cudaStream_t st, const float* a, int lda, const floa
 // One CTA per node; threads own float4 columns; rows are read as contiguous 4*H-byte segments (coalesced).
 __global__ void k_pool_fwd(const MatView a2, const int* __restrict__ row_ptr, const int* __restrict__ ent,
                            const float* __restrict__ cnt, int O, int H, int D, float* pooled) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next contraction may start its prologue (it waits for us before reading)
   int o = blockIdx.x;
   int b = __ldg(row_ptr + o), e = __ldg(row_ptr + o + 1);
   float ic = __ldg(cnt + o);  // true division below: bit-identical to the reference's pooled / counts
@@ -281,6 +322,7 @@ struct ActInfo {  // the activation whose input gradient is being formed: a = re
 template <class Src>
 __global__ void __launch_bounds__(512) k_prep(const Src src, const ActInfo act, float* G, int ldg, BnBwdFin fin, int M, int N,
                                               int rows_per_tile) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int j = blockIdx.x * 128 + threadIdx.x;
   const int r0 = blockIdx.y * rows_per_tile;
   const int r1 = min(M, r0 + rows_per_tile);
@@ -355,10 +397,11 @@ int launch_prep(cudaStream_t st, const Src& src, const ActInfo& act, float* G, i
 template <class AOp>
 __global__ void __launch_bounds__(256) k_skinny_fwd(const AOp A, const float* __restrict__ W, const float* __restrict__ bias, int M, int N, int K,
                                                     float* out, int ldo) {
-  extern __shared__ float s_wt[];   // [K][32]
-  for (int e = threadIdx.x; e < N * K; e += blockDim.x) {   // j fastest: conflict-free shared-memory writes (W is small and L1/L2-resident)
-    int k = e / N, j = e - k * N;
-    s_wt[k * 32 + j] = __ldg(W + (size_t)j * K + k);
+  extern __shared__ float s_wt[];   // [K][33]: coalesced reads of W (k fastest), transposed writes with an odd row stride (conflict-free)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
+    int j = e / K, k = e - j * K;
+    s_wt[k * 33 + j] = __ldg(W + e);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -368,19 +411,19 @@ __global__ void __launch_bounds__(256) k_skinny_fwd(const AOp A, const float* __
     int k = 0;
     for (; k + 8 <= K; k += 8) {
       float4 a = A.ld4(i, k), c = A.ld4(i, k + 4);
-      acc0 = fmaf(a.x, s_wt[(k + 0) * 32 + lane], acc0); acc1 = fmaf(a.y, s_wt[(k + 1) * 32 + lane], acc1);
-      acc0 = fmaf(a.z, s_wt[(k + 2) * 32 + lane], acc0); acc1 = fmaf(a.w, s_wt[(k + 3) * 32 + lane], acc1);
-      acc0 = fmaf(c.x, s_wt[(k + 4) * 32 + lane], acc0); acc1 = fmaf(c.y, s_wt[(k + 5) * 32 + lane], acc1);
-      acc0 = fmaf(c.z, s_wt[(k + 6) * 32 + lane], acc0); acc1 = fmaf(c.w, s_wt[(k + 7) * 32 + lane], acc1);
+      acc0 = fmaf(a.x, s_wt[(k + 0) * 33 + lane], acc0); acc1 = fmaf(a.y, s_wt[(k + 1) * 33 + lane], acc1);
+      acc0 = fmaf(a.z, s_wt[(k + 2) * 33 + lane], acc0); acc1 = fmaf(a.w, s_wt[(k + 3) * 33 + lane], acc1);
+      acc0 = fmaf(c.x, s_wt[(k + 4) * 33 + lane], acc0); acc1 = fmaf(c.y, s_wt[(k + 5) * 33 + lane], acc1);
+      acc0 = fmaf(c.z, s_wt[(k + 6) * 33 + lane], acc0); acc1 = fmaf(c.w, s_wt[(k + 7) * 33 + lane], acc1);
     }
-    for (; k < K; ++k) acc0 = fmaf(A.at_t(i, k), s_wt[k * 32 + lane], acc0);
+    for (; k < K; ++k) acc0 = fmaf(A.at_t(i, k), s_wt[k * 33 + lane], acc0);
     if (lane < N) out[(size_t)i * ldo + lane] = acc0 + acc1;
   }
 }
 template <class AOp>
 int launch_skinny_fwd(cudaStream_t st, const AOp& A, const float* W, const float* bias, int M, int N, int K, float* out, int ldo) {
   if (M <= 0) return SLN_OK;
-  size_t smem = (size_t)K * 32 * sizeof(float);
+  size_t smem = (size_t)K * 33 * sizeof(float);
   if (smem > 48 * 1024) {
     static bool configured = false;
     if (!configured) {
