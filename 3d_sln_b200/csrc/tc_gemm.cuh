@@ -124,19 +124,12 @@ __device__ __forceinline__ uint32_t sw128(int row, int k) { return (uint32_t)(ro
 __device__ __forceinline__ void sts4(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__device__ __forceinline__ void sts1(uint32_t addr, float a) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory"); }
 
 __device__ __forceinline__ void split_store4(uint32_t hi_addr, uint32_t lo_addr, float4 v) {
   const float hx = tf32_hi(v.x), hy = tf32_hi(v.y), hz = tf32_hi(v.z), hw = tf32_hi(v.w);
   sts4(hi_addr, hx, hy, hz, hw);
   sts4(lo_addr, v.x - hx, v.y - hy, v.z - hz, v.w - hw);
 }
-__device__ __forceinline__ void split_store1(uint32_t hi_addr, uint32_t lo_addr, float v) {
-  const float h = tf32_hi(v);
-  sts1(hi_addr, h);
-  sts1(lo_addr, v - h);
-}
-
 // Pre-split, pre-tiled B operand (weights that do not change between launches: convolution kernels at inference, Linear weights
 // between optimizer steps).  sln_pack_weights() writes, for every (32-row group, 32-k chunk) UNIT, the K-major SWIZZLE_128B image of
 // the hi tile (4096 B) followed by the lo tile (4096 B).  The kernel then moves a stage's B tiles with cp.async.bulk (the TMA
