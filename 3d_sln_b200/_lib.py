@@ -127,6 +127,7 @@ SIGNATURES = {
     "sln_raster_setup": (ctypes.c_int, [_P, _I64, _P, _I64, _I32, _P, _P, _P, _F, _I32, _P, _SZ, _P]),
     "sln_raster_face_arrays": (ctypes.c_int, [_P, _I64, _I64, _I32, ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(_P)]),
     "sln_raster_forward": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _F, _F, _P, _P, _P, _P]),
+    "sln_raster_forward2": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "sln_raster_texture_sample": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _P, _I32, _F, _P, _P, _P, _P, _P]),
     "sln_raster_backward_rgb": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _F, _P, _P, _P, _P, _P]),
     "sln_raster_backward_depth": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P]),

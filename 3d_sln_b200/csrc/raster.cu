@@ -123,9 +123,14 @@ constexpr int CHUNK = 256;   // faces examined per round = threads per CTA
 
 struct FaceRec { float v[9]; float inv[9]; int id; };
 
+// TWO: a second z-buffer with its own near plane is kept in the same pass (the reference's depth render clips at the rasterizer
+// default near = 0.1, its class renders at the constructor's near = 0.001; both see identical geometry).
+template <bool TWO>
 __global__ void __launch_bounds__(256) k_raster_tiles(const float* __restrict__ fv, const float* __restrict__ finv, const int4* __restrict__ fbox,
                                                       int F2, int is, float near, float far, int* __restrict__ face_index_map,
-                                                      float* __restrict__ weight_map, float* __restrict__ depth_map) {
+                                                      float* __restrict__ weight_map, float* __restrict__ depth_map, float near2,
+                                                      int* __restrict__ face_index_map2, float* __restrict__ weight_map2,
+                                                      float* __restrict__ depth_map2) {
   __shared__ FaceRec s_rec[CHUNK];
   __shared__ int s_warp_cnt[8];
   __shared__ int s_total;
@@ -137,9 +142,9 @@ __global__ void __launch_bounds__(256) k_raster_tiles(const float* __restrict__ 
   const float yp = dvd(sub(add(mul(2.0f, (float)yi), 1.0f), fis), fis);
   const float xp = dvd(sub(add(mul(2.0f, (float)xi), 1.0f), fis), fis);
   const float fxi = (float)xi, fyi = (float)yi;
-  float depth_min = far;
-  int face_min = -1;
-  float w0m = 0.f, w1m = 0.f, w2m = 0.f;
+  float depth_min = far, depth_min2 = far;
+  int face_min = -1, face_min2 = -1;
+  float w0m = 0.f, w1m = 0.f, w2m = 0.f, w0n = 0.f, w1n = 0.f, w2n = 0.f;
   const int tx1 = min(tx0 + TILE - 1, is - 1), ty1 = min(ty0 + TILE - 1, is - 1);
 
   for (int base = 0; base < F2; base += CHUNK) {
@@ -188,7 +193,9 @@ __global__ void __launch_bounds__(256) k_raster_tiles(const float* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 3; ++k) w[k] = dvd(w[k], wsum);
         const float zp = dvd(1.0f, add(add(dvd(w[0], face[2]), dvd(w[1], face[5])), dvd(w[2], face[8])));
-        if (zp <= near || far <= zp) continue;
+        if (far <= zp) continue;
+        if (TWO && !(zp <= near2) && zp < depth_min2) { depth_min2 = zp; face_min2 = r.id; w0n = w[0]; w1n = w[1]; w2n = w[2]; }
+        if (zp <= near) continue;
         if (zp < depth_min) { depth_min = zp; face_min = r.id; w0m = w[0]; w1m = w[1]; w2m = w[2]; }
       }
     }
@@ -199,6 +206,11 @@ __global__ void __launch_bounds__(256) k_raster_tiles(const float* __restrict__ 
     face_index_map[pn] = face_min;
     depth_map[pn] = depth_min;
     weight_map[3 * pn] = w0m; weight_map[3 * pn + 1] = w1m; weight_map[3 * pn + 2] = w2m;
+    if (TWO) {
+      face_index_map2[pn] = face_min2;
+      depth_map2[pn] = depth_min2;
+      weight_map2[3 * pn] = w0n; weight_map2[3 * pn + 1] = w1n; weight_map2[3 * pn + 2] = w2n;
+    }
   }
 }
 
@@ -523,8 +535,24 @@ int sln_raster_forward(const void* ws, int64_t V, int64_t F, int32_t fill_back, 
   cudaStream_t st = (cudaStream_t)stream;
   const int tiles = ceil_div(image_size, TILE);
   ProfScope prof(st, PROF_RASTER_FWD, 88.0 * F2 + 20.0 * image_size * image_size);
-  k_raster_tiles<<<dim3(tiles, tiles), 256, 0, st>>>(p.fv, p.finv, p.fbox, (int)F2, image_size, near, far, face_index_map, weight_map, depth_map);
+  k_raster_tiles<false><<<dim3(tiles, tiles), 256, 0, st>>>(p.fv, p.finv, p.fbox, (int)F2, image_size, near, far, face_index_map, weight_map, depth_map,
+                                                             0.f, nullptr, nullptr, nullptr);
   return check_launch("raster_tiles");
+}
+
+int sln_raster_forward2(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, float near_a, float near_b, float far,
+                        int32_t* face_index_map_a, float* weight_map_a, float* depth_map_a, int32_t* face_index_map_b, float* weight_map_b,
+                        float* depth_map_b, void* stream) {
+  SLN_TRY(check_raster_args(V, F, image_size));
+  SLN_CHECK_ARG(ws && face_index_map_a && weight_map_a && depth_map_a && face_index_map_b && weight_map_b && depth_map_b, "null pointer");
+  const int64_t F2 = fill_back ? 2 * F : F;
+  RasterPlan p = plan_raster((void*)ws, V, F2);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles = ceil_div(image_size, TILE);
+  ProfScope prof(st, PROF_RASTER_FWD, 88.0 * F2 + 40.0 * image_size * image_size);
+  k_raster_tiles<true><<<dim3(tiles, tiles), 256, 0, st>>>(p.fv, p.finv, p.fbox, (int)F2, image_size, near_a, far, face_index_map_a, weight_map_a,
+                                                            depth_map_a, near_b, face_index_map_b, weight_map_b, depth_map_b);
+  return check_launch("raster_tiles2");
 }
 
 int sln_raster_texture_sample(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, const float* textures,

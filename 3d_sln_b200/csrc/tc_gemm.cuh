@@ -8,7 +8,7 @@
 //   8 PRODUCER warps read A/B through the same operand functors as the SIMT kernel (gather+concat, lazy BatchNorm+ReLU,
 //     BN-backward dy, transposed reads ...), split hi/lo in registers and write four K-major SWIZZLE_128B tiles
 //     (A_hi, A_lo, B_hi, B_lo) of a shared-memory stage, then publish it (fence.proxy.async + mbarrier arrive);
-//   a ninth warp is the MMA ISSUER: per stage 4 k-slices x 3 tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) into TMEM
+//   a ninth warp is the MMA ISSUER: per stage 4 k-slices x 2 tcgen05.mma.kind::tf32 (M=128, N=2BN and N=BN, K=8) into TMEM
 //     accumulators, tcgen05.commit hands the stage back.  A ring of 3-4 stages decouples the two sides;
 //   EPILOGUE (the producer warps): tcgen05.ld 32x32b (thread = accumulator row, 32 columns at a time) -> staging in shared
 //     memory -> epilogue functor with lanes along the columns (bias / ReLU mask / BatchNorm column statistics / RED.ADD).
@@ -333,15 +333,15 @@ struct SmemLayout {
 
 // Accumulation scheme.
 //   * Dependent tcgen05.mma instructions (same TMEM accumulator) serialise on the accumulate latency (~170 cycles measured),
-//     far above the 16-64 cycle occupancy of a 128 x BN x 8 TF32 instruction.  The three products of the 3xTF32 scheme are
-//     therefore kept in SEPARATE accumulators and each of them alternates between an even and an odd k-slice accumulator
-//     (BN <= 64; BN = 128 is occupancy-bound with four chains): 4-6 independent MMA chains per CTA.
+//     far above the 16-64 cycle occupancy of a 128 x BN x 8 TF32 instruction.  The products of the 3xTF32 scheme are
+//     therefore kept in SEPARATE accumulators ([hi*hi | hi*lo] from one N = 2 BN instruction, lo*hi from a second one) and,
+//     for BN <= 64, even and odd k-slices alternate between two accumulator sets: 2-4 independent MMA chains per CTA.
 //   * The tensor core adds into its fp32 accumulator with truncation, so a long dependent chain of accumulator updates
 //     drifts (measured: 1.4e-5 relative after 1488 updates).  Chains are bounded by draining all accumulators into fp32
 //     registers (round-to-nearest adds) every SEG_CHUNKS chunks = 1280 k (80 updates per chain, < 1e-6).  Contractions whose
 //     K range per CTA fits one segment (every contraction of the VAE path, most convolutions) run the MSEG == false variant:
 //     no in-loop drain, so the register accumulators only exist in the epilogue and two chunks are prefetched per operand.
-// TMEM columns: NM main regions, then NC regions for lo*hi, then NC regions for hi*lo, BN columns each.
+// TMEM columns: per accumulator set [hi*hi | hi*lo | lo*hi], BN columns each (one set for BN = 128, an even and an odd set below).
 constexpr int SEG_CHUNKS = 40;
 
 // tuning aid: SM-clock timestamps of CTA (0,0,0) at the phase boundaries of the last tc_gemm launch (sln_debug_tc_trace)
@@ -386,9 +386,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   // Programmatic dependent launch: let the next kernel of the stream start its prologue (TMEM allocation, barrier set-up) on idle
   // SMs while this grid runs; that kernel's own griddepcontrol.wait (below) orders its first global read after our last write.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  constexpr int NM = 2;                       // hi*hi chains (even / odd k-slices)
-  constexpr int NC = BN >= 128 ? 1 : 2;       // chains per cross term
-  constexpr int NREG = NM + 2 * NC;
+  // Accumulator regions (BN columns each).  The hi and lo tiles of B are adjacent in shared memory, so ONE instruction with N = 2 BN
+  // computes A_hi x [B_hi ; B_lo]^T = [hi*hi | hi*lo]; a second one (N = BN) adds A_lo x B_hi^T = lo*hi: 2 tcgen05.mma per k-slice
+  // instead of 3, and A_hi is read from shared memory once.  BN <= 64 keeps two such sets (even / odd k-slices: independent chains).
+  constexpr int NSET = BN >= 128 ? 1 : 2;
+  constexpr int NREG = 3 * NSET;
   constexpr uint32_t TMEM_COLS = (NREG * BN <= 128) ? 128 : ((NREG * BN <= 256) ? 256 : 512);
   static_assert(NREG * BN <= 512, "the accumulators must fit the 512 TMEM columns");
 
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN, !A_RC, !B_RC);
+      constexpr uint32_t idesc = make_idesc(BN, !A_RC, !B_RC), idesc2 = make_idesc(2 * BN, !A_RC, !B_RC);
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % S, use = c / S;
         const int seg = c / SEG_CHUNKS;
@@ -437,14 +439,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
         }
         mbar_wait(full + s, (uint32_t)(use & 1));
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * L::STAGE), a_lo = a_hi + L::A_TILE, b_hi = a_hi + 2 * L::A_TILE, b_lo = b_hi + L::B_TILE;
+        const uint32_t a_hi = smem_u32(smem + s * L::STAGE), a_lo = a_hi + L::A_TILE, b_hi = a_hi + 2 * L::A_TILE;   // b_lo = b_hi + B_TILE: rows BN..2BN-1 of the same tile
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {               // UMMA_K = 8 tf32: one 32-byte slice of every K-major row / one MN-major k-atom
-          const uint32_t d_c1 = tmem_acc + (uint32_t)((NM + (k % NC)) * BN), d_c2 = tmem_acc + (uint32_t)((NM + NC + (k % NC)) * BN);
-          const uint32_t d_main = tmem_acc + (uint32_t)((k % NM) * BN);
-          mma_tf32(d_c1, make_desc_t<A_RC>(a_lo, k), make_desc_t<B_RC>(b_hi, k), idesc, (!seg_first || k >= NC) ? 1u : 0u);
-          mma_tf32(d_c2, make_desc_t<A_RC>(a_hi, k), make_desc_t<B_RC>(b_lo, k), idesc, (!seg_first || k >= NC) ? 1u : 0u);
-          mma_tf32(d_main, make_desc_t<A_RC>(a_hi, k), make_desc_t<B_RC>(b_hi, k), idesc, (!seg_first || k >= NM) ? 1u : 0u);
+          const uint32_t d0 = tmem_acc + (uint32_t)((k % NSET) * 3 * BN);
+          const uint32_t fresh = (!seg_first || k >= NSET) ? 1u : 0u;
+          mma_tf32(d0, make_desc_t<A_RC>(a_hi, k), make_desc_t<B_RC>(b_hi, k), idesc2, fresh);            // [hi*hi | hi*lo]
+          mma_tf32(d0 + 2 * BN, make_desc_t<A_RC>(a_lo, k), make_desc_t<B_RC>(b_hi, k), idesc, fresh);    // lo*hi
         }
         mma_commit(empty + s);                             // stage s may be overwritten once these MMAs retire
         if (seg_last) mma_commit(segfull);

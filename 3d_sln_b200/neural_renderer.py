@@ -57,6 +57,19 @@ class _Raster(object):
                                                w.data_ptr(), d.data_ptr(), self.st), "raster_forward")
         return fi, w, d
 
+    def forward2(self, near_a, near_b, far):
+        """Two z-buffers (near planes near_a / near_b) from one pass over the faces."""
+        n = self.n
+        out = []
+        for _ in range(2):
+            out.append((torch.empty(n, n, dtype=torch.int32, device=self.dev), torch.empty(n, n, 3, dtype=torch.float32, device=self.dev),
+                        torch.empty(n, n, dtype=torch.float32, device=self.dev)))
+        (fa, wa, da), (fb, wb, db) = out
+        _lib.check(self.lib.sln_raster_forward2(self.ws.data_ptr(), self.V, self.F, self.fill_back, n, float(near_a), float(near_b), float(far),
+                                                fa.data_ptr(), wa.data_ptr(), da.data_ptr(), fb.data_ptr(), wb.data_ptr(), db.data_ptr(), self.st),
+                   "raster_forward2")
+        return out[0], out[1]
+
     def face_arrays(self):
         pv, fv, finv = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
         _lib.check(self.lib.sln_raster_face_arrays(self.ws.data_ptr(), self.V, self.F, self.fill_back, ctypes.byref(pv), ctypes.byref(fv),
@@ -142,8 +155,10 @@ class _SceneFn(torch.autograd.Function):
         if cls.numel() != r.F:
             raise ValueError("face_cls must have one entry per face")
         cls2 = torch.cat([cls, cls]) if r.fill_back else cls
-        dmaps = r.forward(cfg["near_depth"], cfg["far"])
-        cmaps = dmaps if cfg["near"] == cfg["near_depth"] else r.forward(cfg["near"], cfg["far"])
+        if cfg["near"] == cfg["near_depth"]:
+            dmaps = cmaps = r.forward(cfg["near_depth"], cfg["far"])
+        else:
+            dmaps, cmaps = r.forward2(cfg["near_depth"], cfg["near"], cfg["far"])
         sval = torch.empty(r.n, r.n, dtype=torch.float32, device=r.dev)
         images = torch.empty(n_cls, r.n, r.n, dtype=torch.float32, device=r.dev)
         _lib.check(r.lib.sln_scene_classes_fwd(r.ws.data_ptr(), r.V, r.F, r.fill_back, r.n, cfg["texture_size"], RASTERIZER_EPS,

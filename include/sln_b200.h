@@ -186,6 +186,11 @@ int sln_raster_face_arrays(void* ws, int64_t V, int64_t F, int32_t fill_back, co
                            const float** face_vertices, const float** face_inv);
 int sln_raster_forward(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, float near, float far,
                        int32_t* face_index_map, float* weight_map, float* depth_map, void* stream);
+/* Two z-buffers with different near planes from ONE pass over the faces (maps *_a clip at near_a, maps *_b at near_b): what
+ * mesh_render_func needs — depth render at the rasterizer default near, class renders at the constructor's near (diff_render.py:366,398). */
+int sln_raster_forward2(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, float near_a, float near_b, float far,
+                        int32_t* face_index_map_a, float* weight_map_a, float* depth_map_a, int32_t* face_index_map_b, float* weight_map_b,
+                        float* depth_map_b, void* stream);
 int sln_raster_texture_sample(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, const float* textures,
                               int32_t texture_size, float eps, const int32_t* face_index_map, const float* weight_map,
                               const float* depth_map, float* rgb_map, void* stream);
