@@ -203,60 +203,49 @@ inline int launch_embed_bwd(cudaStream_t st, const float* a, int lda, const floa
 
 // ================================================================ avg pooling  (reference graph.py:92-108)
 // pooled[o, c] = (1 / cnt[o]) * ( sum_{t: s_t = o} a2[t, c] + sum_{t: o_t = o} a2[t, H + D + c] ),  a2 = relu(bn(y2)) lazily.
-// One CTA per node; threads own float4 columns; rows are read as contiguous 4*H-byte segments (coalesced).
-__global__ void k_pool_fwd(const MatView a2, const int* __restrict__ row_ptr, const int* __restrict__ ent,
-                           const float* __restrict__ cnt, int O, int H, int D, float* pooled) {
+// A group of `lanes` threads (one float4 column each, lanes = H/4 rounded up to a warp multiple) owns one node; a 256-thread
+// CTA holds 256/lanes nodes.  No shared memory, no barrier: every thread of a group reads the (group-uniform, broadcast) CSR
+// entries itself, 8 at a time, then issues the 8 row reads — contiguous 4*H-byte segments — and sums them in CSR order
+// (= the reference's scatter order, so the result is bit-identical to scatter_add + divide).
+__global__ void __launch_bounds__(256) k_pool_fwd(const MatView a2, const int* __restrict__ row_ptr, const int* __restrict__ ent,
+                                                  const float* __restrict__ cnt, int O, int H, int D, float* pooled, int lanes) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next contraction may start its prologue (it waits for us before reading)
-  int o = blockIdx.x;
-  int b = __ldg(row_ptr + o), e = __ldg(row_ptr + o + 1);
-  float ic = __ldg(cnt + o);  // true division below: bit-identical to the reference's pooled / counts
-  __shared__ int s_ent[256];
-  float4 acc[2];
-  acc[0] = acc[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-  // entries are staged through shared memory so that the row reads (the long-latency part) do not depend on a global
-  // index load: 8 independent row reads are in flight per thread, summed in CSR order (= the reference's scatter order)
-  for (int base = b; base < e; base += 256) {
-    int m = min(256, e - base);
-    __syncthreads();
-    for (int k = threadIdx.x; k < m; k += blockDim.x) s_ent[k] = __ldg(ent + base + k);
-    __syncthreads();
+  const int per_cta = blockDim.x / lanes;
+  const int o = blockIdx.x * per_cta + threadIdx.x / lanes;
+  const int c = (threadIdx.x % lanes) * 4;
+  if (o >= O || c >= H) return;
+  const int b = __ldg(row_ptr + o), e = __ldg(row_ptr + o + 1);
+  const float ic = __ldg(cnt + o);  // true division below: bit-identical to the reference's pooled / counts
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  int k = b;
+  for (; k + 8 <= e; k += 8) {
+    int en[8];
+    float4 v[8];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      int c = (threadIdx.x + j * blockDim.x) * 4;
-      if (c >= H) break;
-      float4 a = acc[j];
-      int k = 0;
-      for (; k + 8 <= m; k += 8) {
-        float4 v[8];
+    for (int u = 0; u < 8; ++u) en[u] = __ldg(ent + k + u);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          int en = s_ent[k + u];
-          v[u] = a2.ld4(en & ((1 << 30) - 1), ((en >> 30) ? (H + D) : 0) + c);
-        }
+    for (int u = 0; u < 8; ++u) v[u] = a2.ld4(en[u] & ((1 << 30) - 1), ((en[u] >> 30) ? (H + D) : 0) + c);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
-      }
-      for (; k < m; ++k) {
-        int en = s_ent[k];
-        float4 v = a2.ld4(en & ((1 << 30) - 1), ((en >> 30) ? (H + D) : 0) + c);
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-      }
-      acc[j] = a;
-    }
+    for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
   }
+  if (k < e) {   // tail of up to 7 entries, still issued together
+    int en[7];
+    float4 v[7];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    int c = (threadIdx.x + j * blockDim.x) * 4;
-    if (c >= H) break;
-    float4 a = acc[j];
-    a.x = __fdiv_rn(a.x, ic); a.y = __fdiv_rn(a.y, ic); a.z = __fdiv_rn(a.z, ic); a.w = __fdiv_rn(a.w, ic);
-    float* dst = pooled + (size_t)o * H + c;
-    if (c + 3 < H) *reinterpret_cast<float4*>(dst) = a;
-    else { dst[0] = a.x; if (c + 1 < H) dst[1] = a.y; if (c + 2 < H) dst[2] = a.z; }
+    for (int u = 0; u < 7; ++u) en[u] = k + u < e ? __ldg(ent + k + u) : -1;
+#pragma unroll
+    for (int u = 0; u < 7; ++u) v[u] = en[u] >= 0 ? a2.ld4(en[u] & ((1 << 30) - 1), ((en[u] >> 30) ? (H + D) : 0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 7; ++u)
+      if (en[u] >= 0) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
   }
+  a.x = __fdiv_rn(a.x, ic); a.y = __fdiv_rn(a.y, ic); a.z = __fdiv_rn(a.z, ic); a.w = __fdiv_rn(a.w, ic);
+  float* dst = pooled + (size_t)o * H + c;
+  if (c + 3 < H) *reinterpret_cast<float4*>(dst) = a;
+  else { dst[0] = a.x; if (c + 1 < H) dst[1] = a.y; if (c + 2 < H) dst[2] = a.z; }
 }
-// threads per CTA for k_pool_fwd: one float4 column group per thread, two when H > 1024
-inline int pool_threads(int H) { int t = ceil_div(ceil_div(H, 4), 32) * 32; if (t > 256) t = ceil_div(ceil_div(H, 8), 32) * 32; return max(32, min(t, 1024)); }
+// lanes per node for k_pool_fwd: one float4 column per lane, a whole number of warps, at most one CTA
+inline int pool_lanes(int H) { return min(256, ceil_div(ceil_div(H, 4), 32) * 32); }
 
 // ================================================================ backward "prep" passes
 // G[i,j] = mask(y[i,j]) ? src(i,j) : 0 and the BN-backward column sums, for gradients that are assembled by a gather
