@@ -558,10 +558,8 @@ int gconv_fwd(const Ctx& c, const Graph& g, const Blk* blk, BlkState* st, float*
   SLN_TRY(block_fwd(c, block_out(blk[0], st[0]), T, blk[1], st[1]));
   MatView a2 = block_out(blk[1], st[1]);
   if (O > 0) {
-    SLN_CHECK_ARG(H <= 1024, "hidden_dim above 1024 is not supported by the pooling kernel");
-    const int lanes = pool_lanes(H);
     ProfScope prof(c.st, PROF_POOL, pool_bytes(O, T, H));
-    k_pool_fwd<<<ceil_div(O, 256 / lanes), 256, 0, c.st>>>(a2, g.row_ptr, g.ent, g.cnt, O, H, D, pooled, lanes);
+    launch_pool_fwd(c.st, a2, g.row_ptr, g.ent, O, H, D, pooled);
     SLN_TRY(check_launch("pool_fwd"));
   }
   SLN_TRY(block_fwd(c, make_view(pooled, H, O, H), O, blk[2], st[2]));
@@ -992,10 +990,8 @@ int sln_gconv_pool_fwd(const float* new_t_vecs, int64_t O, int64_t T, int32_t H,
   Graph g; int *deg, *err;
   plan_graph(ar, (int)O, (int)T, &g, &deg, &err);
   MatView a2 = make_view(new_t_vecs, 2 * H + Dout, (int)T, 2 * H + Dout);
-  SLN_CHECK_ARG(H <= 1024, "hidden_dim above 1024 is not supported by the pooling kernel");
-  const int lanes = pool_lanes(H);
   ProfScope prof((cudaStream_t)stream, PROF_POOL, pool_bytes((int)O, (int)T, H));
-  k_pool_fwd<<<ceil_div((int)O, 256 / lanes), 256, 0, (cudaStream_t)stream>>>(a2, g.row_ptr, g.ent, g.cnt, (int)O, H, Dout, pooled, lanes);
+  launch_pool_fwd((cudaStream_t)stream, a2, g.row_ptr, g.ent, (int)O, H, Dout, pooled);
   return check_launch("pool_fwd");
 }
 

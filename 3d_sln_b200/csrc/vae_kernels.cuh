@@ -202,50 +202,142 @@ inline int launch_embed_bwd(cudaStream_t st, const float* a, int lda, const floa
 }
 
 // ================================================================ avg pooling  (reference graph.py:92-108)
-// pooled[o, c] = (1 / cnt[o]) * ( sum_{t: s_t = o} a2[t, c] + sum_{t: o_t = o} a2[t, H + D + c] ),  a2 = relu(bn(y2)) lazily.
-// A group of `lanes` threads (one float4 column each, lanes = H/4 rounded up to a warp multiple) owns one node; a 256-thread
-// CTA holds 256/lanes nodes.  No shared memory, no barrier: every thread of a group reads the (group-uniform, broadcast) CSR
-// entries itself, 8 at a time, then issues the 8 row reads — contiguous 4*H-byte segments — and sums them in CSR order
-// (= the reference's scatter order, so the result is bit-identical to scatter_add + divide).
-__global__ void __launch_bounds__(256) k_pool_fwd(const MatView a2, const int* __restrict__ row_ptr, const int* __restrict__ ent,
-                                                  const float* __restrict__ cnt, int O, int H, int D, float* pooled, int lanes) {
+// pooled[o, c] = ( sum_{t: s_t = o} a2[t, c] + sum_{t: o_t = o} a2[t, H + D + c] ) / max(deg[o], 1),  a2 = relu(bn(y2)) lazily.
+// Streaming segmented sum over the CSR.  A group of `lanes` threads (V columns each; whole warps) owns `npg` <= 32 CONSECUTIVE
+// nodes and walks their concatenated entry list as one stream, so the index chain (row_ptr -> entries -> rows) is paid once
+// per group, not once per node:
+//   * lane j of every warp holds row_ptr[o0 + j + 1] — node boundaries are warp shuffles, not dependent loads;
+//   * entries are read 32 at a time, one per lane (coalesced), the next 32 prefetched while rows are in flight;
+//   * BATCH independent row reads per thread (contiguous V*lanes*4-byte segments per group) are issued before the first add.
+// Sums are taken in CSR order per column (= the reference's two scatter_add calls: all subject-side rows in triple order,
+// then all object-side rows), then truly divided: bit-identical to scatter_add + clamp + divide.  No atomics; the only
+// barrier is the one after staging the lazy-BatchNorm vectors in shared memory.
+template <int V> __device__ __forceinline__ void pool_ld(const float* p, float (&o)[V]);
+template <> __device__ __forceinline__ void pool_ld<1>(const float* p, float (&o)[1]) { o[0] = __ldg(p); }
+template <> __device__ __forceinline__ void pool_ld<2>(const float* p, float (&o)[2]) { float2 t = __ldg(reinterpret_cast<const float2*>(p)); o[0] = t.x; o[1] = t.y; }
+template <> __device__ __forceinline__ void pool_ld<4>(const float* p, float (&o)[4]) { float4 t = ldg4(p); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
+
+template <int V, int BATCH, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_pool_fwd(const MatView a2, const int* __restrict__ row_ptr, const int* __restrict__ ent,
+                                                        int O, int H, int D, float* pooled, int lanes, int npg) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next contraction may start its prologue (it waits for us before reading)
-  const int per_cta = blockDim.x / lanes;
-  const int o = blockIdx.x * per_cta + threadIdx.x / lanes;
-  const int c = (threadIdx.x % lanes) * 4;
-  if (o >= O || c >= H) return;
-  const int b = __ldg(row_ptr + o), e = __ldg(row_ptr + o + 1);
-  const float ic = __ldg(cnt + o);  // true division below: bit-identical to the reference's pooled / counts
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  int k = b;
-  for (; k + 8 <= e; k += 8) {
-    int en[8];
-    float4 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) en[u] = __ldg(ent + k + u);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = a2.ld4(en[u] & ((1 << 30) - 1), ((en[u] >> 30) ? (H + D) : 0) + c);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+  extern __shared__ float s_bn[];                                    // [4][lanes*V]: scale_s, shift_s, scale_o, shift_o of this column block
+  const int W = lanes * V;
+  const int cl = (threadIdx.x % lanes) * V;                          // column within the block
+  const int c = blockIdx.y * W + cl;                                 // first of this thread's V columns
+  const bool bn = a2.scale != nullptr;
+  if (bn) {
+    for (int i = threadIdx.x; i < W; i += 256) {
+      const int cc = blockIdx.y * W + i;
+      const bool ok = cc < H;
+      s_bn[i] = ok ? __ldg(a2.scale + cc) : 0.f;                 s_bn[W + i] = ok ? __ldg(a2.shift + cc) : 0.f;
+      s_bn[2 * W + i] = ok ? __ldg(a2.scale + H + D + cc) : 0.f; s_bn[3 * W + i] = ok ? __ldg(a2.shift + H + D + cc) : 0.f;
+    }
+    __syncthreads();
   }
-  if (k < e) {   // tail of up to 7 entries, still issued together
-    int en[7];
-    float4 v[7];
+  const int per_cta = 256 / lanes;
+  const int g = threadIdx.x / lanes;
+  const int o0 = (blockIdx.x * per_cta + g) * npg;
+  if (g >= per_cta || o0 >= O) return;                               // warp-uniform: lanes is a multiple of 32
+  const int lane = threadIdx.x & 31;
+  const bool col_ok = c < H;                                         // idle lanes stay for the shuffles
+  const int n_nodes = min(O, o0 + npg) - o0;
+  const int rp = __ldg(row_ptr + min(o0 + lane + 1, O));             // lane j: end of node o0 + j
+  int k = __ldg(row_ptr + o0);
+  const int k_end = __shfl_sync(0xffffffffu, rp, n_nodes - 1);
+  int j_node = 0, b = k, e = __shfl_sync(0xffffffffu, rp, 0);        // current node o0 + j_node and its entry range
+  float acc[V];
 #pragma unroll
-    for (int u = 0; u < 7; ++u) en[u] = k + u < e ? __ldg(ent + k + u) : -1;
+  for (int j = 0; j < V; ++j) acc[j] = 0.f;
+  auto flush = [&]() {
+    const float ic = (float)max(e - b, 1);                           // = clamp(count, min=1) of graph.py:102-107
+    if (col_ok) {
+      float* dst = pooled + (size_t)(o0 + j_node) * H + c;
 #pragma unroll
-    for (int u = 0; u < 7; ++u) v[u] = en[u] >= 0 ? a2.ld4(en[u] & ((1 << 30) - 1), ((en[u] >> 30) ? (H + D) : 0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < V; ++j) acc[j] = __fdiv_rn(acc[j], ic);
+      if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      else if (V == 2) *reinterpret_cast<float2*>(dst) = make_float2(acc[0], acc[1]);
+      else dst[0] = acc[0];
+    }
 #pragma unroll
-    for (int u = 0; u < 7; ++u)
-      if (en[u] >= 0) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+  };
+  int en = k + lane < k_end ? __ldg(ent + k + lane) : -1;
+  while (k < k_end) {
+    int nx = -1;
+#pragma unroll
+    for (int h = 0; h < 32 / BATCH; ++h) {
+      float v[BATCH][V];
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int x = __shfl_sync(0xffffffffu, en, h * BATCH + u);
+        if (x >= 0 && col_ok) pool_ld<V>(a2.p + (size_t)(x & ((1 << 30) - 1)) * a2.ld + ((x >> 30) ? (H + D) : 0) + c, v[u]);
+      }
+      if (h == 0 && k + 32 + lane < k_end) nx = __ldg(ent + k + 32 + lane);
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int x = __shfl_sync(0xffffffffu, en, h * BATCH + u);
+        if (x < 0) break;                                            // past the group's last entry (warp-uniform)
+        const int kk = k + h * BATCH + u;
+        while (kk == e) { flush(); ++j_node; b = e; e = __shfl_sync(0xffffffffu, rp, j_node); }   // node boundary (steps over empty nodes too)
+        if (col_ok) {
+          const float* sb = s_bn + ((x >> 30) ? 2 * W : 0) + cl;
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            float t = v[u][j];
+            if (bn) t = fmaf(t, sb[j], sb[W + j]);
+            if (a2.relu) t = fmaxf(t, 0.f);
+            acc[j] += t;
+          }
+        }
+      }
+    }
+    k += 32;
+    en = nx;
   }
-  a.x = __fdiv_rn(a.x, ic); a.y = __fdiv_rn(a.y, ic); a.z = __fdiv_rn(a.z, ic); a.w = __fdiv_rn(a.w, ic);
-  float* dst = pooled + (size_t)o * H + c;
-  if (c + 3 < H) *reinterpret_cast<float4*>(dst) = a;
-  else { dst[0] = a.x; if (c + 1 < H) dst[1] = a.y; if (c + 2 < H) dst[2] = a.z; }
+  for (;;) {                                                         // the last node and any trailing empty ones
+    flush();
+    if (++j_node >= n_nodes) break;
+    b = e; e = __shfl_sync(0xffffffffu, rp, j_node);
+  }
 }
-// lanes per node for k_pool_fwd: one float4 column per lane, a whole number of warps, at most one CTA
-inline int pool_lanes(int H) { return min(256, ceil_div(ceil_div(H, 4), 32) * 32); }
+
+// Launch plan of k_pool_fwd.  V = 4 needs 16-byte aligned rows and halves; anything else takes the scalar-column variant.
+// Tuning override (sweeps only): env SLN_POOL="V,npg,batch".
+struct PoolPlan { int V, lanes, npg, batch; dim3 grid; size_t smem; };
+inline PoolPlan pool_plan(const MatView& a2, int O, int H, int D) {
+  static int env_v = -1, env_npg = 0, env_batch = 0;
+  if (env_v < 0) {
+    env_v = 0;
+    if (const char* s = getenv("SLN_POOL")) sscanf(s, "%d,%d,%d", &env_v, &env_npg, &env_batch);
+  }
+  PoolPlan p;
+  const bool aligned = a2.vec && H % 4 == 0 && D % 4 == 0;
+  p.V = aligned ? 4 : 1;
+  if (aligned && (env_v == 1 || env_v == 2)) p.V = env_v;
+  p.batch = env_batch;
+  p.lanes = min(256, ceil_div(ceil_div(H, p.V), 32) * 32);
+  while (256 % p.lanes) p.lanes += 32;                               // whole groups per CTA
+  const int col_blocks = ceil_div(H, p.lanes * p.V);
+  // Measured on B200 (tools/bench_pool.py, profiles/): a 32-node stream per group with 4 rows in flight per thread and 4 CTAs
+  // per SM is the bandwidth optimum (72-75 % of the HBM peak at O = 262144); small graphs are latency-bound and want one
+  // node per group with 16 rows in flight (a 62-entry hub row = 4 round trips).
+  const int per_cta = 256 / p.lanes;
+  p.npg = env_npg > 0 ? min(env_npg, 32) : max(1, min(32, O / (per_cta * kNumSMs * 2)));
+  if (p.npg > 16 && env_npg <= 0) p.npg = 32;
+  if (p.batch == 0) p.batch = p.npg == 32 ? 4 : 16;
+  p.grid = dim3(ceil_div(ceil_div(O, p.npg), per_cta), col_blocks);
+  p.smem = a2.scale ? (size_t)4 * p.lanes * p.V * sizeof(float) : 0;
+  return p;
+}
+inline void launch_pool_fwd(cudaStream_t st, const MatView& a2, const int* row_ptr, const int* ent, int O, int H, int D, float* pooled) {
+  PoolPlan p = pool_plan(a2, O, H, D);
+  if (p.V == 4 && p.batch == 16) k_pool_fwd<4, 16, 1><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);
+  else if (p.V == 4 && p.batch == 4) k_pool_fwd<4, 4, 4><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);
+  else if (p.V == 4) k_pool_fwd<4, 8, 3><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);
+  else if (p.V == 2) k_pool_fwd<2, 16, 3><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);
+  else k_pool_fwd<1, 32, 4><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);
+}
 
 // ================================================================ backward "prep" passes
 // G[i,j] = mask(y[i,j]) ? src(i,j) : 0 and the BN-backward column sums, for gradients that are assembled by a gather

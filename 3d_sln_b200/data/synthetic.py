@@ -68,6 +68,23 @@ def synthetic_batch(n_scenes, nodes_per_scene=32, seed=42):
     return torch.arange(n_scenes), objs, boxes, triples, angles, attrs, o2i, t2i
 
 
+def synthetic_samples(n_scenes, nodes_per_scene=32, seed=42, ragged=False, empty_every=0):
+    """Un-collated samples as SuncgDataset.__getitem__ returns them (data/suncg_dataset.py:292):
+    [(room_id, objs, boxes, triples, angles, attributes)], triples with scene-local ids.  ragged: node counts vary in
+    [2, nodes_per_scene]; empty_every = k > 0: every k-th sample is a degenerate scene (0-dim objs) that the collate drops."""
+    gen = torch.Generator().manual_seed(seed)
+    rng = random.Random(seed)
+    out = []
+    for i in range(n_scenes):
+        if empty_every and i % empty_every == empty_every - 1:
+            out.append((1000 + i, torch.tensor(0), torch.zeros(0, 6), torch.tensor(0), torch.tensor(0), torch.tensor(0)))
+            continue
+        n = rng.randint(2, nodes_per_scene) if ragged else nodes_per_scene
+        objs, boxes, triples, angles, attrs = synthetic_scene(n, gen, rng)
+        out.append((1000 + i, objs, boxes, triples, angles, attrs))
+    return out
+
+
 def fixture_graph():
     """Config-1 fixture: the 5-object graph of reference testing/test_heatmap.py:41-43 with the layout of test.py:46-50."""
     objs = torch.tensor([30, 11, 18, 9, 13, 0])

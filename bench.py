@@ -165,6 +165,40 @@ def eager_gpu_vae_steps(dev, n_scenes, steps=10, warmup=3):
             "sample": "%d scenes x %d nodes, %d timed steps of oracle/vae_oracle.py train_step on cuda" % (n_scenes, NODES_PER_SCENE, steps)}
 
 
+def scatter_sweep(dev, lib, _lib, syn, hbm_peak, sizes=(512, 8192), reps=7):
+    """The north-star "scatter" stage (sln_gconv_pool_fwd = graph.py:92-108) alone at batch sizes where it is a bandwidth problem:
+    algorithmic bytes / CUDA-event time of one launch, L2 flushed (and cleaned by a read pass) before every launch."""
+    H, D = 256, 128
+    st = _lib.cur_stream(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_rd = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
+    out = []
+    for B in sizes:
+        _, objs, _, triples, _, _, _, _ = syn.synthetic_batch(B, NODES_PER_SCENE, seed=1)
+        O, T = objs.size(0), triples.size(0)
+        edges = triples[:, [0, 2]].contiguous().to(dev)
+        x = torch.randn(T, 2 * H + D, device=dev)
+        pooled = torch.empty(O, H, device=dev)
+        ws = torch.empty(lib.sln_gconv_pool_workspace_bytes(O, T), dtype=torch.uint8, device=dev)
+        _lib.check(lib.sln_csr_build(edges.data_ptr(), 2, O, T, ws.data_ptr(), ws.numel(), st), "csr_build")
+        evs = []
+        for i in range(reps + 2):
+            flush.zero_(); flush_rd.sum()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(lib.sln_gconv_pool_fwd(x.data_ptr(), O, T, H, D, pooled.data_ptr(), ws.data_ptr(), ws.numel(), st), "pool_fwd")
+            b.record()
+            if i >= 2:
+                evs.append((a, b))
+        torch.cuda.synchronize(dev)
+        ms = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
+        nbytes = 4.0 * (2.0 * T * H + 2.0 * T + 2.0 * O + 1.0 + O * H)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out.append({"scenes": B, "O": O, "T": T, "algorithmic_bytes": nbytes, "us": ms * 1e3, "achieved": gbs, "unit": "GB/s", "frac": gbs / hbm_peak})
+        del x, pooled, ws, edges
+    return out
+
+
 def run_reference(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
@@ -330,7 +364,13 @@ def run_vae(args):
         roofline_scatter = {"bound": "hbm", "kernel": "k_pool_fwd (scatter_add+count+divide as a CSR gather-reduce)", "achieved": gbs,
                             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
                             "algorithmic_bytes_per_launch": pool["work"] / pool["launches"], "avg_launch_us": pool["ms"] * 1e3 / pool["launches"],
-                            "note": "10.3 MB per launch at this config: below launch latency; see profiles/ for the large-batch sweep"}
+                            "note": "10.3 MB per launch at this config (1.6 us at the HBM peak): latency-bound; large_batch = the same entry point alone at "
+                                    "512 / 8192 scenes, where it is a bandwidth kernel (ncu: profiles/*_prof_pool.csv)"}
+    if roofline_scatter is not None:
+        try:
+            roofline_scatter["large_batch"] = scatter_sweep(dev, lib, _lib, syn, peaks["hbm_gbs"])
+        except Exception as e:   # context only: never fail the bench line because of it
+            roofline_scatter["large_batch"] = {"unavailable": repr(e)[:200]}
     cpu = None
     if n == 1 and not args.no_cpu_baseline:
         val, dt, used, threads = cpu_vae_steps(SCENES_PER_GPU, steps=8, warmup=2, budget_s=25.0)

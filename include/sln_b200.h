@@ -128,6 +128,18 @@ int sln_gconv_pool_fwd(const float* new_t_vecs, int64_t O, int64_t T, int32_t H,
 /* CSR read-back helpers for tests: copies row_ptr[O+1] / ent[2T] (device pointers inside ws) */
 int sln_csr_pointers(void* ws, int64_t O, int64_t T, const int32_t** row_ptr, const int32_t** ent);
 
+/* GPU-side batch assembly.  Replaces suncg_collate_fn (reference data/suncg_dataset.py:295-337) + the eight
+ * .cuda() copies of tensor_aug (utils.py:114-124).  The host packs the kept scenes of a batch into one pinned wire buffer:
+ *   scene_index[B] i64 (position of the scene in the DataLoader batch, :323-324) | obj_off[B+1] i64 | tri_off[B+1] i64 (prefix
+ *   sums) | ids[B] i64 | objs[O] i64 | angles[O] i64 | attributes[O] i64 | triples[T,3] i64 with SCENE-LOCAL ids | boxes[O,box_dim] f32
+ * at the byte offsets sln_collate_layout() returns (offsets10 = those nine sections in this order, then the total size), copies
+ * it to the device once, and sln_collate_finish() writes triples[T,3] with global ids (:318-320, may alias the wire section),
+ * obj_to_img[O] and triple_to_img[T] (either may be NULL).  objs / angles / attributes / boxes / ids are used in place.
+ * err_count (may be NULL; caller zeroes it): number of triples whose local ids fall outside their scene. */
+int sln_collate_layout(int64_t B, int64_t O, int64_t T, int32_t box_dim, int64_t* offsets10);
+int sln_collate_finish(const void* wire, size_t wire_bytes, int64_t B, int64_t O, int64_t T, int32_t box_dim, int64_t* triples,
+                       int64_t* obj_to_img, int64_t* triple_to_img, int32_t* err_count, void* stream);
+
 /* The contraction primitive under every Linear of the MLP stage (reference graph.py:12 nn.Linear -> aten::addmm / mm):
  *   C[i,j] (+)= sum_k A(i,k) * B(j,k),   i < M, j < N, k < K
  * a_rc != 0: A stored [M][K] row-major with leading dimension lda, else stored [K][M] (the transposed reads of the backward

@@ -34,7 +34,11 @@ def _rand_edges(O, T, seed, hub=True):
 
 
 # ------------------------------------------------------------------------------------------- CSR + pooling (graph.py:92-108)
-@pytest.mark.parametrize("O,T,H,D", [(7, 0, 8, 4), (1, 5, 16, 8), (37, 91, 32, 16), (2048, 3968, 256, 128), (513, 4001, 36, 20)])
+@pytest.mark.parametrize("O,T,H,D", [(7, 0, 8, 4), (1, 5, 16, 8), (37, 91, 32, 16), (2048, 3968, 256, 128), (513, 4001, 36, 20),
+                                     (50, 200, 30, 6),            # unaligned halves: scalar-column variant
+                                     (40000, 90000, 64, 32),      # several nodes per lane group (streaming across node boundaries)
+                                     (300, 2000, 1500, 4),        # more than 1024 columns: two column blocks
+                                     (20000, 33, 128, 128)])      # almost every node empty
 def test_csr_is_bit_exact_and_pool_matches_reference_order(O, T, H, D):
     lib = _lib.load()
     edges = _rand_edges(O, T, seed=O + T)
