@@ -54,7 +54,9 @@ def launch_table(rows, sep_kernel, fname, title):
 
 
 def full_capture(rep, fname, title):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: an .ncu-rep, or the `ncu -i <rep> --page raw --csv` dump of one (tools/gpu_profile.sh writes those on the GPU box because big
+    reports do not fit gpurun's copy-back limit)"""
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
     want = ["Kernel Name", "launch__grid_size", "launch__registers_per_thread", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -82,7 +84,7 @@ def full_capture(rep, fname, title):
         k = "gpu__time_duration.sum"
         v, u = g(r, k), rows[1][hdr.index(k)]
         try:
-            return "%.1f" % (float(v.replace(",", "")) * {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}.get(u, 1.0))
+            return "%.1f" % (float(v.replace(",", "")) * {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6, "s": 1e6}.get(u, 1.0))
         except ValueError:
             return v
     for r in rows[2:]:
@@ -99,8 +101,14 @@ for wl, sep in (("vae", "k_adam"), ("render", "k_project_bwd"), ("spade", "k_to_
     p = os.path.join(SRC, "launches_%s.csv" % wl)
     if os.path.exists(p):
         parts.append(launch_table(read_launches(p), sep, "%s_launches_%s" % (tag, wl), "%s: one step of `bench.py --workload %s` (launch list)" % (tag, wl)))
+p = os.path.join(SRC, "launches_vae_warm.csv")
+if os.path.exists(p):
+    parts.append(launch_table(read_launches(p), "k_adam", "%s_launches_vae_warm" % tag,
+                              "%s: the same VAE step with `--cache-control none` (caches NOT flushed between kernels: closer to the in-graph times)" % tag))
 for name in sorted(os.listdir(SRC)):
-    if name.endswith(".ncu-rep"):
+    if name.endswith("_raw.csv"):
+        parts.append(full_capture(os.path.join(SRC, name), "%s_%s" % (tag, name[:-8]), "%s: %s.ncu-rep" % (tag, name[:-8])))
+    elif name.endswith(".ncu-rep") and not os.path.exists(os.path.join(SRC, name[:-8] + "_raw.csv")):
         parts.append(full_capture(os.path.join(SRC, name), "%s_%s" % (tag, name[:-8]), "%s: %s" % (tag, name)))
 with open(os.path.join(OUT, "%s_summary.md" % tag), "w") as f:
     f.write("\n".join(parts))
