@@ -3,11 +3,17 @@ on the 70-channel render (:332-352), the ``PSP_pool_new`` pyramids (:192-215), `
 hooks ``fix_grad`` / ``quad_grad`` (:220-230) — plus ``scene_refine``, a decoder-free driver of that loop (BASELINE.json
 configs[2]: the layout parameters themselves are optimised; the reference optimises the VAE latent that decodes to them).
 
-The rasterizer is the hot kernel (neural_renderer.render_scene_classes through mesh_render_func); the loss is a handful of
-small torch ops on [1,70,256,256] tensors, exactly the ops the reference uses.
+The rasterizer is the hot kernel (neural_renderer.render_scene_classes through mesh_render_func).  The loss exists twice:
+``refine_loss`` — the reference's own torch ops (≈150 small kernels per iteration, forward + autograd; kept as the checker and for
+CPU tensors) — and ``FusedRefineLoss`` — the same arithmetic as six launches of csrc/refine_loss.cu (forward and the gradient
+w.r.t. the render in one call), which RefineStep uses.
 """
+import ctypes
+
 import torch
 import torch.nn.functional as F
+
+from .. import _lib
 
 
 PSP_SIZES = (32, 48, 64, 96)
@@ -71,6 +77,66 @@ def refine_loss(iter_image, target_depth, target_labels, size_loss=None):
     return loss
 
 
+class _FusedRefineLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, holder):
+        lib = _lib.load()
+        img = image.contiguous().float()
+        need_grad = bool(ctx.needs_input_grad[0])      # False under no_grad / for detached images: forward-only call
+        d_image = torch.empty_like(img) if need_grad else None
+        loss3 = torch.empty(3, device=img.device, dtype=torch.float32)
+        _lib.check(lib.sln_refine_loss(img.data_ptr(), img.size(-1), holder.sizes_c, holder.n_sem, holder.n_dep, holder.t_depth.data_ptr(),
+                                       holder.t_labels.data_ptr(), holder.counts_c, loss3.data_ptr(),
+                                       d_image.data_ptr() if need_grad else None, holder.ws.data_ptr(), holder.ws.numel(),
+                                       _lib.cur_stream(img.device)), "refine_loss")
+        ctx.d_image = d_image
+        holder.last_terms = loss3
+        return loss3[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        return (ctx.d_image * g if ctx.d_image is not None else None), None
+
+
+class FusedRefineLoss(object):
+    """refine_loss (test_render_refine.py:332-352) for a FIXED target as one library call (csrc/refine_loss.cu).
+
+    target_depth [1, 4*n_dep, top, top], target_labels: 4 x [1, top, top] int64 (refine_targets).  ``loss = f(image, size_loss)``
+    with image [1, 1+n_sem+n_dep, S, S] on CUDA; the gradient w.r.t. the image is produced by the same call (no atomics)."""
+
+    def __init__(self, target_depth, target_labels, n_sem=40, sizes=PSP_SIZES):
+        dev = target_depth.device
+        if dev.type != "cuda":
+            raise RuntimeError("FusedRefineLoss runs on CUDA only (refine_loss is the torch restatement)")
+        if len(sizes) != 4 or len(target_labels) != 4:
+            raise ValueError("FusedRefineLoss: four pyramid levels expected")
+        self.lib = _lib.load()
+        self.n_sem, self.n_dep = int(n_sem), int(target_depth.size(1)) // 4
+        self.sizes = tuple(int(s) for s in sizes)
+        self.sizes_c = (ctypes.c_int32 * 4)(*self.sizes)
+        self.t_depth = target_depth.detach().contiguous().float()
+        self.t_labels = torch.stack([t.reshape(self.sizes[-1], self.sizes[-1]) for t in target_labels]).contiguous().long()
+        self.counts_c = (ctypes.c_float * 4)(*[float((t >= 0).sum().item()) for t in self.t_labels])
+        self.image_size = None
+        self.ws = None
+        self.last_terms = None      # device [3]: total, depth term, semantic term of the last call
+
+    def __call__(self, iter_image, size_loss=None):
+        if iter_image.device.type != "cuda":
+            raise RuntimeError("FusedRefineLoss needs a CUDA image (no CPU fallback)")
+        if iter_image.dim() != 4 or iter_image.size(0) != 1 or iter_image.size(1) != 1 + self.n_sem + self.n_dep or iter_image.size(2) != iter_image.size(3):
+            raise ValueError("FusedRefineLoss: image must be [1, %d, S, S], got %s" % (1 + self.n_sem + self.n_dep, tuple(iter_image.shape)))
+        S = iter_image.size(-1)
+        if self.image_size != S:
+            nbytes = self.lib.sln_refine_loss_workspace_bytes(S, self.sizes_c, self.n_sem, self.n_dep)
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=iter_image.device)
+            self.image_size = S
+        loss = _FusedRefineLossFn.apply(iter_image, self)
+        if size_loss is not None:
+            loss = loss + size_loss * 2.0
+        return loss
+
+
 def scene_refine(boxes, angles, objs, target_boxes=None, target_angles=None, n_iters=200, lr=2e-4, use_graph=True, callback=None):
     """Refine the layout of ONE scene by gradient descent through the differentiable renderer (BASELINE.json configs[2]).
 
@@ -100,7 +166,7 @@ class RefineStep(object):
     the graph and returns the (device) loss of that iteration.  Same arithmetic as ``scene_refine`` — the graph removes the
     ~600 kernel-launch / Python overheads per iteration that otherwise dominate (the rasterizer itself takes < 1 ms)."""
 
-    def __init__(self, boxes, angles, objs, target_boxes, target_angles, lr=2e-4, use_graph=True, library=None):
+    def __init__(self, boxes, angles, objs, target_boxes, target_angles, lr=2e-4, use_graph=True, library=None, fused_loss=True):
         from . import diff_render as dr
         dev = boxes.device
         if dev.type != "cuda":
@@ -110,6 +176,7 @@ class RefineStep(object):
         with torch.no_grad():
             target, tsize = dr.render_static(self.static, target_boxes.to(dev), target_angles.to(dev).float())
         self.t_depth, self.t_labels = refine_targets(target)
+        self.fused_loss = FusedRefineLoss(self.t_depth, self.t_labels) if fused_loss else None
         self.size_target = tsize.detach()
         self.room_row = boxes[-1:].detach().clone()
         self.angle_room = angles[-1:].detach().float().clone()
@@ -129,7 +196,10 @@ class RefineStep(object):
         aa.register_hook(quad_grad)
         image, size = self._dr.render_static(self.static, bb, aa)
         size_loss = ((size - self.size_target) ** 2).mean(dim=1).sum()        # :98: sum over objects of mse(size, size of the first render)
-        loss = refine_loss(image, self.t_depth, self.t_labels, size_loss)
+        if self.fused_loss is not None:
+            loss = self.fused_loss(image, size_loss)
+        else:
+            loss = refine_loss(image, self.t_depth, self.t_labels, size_loss)
         self.opt.zero_grad(set_to_none=False)
         loss.backward()
         self.opt.step()

@@ -128,6 +128,20 @@ int sln_gconv_pool_fwd(const float* new_t_vecs, int64_t O, int64_t T, int32_t H,
 /* CSR read-back helpers for tests: copies row_ptr[O+1] / ent[2T] (device pointers inside ws) */
 int sln_csr_pointers(void* ws, int64_t O, int64_t T, const int32_t** row_ptr, const int32_t** ent);
 
+/* Fused multi-scale refinement loss.  Replaces testing/test_render_refine.py:332-352 + PSP_pool_new :192-215:
+ *   image[1 + n_sem + n_dep, S, S] (the [1,70,256,256] render of mesh_render_func: channel 0 depth, 1..n_sem class masks, then the
+ *   normalised per-class depth planes) -> null-fill of the last plane where the depth planes sum to < 0.5 (:333), every plane resized
+ *   S -> sizes4[i] (bilinear, align_corners=True) -> sizes4[3] (bilinear, align_corners=False),
+ *   loss3[0] = 100 * 0.5 * mean|pooled depth - t_depth| + 100 * sum_i CrossEntropy_i(pooled classes, t_labels[i]; ignore < 0) / 800,
+ *   loss3[1], loss3[2] = the depth and semantic terms before the factor 100.
+ * t_depth [4 * n_dep, top, top] (level-major, as torch.cat(priors, 1)), t_labels [4, top, top] int64, label_counts4 = HOST array with
+ * the number of labels >= 0 per level (CrossEntropyLoss averages over them).  d_image [1 + n_sem + n_dep, S, S] (may be NULL):
+ * d loss3[0] / d image, fully overwritten, computed without atomics (bit-reproducible). */
+size_t sln_refine_loss_workspace_bytes(int32_t image_size, const int32_t* sizes4, int32_t n_sem, int32_t n_dep);
+int sln_refine_loss(const float* image, int32_t image_size, const int32_t* sizes4, int32_t n_sem, int32_t n_dep, const float* t_depth,
+                    const int64_t* t_labels, const float* label_counts4, float* loss3, float* d_image, void* ws, size_t ws_bytes,
+                    void* stream);
+
 /* GPU-side batch assembly.  Replaces suncg_collate_fn (reference data/suncg_dataset.py:295-337) + the eight
  * .cuda() copies of tensor_aug (utils.py:114-124).  The host packs the kept scenes of a batch into one pinned wire buffer:
  *   scene_index[B] i64 (position of the scene in the DataLoader batch, :323-324) | obj_off[B+1] i64 | tri_off[B+1] i64 (prefix

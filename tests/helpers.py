@@ -64,3 +64,21 @@ def with_eps(eps):
         finally:
             torch.randn_like = orig
     return cm()
+
+
+def synthetic_render(seed, S=256, n_sem=40, n_dep=29):
+    """A render-like [1, 1+n_sem+n_dep, S, S] image (what mesh_render_func returns): channel 0 depth, then 0/1 class masks made of
+    random rectangles (with soft edges so that pooled logits are not all ties), then per-class depth planes that are non-zero only
+    inside their class mask; a band of pixels is left empty so that the null-fill of the last plane triggers."""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.zeros(1, 1 + n_sem + n_dep, S, S)
+    img[0, 0] = torch.rand(S, S, generator=g)
+    for c in range(n_sem):
+        for _ in range(2):
+            y0, x0 = [int(v) for v in torch.randint(0, S - S // 8, (2,), generator=g)]
+            h, w = [int(v) for v in torch.randint(S // 16, S // 3, (2,), generator=g)]
+            img[0, 1 + c, y0:y0 + h, x0:min(S - S // 10, x0 + w)] = 1.0
+    img[0, 1:1 + n_sem] *= 0.75 + 0.25 * torch.rand(n_sem, S, S, generator=g)
+    for d in range(n_dep):
+        img[0, 1 + n_sem + d] = img[0, 1 + d] * torch.rand(S, S, generator=g)
+    return img
