@@ -14,7 +14,7 @@ _CSRC = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libsln_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
 
-SOURCES = ["runtime.cu", "vae_engine.cu", "raster.cu", "spade.cu", "collate.cu", "refine_loss.cu"]
+SOURCES = ["runtime.cu", "vae_engine.cu", "raster.cu", "spade.cu", "collate.cu", "refine_loss.cu", "scene.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -122,6 +122,9 @@ SIGNATURES = {
     "sln_gconv_pool_fwd": (ctypes.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     "sln_csr_pointers": (ctypes.c_int, [_P, _I64, _I64, ctypes.POINTER(_P), ctypes.POINTER(_P)]),
     "sln_set_engine": (ctypes.c_int, [ctypes.c_int]),
+    "sln_scene_assemble_workspace_bytes": (_SZ, [_I64]),
+    "sln_scene_assemble_fwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),
+    "sln_scene_assemble_bwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P]),
     "sln_refine_loss_workspace_bytes": (_SZ, [_I32, _P, _I32, _I32]),
     "sln_refine_loss": (ctypes.c_int, [_P, _I32, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "sln_collate_layout": (ctypes.c_int, [_I64, _I64, _I64, _I32, ctypes.POINTER(_I64)]),

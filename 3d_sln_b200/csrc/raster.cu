@@ -7,7 +7,7 @@
 //             culled against the tile with a block-wide ORDER-PRESERVING ballot compaction, the survivors' records are
 //             staged in shared memory and every pixel thread walks them in ascending face order (strict '<' z-test, so
 //             ties keep the lower face index exactly as upstream).  Work drops from P*F to P*(faces touching the tile).
-//   backward  k_backward_rgb: one WARP per (face, edge, axis) job, lanes stride the edge's d0 range and sweep d1 serially,
+//   backward  k_backward_rgb: one WARP per (face, edge, axis) job, the edge's d0 columns serially, lanes stride each d1 sweep,
 //             warp-shuffle reduction, one RED.ADD per touched gradient slot; k_backward_depth: per covered pixel.
 //   The arithmetic that decides coverage and depth order uses explicit round-to-nearest intrinsics (no FMA contraction)
 //   in the oracle's operation order, so face_index maps are bit-identical to the CPU oracle.
@@ -320,7 +320,9 @@ __global__ void __launch_bounds__(256) k_backward_rgb(const RgbBwdArgs a) {
   const int d0_from = (int)fmaxf(ceilf(fminf(p[0][0], p[1][0])), 0.f);
   const int d0_to = (int)fminf(fmaxf(p[0][0], p[1][0]), fis - 1.f);
   float g0 = 0.f, g1 = 0.f;   // gradient of vertex pi[0] / pi[1], component (1 - axis)
-  for (int d0 = d0_from + lane; d0 <= d0_to; d0 += 32) {
+  // Triangles are a few pixels wide but the out sweep runs to the image border: the d0 columns of the edge are walked
+  // serially (warp-uniform set-up) and the LANES stride each sweep along d1.
+  for (int d0 = d0_from; d0 <= d0_to; ++d0) {
     const float fd0 = (float)d0;
     const float d1_cross = add(mul(dvd(sub(p[1][1], p[0][1]), sub(p[1][0], p[0][0])), sub(fd0, p[0][0])), p[0][1]);
     const int d1_in = (0 < direction) ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(256) k_backward_rgb(const RgbBwdArgs a) {
     if (a.face_index_map[idx_in] == fn) {   // out sweep: from the out-pixel to the image border
       const int d1_limit = (0 < direction) ? is - 1 : 0;
       const int d1_from = max(min(d1_out, d1_limit), 0), d1_to = min(max(d1_out, d1_limit), is - 1);
-      for (int d1 = d1_from; d1 <= d1_to; ++d1) {
+      for (int d1 = d1_from + lane; d1 <= d1_to; d1 += 32) {
         const int idx = axis == 0 ? d1 * is + d0 : d0 * is + d1;
         const float dg = pix_diff_grad(a, idx, idx_in);
         if (dg <= 0.f) continue;
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(256) k_backward_rgb(const RgbBwdArgs a) {
         d0_cross2 = add(mul(dvd(sub(p[1][1], p[2][1]), sub(p[1][0], p[2][0])), sub(fd0, p[2][0])), p[2][1]);
       const int d1_limit = (0 < direction) ? (int)ceilf(d0_cross2) : (int)floorf(d0_cross2);
       const int d1_from = max(min(d1_in, d1_limit), 0), d1_to = min(max(d1_in, d1_limit), is - 1);
-      for (int d1 = d1_from; d1 <= d1_to; ++d1) {
+      for (int d1 = d1_from + lane; d1 <= d1_to; d1 += 32) {
         const int idx = axis == 0 ? d1 * is + d0 : d0 * is + d1;
         if (a.face_index_map[idx] != fn) continue;
         const float dg = pix_diff_grad(a, idx, idx_out);

@@ -10,12 +10,14 @@ What differs from the reference, by design:
     (neural_renderer.render_scene_classes) and the per-class loop of the compositing is vectorised over classes.
 The result tensor has the reference's layout: [1, 1 + 40 + (n_classes - 3), 256, 256] = depth | one-hot(40) | depth planes.
 """
+import ctypes
 import math
 
 import numpy as np
 import torch
 import torch.nn as nn
 
+from .. import _lib
 from .. import neural_renderer as nr
 from ..data.synthetic import OBJECT_NAMES
 from ..data.synthetic_meshes import MeshLibrary, room_shell
@@ -235,6 +237,18 @@ class SceneStatic(object):
         self.index = torch.tensor([nyu_class.index(n.replace("_", " ")) + 1 for n in names], device=dev)
         self.keep = torch.tensor([i for i, n in enumerate(names) if n not in ("wall", "floor", "ceiling")], device=dev)
         self.wall = names.index("wall")
+        # int32 / host mirrors for the fused assembly (csrc/scene.cu)
+        self.kept32 = self.kept_idx.to(torch.int32)
+        self.vobj32 = self.vobj.to(torch.int32)
+        counts = [m["vertices"].size(0) for m in models]
+        self.vstart32 = torch.tensor([sum(counts[:j]) for j in range(len(counts) + 1)], dtype=torch.int32, device=dev)
+        r2k = [-1] * len(self.objs)
+        for j, r in enumerate(self.kept):
+            r2k[r] = j
+        self.row_to_kept32 = torch.tensor(r2k, dtype=torch.int32, device=dev)
+        self.room3_c = (ctypes.c_float * 3)(*[float(v) for v in room_box[3:]])
+        self.mv, self.shell_v, self.msize, self.mcent = [t.contiguous().float() for t in (self.mv, self.shell_v, self.msize, self.mcent)]
+        self.R9, self.t3 = self.R.reshape(9).contiguous().float(), self.t.reshape(3).contiguous().float()
 
     def vertices(self, boxes, angles):
         """[1, V, 3] world-space vertices, differentiable w.r.t. boxes [n+1, 6] and angles [n+1] (reference diff_render.py:76-159)."""
@@ -252,6 +266,11 @@ class SceneStatic(object):
         v = scale[self.vobj, None] * torch.einsum("vij,vj->vi", rot[self.vobj], self.mv) + trans[self.vobj]
         return torch.cat([v, self.shell_v])[None], size
 
+    def assemble(self, boxes, angles, eps=0.06):
+        """vertices() + culled_faces() as one library call each way (csrc/scene.cu): -> (vertices [1,V,3], size [n_kept,3],
+        faces [1,F,3] int32).  Differentiable w.r.t. boxes and angles."""
+        return _AssembleFn.apply(boxes, angles, self, float(eps))
+
     def culled_faces(self, vertices, eps=0.06):
         """Reference :345-356 without a dynamic shape: a face with any vertex closer than eps keeps its slot but collapses to a
         zero-area triangle (vertex 0 three times), which the rasterizer never draws."""
@@ -261,10 +280,51 @@ class SceneStatic(object):
         return torch.where(valid[None, :, None], self.faces, torch.zeros_like(self.faces))
 
 
-def render_static(static, boxes, angles):
-    """final [1, 70, 256, 256] of the scene described by `static` at layout (boxes, angles): tensor ops + one rasterization."""
-    vertices, size = static.vertices(boxes, angles)
-    faces = static.culled_faces(vertices)
+class _AssembleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, boxes, angles, st, eps):
+        lib = _lib.load()
+        dev = st.dev
+        b, a = boxes.contiguous().float(), angles.contiguous().float()
+        if b.device.type != "cuda":
+            raise RuntimeError("3d_sln_b200 scene assembly runs on CUDA only (no CPU fallback)")
+        n_rows, n_obj, n_shell, F = b.size(0), st.mv.size(0), st.shell_v.size(0), st.faces.size(1)
+        verts = torch.empty(1, n_obj + n_shell, 3, device=dev, dtype=torch.float32)
+        size = torch.empty(st.n_kept, 3, device=dev, dtype=torch.float32)
+        faces = torch.empty_like(st.faces)
+        ws = torch.empty(lib.sln_scene_assemble_workspace_bytes(st.n_kept), dtype=torch.uint8, device=dev)
+        _lib.check(lib.sln_scene_assemble_fwd(b.data_ptr(), a.data_ptr(), n_rows, _lib.ptr(st.kept32), st.n_kept, st.room3_c, _lib.ptr(st.mv),
+                                              _lib.ptr(st.vobj32), n_obj, _lib.ptr(st.shell_v), n_shell, _lib.ptr(st.msize), _lib.ptr(st.mcent),
+                                              _lib.ptr(st.faces), F, st.R9.data_ptr(), st.t3.data_ptr(), eps, verts.data_ptr(),
+                                              _lib.ptr(size), _lib.ptr(faces), ws.data_ptr(), ws.numel(), _lib.cur_stream(dev)), "scene_assemble_fwd")
+        ctx.st, ctx.ws, ctx.n_rows = st, ws, n_rows
+        ctx.mark_non_differentiable(faces)
+        return verts, size, faces
+
+    @staticmethod
+    def backward(ctx, g_verts, g_size, _g_faces):
+        lib = _lib.load()
+        st, dev = ctx.st, ctx.st.dev
+        n_obj, n_shell = st.mv.size(0), st.shell_v.size(0)
+        gv = torch.zeros(n_obj + n_shell, 3, device=dev) if g_verts is None else g_verts.reshape(-1, 3).contiguous().float()
+        gs = None if g_size is None else g_size.contiguous().float()
+        d_boxes = torch.empty(ctx.n_rows, 6, device=dev, dtype=torch.float32)
+        d_angles = torch.empty(ctx.n_rows, device=dev, dtype=torch.float32)
+        _lib.check(lib.sln_scene_assemble_bwd(gv.data_ptr(), gs.data_ptr() if gs is not None else None, ctx.n_rows, _lib.ptr(st.row_to_kept32),
+                                              st.n_kept, st.room3_c, _lib.ptr(st.mv), _lib.ptr(st.vstart32), _lib.ptr(st.msize), _lib.ptr(st.mcent),
+                                              ctx.ws.data_ptr(), ctx.ws.numel(), d_boxes.data_ptr(), d_angles.data_ptr(), _lib.cur_stream(dev)),
+                   "scene_assemble_bwd")
+        return d_boxes, d_angles, None, None
+
+
+def render_static(static, boxes, angles, fused=True):
+    """final [1, 70, 256, 256] of the scene described by `static` at layout (boxes, angles): scene assembly (one library call;
+    fused=False: the torch-op restatement of the reference's arithmetic, kept as the checker) + one rasterization + compositing."""
+    if fused:
+        vertices, size, faces = static.assemble(boxes, angles)
+    else:
+        vertices, size = static.vertices(boxes, angles)
+        faces = static.culled_faces(vertices)
     depth, images = nr.render_scene_classes(vertices, faces, static.face_cls, len(static.names), static.K, static.R, static.t,
                                             image_size=final_out, orig_size=inter_out, near=0.001)
     return composite(depth, images, static.names, static.index, static.keep), size

@@ -128,6 +128,27 @@ int sln_gconv_pool_fwd(const float* new_t_vecs, int64_t O, int64_t T, int32_t H,
 /* CSR read-back helpers for tests: copies row_ptr[O+1] / ent[2T] (device pointers inside ws) */
 int sln_csr_pointers(void* ws, int64_t O, int64_t T, const int32_t** row_ptr, const int32_t** ent);
 
+/* Scene assembly (SURVEY §8 a10 i-iii / §8f N3).  Replaces the per-object Python loop of mesh_render_func (reference
+ * models/diff_render.py:76-159: scale = min(box size / model size), Ry(-angle * 2pi/24), trans = centre - scale * R * model centre,
+ * vertices = scale * R * v + trans) and the near-plane face cull (:344-356) for meshes that stay resident on the device.
+ *   boxes [n_rows,6] (objects normalised to the room), angles [n_rows] fp32, kept [n_kept] int32 = layout rows that own a mesh,
+ *   room3_host = HOST array {x,y,z} of the room size, model_verts [n_obj_verts,3] (objects contiguous, in `kept` order),
+ *   vert_obj [n_obj_verts] int32 = kept-object of each vertex, shell_verts [n_shell,3] = wall/floor/ceiling (copied through),
+ *   model_size / model_center [n_kept,3], faces [F,3] int32 into the concatenated vertex array, R [3,3], t [3] = camera.
+ *   -> vertices [n_obj_verts + n_shell, 3], sizes [n_kept,3] (box sizes, for the size loss :98), faces_out [F,3]: faces with a
+ *   vertex at camera depth < cull_eps become the zero-area triangle (0,0,0) (static shapes; the rasterizer never draws them).
+ * bwd: grad_vertices [V,3], grad_sizes [n_kept,3] or NULL, row_to_kept [n_rows] int32 (-1 = no mesh), vert_start [n_kept+1] int32
+ *   -> d_boxes [n_rows,6], d_angles [n_rows], fully overwritten; fixed-order reductions (bit-reproducible).  ws: the buffer the
+ *   forward call filled (sln_scene_assemble_workspace_bytes). */
+size_t sln_scene_assemble_workspace_bytes(int64_t n_kept);
+int sln_scene_assemble_fwd(const float* boxes, const float* angles, int64_t n_rows, const int32_t* kept, int64_t n_kept, const float* room3_host,
+                           const float* model_verts, const int32_t* vert_obj, int64_t n_obj_verts, const float* shell_verts, int64_t n_shell,
+                           const float* model_size, const float* model_center, const int32_t* faces, int64_t F, const float* R, const float* t,
+                           float cull_eps, float* vertices, float* sizes, int32_t* faces_out, void* ws, size_t ws_bytes, void* stream);
+int sln_scene_assemble_bwd(const float* grad_vertices, const float* grad_sizes, int64_t n_rows, const int32_t* row_to_kept, int64_t n_kept,
+                           const float* room3_host, const float* model_verts, const int32_t* vert_start, const float* model_size,
+                           const float* model_center, const void* ws, size_t ws_bytes, float* d_boxes, float* d_angles, void* stream);
+
 /* Fused multi-scale refinement loss.  Replaces testing/test_render_refine.py:332-352 + PSP_pool_new :192-215:
  *   image[1 + n_sem + n_dep, S, S] (the [1,70,256,256] render of mesh_render_func: channel 0 depth, 1..n_sem class masks, then the
  *   normalised per-class depth planes) -> null-fill of the last plane where the depth planes sum to < 0.5 (:333), every plane resized
