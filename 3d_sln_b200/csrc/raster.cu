@@ -3,10 +3,11 @@
 //
 // B200 design (not upstream's one-thread-per-pixel loop over ALL faces / one-thread-per-face serial backward):
 //   forward   k_project -> k_face_setup (per face: back-face test, pixel-space inverse, conservative pixel bounding box)
-//             -> k_raster_tiles: one CTA per 16x16 pixel tile; the face list is streamed in chunks of 256 bounding boxes,
-//             culled against the tile with a block-wide ORDER-PRESERVING ballot compaction, the survivors' records are
-//             staged in shared memory and every pixel thread walks them in ascending face order (strict '<' z-test, so
-//             ties keep the lower face index exactly as upstream).  Work drops from P*F to P*(faces touching the tile).
+//             -> k_raster_tiles: one CTA per 16x16 pixel tile; first the whole face list is culled against the tile (256
+//             bounding boxes per round, block-wide ORDER-PRESERVING ballot compaction into a shared id list, one barrier per
+//             round, next round's boxes prefetched), then the survivors' records are staged in shared memory 256 at a time and
+//             every pixel thread walks them in ascending face order (strict '<' z-test, so ties keep the lower face index
+//             exactly as upstream).  Work drops from P*F to P*(faces touching the tile).
 //   backward  k_backward_rgb: one WARP per (face, edge, axis) job, the edge's d0 columns serially, lanes stride each d1 sweep,
 //             warp-shuffle reduction, one RED.ADD per touched gradient slot; k_backward_depth: per covered pixel.
 //   The arithmetic that decides coverage and depth order uses explicit round-to-nearest intrinsics (no FMA contraction)
@@ -120,6 +121,7 @@ __global__ void k_face_setup(const float* __restrict__ pv, const int* __restrict
 // ------------------------------------------------------------------------------------------------ tiled z-buffer
 constexpr int TILE = 16;
 constexpr int CHUNK = 256;   // faces examined per round = threads per CTA
+constexpr int LIST_CAP = 4096;   // survivor ids a tile collects before it draws (more survivors: cull / draw alternate)
 
 struct FaceRec { float v[9]; float inv[9]; int id; };
 
@@ -132,8 +134,8 @@ __global__ void __launch_bounds__(256) k_raster_tiles(const float* __restrict__ 
                                                       int* __restrict__ face_index_map2, float* __restrict__ weight_map2,
                                                       float* __restrict__ depth_map2) {
   __shared__ FaceRec s_rec[CHUNK];
-  __shared__ int s_warp_cnt[8];
-  __shared__ int s_total;
+  __shared__ int s_ids[LIST_CAP];
+  __shared__ int s_cnt[2][8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
   const int xi = tx0 + (tid % TILE), yi = ty0 + (tid / TILE);
@@ -146,60 +148,66 @@ __global__ void __launch_bounds__(256) k_raster_tiles(const float* __restrict__ 
   int face_min = -1, face_min2 = -1;
   float w0m = 0.f, w1m = 0.f, w2m = 0.f, w0n = 0.f, w1n = 0.f, w2n = 0.f;
   const int tx1 = min(tx0 + TILE - 1, is - 1), ty1 = min(ty0 + TILE - 1, is - 1);
+  const int4 none = make_int4(1, 0, 1, 0);
 
-  for (int base = 0; base < F2; base += CHUNK) {
-    const int f = base + tid;
-    bool hit = false;
-    if (f < F2) {
-      int4 b = __ldg(fbox + f);
-      hit = b.x <= b.y && b.x <= tx1 && b.y >= tx0 && b.z <= ty1 && b.w >= ty0;
-    }
-    // order-preserving compaction: position = (# hits in lower warps) + (# hits in lower lanes)
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) s_warp_cnt[warp] = __popc(m);
-    __syncthreads();
-    int off = 0;
+  int base = 0;
+  while (base < F2) {
+    // ---- cull: the ORDERED list of the faces whose bounding box touches this tile.  One barrier per 256 faces, the next
+    // round's boxes are in flight while this round is compacted; nothing else happens until the list is complete (or full).
+    int n = 0, round = 0;                                       // CTA-uniform
+    int4 b_next = base + tid < F2 ? __ldg(fbox + base + tid) : none;
+    while (base < F2 && n + CHUNK <= LIST_CAP) {
+      const int f = base + tid;
+      const int4 b = b_next;
+      b_next = base + CHUNK + tid < F2 ? __ldg(fbox + base + CHUNK + tid) : none;
+      const bool hit = b.x <= b.y && b.x <= tx1 && b.y >= tx0 && b.z <= ty1 && b.w >= ty0;
+      // order-preserving compaction: position = (# hits in lower warps) + (# hits in lower lanes)
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) s_cnt[round & 1][warp] = __popc(m);
+      __syncthreads();
+      int off = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) off += (w < warp) ? s_warp_cnt[w] : 0;
-    if (tid == 0) {
-      int tot = 0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) tot += s_warp_cnt[w];
-      s_total = tot;
-    }
-    if (hit) {
-      const int pos = off + __popc(m & ((1u << lane) - 1u));
-      FaceRec& r = s_rec[pos];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) { r.v[k] = __ldg(fv + 9 * (size_t)f + k); r.inv[k] = __ldg(finv + 9 * (size_t)f + k); }
-      r.id = f;
+      for (int w = 0; w < 8; ++w) { const int c = s_cnt[round & 1][w]; off += (w < warp) ? c : 0; tot += c; }
+      if (hit) s_ids[n + off + __popc(m & ((1u << lane) - 1u))] = f;
+      n += tot; base += CHUNK; ++round;
     }
     __syncthreads();
-    const int n = s_total;
-    if (live) {
-      for (int q = 0; q < n; ++q) {
-        const FaceRec& r = s_rec[q];
-        const float* face = r.v;
-        if (mul(sub(yp, face[1]), sub(face[3], face[0])) < mul(sub(xp, face[0]), sub(face[4], face[1])) ||
-            mul(sub(yp, face[4]), sub(face[6], face[3])) < mul(sub(xp, face[3]), sub(face[7], face[4])) ||
-            mul(sub(yp, face[7]), sub(face[0], face[6])) < mul(sub(xp, face[6]), sub(face[1], face[7])))
-          continue;
-        float w[3];
+    // ---- draw: survivors staged 256 records at a time, every pixel thread walks them in ascending face order
+    for (int q0 = 0; q0 < n; q0 += CHUNK) {
+      const int cnt = min(CHUNK, n - q0);
+      if (tid < cnt) {
+        const int f = s_ids[q0 + tid];
+        FaceRec& r = s_rec[tid];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) w[k] = add(add(mul(r.inv[3 * k], fxi), mul(r.inv[3 * k + 1], fyi)), r.inv[3 * k + 2]);
-        float wsum = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { w[k] = fminf(fmaxf(w[k], 0.f), 1.f); wsum = add(wsum, w[k]); }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) w[k] = dvd(w[k], wsum);
-        const float zp = dvd(1.0f, add(add(dvd(w[0], face[2]), dvd(w[1], face[5])), dvd(w[2], face[8])));
-        if (far <= zp) continue;
-        if (TWO && !(zp <= near2) && zp < depth_min2) { depth_min2 = zp; face_min2 = r.id; w0n = w[0]; w1n = w[1]; w2n = w[2]; }
-        if (zp <= near) continue;
-        if (zp < depth_min) { depth_min = zp; face_min = r.id; w0m = w[0]; w1m = w[1]; w2m = w[2]; }
+        for (int k = 0; k < 9; ++k) { r.v[k] = __ldg(fv + 9 * (size_t)f + k); r.inv[k] = __ldg(finv + 9 * (size_t)f + k); }
+        r.id = f;
       }
+      __syncthreads();
+      if (live) {
+        for (int q = 0; q < cnt; ++q) {
+          const FaceRec& r = s_rec[q];
+          const float* face = r.v;
+          if (mul(sub(yp, face[1]), sub(face[3], face[0])) < mul(sub(xp, face[0]), sub(face[4], face[1])) ||
+              mul(sub(yp, face[4]), sub(face[6], face[3])) < mul(sub(xp, face[3]), sub(face[7], face[4])) ||
+              mul(sub(yp, face[7]), sub(face[0], face[6])) < mul(sub(xp, face[6]), sub(face[1], face[7])))
+            continue;
+          float w[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) w[k] = add(add(mul(r.inv[3 * k], fxi), mul(r.inv[3 * k + 1], fyi)), r.inv[3 * k + 2]);
+          float wsum = 0.f;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { w[k] = fminf(fmaxf(w[k], 0.f), 1.f); wsum = add(wsum, w[k]); }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) w[k] = dvd(w[k], wsum);
+          const float zp = dvd(1.0f, add(add(dvd(w[0], face[2]), dvd(w[1], face[5])), dvd(w[2], face[8])));
+          if (far <= zp) continue;
+          if (TWO && !(zp <= near2) && zp < depth_min2) { depth_min2 = zp; face_min2 = r.id; w0n = w[0]; w1n = w[1]; w2n = w[2]; }
+          if (zp <= near) continue;
+          if (zp < depth_min) { depth_min = zp; face_min = r.id; w0m = w[0]; w1m = w[1]; w2m = w[2]; }
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   if (live) {
     const int pn = yi * is + xi;
@@ -297,9 +305,16 @@ __device__ __forceinline__ float pix_diff_grad(const RgbBwdArgs& a, int idx, int
   return tot;
 }
 
+// WPJ warps per (face, edge, axis) job: 1 = a warp per job for edges spanning at most kSplitCols pixel columns, 8 = a whole CTA per
+// job for the longer ones (room-shell triangles span hundreds of columns, each with a sweep to the image border: as single-warp
+// jobs they were a 400 us tail behind 25 us of work).  The split keeps the result deterministic: the CTA's warps are summed in
+// a fixed order before the one RED.ADD per gradient slot.
+constexpr int kSplitCols = 16;
+template <int WPJ>
 __global__ void __launch_bounds__(256) k_backward_rgb(const RgbBwdArgs a) {
-  const int job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int job = WPJ == 1 ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x;
   const int lane = threadIdx.x & 31;
+  const int w_idx = WPJ == 1 ? 0 : (threadIdx.x >> 5);
   if (job >= a.F2 * 6) return;
   const int fn = job / 6, edge = (job % 6) >> 1, axis = job & 1;
   const float* face = a.fv + 9 * (size_t)fn;
@@ -319,10 +334,11 @@ __global__ void __launch_bounds__(256) k_backward_rgb(const RgbBwdArgs a) {
   else direction = (p[0][0] < p[1][0]) ? 1 : -1;
   const int d0_from = (int)fmaxf(ceilf(fminf(p[0][0], p[1][0])), 0.f);
   const int d0_to = (int)fminf(fmaxf(p[0][0], p[1][0]), fis - 1.f);
+  if ((d0_to - d0_from + 1 > kSplitCols) != (WPJ > 1)) return;   // the other launch owns this job (job-uniform: whole warp / CTA)
   float g0 = 0.f, g1 = 0.f;   // gradient of vertex pi[0] / pi[1], component (1 - axis)
   // Triangles are a few pixels wide but the out sweep runs to the image border: the d0 columns of the edge are walked
   // serially (warp-uniform set-up) and the LANES stride each sweep along d1.
-  for (int d0 = d0_from; d0 <= d0_to; ++d0) {
+  for (int d0 = d0_from + w_idx; d0 <= d0_to; d0 += WPJ) {
     const float fd0 = (float)d0;
     const float d1_cross = add(mul(dvd(sub(p[1][1], p[0][1]), sub(p[1][0], p[0][0])), sub(fd0, p[0][0])), p[0][1]);
     const int d1_in = (0 < direction) ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
@@ -366,10 +382,24 @@ __global__ void __launch_bounds__(256) k_backward_rgb(const RgbBwdArgs a) {
     }
   }
   g0 = warp_sum(g0); g1 = warp_sum(g1);
+  if (WPJ > 1) {
+    __shared__ float sh[2][8];
+    if (lane == 0) { sh[0][w_idx] = g0; sh[1][w_idx] = g1; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    g0 = g1 = 0.f;
+    for (int w = 0; w < WPJ; ++w) { g0 += sh[0][w]; g1 += sh[1][w]; }
+  }
   if (lane == 0) {
     if (g0 != 0.f) atomicAdd(a.grad_faces + 9 * (size_t)fn + pi[0] * 3 + (1 - axis), g0);
     if (g1 != 0.f) atomicAdd(a.grad_faces + 9 * (size_t)fn + pi[1] * 3 + (1 - axis), g1);
   }
+}
+inline int launch_backward_rgb(const RgbBwdArgs& a, cudaStream_t st, const char* what) {
+  k_backward_rgb<1><<<ceil_div(a.F2 * 6, 8), 256, 0, st>>>(a);
+  SLN_TRY(check_launch(what));
+  k_backward_rgb<8><<<a.F2 * 6, 256, 0, st>>>(a);
+  return check_launch(what);
 }
 
 // ------------------------------------------------------------------------------------------------ backward: depth
@@ -581,8 +611,7 @@ int sln_raster_backward_rgb(const void* ws, int64_t V, int64_t F, int32_t fill_b
   a.fv = p.fv; a.face_index_map = face_index_map; a.F2 = (int)F2; a.is = image_size; a.eps = eps;
   a.img = rgb_map; a.gimg = grad_rgb_map; a.C = 3; a.grad_faces = grad_faces;
   ProfScope prof((cudaStream_t)stream, PROF_RASTER_BWD, 36.0 * F2 + 28.0 * image_size * image_size);
-  k_backward_rgb<<<ceil_div((int)F2 * 6, 8), 256, 0, (cudaStream_t)stream>>>(a);
-  return check_launch("backward_rgb");
+  return launch_backward_rgb(a, (cudaStream_t)stream, "backward_rgb");
 }
 
 int sln_raster_backward_depth(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, const int32_t* face_index_map,
@@ -640,8 +669,7 @@ int sln_scene_classes_bwd(const void* ws, int64_t V, int64_t F, int32_t fill_bac
   a.fv = p.fv; a.face_index_map = face_index_map; a.F2 = (int)F2; a.is = image_size; a.eps = eps;
   a.face_cls = face_cls; a.sval = sval; a.gcls = grad_class_images_internal; a.n_cls = n_cls; a.grad_faces = grad_faces;
   ProfScope prof((cudaStream_t)stream, PROF_RASTER_BWD, 36.0 * F2 + (12.0 + 4.0 * n_cls) * image_size * image_size);
-  k_backward_rgb<<<ceil_div((int)F2 * 6, 8), 256, 0, (cudaStream_t)stream>>>(a);
-  return check_launch("scene_backward_rgb");
+  return launch_backward_rgb(a, (cudaStream_t)stream, "scene_backward_rgb");
 }
 
 }  // extern "C"

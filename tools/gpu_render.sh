@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests/test_refine_loss.py tests/test_raster_gpu.py tests/test_collate.py tests/test_sampling.py -m gpu -x -q 2>&1 | tail -15
+timeout 600 python -m pytest tests/test_refine_loss.py tests/test_raster_gpu.py -m gpu -x -q 2>&1 | tail -8
 timeout 600 python bench.py --workload render --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_render.json 2> gpurun_out/bench_render.err
 tail -c 400 gpurun_out/bench_render.err
 python - <<'PY'
