@@ -3,9 +3,9 @@
 //
 // B200 design (not upstream's one-thread-per-pixel loop over ALL faces / one-thread-per-face serial backward):
 //   forward   k_project -> k_face_setup (per face: back-face test, pixel-space inverse, conservative pixel bounding box)
-//             -> k_raster_tiles: one CTA per 16x16 pixel tile; first the whole face list is culled against the tile (256
-//             bounding boxes per round, block-wide ORDER-PRESERVING ballot compaction into a shared id list, one barrier per
-//             round, next round's boxes prefetched), then the survivors' records are staged in shared memory 256 at a time and
+//             -> k_raster_tiles: one CTA per 16x16 pixel tile; 4096 faces at a time are culled against the tile (warps ballot
+//             32 bounding boxes per step into a shared bit mask, barrier-free, each CTA starting at a different offset of the
+//             box array; a block scan turns the mask into the ORDERED id list), then the survivors' records are staged in shared memory 256 at a time and
 //             every pixel thread walks them in ascending face order (strict '<' z-test, so ties keep the lower face index
 //             exactly as upstream).  Work drops from P*F to P*(faces touching the tile).
 //   backward  k_backward_rgb: one WARP per (face, edge, axis) job, the edge's d0 columns serially, lanes stride each d1 sweep,
@@ -121,103 +121,129 @@ __global__ void k_face_setup(const float* __restrict__ pv, const int* __restrict
 // ------------------------------------------------------------------------------------------------ tiled z-buffer
 constexpr int TILE = 16;
 constexpr int CHUNK = 256;   // faces examined per round = threads per CTA
-constexpr int LIST_CAP = 4096;   // survivor ids a tile collects before it draws (more survivors: cull / draw alternate)
+constexpr int LIST_CAP = 4096;   // faces culled per macro round = capacity of the tile's survivor list (LIST_CAP / 32 <= 256 threads)
 
-struct FaceRec { float v[9]; float inv[9]; int id; };
 
 // TWO: a second z-buffer with its own near plane is kept in the same pass (the reference's depth render clips at the rasterizer
 // default near = 0.1, its class renders at the constructor's near = 0.001; both see identical geometry).
 template <bool TWO>
-__global__ void __launch_bounds__(256) k_raster_tiles(const float* __restrict__ fv, const float* __restrict__ finv, const int4* __restrict__ fbox,
+__global__ void __launch_bounds__(256, 2) k_raster_tiles(const float* __restrict__ fv, const float* __restrict__ finv, const int4* __restrict__ fbox,
                                                       int F2, int is, float near, float far, int* __restrict__ face_index_map,
                                                       float* __restrict__ weight_map, float* __restrict__ depth_map, float near2,
                                                       int* __restrict__ face_index_map2, float* __restrict__ weight_map2,
                                                       float* __restrict__ depth_map2) {
-  __shared__ FaceRec s_rec[CHUNK];
   __shared__ int s_ids[LIST_CAP];
-  __shared__ int s_cnt[2][8];
+  __shared__ unsigned s_mask[LIST_CAP / 32];
+  __shared__ int s_cnt[8];
+  __shared__ unsigned long long s_key[TWO ? 2 : 1][TILE * TILE];   // per pixel: (depth bits << 32) | face id; min = nearest, ties -> lower id
+  __shared__ float s_xp[TILE], s_yp[TILE];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
-  const int xi = tx0 + (tid % TILE), yi = ty0 + (tid / TILE);
-  const bool live = xi < is && yi < is;
   const float fis = (float)is;
-  const float yp = dvd(sub(add(mul(2.0f, (float)yi), 1.0f), fis), fis);
-  const float xp = dvd(sub(add(mul(2.0f, (float)xi), 1.0f), fis), fis);
-  const float fxi = (float)xi, fyi = (float)yi;
-  float depth_min = far, depth_min2 = far;
-  int face_min = -1, face_min2 = -1;
-  float w0m = 0.f, w1m = 0.f, w2m = 0.f, w0n = 0.f, w1n = 0.f, w2n = 0.f;
   const int tx1 = min(tx0 + TILE - 1, is - 1), ty1 = min(ty0 + TILE - 1, is - 1);
   const int4 none = make_int4(1, 0, 1, 0);
+  const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const unsigned long long empty = ((unsigned long long)__float_as_uint(far) << 32) | 0xffffffffull;
+  s_key[0][tid] = empty;
+  if (TWO) s_key[1][tid] = empty;
+  if (tid < TILE) s_xp[tid] = dvd(sub(add(mul(2.0f, (float)(tx0 + tid)), 1.0f), fis), fis);
+  else if (tid < 2 * TILE) s_yp[tid - TILE] = dvd(sub(add(mul(2.0f, (float)(ty0 + tid - TILE)), 1.0f), fis), fis);
 
-  int base = 0;
-  while (base < F2) {
-    // ---- cull: the ORDERED list of the faces whose bounding box touches this tile.  One barrier per 256 faces, the next
-    // round's boxes are in flight while this round is compacted; nothing else happens until the list is complete (or full).
-    int n = 0, round = 0;                                       // CTA-uniform
-    int4 b_next = base + tid < F2 ? __ldg(fbox + base + tid) : none;
-    while (base < F2 && n + CHUNK <= LIST_CAP) {
-      const int f = base + tid;
-      const int4 b = b_next;
-      b_next = base + CHUNK + tid < F2 ? __ldg(fbox + base + CHUNK + tid) : none;
+  for (int base = 0; base < F2; base += LIST_CAP) {
+    // ---- cull: which of the next LIST_CAP faces touch this tile?  Every warp tests 32-face groups on its own (one ballot word per
+    // group into s_mask, no barrier, loads pipelined), and every CTA starts at a different group of the shared box array.
+    const int ng = min(LIST_CAP / 32, (F2 - base + 31) / 32);
+    const int rot = (cta * 37) % ng;
+#pragma unroll 4
+    for (int i = warp; i < ng; i += 8) {
+      int g = i + rot; if (g >= ng) g -= ng;
+      const int f = base + g * 32 + lane;
+      const int4 b = f < F2 ? __ldg(fbox + f) : none;
       const bool hit = b.x <= b.y && b.x <= tx1 && b.y >= tx0 && b.z <= ty1 && b.w >= ty0;
-      // order-preserving compaction: position = (# hits in lower warps) + (# hits in lower lanes)
       const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (lane == 0) s_cnt[round & 1][warp] = __popc(m);
-      __syncthreads();
-      int off = 0, tot = 0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) { const int c = s_cnt[round & 1][w]; off += (w < warp) ? c : 0; tot += c; }
-      if (hit) s_ids[n + off + __popc(m & ((1u << lane) - 1u))] = f;
-      n += tot; base += CHUNK; ++round;
+      if (lane == 0) s_mask[g] = m;
     }
     __syncthreads();
-    // ---- draw: survivors staged 256 records at a time, every pixel thread walks them in ascending face order
-    for (int q0 = 0; q0 < n; q0 += CHUNK) {
-      const int cnt = min(CHUNK, n - q0);
-      if (tid < cnt) {
-        const int f = s_ids[q0 + tid];
-        FaceRec& r = s_rec[tid];
+    // compact id list from the masks: exclusive scan of the group counts, then each thread expands its group's bits
+    const unsigned mine = tid < ng ? s_mask[tid] : 0u;
+    const int c = __popc(mine);
+    int x = c;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) { r.v[k] = __ldg(fv + 9 * (size_t)f + k); r.inv[k] = __ldg(finv + 9 * (size_t)f + k); }
-        r.id = f;
-      }
-      __syncthreads();
-      if (live) {
-        for (int q = 0; q < cnt; ++q) {
-          const FaceRec& r = s_rec[q];
-          const float* face = r.v;
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_cnt[warp] = x;
+    __syncthreads();
+    int off = x - c, n = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const int cw = s_cnt[w]; off += (w < warp) ? cw : 0; n += cw; }
+    for (unsigned m = mine; m; m &= m - 1) s_ids[off++] = base + tid * 32 + (__ffs(m) - 1);
+    __syncthreads();
+    // ---- draw, FACE-parallel: a thread owns a surviving face and visits only the pixels of its bounding box inside the tile.
+    // Scene meshes project to triangles of a few pixels, hundreds to thousands of them per tile: testing every face at every pixel
+    // (the pixel-parallel walk this replaces) spent > 99 % of its tests on misses and made the dense tiles the kernel's tail.
+    // The shared 64-bit min picks the nearest face and, on equal depth, the lower face index = upstream's strict '<' in ascending
+    // face order; coverage and depth use the same expressions as before, so the maps stay bit-identical to the oracle.
+    for (int q = tid; q < n; q += CHUNK) {
+      const int f = s_ids[q];
+      float face[9], inv[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { face[k] = __ldg(fv + 9 * (size_t)f + k); inv[k] = __ldg(finv + 9 * (size_t)f + k); }
+      const int4 b = __ldg(fbox + f);
+      const int x0 = max(b.x, tx0), x1 = min(b.y, tx1), y0 = max(b.z, ty0), y1 = min(b.w, ty1);
+      for (int yi = y0; yi <= y1; ++yi) {
+        const float yp = s_yp[yi - ty0], fyi = (float)yi;
+        for (int xi = x0; xi <= x1; ++xi) {
+          const float xp = s_xp[xi - tx0], fxi = (float)xi;
           if (mul(sub(yp, face[1]), sub(face[3], face[0])) < mul(sub(xp, face[0]), sub(face[4], face[1])) ||
               mul(sub(yp, face[4]), sub(face[6], face[3])) < mul(sub(xp, face[3]), sub(face[7], face[4])) ||
               mul(sub(yp, face[7]), sub(face[0], face[6])) < mul(sub(xp, face[6]), sub(face[1], face[7])))
             continue;
           float w[3];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) w[k] = add(add(mul(r.inv[3 * k], fxi), mul(r.inv[3 * k + 1], fyi)), r.inv[3 * k + 2]);
+          for (int k = 0; k < 3; ++k) w[k] = add(add(mul(inv[3 * k], fxi), mul(inv[3 * k + 1], fyi)), inv[3 * k + 2]);
           float wsum = 0.f;
 #pragma unroll
           for (int k = 0; k < 3; ++k) { w[k] = fminf(fmaxf(w[k], 0.f), 1.f); wsum = add(wsum, w[k]); }
 #pragma unroll
           for (int k = 0; k < 3; ++k) w[k] = dvd(w[k], wsum);
           const float zp = dvd(1.0f, add(add(dvd(w[0], face[2]), dvd(w[1], face[5])), dvd(w[2], face[8])));
-          if (far <= zp) continue;
-          if (TWO && !(zp <= near2) && zp < depth_min2) { depth_min2 = zp; face_min2 = r.id; w0n = w[0]; w1n = w[1]; w2n = w[2]; }
+          if (!(zp < far)) continue;                       // far <= zp, or NaN (never selected by the '<' test either)
+          const unsigned long long key = ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)f;
+          const int px = (yi - ty0) * TILE + (xi - tx0);
+          if (TWO && !(zp <= near2)) atomicMin(&s_key[1][px], key);
           if (zp <= near) continue;
-          if (zp < depth_min) { depth_min = zp; face_min = r.id; w0m = w[0]; w1m = w[1]; w2m = w[2]; }
+          atomicMin(&s_key[0][px], key);
         }
       }
-      __syncthreads();
     }
+    __syncthreads();
   }
-  if (live) {
+  // ---- resolve: the winning face's barycentric weights are recomputed for the pixel (same expressions as in the draw loop)
+  const int xi = tx0 + (tid % TILE), yi = ty0 + (tid / TILE);
+  if (xi < is && yi < is) {
     const int pn = yi * is + xi;
-    face_index_map[pn] = face_min;
-    depth_map[pn] = depth_min;
-    weight_map[3 * pn] = w0m; weight_map[3 * pn + 1] = w1m; weight_map[3 * pn + 2] = w2m;
-    if (TWO) {
-      face_index_map2[pn] = face_min2;
-      depth_map2[pn] = depth_min2;
-      weight_map2[3 * pn] = w0n; weight_map2[3 * pn + 1] = w1n; weight_map2[3 * pn + 2] = w2n;
+    const float fxi = (float)xi, fyi = (float)yi;
+#pragma unroll
+    for (int z = 0; z < (TWO ? 2 : 1); ++z) {
+      const unsigned long long key = s_key[z][tid];
+      const int f = (int)(unsigned)(key & 0xffffffffull);
+      float w[3] = {0.f, 0.f, 0.f};
+      float depth = far;
+      if (f >= 0) {
+        depth = __uint_as_float((unsigned)(key >> 32));
+        float wsum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          w[k] = add(add(mul(__ldg(finv + 9 * (size_t)f + 3 * k), fxi), mul(__ldg(finv + 9 * (size_t)f + 3 * k + 1), fyi)), __ldg(finv + 9 * (size_t)f + 3 * k + 2));
+          w[k] = fminf(fmaxf(w[k], 0.f), 1.f); wsum = add(wsum, w[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = dvd(w[k], wsum);
+      }
+      int* fim = z == 0 ? face_index_map : face_index_map2;
+      float* wm = z == 0 ? weight_map : weight_map2;
+      float* dm = z == 0 ? depth_map : depth_map2;
+      fim[pn] = f; dm[pn] = depth;
+      wm[3 * pn] = w[0]; wm[3 * pn + 1] = w[1]; wm[3 * pn + 2] = w[2];
     }
   }
 }
@@ -275,18 +301,31 @@ struct RgbBwdArgs {
   float* grad_faces;
 };
 
-__device__ __forceinline__ float pix_diff_grad(const RgbBwdArgs& a, int idx, int idx_ref) {
+// The reference pixel of a sweep is fixed (the in-pixel for the out sweep, the out-pixel for the in sweep): its class and sample
+// are read once per column instead of once per visited pixel.
+struct RefPix { int idx, cls; float val; };
+__device__ __forceinline__ RefPix ref_pixel(const RgbBwdArgs& a, int idx_ref) {
+  RefPix r; r.idx = idx_ref; r.cls = -1; r.val = 0.f;
+  if (a.face_cls != nullptr) {
+    const int fb = a.face_index_map[idx_ref];
+    if (fb >= 0) { r.cls = a.face_cls[fb]; r.val = a.sval[idx_ref]; }
+  }
+  return r;
+}
+__device__ __forceinline__ float pix_diff_grad(const RgbBwdArgs& a, int idx, const RefPix& ref) {
   float d = 0.f;
   if (a.face_cls == nullptr) {
-    for (int k = 0; k < a.C; ++k) d += (a.img[(size_t)a.C * idx + k] - a.img[(size_t)a.C * idx_ref + k]) * a.gimg[(size_t)a.C * idx + k];
+    for (int k = 0; k < a.C; ++k) d += (a.img[(size_t)a.C * idx + k] - a.img[(size_t)a.C * ref.idx + k]) * a.gimg[(size_t)a.C * idx + k];
     return d > 0.f ? d : 0.f;
   }
   // fused: only the classes of the two pixels' faces have a non-zero image difference; each class is a separate render
   // (3 identical channels whose gradient is g/3 each), clamped separately
-  const int fa = a.face_index_map[idx], fb = a.face_index_map[idx_ref];
-  const int ca = fa >= 0 ? a.face_cls[fa] : -1, cb = fb >= 0 ? a.face_cls[fb] : -1;
-  const float va = fa >= 0 ? a.sval[idx] : 0.f, vb = fb >= 0 ? a.sval[idx_ref] : 0.f;
+  const int fa = a.face_index_map[idx];
+  const float sv = a.sval[idx];
+  const int ca = fa >= 0 ? a.face_cls[fa] : -1, cb = ref.cls;
+  const float va = fa >= 0 ? sv : 0.f, vb = ref.val;
   const size_t P = (size_t)a.is * a.is;
+  const float gb = (cb >= 0 && cb != ca) ? a.gcls[(size_t)cb * P + idx] : 0.f;     // independent of the fa -> ca chain
   float tot = 0.f;
   if (ca >= 0) {
     const float g3 = a.gcls[(size_t)ca * P + idx] * (1.0f / 3.0f);
@@ -296,7 +335,7 @@ __device__ __forceinline__ float pix_diff_grad(const RgbBwdArgs& a, int idx, int
     if (dg > 0.f) tot += dg;
   }
   if (cb >= 0 && cb != ca) {
-    const float g3 = a.gcls[(size_t)cb * P + idx] * (1.0f / 3.0f);
+    const float g3 = gb * (1.0f / 3.0f);
     const float diff = 0.f - vb;
     float dg = 0.f;
     for (int k = 0; k < 3; ++k) dg += diff * g3;
@@ -353,9 +392,10 @@ __global__ void __launch_bounds__(256) k_backward_rgb(const RgbBwdArgs a) {
     if (a.face_index_map[idx_in] == fn) {   // out sweep: from the out-pixel to the image border
       const int d1_limit = (0 < direction) ? is - 1 : 0;
       const int d1_from = max(min(d1_out, d1_limit), 0), d1_to = min(max(d1_out, d1_limit), is - 1);
+      const RefPix ref = ref_pixel(a, idx_in);
       for (int d1 = d1_from + lane; d1 <= d1_to; d1 += 32) {
         const int idx = axis == 0 ? d1 * is + d0 : d0 * is + d1;
-        const float dg = pix_diff_grad(a, idx, idx_in);
+        const float dg = pix_diff_grad(a, idx, ref);
         if (dg <= 0.f) continue;
         const float t = sub((float)d1, d1_cross);
         if (use0) { float dist = dvd(mul(mul(c0, t), 2.0f), fis); dist = (0.f < dist) ? dist + a.eps : dist - a.eps; g0 -= dg / dist; }
@@ -370,10 +410,11 @@ __global__ void __launch_bounds__(256) k_backward_rgb(const RgbBwdArgs a) {
         d0_cross2 = add(mul(dvd(sub(p[1][1], p[2][1]), sub(p[1][0], p[2][0])), sub(fd0, p[2][0])), p[2][1]);
       const int d1_limit = (0 < direction) ? (int)ceilf(d0_cross2) : (int)floorf(d0_cross2);
       const int d1_from = max(min(d1_in, d1_limit), 0), d1_to = min(max(d1_in, d1_limit), is - 1);
+      const RefPix ref = ref_pixel(a, idx_out);
       for (int d1 = d1_from + lane; d1 <= d1_to; d1 += 32) {
         const int idx = axis == 0 ? d1 * is + d0 : d0 * is + d1;
         if (a.face_index_map[idx] != fn) continue;
-        const float dg = pix_diff_grad(a, idx, idx_out);
+        const float dg = pix_diff_grad(a, idx, ref);
         if (dg <= 0.f) continue;
         const float t = sub((float)d1, d1_cross);
         if (use0) { float dist = dvd(mul(mul(c0, t), 2.0f), fis); dist = (0.f < dist) ? dist + a.eps : dist - a.eps; g0 -= dg / dist; }

@@ -128,14 +128,21 @@ __global__ void __launch_bounds__(256) k_psp_loss(const float* __restrict__ inte
 // loss = 100 * 0.5 * mean|depth diff| + 100 * sum_s (sum NLL_s / count_s) / 800   (test_render_refine.py:347-349)
 __global__ void k_refine_loss_final(const float* __restrict__ partial, int ctas_per_scale, float inv_n_depth, float4 inv_count,
                                     float* __restrict__ loss3) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  float d = 0.f, sem = 0.f;
-  for (int s = 0; s < kScales; ++s) {
-    float n = 0.f;
-    for (int i = 0; i < ctas_per_scale; ++i) { d += partial[(s * ctas_per_scale + i) * 2]; n += partial[(s * ctas_per_scale + i) * 2 + 1]; }
-    sem += n * (s == 0 ? inv_count.x : s == 1 ? inv_count.y : s == 2 ? inv_count.z : inv_count.w) / 800.f;
+  // one warp per level; lanes stride the level's CTA partials, fixed shuffle tree: deterministic
+  __shared__ float sh[kScales][2];
+  const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float d = 0.f, n = 0.f;
+  for (int i = lane; i < ctas_per_scale; i += 32) { d += partial[(s * ctas_per_scale + i) * 2]; n += partial[(s * ctas_per_scale + i) * 2 + 1]; }
+  d = warp_sum(d); n = warp_sum(n);
+  if (lane == 0) { sh[s][0] = d; sh[s][1] = n; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  float dsum = 0.f, sem = 0.f;
+  for (int k = 0; k < kScales; ++k) {
+    dsum += sh[k][0];
+    sem += sh[k][1] * (k == 0 ? inv_count.x : k == 1 ? inv_count.y : k == 2 ? inv_count.z : inv_count.w) / 800.f;
   }
-  const float depth = d * inv_n_depth * 0.5f;
+  const float depth = dsum * inv_n_depth * 0.5f;
   loss3[0] = depth * 100.f + sem * 100.f;
   loss3[1] = depth;
   loss3[2] = sem;
@@ -189,32 +196,35 @@ __global__ void __launch_bounds__(256) k_psp_up_bwd(const float* __restrict__ d_
   d_inter[(size_t)p * g.off[kScales] + i] = acc;
 }
 
-// d_image[ch][y][x]: transpose of the four downsamples.  grid = (ceil(S*S/256), 1 + planes); channel 0 (plain depth) gets zeros.
+// d_image[ch][y][x]: transpose of the four downsamples.  One thread per PIXEL: the (level, row, column) taps of the pixel are the
+// same for every plane, so they are gathered once (<= 3 x 3 per level in practice, kMaxDownTaps) and reused for all planes.
+constexpr int kMaxDownTaps = 36;
 __global__ void __launch_bounds__(256) k_psp_down_bwd(const float* __restrict__ d_inter, PspGeom g, const TapList* __restrict__ tables, int stride,
                                                       const unsigned char* __restrict__ mask, float* __restrict__ d_image) {
   const int planes = g.n_sem + g.n_dep, P = g.S * g.S;
-  const int ch = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
-  if (ch == 0) { d_image[i] = 0.f; return; }
-  const int p = ch - 1, y = i / g.S, x = i % g.S;
-  float acc = 0.f;
-  if (!(p == planes - 1 && mask[i])) {                                // null-filled pixels of the last plane are constants (:333)
-    for (int s = 0; s < kScales; ++s) {
-      const int n = g.size[s];
-      const TapList* ty = tables + (size_t)(kScales + s) * stride + y;
-      const TapList* tx = tables + (size_t)(kScales + s) * stride + x;
-      const int ny = ty->n, nx = tx->n;
-      if (ny == 0 || nx == 0) continue;                               // most pixels are not tapped by a coarse level at all
-      const float* di = d_inter + (size_t)p * g.off[kScales] + g.off[s];
-      for (int a = 0; a < ny; ++a) {
-        float row = 0.f;
-        for (int b = 0; b < nx; ++b) row += tx->w[b] * __ldg(di + ty->o[a] * n + tx->o[b]);
-        acc += ty->w[a] * row;
-      }
-    }
+  const int y = i / g.S, x = i % g.S;
+  int t_off[kMaxDownTaps]; float t_w[kMaxDownTaps];
+  int nt = 0;
+  for (int s = 0; s < kScales; ++s) {
+    const int n = g.size[s];
+    const TapList* ty = tables + (size_t)(kScales + s) * stride + y;
+    const TapList* tx = tables + (size_t)(kScales + s) * stride + x;
+    const int ny = ty->n, nx = tx->n;
+    for (int a = 0; a < ny; ++a)
+      for (int b = 0; b < nx; ++b)
+        if (nt < kMaxDownTaps) { t_off[nt] = g.off[s] + ty->o[a] * n + tx->o[b]; t_w[nt] = ty->w[a] * tx->w[b]; ++nt; }
   }
-  d_image[(size_t)ch * P + i] = acc;
+  const bool null = mask[i] != 0;
+  d_image[i] = 0.f;                                                   // channel 0 (the plain depth render) is not part of the loss
+  for (int p = 0; p < planes; ++p) {
+    const float* di = d_inter + (size_t)p * g.off[kScales];
+    float acc = 0.f;
+    for (int k = 0; k < nt; ++k) acc += t_w[k] * __ldg(di + t_off[k]);
+    if (p == planes - 1 && null) acc = 0.f;                           // null-filled pixels of the last plane are constants (:333)
+    d_image[(size_t)(1 + p) * P + i] = acc;
+  }
 }
 
 struct Ws { float* filled; unsigned char* mask; float* inter; float* d_up; float* d_inter; float* partial; TapList* tables; int stride; int* overflow; size_t total; };
@@ -268,6 +278,7 @@ int sln_refine_loss(const float* image, int32_t image_size, const int32_t* sizes
   for (int i = 0; i < kScales; ++i) {
     // a source coordinate is tapped by <= 2*ceil(ratio)+1 destinations; the lists hold kMaxTaps
     const int up = (g.top + g.size[i] - 1) / g.size[i], down = (g.size[i] + g.S - 1) / g.S;
+    SLN_CHECK_ARG(g.size[i] <= g.S, "refine_loss: pyramid level %d (%d) is larger than the image", i, g.size[i]);   // <= 3 x 3 taps per pixel and level
     SLN_CHECK_ARG(2 * up + 1 <= kMaxTaps && 2 * down + 1 <= kMaxTaps && g.size[i] <= g.top && g.S <= kMaxCoord,
                   "refine_loss: pyramid level %d (%d) needs more than %d taps per coordinate", i, g.size[i], kMaxTaps);
   }
@@ -287,14 +298,14 @@ int sln_refine_loss(const float* image, int32_t image_size, const int32_t* sizes
   float4 g_sem = make_float4(inv_cnt.x * 0.125f, inv_cnt.y * 0.125f, inv_cnt.z * 0.125f, inv_cnt.w * 0.125f);
   k_psp_loss<<<dim3(ctas, kScales), 256, 0, st>>>(w.inter, g, t_depth, t_labels, 50.f * inv_nd, g_sem, w.partial, d_image ? w.d_up : nullptr);
   SLN_TRY(check_launch("psp_loss"));
-  k_refine_loss_final<<<1, 32, 0, st>>>(w.partial, ctas, inv_nd, inv_cnt, loss3);
+  k_refine_loss_final<<<1, 32 * kScales, 0, st>>>(w.partial, ctas, inv_nd, inv_cnt, loss3);
   SLN_TRY(check_launch("refine_loss_final"));
   if (d_image) {
     k_psp_tables<<<dim3(kScales, 2), 256, 0, st>>>(g, w.tables, w.stride, w.overflow);
     SLN_TRY(check_launch("psp_tables"));
     k_psp_up_bwd<<<dim3((g.off[kScales] + 255) / 256, planes), 256, 0, st>>>(w.d_up, g, w.tables, w.stride, w.d_inter);
     SLN_TRY(check_launch("psp_up_bwd"));
-    k_psp_down_bwd<<<dim3((P + 255) / 256, 1 + planes), 256, 0, st>>>(w.d_inter, g, w.tables, w.stride, w.mask, d_image);
+    k_psp_down_bwd<<<(P + 255) / 256, 256, 0, st>>>(w.d_inter, g, w.tables, w.stride, w.mask, d_image);
     SLN_TRY(check_launch("psp_down_bwd"));
   }
   return SLN_OK;
