@@ -121,6 +121,7 @@ __global__ void k_face_setup(const float* __restrict__ pv, const int* __restrict
 // ------------------------------------------------------------------------------------------------ tiled z-buffer
 constexpr int TILE = 16;
 constexpr int CHUNK = 256;   // faces examined per round = threads per CTA
+constexpr int BIG_AREA = 32;     // pixels of the tile a face's box may cover and still be drawn by a single thread
 constexpr int LIST_CAP = 4096;   // faces culled per macro round = capacity of the tile's survivor list (LIST_CAP / 32 <= 256 threads)
 
 
@@ -137,6 +138,8 @@ __global__ void __launch_bounds__(256, 2) k_raster_tiles(const float* __restrict
   __shared__ int s_cnt[8];
   __shared__ unsigned long long s_key[TWO ? 2 : 1][TILE * TILE];   // per pixel: (depth bits << 32) | face id; min = nearest, ties -> lower id
   __shared__ float s_xp[TILE], s_yp[TILE];
+  __shared__ int s_big[LIST_CAP];   // faces covering more than BIG_AREA pixels of the tile: drawn pixel-parallel after the small ones
+  __shared__ int s_nbig;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
   const float fis = (float)is;
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(256, 2) k_raster_tiles(const float* __restrict
   const int cta = blockIdx.y * gridDim.x + blockIdx.x;
   const unsigned long long empty = ((unsigned long long)__float_as_uint(far) << 32) | 0xffffffffull;
   s_key[0][tid] = empty;
+  if (tid == 0) s_nbig = 0;
   if (TWO) s_key[1][tid] = empty;
   if (tid < TILE) s_xp[tid] = dvd(sub(add(mul(2.0f, (float)(tx0 + tid)), 1.0f), fis), fis);
   else if (tid < 2 * TILE) s_yp[tid - TILE] = dvd(sub(add(mul(2.0f, (float)(ty0 + tid - TILE)), 1.0f), fis), fis);
@@ -189,6 +193,7 @@ __global__ void __launch_bounds__(256, 2) k_raster_tiles(const float* __restrict
       for (int k = 0; k < 9; ++k) { face[k] = __ldg(fv + 9 * (size_t)f + k); inv[k] = __ldg(finv + 9 * (size_t)f + k); }
       const int4 b = __ldg(fbox + f);
       const int x0 = max(b.x, tx0), x1 = min(b.y, tx1), y0 = max(b.z, ty0), y1 = min(b.w, ty1);
+      if ((x1 - x0 + 1) * (y1 - y0 + 1) > BIG_AREA) { s_big[atomicAdd(&s_nbig, 1)] = f; continue; }   // order is irrelevant: min-keys
       for (int yi = y0; yi <= y1; ++yi) {
         const float yp = s_yp[yi - ty0], fyi = (float)yi;
         for (int xi = x0; xi <= x1; ++xi) {
@@ -216,6 +221,43 @@ __global__ void __launch_bounds__(256, 2) k_raster_tiles(const float* __restrict
       }
     }
     __syncthreads();
+    // ---- the large faces of this round (room shell, close-ups), PIXEL-parallel: one thread per pixel walks the short list
+    const int nbig = s_nbig;
+    if (nbig > 0) {
+      const int xi = tx0 + (tid % TILE), yi = ty0 + (tid / TILE);
+      const float xp = s_xp[tid % TILE], yp = s_yp[tid / TILE], fxi = (float)xi, fyi = (float)yi;
+      unsigned long long best = s_key[0][tid], best2 = TWO ? s_key[1][tid] : 0ull;
+      if (xi < is && yi < is) {
+        for (int k = 0; k < nbig; ++k) {
+          const int f = s_big[k];
+          const float* face = fv + 9 * (size_t)f;
+          const float f0 = __ldg(face), f1 = __ldg(face + 1), f3 = __ldg(face + 3), f4 = __ldg(face + 4), f6 = __ldg(face + 6), f7 = __ldg(face + 7);
+          if (mul(sub(yp, f1), sub(f3, f0)) < mul(sub(xp, f0), sub(f4, f1)) ||
+              mul(sub(yp, f4), sub(f6, f3)) < mul(sub(xp, f3), sub(f7, f4)) ||
+              mul(sub(yp, f7), sub(f0, f6)) < mul(sub(xp, f6), sub(f1, f7)))
+            continue;
+          const float* inv = finv + 9 * (size_t)f;
+          float w[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) w[j] = add(add(mul(__ldg(inv + 3 * j), fxi), mul(__ldg(inv + 3 * j + 1), fyi)), __ldg(inv + 3 * j + 2));
+          float wsum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { w[j] = fminf(fmaxf(w[j], 0.f), 1.f); wsum = add(wsum, w[j]); }
+#pragma unroll
+          for (int j = 0; j < 3; ++j) w[j] = dvd(w[j], wsum);
+          const float zp = dvd(1.0f, add(add(dvd(w[0], __ldg(face + 2)), dvd(w[1], __ldg(face + 5))), dvd(w[2], __ldg(face + 8))));
+          if (!(zp < far)) continue;
+          const unsigned long long key = ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)f;
+          if (TWO && !(zp <= near2) && key < best2) best2 = key;
+          if (zp <= near) continue;
+          if (key < best) best = key;
+        }
+      }
+      s_key[0][tid] = best;                               // this phase: a pixel is touched by its own thread only
+      if (TWO) s_key[1][tid] = best2;
+      __syncthreads();
+      if (tid == 0) s_nbig = 0;                           // ordered before the next round's draw by that round's cull barriers
+    }
   }
   // ---- resolve: the winning face's barycentric weights are recomputed for the pixel (same expressions as in the draw loop)
   const int xi = tx0 + (tid % TILE), yi = ty0 + (tid / TILE);
