@@ -125,6 +125,9 @@ SIGNATURES = {
     "sln_scene_assemble_workspace_bytes": (_SZ, [_I64]),
     "sln_scene_assemble_fwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),
     "sln_scene_assemble_bwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P]),
+    "sln_composite_workspace_bytes": (_SZ, [_I32]),
+    "sln_composite_fwd": (ctypes.c_int, [_P, _P, _I32, _I64, _I32, _P, _I32, _P, _I32, _P, _P, _P, _SZ, _P]),
+    "sln_composite_bwd": (ctypes.c_int, [_P, _P, _P, _I32, _I64, _P, _I32, _P, _I32, _P, _P, _P, _P, _SZ, _P]),
     "sln_refine_loss_workspace_bytes": (_SZ, [_I32, _P, _I32, _I32]),
     "sln_refine_loss": (ctypes.c_int, [_P, _I32, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "sln_collate_layout": (ctypes.c_int, [_I64, _I64, _I64, _I32, ctypes.POINTER(_I64)]),

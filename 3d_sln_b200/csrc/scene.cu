@@ -128,6 +128,118 @@ __global__ void __launch_bounds__(256) k_assemble_bwd(const float* __restrict__ 
   d_angles[r] = -d_theta * kAngleStep;
 }
 
+
+// ------------------------------------------------------------------------------------------------ compositing (diff_render.py:366-434)
+// depth [P] (one z-buffer render), images [C, P] (class masks) -> out [1 + (n_onehot - 1) + n_keep, P]:
+//   out[0] = d = depth > 15 ? -1 : depth (:367);  out[ch] = images[c] for the class c with index[c] == ch, else 0 (:429-431);
+//   out[n_onehot + k] = images[keep[k]] > 0.1 ? d / wall_max : mean_c / wall_max  (:401-421), mean_c = mean of d over the hard mask
+//   of class c (wall_max if the mask is empty), wall_max = max of d over the wall mask (10 if empty; detached).
+// Reductions are two-level with fixed order (deterministic).  stats [2C + 1] = cnt[C] | fill[C] = mean_c / wall_max | wall_max.
+constexpr int kCompBlocks = 16;
+constexpr float kHard = 0.1f;
+
+__global__ void __launch_bounds__(256) k_comp_reduce(const float* __restrict__ depth, const float* __restrict__ images, int P, int wall,
+                                                     float* __restrict__ partial) {
+  const int c = blockIdx.x, b = blockIdx.y;
+  const int per = (P + kCompBlocks - 1) / kCompBlocks, lo = b * per, hi = min(P, lo + per);
+  float cnt = 0.f, sum = 0.f, mx = -INFINITY;
+  for (int p = lo + threadIdx.x; p < hi; p += blockDim.x) {
+    if (__ldg(images + (size_t)c * P + p) > kHard) {
+      float d = __ldg(depth + p); d = d > 15.f ? -1.f : d;
+      cnt += 1.f; sum += d; mx = fmaxf(mx, d);
+    }
+  }
+  __shared__ float sh[3][8];
+  cnt = warp_sum(cnt); sum = warp_sum(sum); mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = cnt; sh[1][threadIdx.x >> 5] = sum; sh[2][threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, s2 = 0.f, m = -INFINITY;
+    for (int w = 0; w < 8; ++w) { a += sh[0][w]; s2 += sh[1][w]; m = fmaxf(m, sh[2][w]); }
+    float* o = partial + ((size_t)c * kCompBlocks + b) * 3;
+    o[0] = a; o[1] = s2; o[2] = (c == wall) ? m : 0.f;
+  }
+}
+
+__global__ void k_comp_stats(const float* __restrict__ partial, int C, int wall, float* __restrict__ stats) {
+  __shared__ float s_wall;
+  const int c = threadIdx.x;
+  float cnt = 0.f, sum = 0.f, mx = -INFINITY;
+  if (c < C)
+    for (int b = 0; b < kCompBlocks; ++b) {
+      const float* o = partial + ((size_t)c * kCompBlocks + b) * 3;
+      cnt += o[0]; sum += o[1]; if (c == wall) mx = fmaxf(mx, o[2]);
+    }
+  if (c == wall) s_wall = cnt > 0.f ? mx : 10.0f;                       // :408-410
+  __syncthreads();
+  if (c >= C) return;
+  const float wm = s_wall;
+  const float mean = cnt > 0.f ? sum / fmaxf(cnt, 1.f) : wm;             // :411-419
+  stats[c] = cnt; stats[C + c] = mean / wm;
+  if (c == 0) stats[2 * C] = wm;
+}
+
+// inv_index [n_onehot]: class whose image goes to one-hot channel ch, or -1
+__global__ void __launch_bounds__(256) k_comp_assemble(const float* __restrict__ depth, const float* __restrict__ images, int C, int P,
+                                                       const int* __restrict__ inv_index, int n_onehot, const int* __restrict__ keep, int n_keep,
+                                                       const float* __restrict__ stats, float* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float d = __ldg(depth + p); d = d > 15.f ? -1.f : d;
+  const float wm = stats[2 * C];
+  out[p] = d;
+  for (int ch = 1; ch < n_onehot; ++ch) {
+    const int c = inv_index[ch];
+    out[(size_t)ch * P + p] = c >= 0 ? __ldg(images + (size_t)c * P + p) : 0.f;
+  }
+  const float dn = d / wm;
+  for (int k = 0; k < n_keep; ++k) {
+    const int c = keep[k];
+    out[(size_t)(n_onehot + k) * P + p] = __ldg(images + (size_t)c * P + p) > kHard ? dn : stats[C + c];
+  }
+}
+
+// S_k = sum over the pixels OUTSIDE the hard mask of class keep[k] of g_out[n_onehot + k]  (the gradient of the fill value)
+__global__ void __launch_bounds__(256) k_comp_bwd_reduce(const float* __restrict__ images, const float* __restrict__ g_out, int P, const int* __restrict__ keep,
+                                                         int n_onehot, float* __restrict__ partial) {
+  const int k = blockIdx.x, b = blockIdx.y, c = keep[k];
+  const int per = (P + kCompBlocks - 1) / kCompBlocks, lo = b * per, hi = min(P, lo + per);
+  float s = 0.f;
+  for (int p = lo + threadIdx.x; p < hi; p += blockDim.x)
+    if (!(__ldg(images + (size_t)c * P + p) > kHard)) s += __ldg(g_out + (size_t)(n_onehot + k) * P + p);
+  __shared__ float sh[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { float a = 0.f; for (int w = 0; w < 8; ++w) a += sh[w]; partial[k * kCompBlocks + b] = a; }
+}
+
+__global__ void __launch_bounds__(256) k_comp_bwd(const float* __restrict__ depth, const float* __restrict__ images, const float* __restrict__ g_out, int C,
+                                                  int P, const int* __restrict__ index, const int* __restrict__ keep, int n_keep, int n_onehot,
+                                                  const float* __restrict__ stats, const float* __restrict__ partial, float* __restrict__ g_depth,
+                                                  float* __restrict__ g_images) {
+  __shared__ float s_fill[64];     // per kept class: d(loss)/d(mean_c) / wall_max / cnt_c, 0 when the mask is empty
+  if (threadIdx.x < n_keep) {
+    const int k = threadIdx.x, c = keep[k];
+    float a = 0.f;
+    for (int b = 0; b < kCompBlocks; ++b) a += partial[k * kCompBlocks + b];
+    const float cnt = stats[c];
+    s_fill[k] = cnt > 0.f ? a / stats[2 * C] / fmaxf(cnt, 1.f) : 0.f;
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  for (int c = 0; c < C; ++c) {
+    const int ch = index[c];
+    g_images[(size_t)c * P + p] = (ch >= 1 && ch < n_onehot) ? __ldg(g_out + (size_t)ch * P + p) : 0.f;   // the mask threshold is not differentiable (.detach(), :401)
+  }
+  float g = __ldg(g_out + p);
+  const float wm = stats[2 * C];
+  for (int k = 0; k < n_keep; ++k)
+    if (__ldg(images + (size_t)keep[k] * P + p) > kHard) g += __ldg(g_out + (size_t)(n_onehot + k) * P + p) / wm + s_fill[k];
+  g_depth[p] = __ldg(depth + p) > 15.f ? 0.f : g;
+}
+
 }  // namespace
 }  // namespace sln
 
@@ -177,6 +289,40 @@ int sln_scene_assemble_bwd(const float* grad_vertices, const float* grad_sizes, 
                                                                     model_size, (const ObjParams*)ws, room3_host[0], room3_host[1], room3_host[2],
                                                                     d_boxes, d_angles);
   return check_launch("assemble_bwd");
+}
+
+
+size_t sln_composite_workspace_bytes(int32_t C) { return (size_t)(C > 0 ? C : 1) * kCompBlocks * 3 * sizeof(float); }
+
+int sln_composite_fwd(const float* depth, const float* images, int32_t C, int64_t P, int32_t wall, const int32_t* inv_index, int32_t n_onehot,
+                      const int32_t* keep, int32_t n_keep, float* out, float* stats, void* ws, size_t ws_bytes, void* stream) {
+  SLN_CHECK_ARG(depth && images && inv_index && out && stats && ws && (n_keep == 0 || keep), "composite_fwd: null pointer");
+  SLN_CHECK_ARG(C >= 1 && C <= 1024 && P >= 1 && P < (1ll << 30) && wall >= 0 && wall < C && n_onehot >= 1 && n_keep >= 0 && n_keep <= 64,
+                "composite_fwd: bad extents (C <= 1024, n_keep <= 64)");
+  if (ws_bytes < sln_composite_workspace_bytes(C)) { set_error("composite_fwd: workspace too small"); return SLN_EWORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  k_comp_reduce<<<dim3(C, kCompBlocks), 256, 0, st>>>(depth, images, (int)P, wall, (float*)ws);
+  SLN_TRY(check_launch("comp_reduce"));
+  k_comp_stats<<<1, ((C + 31) / 32) * 32, 0, st>>>((const float*)ws, C, wall, stats);
+  SLN_TRY(check_launch("comp_stats"));
+  k_comp_assemble<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(depth, images, C, (int)P, inv_index, n_onehot, keep, n_keep, stats, out);
+  return check_launch("comp_assemble");
+}
+
+int sln_composite_bwd(const float* depth, const float* images, const float* grad_out, int32_t C, int64_t P, const int32_t* index, int32_t n_onehot,
+                      const int32_t* keep, int32_t n_keep, const float* stats, float* grad_depth, float* grad_images, void* ws, size_t ws_bytes,
+                      void* stream) {
+  SLN_CHECK_ARG(depth && images && grad_out && index && stats && grad_depth && grad_images && ws && (n_keep == 0 || keep), "composite_bwd: null pointer");
+  SLN_CHECK_ARG(C >= 1 && C <= 1024 && P >= 1 && P < (1ll << 30) && n_onehot >= 1 && n_keep >= 0 && n_keep <= 64, "composite_bwd: bad extents");
+  if (ws_bytes < sln_composite_workspace_bytes(C > n_keep ? C : n_keep)) { set_error("composite_bwd: workspace too small"); return SLN_EWORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_keep > 0) {
+    k_comp_bwd_reduce<<<dim3(n_keep, kCompBlocks), 256, 0, st>>>(images, grad_out, (int)P, keep, n_onehot, (float*)ws);
+    SLN_TRY(check_launch("comp_bwd_reduce"));
+  }
+  k_comp_bwd<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(depth, images, grad_out, C, (int)P, index, keep, n_keep, n_onehot, stats, (const float*)ws,
+                                                          grad_depth, grad_images);
+  return check_launch("comp_bwd");
 }
 
 }  // extern "C"

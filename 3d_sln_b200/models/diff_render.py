@@ -159,6 +159,44 @@ def composite(depth_data, images, names, index=None, keep=None):
     return torch.cat((depth_data, one_hot[1:], planes.index_select(0, keep)), dim=0)[None]              # :433-434
 
 
+class _CompositeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, images, st):
+        lib = _lib.load()
+        dev = depth.device
+        d, im = depth.contiguous().float(), images.contiguous().float()
+        C, P = im.size(0), im.size(-1) * im.size(-2)
+        n_keep, n_onehot = st.keep32.numel(), st.inv_index32.numel()
+        out = torch.empty(1, n_onehot + n_keep, im.size(-2), im.size(-1), device=dev, dtype=torch.float32)
+        stats = torch.empty(2 * C + 1, device=dev, dtype=torch.float32)
+        ws = torch.empty(lib.sln_composite_workspace_bytes(max(C, n_keep)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.sln_composite_fwd(d.data_ptr(), im.data_ptr(), C, P, st.wall, st.inv_index32.data_ptr(), n_onehot, _lib.ptr(st.keep32), n_keep,
+                                         out.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws.numel(), _lib.cur_stream(dev)), "composite_fwd")
+        ctx.save_for_backward(d, im, stats)
+        ctx.st, ctx.ws = st, ws
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        d, im, stats = ctx.saved_tensors
+        st, dev = ctx.st, d.device
+        C, P = im.size(0), im.size(-1) * im.size(-2)
+        g = g_out.contiguous().float()
+        g_depth, g_images = torch.empty_like(d), torch.empty_like(im)
+        _lib.check(lib.sln_composite_bwd(d.data_ptr(), im.data_ptr(), g.data_ptr(), C, P, st.index32.data_ptr(), st.inv_index32.numel(), _lib.ptr(st.keep32),
+                                         st.keep32.numel(), stats.data_ptr(), g_depth.data_ptr(), g_images.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(),
+                                         _lib.cur_stream(dev)), "composite_bwd")
+        return g_depth, g_images, None
+
+
+def composite_fused(depth_data, images, static):
+    """composite() as one library call each way (csrc/scene.cu); `static` carries the class -> channel tables of the scene."""
+    if depth_data.device.type != "cuda":
+        raise RuntimeError("3d_sln_b200 compositing runs on CUDA only (composite() is the torch restatement)")
+    return _CompositeFn.apply(depth_data, images, static)
+
+
 def mesh_render_func(boxes, angles, objs, model_ids_old=None, obj_size_target=None):
     """Same contract as the reference: -> (final [1,70,256,256], model_ids_return, obj_size_return, size_loss)."""
     dev = boxes[-1].device
@@ -237,6 +275,13 @@ class SceneStatic(object):
         self.index = torch.tensor([nyu_class.index(n.replace("_", " ")) + 1 for n in names], device=dev)
         self.keep = torch.tensor([i for i, n in enumerate(names) if n not in ("wall", "floor", "ceiling")], device=dev)
         self.wall = names.index("wall")
+        # class -> channel tables of the fused compositing (csrc/scene.cu)
+        self.index32 = self.index.to(torch.int32).contiguous()
+        inv = [-1] * 41
+        for c, ch in enumerate(self.index.tolist()):
+            inv[ch] = c
+        self.inv_index32 = torch.tensor(inv, dtype=torch.int32, device=dev)
+        self.keep32 = self.keep.to(torch.int32).contiguous()
         # int32 / host mirrors for the fused assembly (csrc/scene.cu)
         self.kept32 = self.kept_idx.to(torch.int32)
         self.vobj32 = self.vobj.to(torch.int32)
@@ -327,4 +372,6 @@ def render_static(static, boxes, angles, fused=True):
         faces = static.culled_faces(vertices)
     depth, images = nr.render_scene_classes(vertices, faces, static.face_cls, len(static.names), static.K, static.R, static.t,
                                             image_size=final_out, orig_size=inter_out, near=0.001)
+    if fused:
+        return composite_fused(depth, images, static), size
     return composite(depth, images, static.names, static.index, static.keep), size

@@ -149,6 +149,21 @@ int sln_scene_assemble_bwd(const float* grad_vertices, const float* grad_sizes, 
                            const float* room3_host, const float* model_verts, const int32_t* vert_start, const float* model_size,
                            const float* model_center, const void* ws, size_t ws_bytes, float* d_boxes, float* d_angles, void* stream);
 
+/* Compositing of the 70-channel render (reference models/diff_render.py:366-434, the per-class loop vectorised):
+ *   depth [P] (depth render), images [C,P] (class masks, class order of the caller) ->
+ *   out [1 + (n_onehot-1) + n_keep, P]: out[0] = d = depth > 15 ? -1 : depth (:367); out[ch], 1 <= ch < n_onehot = images[inv_index[ch]]
+ *   (0 where inv_index[ch] < 0; :429-431); out[n_onehot + k] = images[keep[k]] > 0.1 ? d / wall_max : mean_c / wall_max (:401-421) with
+ *   mean_c = mean of d over the class mask (wall_max when empty) and wall_max = max of d over the mask of class `wall` (10 when empty).
+ *   stats [2C+1] = cnt | fill | wall_max is kept for the backward call.  index [C] / inv_index [n_onehot] / keep [n_keep]: device int32.
+ * bwd: grad_out (same shape as out) -> grad_depth [P], grad_images [C,P], fully overwritten; the mask threshold and wall_max carry no
+ * gradient, as in the reference (.detach()).  Two-level fixed-order reductions: bit-reproducible. */
+size_t sln_composite_workspace_bytes(int32_t C);
+int sln_composite_fwd(const float* depth, const float* images, int32_t C, int64_t P, int32_t wall, const int32_t* inv_index, int32_t n_onehot,
+                      const int32_t* keep, int32_t n_keep, float* out, float* stats, void* ws, size_t ws_bytes, void* stream);
+int sln_composite_bwd(const float* depth, const float* images, const float* grad_out, int32_t C, int64_t P, const int32_t* index, int32_t n_onehot,
+                      const int32_t* keep, int32_t n_keep, const float* stats, float* grad_depth, float* grad_images, void* ws, size_t ws_bytes,
+                      void* stream);
+
 /* Fused multi-scale refinement loss.  Replaces testing/test_render_refine.py:332-352 + PSP_pool_new :192-215:
  *   image[1 + n_sem + n_dep, S, S] (the [1,70,256,256] render of mesh_render_func: channel 0 depth, 1..n_sem class masks, then the
  *   normalised per-class depth planes) -> null-fill of the last plane where the depth planes sum to < 0.5 (:333), every plane resized

@@ -238,3 +238,32 @@ def test_fused_scene_assembly_matches_torch_restatement():
     final1, _ = dr.render_static(static, boxes, angles, fused=True)
     final0, _ = dr.render_static(static, boxes, angles, fused=False)
     assert maxnorm(final1.cpu().numpy(), final0.cpu().numpy()) < 1e-4
+
+
+def test_fused_compositing_matches_torch_restatement():
+    """csrc/scene.cu compositing (diff_render.py:366-434) vs the vectorised torch restatement: the [1,70,H,W] image and the gradients
+    w.r.t. the depth render and the class masks, incl. an empty class (fill = wall_max) and pixels beyond depth 15."""
+    boxes, angles, objs = meshes.synthetic_layout(10, seed=13)
+    boxes, angles = boxes.to(DEV), angles.to(DEV)
+    static = dr.SceneStatic(objs, boxes[-1], dr.mesh_library(torch.device(DEV)), DEV)
+    g = torch.Generator().manual_seed(3)
+    C, H = len(static.names), 64
+    cls = torch.randint(0, C, (H, H), generator=g)
+    cls[cls == 5] = 6                                              # class 5 owns no pixel
+    images = torch.zeros(C, H, H)
+    images.scatter_(0, cls[None], 0.05 + torch.rand(1, H, H, generator=g))    # some values below the 0.1 threshold
+    depth = 0.5 + 4 * torch.rand(1, H, H, generator=g)
+    depth[0, :3] = 100.0                                           # background rows (> 15 -> -1)
+    gout = torch.randn(1, 70, H, H, generator=g).to(DEV)
+    outs = []
+    for fused in (True, False):
+        d = depth.clone().to(DEV).requires_grad_(True)
+        im = images.clone().to(DEV).requires_grad_(True)
+        out = dr.composite_fused(d, im, static) if fused else dr.composite(d, im, static.names, static.index, static.keep)
+        (out * gout).sum().backward()
+        outs.append((out.detach(), d.grad, im.grad))
+    (o1, gd1, gi1), (o0, gd0, gi0) = outs
+    assert o1.shape == o0.shape == (1, 70, H, H)
+    assert maxnorm(o1.cpu().numpy(), o0.cpu().numpy()) < 1e-6
+    assert maxnorm(gd1.cpu().numpy(), gd0.cpu().numpy()) < 1e-5
+    assert torch.equal(gi1, gi0)
