@@ -8,7 +8,7 @@
 //             box array; a block scan turns the mask into the ORDERED id list), then the survivors' records are staged in shared memory 256 at a time and
 //             every pixel thread walks them in ascending face order (strict '<' z-test, so ties keep the lower face index
 //             exactly as upstream).  Work drops from P*F to P*(faces touching the tile).
-//   backward  k_backward_rgb: one WARP per (face, edge, axis) job, the edge's d0 columns serially, lanes stride each d1 sweep,
+//   backward  k_backward_rgb_warp / _cta: a WARP per (face, edge, axis) job, long edges deferred to 32-warp CTAs; lanes stride each d1 sweep,
 //             warp-shuffle reduction, one RED.ADD per touched gradient slot; k_backward_depth: per covered pixel.
 //   The arithmetic that decides coverage and depth order uses explicit round-to-nearest intrinsics (no FMA contraction)
 //   in the oracle's operation order, so face_index maps are bit-identical to the CPU oracle.
@@ -336,6 +336,7 @@ __global__ void k_texture_sample(const float* __restrict__ fv, const float* __re
 // else 0, and the per-class clamp `diff_grad <= 0 -> skip` is applied per class exactly as 32 separate renders would.
 struct RgbBwdArgs {
   const float* fv; const int* face_index_map; int F2, is; float eps;
+  const int* fvis;   // [F2] 1 = the face shows at >= 1 pixel (a face that shows nowhere contributes to neither sweep)
   // explicit image mode
   const float* img; const float* gimg; int C;
   // fused class mode
@@ -386,23 +387,22 @@ __device__ __forceinline__ float pix_diff_grad(const RgbBwdArgs& a, int idx, con
   return tot;
 }
 
-// WPJ warps per (face, edge, axis) job: 1 = a warp per job for edges spanning at most kSplitCols pixel columns, 8 = a whole CTA per
-// job for the longer ones (room-shell triangles span hundreds of columns, each with a sweep to the image border: as single-warp
-// jobs they were a 400 us tail behind 25 us of work).  The split keeps the result deterministic: the CTA's warps are summed in
-// a fixed order before the one RED.ADD per gradient slot.
-constexpr int kSplitCols = 16;
+// Work split of the Kato backward.  A job = (face, edge, axis).  Launch 1: a WARP per job; edges spanning more than kSplitCols pixel
+// columns are not processed but appended to a job list.  Launch 2: 1024-thread CTAs walk that list, 32 warps striding the edge's
+// columns (room-shell triangles span hundreds of columns, each with a sweep to the image border: as single-warp jobs they were a
+// 400 us tail behind 25 us of work).  Per job the warps are summed in a fixed order before the one RED.ADD per gradient slot, so
+// the result does not depend on the order of the list.
+constexpr int kSplitCols = 4;
+constexpr int kBigWarps = 32;
+// returns 0 = nothing to add, 1 = g0/g1 hold this warp's partial sums for slots (pi[0], 1-axis), (pi[1], 1-axis), 2 = deferred
 template <int WPJ>
-__global__ void __launch_bounds__(256) k_backward_rgb(const RgbBwdArgs a) {
-  const int job = WPJ == 1 ? blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5) : blockIdx.x;
-  const int lane = threadIdx.x & 31;
-  const int w_idx = WPJ == 1 ? 0 : (threadIdx.x >> 5);
-  if (job >= a.F2 * 6) return;
+__device__ __forceinline__ int rgb_job(const RgbBwdArgs& a, int job, int w_idx, int lane, float& g0, float& g1, int (&pi)[3], int& axis_out) {
   const int fn = job / 6, edge = (job % 6) >> 1, axis = job & 1;
+  if (!a.fvis[fn]) return 0;   // both sweeps only add where face_index_map == fn
   const float* face = a.fv + 9 * (size_t)fn;
-  if (backside(face)) return;
+  if (backside(face)) return 0;
   const int is = a.is;
   const float fis = (float)is;
-  int pi[3];
   float p[3][2];
 #pragma unroll
   for (int n = 0; n < 3; ++n) pi[n] = (edge + n) % 3;
@@ -415,8 +415,8 @@ __global__ void __launch_bounds__(256) k_backward_rgb(const RgbBwdArgs a) {
   else direction = (p[0][0] < p[1][0]) ? 1 : -1;
   const int d0_from = (int)fmaxf(ceilf(fminf(p[0][0], p[1][0])), 0.f);
   const int d0_to = (int)fminf(fmaxf(p[0][0], p[1][0]), fis - 1.f);
-  if ((d0_to - d0_from + 1 > kSplitCols) != (WPJ > 1)) return;   // the other launch owns this job (job-uniform: whole warp / CTA)
-  float g0 = 0.f, g1 = 0.f;   // gradient of vertex pi[0] / pi[1], component (1 - axis)
+  if (WPJ == 1 && d0_to - d0_from + 1 > kSplitCols) return 2;      // deferred to the CTA-per-job launch
+  g0 = 0.f; g1 = 0.f;   // gradient of vertex pi[0] / pi[1], component (1 - axis)
   // Triangles are a few pixels wide but the out sweep runs to the image border: the d0 columns of the edge are walked
   // serially (warp-uniform set-up) and the LANES stride each sweep along d1.
   for (int d0 = d0_from + w_idx; d0 <= d0_to; d0 += WPJ) {
@@ -464,24 +464,65 @@ __global__ void __launch_bounds__(256) k_backward_rgb(const RgbBwdArgs a) {
       }
     }
   }
+  axis_out = axis;
+  return 1;
+}
+
+__global__ void __launch_bounds__(256) k_backward_rgb_warp(const RgbBwdArgs a, int* __restrict__ big_jobs) {
+  const int job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (job >= a.F2 * 6) return;
+  float g0, g1; int pi[3], axis;
+  const int r = rgb_job<1>(a, job, 0, lane, g0, g1, pi, axis);
+  if (r == 2) { if (lane == 0) big_jobs[1 + atomicAdd(big_jobs, 1)] = job; return; }
+  if (r == 0) return;
   g0 = warp_sum(g0); g1 = warp_sum(g1);
-  if (WPJ > 1) {
-    __shared__ float sh[2][8];
-    if (lane == 0) { sh[0][w_idx] = g0; sh[1][w_idx] = g1; }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    g0 = g1 = 0.f;
-    for (int w = 0; w < WPJ; ++w) { g0 += sh[0][w]; g1 += sh[1][w]; }
-  }
   if (lane == 0) {
+    const int fn = job / 6;
     if (g0 != 0.f) atomicAdd(a.grad_faces + 9 * (size_t)fn + pi[0] * 3 + (1 - axis), g0);
     if (g1 != 0.f) atomicAdd(a.grad_faces + 9 * (size_t)fn + pi[1] * 3 + (1 - axis), g1);
   }
 }
-inline int launch_backward_rgb(const RgbBwdArgs& a, cudaStream_t st, const char* what) {
-  k_backward_rgb<1><<<ceil_div(a.F2 * 6, 8), 256, 0, st>>>(a);
+
+__global__ void __launch_bounds__(32 * kBigWarps) k_backward_rgb_cta(const RgbBwdArgs a, const int* __restrict__ big_jobs) {
+  __shared__ float sh[2][kBigWarps];
+  const int lane = threadIdx.x & 31, w_idx = threadIdx.x >> 5;
+  const int n = big_jobs[0];
+  for (int li = blockIdx.x; li < n; li += gridDim.x) {
+    const int job = big_jobs[1 + li];
+    float g0, g1; int pi[3], axis;
+    const int r = rgb_job<kBigWarps>(a, job, w_idx, lane, g0, g1, pi, axis);   // CTA-uniform return value
+    if (r != 1) continue;
+    g0 = warp_sum(g0); g1 = warp_sum(g1);
+    if (lane == 0) { sh[0][w_idx] = g0; sh[1][w_idx] = g1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t0 = 0.f, t1 = 0.f;
+      for (int w = 0; w < kBigWarps; ++w) { t0 += sh[0][w]; t1 += sh[1][w]; }
+      const int fn = job / 6;
+      if (t0 != 0.f) atomicAdd(a.grad_faces + 9 * (size_t)fn + pi[0] * 3 + (1 - axis), t0);
+      if (t1 != 0.f) atomicAdd(a.grad_faces + 9 * (size_t)fn + pi[1] * 3 + (1 - axis), t1);
+    }
+    __syncthreads();
+  }
+}
+__global__ void k_mark_visible(const int* __restrict__ face_index_map, int P, int F2, int* __restrict__ fvis) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int f = face_index_map[p];
+  if (f >= 0 && f < F2) fvis[f] = 1;   // benign race: every writer stores the same value
+}
+inline int launch_backward_rgb(RgbBwdArgs a, int* fvis, int* big_jobs, cudaStream_t st, const char* what) {
+  const int P = a.is * a.is;
+  // fvis [F2] and the job counter big_jobs[0] are adjacent in the workspace plan: one memset clears both
+  cudaError_t e = cudaMemsetAsync(fvis, 0, ((size_t)a.F2 + 1) * sizeof(int), st);
+  if (e != cudaSuccess) { set_error("%s: cudaMemsetAsync failed: %s", what, cudaGetErrorString(e)); return SLN_ECUDA; }
+  k_mark_visible<<<ceil_div(P, 256), 256, 0, st>>>(a.face_index_map, P, a.F2, fvis);
   SLN_TRY(check_launch(what));
-  k_backward_rgb<8><<<a.F2 * 6, 256, 0, st>>>(a);
+  a.fvis = fvis;
+  k_backward_rgb_warp<<<ceil_div(a.F2 * 6, 8), 256, 0, st>>>(a, big_jobs);
+  SLN_TRY(check_launch(what));
+  k_backward_rgb_cta<<<min(a.F2 * 6, 4 * kNumSMs), 32 * kBigWarps, 0, st>>>(a, big_jobs);
   return check_launch(what);
 }
 
@@ -590,7 +631,7 @@ using namespace sln;
 
 // workspace layout (all 256-byte aligned): pv [V,3] | fv [F2,9] | finv [F2,9] | fbox [F2] int4
 namespace {
-struct RasterPlan { float* pv; float* fv; float* finv; int4* fbox; size_t bytes; };
+struct RasterPlan { float* pv; float* fv; float* finv; int4* fbox; int* fvis; size_t bytes; };
 RasterPlan plan_raster(void* ws, int64_t V, int64_t F2) {
   Arena ar(ws, (size_t)-1);
   RasterPlan p;
@@ -598,6 +639,7 @@ RasterPlan plan_raster(void* ws, int64_t V, int64_t F2) {
   p.fv = ar.take<float>(9 * (size_t)F2);
   p.finv = ar.take<float>(9 * (size_t)F2);
   p.fbox = ar.take<int4>((size_t)F2);
+  p.fvis = ar.take<int>((size_t)F2 + 1 + 6 * (size_t)F2);   // backward scratch: fvis [F2] (does the face own a pixel?) | big_jobs [1 + 6 F2] (count, job ids)
   p.bytes = ar.off;
   return p;
 }
@@ -694,7 +736,7 @@ int sln_raster_backward_rgb(const void* ws, int64_t V, int64_t F, int32_t fill_b
   a.fv = p.fv; a.face_index_map = face_index_map; a.F2 = (int)F2; a.is = image_size; a.eps = eps;
   a.img = rgb_map; a.gimg = grad_rgb_map; a.C = 3; a.grad_faces = grad_faces;
   ProfScope prof((cudaStream_t)stream, PROF_RASTER_BWD, 36.0 * F2 + 28.0 * image_size * image_size);
-  return launch_backward_rgb(a, (cudaStream_t)stream, "backward_rgb");
+  return launch_backward_rgb(a, p.fvis, p.fvis + F2, (cudaStream_t)stream, "backward_rgb");
 }
 
 int sln_raster_backward_depth(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, const int32_t* face_index_map,
@@ -752,7 +794,7 @@ int sln_scene_classes_bwd(const void* ws, int64_t V, int64_t F, int32_t fill_bac
   a.fv = p.fv; a.face_index_map = face_index_map; a.F2 = (int)F2; a.is = image_size; a.eps = eps;
   a.face_cls = face_cls; a.sval = sval; a.gcls = grad_class_images_internal; a.n_cls = n_cls; a.grad_faces = grad_faces;
   ProfScope prof((cudaStream_t)stream, PROF_RASTER_BWD, 36.0 * F2 + (12.0 + 4.0 * n_cls) * image_size * image_size);
-  return launch_backward_rgb(a, (cudaStream_t)stream, "scene_backward_rgb");
+  return launch_backward_rgb(a, p.fvis, p.fvis + F2, (cudaStream_t)stream, "scene_backward_rgb");
 }
 
 }  // extern "C"

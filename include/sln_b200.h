@@ -235,6 +235,8 @@ int sln_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  *                        depth pass uses the rasterizer defaults (0.1, 100) while the rgb pass uses the constructor's near.
  * sln_raster_texture_sample  trilinear face-texture sampling, textures [F,ts,ts,ts,3] -> rgb_map [is,is,3] (background 0).
  * sln_raster_backward_rgb    Kato's gradient of the rgb image w.r.t. the face vertices' x,y: grad_faces [F2,9] += (caller zeroes).
+ *                            (both rgb backward calls first mark, in a scratch array inside ws, the faces that own a pixel of
+ *                            face_index_map: a face that shows nowhere contributes to neither sweep and is skipped)
  * sln_raster_backward_depth  gradient of depth_map w.r.t. face vertices: grad_faces [F2,9] +=.
  * sln_raster_vertex_grad     grad_faces [F2,9] -> grad w.r.t. the world vertices [V,3] (transpose of vertices_to_faces, then
  *                            the projection's Jacobian); grad_proj_scratch [V,3] is caller-owned scratch.
