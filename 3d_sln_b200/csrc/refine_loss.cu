@@ -155,20 +155,29 @@ constexpr int kMaxTaps = 8;
 constexpr int kMaxCoord = 4096;
 struct TapList { int n; int o[kMaxTaps]; float w[kMaxTaps]; };
 
-// grid = (kScales, 2), one thread per source coordinate
+// grid = (kScales, 2), one WARP per source coordinate: the lanes scan the destinations 32 at a time, an ordered ballot compaction
+// appends the ones that tap it
 __global__ void __launch_bounds__(256) k_psp_tables(PspGeom g, TapList* __restrict__ tables, int stride, int* __restrict__ overflow) {
   const int s = blockIdx.x, dir = blockIdx.y, n = g.size[s];
   const int n_src = dir == 0 ? n : g.S, n_dst = dir == 0 ? g.top : n;
-  for (int i = threadIdx.x; i < n_src; i += blockDim.x) {
-    TapList t; t.n = 0;
-    for (int o = 0; o < n_dst; ++o) {
-      const Tap tp = dir == 0 ? tap_centers(o, n, g.top) : tap_corners(o, g.S, n);
-      const float w = (tp.i0 == i ? tp.w0 : 0.f) + (tp.i1 == i ? tp.w1 : 0.f);
-      if (tp.i0 == i || tp.i1 == i) {
-        if (t.n < kMaxTaps) { t.o[t.n] = o; t.w[t.n] = w; ++t.n; } else atomicExch(overflow, 1);
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x >> 5; i < n_src; i += blockDim.x >> 5) {
+    TapList* t = tables + (size_t)(dir * kScales + s) * stride + i;
+    int cnt = 0;
+    for (int o0 = 0; o0 < n_dst; o0 += 32) {
+      const int o = o0 + lane;
+      bool hit = false; float w = 0.f;
+      if (o < n_dst) {
+        const Tap tp = dir == 0 ? tap_centers(o, n, g.top) : tap_corners(o, g.S, n);
+        hit = tp.i0 == i || tp.i1 == i;
+        w = (tp.i0 == i ? tp.w0 : 0.f) + (tp.i1 == i ? tp.w1 : 0.f);
       }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+      if (hit) { if (pos < kMaxTaps) { t->o[pos] = o; t->w[pos] = w; } else atomicExch(overflow, 1); }
+      cnt += __popc(m);
     }
-    tables[(size_t)(dir * kScales + s) * stride + i] = t;
+    if (lane == 0) t->n = min(cnt, kMaxTaps);
   }
 }
 
@@ -217,8 +226,10 @@ __global__ void __launch_bounds__(256) k_psp_down_bwd(const float* __restrict__ 
         if (nt < kMaxDownTaps) { t_off[nt] = g.off[s] + ty->o[a] * n + tx->o[b]; t_w[nt] = ty->w[a] * tx->w[b]; ++nt; }
   }
   const bool null = mask[i] != 0;
-  d_image[i] = 0.f;                                                   // channel 0 (the plain depth render) is not part of the loss
-  for (int p = 0; p < planes; ++p) {
+  if (blockIdx.y == 0) d_image[i] = 0.f;                              // channel 0 (the plain depth render) is not part of the loss
+  const int per = (planes + gridDim.y - 1) / gridDim.y;               // the planes are split over grid.y for parallelism
+  const int p_lo = blockIdx.y * per, p_hi = min(planes, p_lo + per);
+  for (int p = p_lo; p < p_hi; ++p) {
     const float* di = d_inter + (size_t)p * g.off[kScales];
     float acc = 0.f;
     for (int k = 0; k < nt; ++k) acc += t_w[k] * __ldg(di + t_off[k]);
@@ -305,7 +316,7 @@ int sln_refine_loss(const float* image, int32_t image_size, const int32_t* sizes
     SLN_TRY(check_launch("psp_tables"));
     k_psp_up_bwd<<<dim3((g.off[kScales] + 255) / 256, planes), 256, 0, st>>>(w.d_up, g, w.tables, w.stride, w.d_inter);
     SLN_TRY(check_launch("psp_up_bwd"));
-    k_psp_down_bwd<<<(P + 255) / 256, 256, 0, st>>>(w.d_inter, g, w.tables, w.stride, w.mask, d_image);
+    k_psp_down_bwd<<<dim3((P + 255) / 256, 8), 256, 0, st>>>(w.d_inter, g, w.tables, w.stride, w.mask, d_image);
     SLN_TRY(check_launch("psp_down_bwd"));
   }
   return SLN_OK;

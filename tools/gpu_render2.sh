@@ -5,7 +5,7 @@ import json
 d=json.loads(open('gpurun_out/bench_render.json').read().strip().splitlines()[-1])
 print(d['ms_per_step'], d['value'], d['e2e']['value'], d.get('kernel_classes_ms'), d.get('loss_after_timed_iters'))
 PY
-timeout 300 ncu --set full --clock-control none --cache-control none --import-source on -f -k regex:k_raster_tiles -s 3 -c 1 -o gpurun_out/prof_raster2 python bench.py --workload render --no-graph --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+timeout 300 ncu --set full --clock-control none --cache-control none --import-source on -f -k regex:'k_raster_tiles|k_backward_rgb_cta' -s 6 -c 2 -o gpurun_out/prof_raster2 python bench.py --workload render --no-graph --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 ncu -i gpurun_out/prof_raster2.ncu-rep --page raw --csv > gpurun_out/prof_raster2_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_raster2.ncu-rep --page source --csv > gpurun_out/prof_raster2_source.csv 2>/dev/null
 ls -la gpurun_out/prof_raster2*
