@@ -166,7 +166,7 @@ class RefineStep(object):
     the graph and returns the (device) loss of that iteration.  Same arithmetic as ``scene_refine`` — the graph removes the
     ~600 kernel-launch / Python overheads per iteration that otherwise dominate (the rasterizer itself takes < 1 ms)."""
 
-    def __init__(self, boxes, angles, objs, target_boxes, target_angles, lr=2e-4, use_graph=True, library=None, fused_loss=True):
+    def __init__(self, boxes, angles, objs, target_boxes, target_angles, lr=2e-4, use_graph=True, library=None, fused_loss=True, fused_scene=True):
         from . import diff_render as dr
         dev = boxes.device
         if dev.type != "cuda":
@@ -174,9 +174,10 @@ class RefineStep(object):
         lib = library if library is not None else dr.mesh_library(dev)
         self.static = dr.SceneStatic(objs, boxes[-1], lib, dev)
         with torch.no_grad():
-            target, tsize = dr.render_static(self.static, target_boxes.to(dev), target_angles.to(dev).float())
+            target, tsize = dr.render_static(self.static, target_boxes.to(dev), target_angles.to(dev).float(), fused=fused_scene)
         self.t_depth, self.t_labels = refine_targets(target)
         self.fused_loss = FusedRefineLoss(self.t_depth, self.t_labels) if fused_loss else None
+        self.fused_scene = fused_scene   # False: scene assembly and compositing through the torch-op restatements (checker)
         self.size_target = tsize.detach()
         self.room_row = boxes[-1:].detach().clone()
         self.angle_room = angles[-1:].detach().float().clone()
@@ -194,7 +195,7 @@ class RefineStep(object):
         bb.register_hook(fix_grad)
         aa = torch.cat([self.a[:-1], self.angle_room], 0)
         aa.register_hook(quad_grad)
-        image, size = self._dr.render_static(self.static, bb, aa)
+        image, size = self._dr.render_static(self.static, bb, aa, fused=self.fused_scene)
         size_loss = ((size - self.size_target) ** 2).mean(dim=1).sum()        # :98: sum over objects of mse(size, size of the first render)
         if self.fused_loss is not None:
             loss = self.fused_loss(image, size_loss)

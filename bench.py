@@ -348,7 +348,9 @@ def run_vae(args):
     roofline = {
         "bound": "tensor", "kernel": "tc::tc_gemm_kernel (tcgen05 kind::tf32 3xTF32 contraction of the graph-conv MLPs: fwd + bwd-data + bwd-weight)",
         "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
-        "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a step)",
+        "traffic": 3.62e6, "traffic_source": "dram__bytes_read+write per launch, mean of the 4 forward contractions of one GraphTripleConv layer in "
+                                             "profiles/r1_prof_tc_vae.csv (ncu --set full): operands are L2-resident, DRAM traffic = first touch only",
+        "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a step)",
         "algorithmic_flops_per_launch": g_fl / max(g_n, 1), "launches_per_step": g_n, "avg_launch_us": g_ms * 1e3 / max(g_n, 1),
         "share_of_step": share, "achieved_event_pairs_ungraphed": achieved_events,
         "note": "achieved = useful (algorithmic) 2MNK FLOPs of all contraction launches of a step / (their share of the step x ms_per_step); the "
@@ -363,6 +365,8 @@ def run_vae(args):
         gbs = pool["work"] / (pool["ms"] * 1e-3) / 1e9
         roofline_scatter = {"bound": "hbm", "kernel": "k_pool_fwd (scatter_add+count+divide as a CSR gather-reduce)", "achieved": gbs,
                             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                            "traffic_large_batch": 1.303e9, "traffic_source": "ncu --set full of the 8192-scene launch (profiles/r1_prof_pool.csv): DRAM read 1.047 GB + "
+                            "write 0.256 GB = the algorithmic 1.315 GB (no re-reads)",
                             "algorithmic_bytes_per_launch": pool["work"] / pool["launches"], "avg_launch_us": pool["ms"] * 1e3 / pool["launches"],
                             "note": "10.3 MB per launch at this config (1.6 us at the HBM peak): latency-bound; large_batch = the same entry point alone at "
                                     "512 / 8192 scenes, where it is a bandwidth kernel (ncu: profiles/*_prof_pool.csv)"}

@@ -130,7 +130,8 @@ def run(args):
     if fwd:
         gbs = fwd["work"] / (fwd["ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "raster_fwd class (k_project, k_face_setup, k_raster_tiles, k_scene_sval, k_scene_class_images)",
-                    "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+                    "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": 0.57e6,
+                    "traffic_source": "dram bytes of one k_raster_tiles launch, ncu --set full (profiles/r1_prof_raster.csv): the scene is L2-resident",
                     "algorithmic_bytes_per_iter": fwd["work"], "launches_per_iter": fwd["launches"], "ms_per_iter": fwd["ms"],
                     "peak_source": peaks["source"],
                     "note": "a 256x256 scene moves ~5 MB: the rasterizer is latency/launch-bound, not HBM-bound (SURVEY 8d); backward class: %s" % (

@@ -107,7 +107,9 @@ def run(args):
     if conv:
         tf = conv["work"] / (conv["ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<Im2col, MatView, TcEpiStore|TcEpiSpade> (3xTF32 implicit-GEMM convolutions)",
-                    "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                    "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"], "traffic": 1.591e9,
+                    "traffic_source": "dram bytes of the largest launch (up_3 modulation conv), ncu --set full (profiles/r1_prof_tc_spade.csv): 1.076 GB read + 0.515 GB "
+                                      "written = activation in, x in, modulated activation out",
                     "algorithmic_flops_per_step": conv["work"], "launches_per_step": conv["launches"], "ms_per_step": conv["ms"],
                     "share_of_step": conv["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9),
                     "peak_source": peaks["source"] + ", sustained bf16",

@@ -109,7 +109,7 @@ def test_refine_step_with_fused_loss_tracks_the_torch_loss():
     boxes, angles, objs = [t.to(dev) for t in syn_m.synthetic_layout(6, seed=13)]
     start = boxes.clone(); start[:-1, [0, 3]] += 0.03
     a = refine.RefineStep(start, angles, objs, boxes, angles, use_graph=False, fused_loss=True)
-    b = refine.RefineStep(start, angles, objs, boxes, angles, use_graph=False, fused_loss=False)
+    b = refine.RefineStep(start, angles, objs, boxes, angles, use_graph=False, fused_loss=False, fused_scene=False)
     for _ in range(5):
         la, lb = a.step().item(), b.step().item()
         assert abs(la - lb) <= 2e-3 * abs(lb)

@@ -2,6 +2,8 @@
 # gpurun copies back at most 64 MiB: every .ncu-rep is converted to its raw-page CSV on the box and big reports are dropped.
 NCU_L="ncu --metrics gpu__time_duration.sum --clock-control none --csv"
 NCU_F="ncu --set full --clock-control none -f"
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -5 > gpurun_out/pytest_gpu.txt; cat gpurun_out/pytest_gpu.txt
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.txt 2>&1; tail -8 gpurun_out/smoke.txt
 if [ -z "$SKIP_BENCH" ]; then
 timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_vae.json 2> gpurun_out/bench_vae.err
 timeout 600 python bench.py --workload render --steps 50 --warmup 5 > gpurun_out/bench_render.json 2> gpurun_out/bench_render.err
@@ -10,6 +12,7 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 fi
 timeout 300 $NCU_L --log-file gpurun_out/launches_vae.csv python tools/prof_step.py 3 > /dev/null 2>&1
 timeout 300 $NCU_L --cache-control none --log-file gpurun_out/launches_vae_warm.csv python tools/prof_step.py 3 > /dev/null 2>&1
+timeout 400 $NCU_L --cache-control none -c 1400 --log-file gpurun_out/launches_render_warm.csv python bench.py --workload render --no-graph --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 400 $NCU_L -c 1400 --log-file gpurun_out/launches_render.csv python bench.py --workload render --no-graph --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 300 $NCU_L --log-file gpurun_out/launches_spade.csv python tools/prof_spade.py 16 > /dev/null 2>&1
 timeout 300 $NCU_F -k regex:tc_gemm -s 171 -c 4 -o gpurun_out/prof_tc_vae python tools/prof_step.py 2 > /dev/null 2>&1

@@ -105,6 +105,10 @@ p = os.path.join(SRC, "launches_vae_warm.csv")
 if os.path.exists(p):
     parts.append(launch_table(read_launches(p), "k_adam", "%s_launches_vae_warm" % tag,
                               "%s: the same VAE step with `--cache-control none` (caches NOT flushed between kernels: closer to the in-graph times)" % tag))
+p = os.path.join(SRC, "launches_render_warm.csv")
+if os.path.exists(p):
+    parts.append(launch_table(read_launches(p), "k_project_bwd", "%s_launches_render_warm" % tag,
+                              "%s: the same render iteration with `--cache-control none`" % tag))
 for name in sorted(os.listdir(SRC)):
     if name.endswith("_raw.csv"):
         parts.append(full_capture(os.path.join(SRC, name), "%s_%s" % (tag, name[:-8]), "%s: %s.ncu-rep" % (tag, name[:-8])))
