@@ -181,19 +181,37 @@ class RefineStep(object):
         self.size_target = tsize.detach()
         self.room_row = boxes[-1:].detach().clone()
         self.angle_room = angles[-1:].detach().float().clone()
-        self.b = boxes.detach().clone().requires_grad_(True)
-        self.a = angles.detach().float().clone().requires_grad_(True)
-        self.opt = torch.optim.Adam([self.b, self.a], lr=lr, capturable=True)
+        # the layout lives in ONE flat leaf (boxes | angles): one gradient buffer, one library Adam launch (sln_adam_step,
+        # the same kernel as the VAE train step) instead of the ~15 launches of torch's capturable Adam
+        n = boxes.size(0)
+        self.flat = torch.cat([boxes.detach().float().reshape(-1), angles.detach().float().reshape(-1)]).clone().requires_grad_(True)
+        self.flat.grad = torch.zeros_like(self.flat)
+        self.n_rows = n
+        self.lr = lr
+        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.step_count = torch.zeros(1, device=dev, dtype=torch.int64)
+        self.lib = _lib.load()
         self.loss = torch.zeros((), device=dev)
         self.graph = None
         self._dr = dr
         if use_graph:
             self.capture()
 
+    @property
+    def b(self):
+        """boxes [n+1, 6]: a view of the flat layout leaf"""
+        return self.flat[:6 * self.n_rows].view(self.n_rows, 6)
+
+    @property
+    def a(self):
+        """angles [n+1]: a view of the flat layout leaf"""
+        return self.flat[6 * self.n_rows:]
+
     def _iteration(self):
-        bb = torch.cat([self.b[:-1], self.room_row], 0)
+        b, a = self.b, self.a
+        bb = torch.cat([b[:-1], self.room_row], 0)
         bb.register_hook(fix_grad)
-        aa = torch.cat([self.a[:-1], self.angle_room], 0)
+        aa = torch.cat([a[:-1], self.angle_room], 0)
         aa.register_hook(quad_grad)
         image, size = self._dr.render_static(self.static, bb, aa, fused=self.fused_scene)
         size_loss = ((size - self.size_target) ** 2).mean(dim=1).sum()        # :98: sum over objects of mse(size, size of the first render)
@@ -201,9 +219,11 @@ class RefineStep(object):
             loss = self.fused_loss(image, size_loss)
         else:
             loss = refine_loss(image, self.t_depth, self.t_labels, size_loss)
-        self.opt.zero_grad(set_to_none=False)
+        self.flat.grad.zero_()
         loss.backward()
-        self.opt.step()
+        _lib.check(self.lib.sln_adam_step(self.flat.data_ptr(), self.flat.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.flat.numel(),
+                                          self.lr, 0.9, 0.999, 1e-8, 0.0, 1.0, self.step_count.data_ptr(), 1, _lib.cur_stream(self.flat.device)),
+                   "adam_step")       # torch.optim.Adam defaults (BASELINE configs[2]: Adam lr 2e-4 over boxes + angles)
         self.loss.copy_(loss.detach())
 
     def capture(self):
@@ -225,10 +245,7 @@ class RefineStep(object):
         """Restart from a layout (also clears the Adam moments)."""
         with torch.no_grad():
             self.b.copy_(boxes); self.a.copy_(angles.float())
-            for st in self.opt.state.values():
-                for k, v in st.items():
-                    if torch.is_tensor(v):
-                        v.zero_()
+            self.m.zero_(); self.v.zero_(); self.step_count.zero_()
 
     def step(self):
         if self.graph is not None:
