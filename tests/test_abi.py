@@ -69,3 +69,32 @@ def test_state_dict_keys_and_init_match_reference_when_available():
         a, b = r.state_dict(), o.state_dict()
         assert list(a.keys()) == list(b.keys())
         assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_host_side_argument_checks_of_collate_refine_scene_entry_points():
+    """Argument validation happens on the host before any launch, so the error convention (negative code + message, no exception
+    across the ABI) can be checked without a GPU: collate wire layout, refinement-loss pyramid limits, scene assembly / compositing."""
+    lib = importlib.import_module("3d_sln_b200._lib").load()
+    off = (ctypes.c_int64 * 10)()
+    assert lib.sln_collate_layout(3, 50, 75, 6, off) == 0
+    o = list(off)
+    assert o == sorted(o) and all(v % 16 == 0 for v in o)                       # sections ascending, 16-byte aligned
+    assert o[1] - o[0] >= 8 * 3 and o[5] - o[4] >= 8 * 50 and o[8] - o[7] >= 8 * 3 * 75 and o[9] - o[8] >= 4 * 6 * 50
+    assert lib.sln_collate_layout(-1, 0, 0, 6, off) < 0 and b"collate_layout" in lib.sln_last_error()
+    assert lib.sln_collate_finish(None, 0, 1, 1, 1, 6, None, None, None, None, None) < 0
+    sizes = (ctypes.c_int32 * 4)(32, 48, 64, 96)
+    assert lib.sln_refine_loss_workspace_bytes(256, sizes, 40, 29) > 4 * 69 * (32 * 32 + 48 * 48 + 64 * 64 + 96 * 96)
+    assert lib.sln_refine_loss_workspace_bytes(256, sizes, 0, 29) == 0
+    dummy = ctypes.c_void_p(256)                                                 # never dereferenced: the checks fail first
+    counts = (ctypes.c_float * 4)(1, 1, 1, 1)
+    too_coarse = (ctypes.c_int32 * 4)(8, 48, 64, 96)                             # 96 / 8 = 12 destinations per source: beyond the tap lists
+    assert lib.sln_refine_loss(dummy, 256, too_coarse, 40, 29, dummy, dummy, counts, dummy, None, dummy, 1 << 30, None) < 0
+    assert b"taps" in lib.sln_last_error()
+    assert lib.sln_refine_loss(dummy, 256, sizes, 65, 29, dummy, dummy, counts, dummy, None, dummy, 1 << 30, None) < 0   # n_sem > 64
+    assert lib.sln_refine_loss(dummy, 256, sizes, 40, 29, dummy, dummy, counts, dummy, None, dummy, 16, None) == -2      # SLN_EWORKSPACE
+    assert lib.sln_scene_assemble_workspace_bytes(10) >= 10 * 32
+    assert lib.sln_scene_assemble_fwd(None, None, 1, None, 0, None, None, None, 0, None, 0, None, None, None, 0, None, None, 0.06, None, None,
+                                      None, None, 0, None) < 0
+    assert lib.sln_composite_workspace_bytes(32) > 0
+    assert lib.sln_composite_fwd(dummy, dummy, 32, 65536, 40, dummy, 41, dummy, 29, dummy, dummy, dummy, 1 << 20, None) < 0   # wall >= C
+    assert b"composite_fwd" in lib.sln_last_error()
