@@ -124,7 +124,7 @@ SIGNATURES = {
     "sln_set_engine": (ctypes.c_int, [ctypes.c_int]),
     "sln_scene_assemble_workspace_bytes": (_SZ, [_I64]),
     "sln_scene_assemble_fwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _P, _F, _P, _P, _P, _P, _SZ, _P]),
-    "sln_scene_assemble_bwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _P, _SZ, _P, _P, _P]),
+    "sln_scene_assemble_bwd": (ctypes.c_int, [_P, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _P, _SZ, _I32, _F, _P, _P, _P]),
     "sln_composite_workspace_bytes": (_SZ, [_I32]),
     "sln_composite_fwd": (ctypes.c_int, [_P, _P, _I32, _I64, _I32, _P, _I32, _P, _I32, _P, _P, _P, _SZ, _P]),
     "sln_composite_bwd": (ctypes.c_int, [_P, _P, _P, _I32, _I64, _P, _I32, _P, _I32, _P, _P, _P, _P, _SZ, _P]),

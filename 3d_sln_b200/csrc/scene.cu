@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(256) k_assemble_bwd(const float* __restrict__ 
                                                       const float* __restrict__ mv, const int* __restrict__ vstart,
                                                       const int* __restrict__ row_to_kept, const float* __restrict__ mcent,
                                                       const float* __restrict__ msize, const ObjParams* __restrict__ prm, float rx, float ry,
-                                                      float rz, float* __restrict__ d_boxes, float* __restrict__ d_angles) {
+                                                      float rz, int fix_corners, float angle_scale, float* __restrict__ d_boxes,
+                                                      float* __restrict__ d_angles) {
   const int r = blockIdx.x;
   const int j = row_to_kept[r];
   if (j < 0) {
@@ -122,10 +123,12 @@ __global__ void __launch_bounds__(256) k_assemble_bwd(const float* __restrict__ 
   for (int k = 0; k < 3; ++k) {
     float d_size = g_size ? g_size[3 * j + k] : 0.f;
     if (k == p.kmin) d_size += d_s / msize[3 * j + k];
-    d_boxes[6 * r + k] = (t[k] * 0.5f - d_size) * room[k];
-    d_boxes[6 * r + 3 + k] = (t[k] * 0.5f + d_size) * room[k];
+    float lo = (t[k] * 0.5f - d_size) * room[k], hi = (t[k] * 0.5f + d_size) * room[k];
+    if (fix_corners) { const float avg = hi / 2.0f + lo / 2.0f; lo = hi = avg; }   // fix_grad (test_render_refine.py:220-225): boxes translate, sizes stay
+    d_boxes[6 * r + k] = lo;
+    d_boxes[6 * r + 3 + k] = hi;
   }
-  d_angles[r] = -d_theta * kAngleStep;
+  d_angles[r] = -d_theta * kAngleStep * angle_scale;                               // quad_grad (:227-230) when angle_scale = 4
 }
 
 
@@ -280,14 +283,15 @@ int sln_scene_assemble_fwd(const float* boxes, const float* angles, int64_t n_ro
 
 int sln_scene_assemble_bwd(const float* grad_vertices, const float* grad_sizes, int64_t n_rows, const int32_t* row_to_kept, int64_t n_kept,
                            const float* room3_host, const float* model_verts, const int32_t* vert_start, const float* model_size,
-                           const float* model_center, const void* ws, size_t ws_bytes, float* d_boxes, float* d_angles, void* stream) {
+                           const float* model_center, const void* ws, size_t ws_bytes, int32_t fix_corners, float angle_grad_scale,
+                           float* d_boxes, float* d_angles, void* stream) {
   SLN_CHECK_ARG(grad_vertices && row_to_kept && room3_host && ws && d_boxes && d_angles, "scene_assemble_bwd: null pointer");
   SLN_CHECK_ARG(n_rows >= 1 && n_kept >= 0, "scene_assemble_bwd: bad extents");
   SLN_CHECK_ARG(n_kept == 0 || (model_verts && vert_start && model_size && model_center), "scene_assemble_bwd: null object arrays");
   if (ws_bytes < sln_scene_assemble_workspace_bytes(n_kept)) { set_error("scene_assemble_bwd: workspace too small"); return SLN_EWORKSPACE; }
   k_assemble_bwd<<<(unsigned)n_rows, 256, 0, (cudaStream_t)stream>>>(grad_vertices, grad_sizes, model_verts, vert_start, row_to_kept, model_center,
                                                                     model_size, (const ObjParams*)ws, room3_host[0], room3_host[1], room3_host[2],
-                                                                    d_boxes, d_angles);
+                                                                    fix_corners, angle_grad_scale, d_boxes, d_angles);
   return check_launch("assemble_bwd");
 }
 

@@ -311,10 +311,11 @@ class SceneStatic(object):
         v = scale[self.vobj, None] * torch.einsum("vij,vj->vi", rot[self.vobj], self.mv) + trans[self.vobj]
         return torch.cat([v, self.shell_v])[None], size
 
-    def assemble(self, boxes, angles, eps=0.06):
+    def assemble(self, boxes, angles, eps=0.06, refine_hooks=False):
         """vertices() + culled_faces() as one library call each way (csrc/scene.cu): -> (vertices [1,V,3], size [n_kept,3],
-        faces [1,F,3] int32).  Differentiable w.r.t. boxes and angles."""
-        return _AssembleFn.apply(boxes, angles, self, float(eps))
+        faces [1,F,3] int32).  Differentiable w.r.t. boxes and angles.  refine_hooks: the backward kernel also applies the
+        refinement loop's gradient hooks (fix_grad on the boxes, quad_grad on the angles; test_render_refine.py:220-230,288,297)."""
+        return _AssembleFn.apply(boxes, angles, self, float(eps), bool(refine_hooks))
 
     def culled_faces(self, vertices, eps=0.06):
         """Reference :345-356 without a dynamic shape: a face with any vertex closer than eps keeps its slot but collapses to a
@@ -327,9 +328,10 @@ class SceneStatic(object):
 
 class _AssembleFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, boxes, angles, st, eps):
+    def forward(ctx, boxes, angles, st, eps, refine_hooks=False):
         lib = _lib.load()
         dev = st.dev
+        ctx.hooks = refine_hooks
         b, a = boxes.contiguous().float(), angles.contiguous().float()
         if b.device.type != "cuda":
             raise RuntimeError("3d_sln_b200 scene assembly runs on CUDA only (no CPU fallback)")
@@ -357,16 +359,16 @@ class _AssembleFn(torch.autograd.Function):
         d_angles = torch.empty(ctx.n_rows, device=dev, dtype=torch.float32)
         _lib.check(lib.sln_scene_assemble_bwd(gv.data_ptr(), gs.data_ptr() if gs is not None else None, ctx.n_rows, _lib.ptr(st.row_to_kept32),
                                               st.n_kept, st.room3_c, _lib.ptr(st.mv), _lib.ptr(st.vstart32), _lib.ptr(st.msize), _lib.ptr(st.mcent),
-                                              ctx.ws.data_ptr(), ctx.ws.numel(), d_boxes.data_ptr(), d_angles.data_ptr(), _lib.cur_stream(dev)),
-                   "scene_assemble_bwd")
-        return d_boxes, d_angles, None, None
+                                              ctx.ws.data_ptr(), ctx.ws.numel(), 1 if ctx.hooks else 0, 4.0 if ctx.hooks else 1.0, d_boxes.data_ptr(),
+                                              d_angles.data_ptr(), _lib.cur_stream(dev)), "scene_assemble_bwd")
+        return d_boxes, d_angles, None, None, None
 
 
-def render_static(static, boxes, angles, fused=True):
+def render_static(static, boxes, angles, fused=True, refine_hooks=False):
     """final [1, 70, 256, 256] of the scene described by `static` at layout (boxes, angles): scene assembly (one library call;
     fused=False: the torch-op restatement of the reference's arithmetic, kept as the checker) + one rasterization + compositing."""
     if fused:
-        vertices, size, faces = static.assemble(boxes, angles)
+        vertices, size, faces = static.assemble(boxes, angles, refine_hooks=refine_hooks)
     else:
         vertices, size = static.vertices(boxes, angles)
         faces = static.culled_faces(vertices)

@@ -209,11 +209,16 @@ class RefineStep(object):
 
     def _iteration(self):
         b, a = self.b, self.a
-        bb = torch.cat([b[:-1], self.room_row], 0)
-        bb.register_hook(fix_grad)
-        aa = torch.cat([a[:-1], self.angle_room], 0)
-        aa.register_hook(quad_grad)
-        image, size = self._dr.render_static(self.static, bb, aa, fused=self.fused_scene)
+        if self.fused_scene:
+            # the room row owns no mesh: its gradient is exactly 0 and Adam leaves it alone, so the layout leaf itself is the render
+            # input; fix_grad / quad_grad (:220-230) are applied inside the assembly's backward kernel
+            image, size = self._dr.render_static(self.static, b, a, fused=True, refine_hooks=True)
+        else:
+            bb = torch.cat([b[:-1], self.room_row], 0)
+            bb.register_hook(fix_grad)
+            aa = torch.cat([a[:-1], self.angle_room], 0)
+            aa.register_hook(quad_grad)
+            image, size = self._dr.render_static(self.static, bb, aa, fused=False)
         size_loss = ((size - self.size_target) ** 2).mean(dim=1).sum()        # :98: sum over objects of mse(size, size of the first render)
         if self.fused_loss is not None:
             loss = self.fused_loss(image, size_loss)

@@ -139,7 +139,9 @@ int sln_csr_pointers(void* ws, int64_t O, int64_t T, const int32_t** row_ptr, co
  *   vertex at camera depth < cull_eps become the zero-area triangle (0,0,0) (static shapes; the rasterizer never draws them).
  * bwd: grad_vertices [V,3], grad_sizes [n_kept,3] or NULL, row_to_kept [n_rows] int32 (-1 = no mesh), vert_start [n_kept+1] int32
  *   -> d_boxes [n_rows,6], d_angles [n_rows], fully overwritten; fixed-order reductions (bit-reproducible).  ws: the buffer the
- *   forward call filled (sln_scene_assemble_workspace_bytes). */
+ *   forward call filled (sln_scene_assemble_workspace_bytes).  fix_corners != 0 / angle_grad_scale apply the refinement loop's gradient
+ *   hooks in place (testing/test_render_refine.py:220-230: fix_grad averages the min- and max-corner gradients, quad_grad = x4; pass 0 / 1
+ *   for plain gradients). */
 size_t sln_scene_assemble_workspace_bytes(int64_t n_kept);
 int sln_scene_assemble_fwd(const float* boxes, const float* angles, int64_t n_rows, const int32_t* kept, int64_t n_kept, const float* room3_host,
                            const float* model_verts, const int32_t* vert_obj, int64_t n_obj_verts, const float* shell_verts, int64_t n_shell,
@@ -147,7 +149,8 @@ int sln_scene_assemble_fwd(const float* boxes, const float* angles, int64_t n_ro
                            float cull_eps, float* vertices, float* sizes, int32_t* faces_out, void* ws, size_t ws_bytes, void* stream);
 int sln_scene_assemble_bwd(const float* grad_vertices, const float* grad_sizes, int64_t n_rows, const int32_t* row_to_kept, int64_t n_kept,
                            const float* room3_host, const float* model_verts, const int32_t* vert_start, const float* model_size,
-                           const float* model_center, const void* ws, size_t ws_bytes, float* d_boxes, float* d_angles, void* stream);
+                           const float* model_center, const void* ws, size_t ws_bytes, int32_t fix_corners, float angle_grad_scale,
+                           float* d_boxes, float* d_angles, void* stream);
 
 /* Compositing of the 70-channel render (reference models/diff_render.py:366-434, the per-class loop vectorised):
  *   depth [P] (depth render), images [C,P] (class masks, class order of the caller) ->
