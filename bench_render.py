@@ -88,16 +88,19 @@ def run(args):
     # e2e: the layout comes from pinned host memory every iteration and the loss goes back to the host
     hb, ha = start.detach().cpu().pin_memory(), a0.detach().cpu().pin_memory()
     loss_host = torch.empty(1).pin_memory()
+    # an iteration is ~0.5 ms: K of them end before nvidia-smi (100 ms period) delivers its first sample, so the e2e loop runs long
+    # enough (>= 0.8 s, back to back with the `value` loop) for the clock / throttle sampler to see the GPU under this load
+    e2e_steps = max(args.steps, int(0.8 / max(dev_ms / args.steps * 1e-3, 1e-5)) + 1)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         with torch.no_grad():
             b.copy_(hb, non_blocking=True); a.copy_(ha, non_blocking=True)
         loss = iteration()
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = (time.perf_counter() - t0) * args.steps / e2e_steps      # seconds per K iterations
     clocks = sampler.stop() if sampler else None
     # roofline of the dominant kernel class (rasterizer forward): event pair around every library launch
     prof = {}
@@ -142,7 +145,8 @@ def run(args):
     return {
         "metric": METRIC, "value": n * 1e3 / ms_per_step, "unit": "iters/s", "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": _config(n), "e2e": {"value": n * args.steps / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": 11 * 6 * 4 + 11 * 4, "d2h_bytes_per_step": 4},
+        "config": _config(n), "e2e": {"value": n * args.steps / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": 11 * 6 * 4 + 11 * 4, "d2h_bytes_per_step": 4,
+                                      "timed_iterations": e2e_steps},
         "gpu_launches": launches_per_iter * args.steps, "launches_per_step": launches_per_iter, "roofline": roofline, "cpu_baseline": cpu,
         "clocks": clocks, "kernel_classes_ms": {k: round(v["ms"], 4) for k, v in prof.items()}, "first_loss": first, "loss_after_timed_iters": loss_after_value_loop,
     }
