@@ -131,6 +131,9 @@ class DevicePrefetcher(object):
         dev = self.collate.dev
         nxt = None
         for samples in self.loader:
+            # a slot's device buffer is reused three batches later: everything the caller has enqueued so far (the consumers of
+            # the batch that last lived in it) must precede the new copy, which still overlaps the step enqueued next
+            self.stream.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(self.stream):
                 cur = self.collate(samples)
                 done = torch.cuda.Event(); done.record(self.stream)
