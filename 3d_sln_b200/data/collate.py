@@ -42,6 +42,55 @@ def suncg_collate_fn(batch):
     return (ids, objs, boxes, triples, angles, attrs, torch.repeat_interleave(pos, n_obj), torch.repeat_interleave(pos, n_tri))
 
 
+def wire_layout(lib, kept):
+    """(B, O, T, box_dim, offsets10) of the wire buffer for the kept scenes (include/sln_b200.h, sln_collate_layout)."""
+    B = len(kept)
+    O = sum(s[1].size(0) for _, s in kept)
+    T = sum(s[3].size(0) for _, s in kept)
+    box_dim = kept[0][1][2].size(1)
+    off = (ctypes.c_int64 * 10)()
+    _lib.check(lib.sln_collate_layout(B, O, T, box_dim, off), "collate_layout")
+    return B, O, T, box_dim, list(off)
+
+
+def pack_wire(kept, lay, pin):
+    """Host side of the batch assembly: write the kept scenes into the (pinned) uint8 buffer `pin` in wire layout.  Pure CPU work —
+    what a DataLoader worker does instead of suncg_collate_fn; the device finishes it with sln_collate_finish."""
+    o_si, o_oo, o_to, o_ids, o_objs, o_ang, o_att, o_tri, o_box, total = lay
+    B = len(kept)
+    n_obj = [s[1].size(0) for _, s in kept]
+    n_tri = [s[3].size(0) for _, s in kept]
+    O, T = sum(n_obj), sum(n_tri)
+    box_dim = kept[0][1][2].size(1)
+    i64, f32 = torch.int64, torch.float32
+
+    def hv(off, n, dt):
+        return pin[off: off + n * dt.itemsize].view(dt)
+    hv(o_si, B, i64).copy_(torch.tensor([i for i, _ in kept], dtype=i64))
+    oo = hv(o_oo, B + 1, i64); oo[0] = 0; torch.cumsum(torch.tensor(n_obj, dtype=i64), 0, out=oo[1:])
+    to = hv(o_to, B + 1, i64); to[0] = 0; torch.cumsum(torch.tensor(n_tri, dtype=i64), 0, out=to[1:])
+    hv(o_ids, B, i64).copy_(torch.tensor([int(s[0]) for _, s in kept], dtype=i64))
+    torch.cat([s[1] for _, s in kept], out=hv(o_objs, O, i64))
+    torch.cat([s[4] for _, s in kept], out=hv(o_ang, O, i64))
+    torch.cat([s[5] for _, s in kept], out=hv(o_att, O, i64))
+    torch.cat([s[3] for _, s in kept], out=hv(o_tri, 3 * T, i64).view(T, 3))
+    torch.cat([s[2] for _, s in kept], out=hv(o_box, O * box_dim, f32).view(O, box_dim))
+    return pin
+
+
+def packed_batch(batch, lib=None):
+    """un-collated samples -> (pinned wire buffer [total] uint8, (B, O, T, box_dim, offsets10)): the host-resident form of a batch that
+    VAETrainStep.step_wire() consumes with ONE host->device copy."""
+    lib = lib if lib is not None else _lib.load()
+    kept = _keep(batch)
+    if not kept:
+        raise ValueError("packed_batch: every scene of the batch is empty")
+    meta = wire_layout(lib, kept)
+    pin = torch.empty(meta[4][9], dtype=torch.uint8).pin_memory()
+    pack_wire(kept, meta[4], pin)
+    return pin, meta
+
+
 class DeviceCollator(object):
     """list of (room_id, objs, boxes, triples, angles, attributes) CPU samples -> the collated 8-tuple as CUDA tensors.
 
@@ -60,21 +109,11 @@ class DeviceCollator(object):
         self.check_ids = check_ids
         self.h2d_bytes = 0      # bytes of the last call's single host->device copy
 
-    def _layout(self, B, O, T, box_dim):
-        off = (ctypes.c_int64 * 10)()
-        _lib.check(self.lib.sln_collate_layout(B, O, T, box_dim, off), "collate_layout")
-        return list(off)
-
     def __call__(self, batch):
         kept = _keep(batch)
         if not kept:
             raise ValueError("DeviceCollator: every scene of the batch is empty")
-        B = len(kept)
-        n_obj = [s[1].size(0) for _, s in kept]
-        n_tri = [s[3].size(0) for _, s in kept]
-        O, T = sum(n_obj), sum(n_tri)
-        box_dim = kept[0][1][2].size(1)
-        lay = self._layout(B, O, T, box_dim)
+        B, O, T, box_dim, lay = wire_layout(self.lib, kept)
         o_si, o_oo, o_to, o_ids, o_objs, o_ang, o_att, o_tri, o_box, total = lay
         slot = self.slots[self.turn]
         self.turn = (self.turn + 1) % len(self.slots)
@@ -85,22 +124,11 @@ class DeviceCollator(object):
         elif slot["evt"] is not None:
             slot["evt"].synchronize()          # the previous copy out of this pinned buffer must have finished
         pin, dbuf = slot["pin"], slot["dev"]
-
-        def hv(off, n, dt):
-            return pin[off: off + n * dt.itemsize].view(dt)
+        pack_wire(kept, lay, pin)
 
         def dv(off, n, dt):
             return dbuf[off: off + n * dt.itemsize].view(dt)
         i64, f32 = torch.int64, torch.float32
-        hv(o_si, B, i64).copy_(torch.tensor([i for i, _ in kept], dtype=i64))
-        oo = hv(o_oo, B + 1, i64); oo[0] = 0; torch.cumsum(torch.tensor(n_obj, dtype=i64), 0, out=oo[1:])
-        to = hv(o_to, B + 1, i64); to[0] = 0; torch.cumsum(torch.tensor(n_tri, dtype=i64), 0, out=to[1:])
-        hv(o_ids, B, i64).copy_(torch.tensor([int(s[0]) for _, s in kept], dtype=i64))
-        torch.cat([s[1] for _, s in kept], out=hv(o_objs, O, i64))
-        torch.cat([s[4] for _, s in kept], out=hv(o_ang, O, i64))
-        torch.cat([s[5] for _, s in kept], out=hv(o_att, O, i64))
-        torch.cat([s[3] for _, s in kept], out=hv(o_tri, 3 * T, i64).view(T, 3))
-        torch.cat([s[2] for _, s in kept], out=hv(o_box, O * box_dim, f32).view(O, box_dim))
         dbuf[:total].copy_(pin[:total], non_blocking=True)
         slot["evt"] = torch.cuda.Event()
         slot["evt"].record(torch.cuda.current_stream(self.dev))

@@ -186,7 +186,7 @@ class VAETrainStep(object):
     """
 
     def __init__(self, model, O, T, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, kl_weight=0.1, use_graph=True, process_group=None,
-                 world_size=1, sample_eps=True, pack_weights=True):
+                 world_size=1, sample_eps=True, pack_weights=True, wire_meta=None):
         self.lib = _lib.load()
         self.model = model
         dev = next(model.parameters()).device
@@ -222,6 +222,22 @@ class VAETrainStep(object):
         f32 = dict(device=dev, dtype=torch.float32)
         self.objs = torch.zeros(O, **i64); self.triples = torch.zeros(T, 3, **i64); self.boxes = torch.zeros(O, BD, **f32)
         self.angles = torch.zeros(O, **i64); self.attrs = torch.zeros(O, **i64)
+        # wire_meta = (B, O, T, box_dim, offsets10) of data.collate.packed_batch: the static inputs become views of ONE device buffer in
+        # the batch-assembly wire layout (include/sln_b200.h, sln_collate_layout), so that step_wire() feeds a step with one H2D copy +
+        # sln_collate_finish instead of suncg_collate_fn + five copies (reference train.py:69, utils.py:114-124)
+        self.wire_meta = wire_meta
+        if wire_meta is not None:
+            wB, wO, wT, wbd, lay = wire_meta
+            if (wO, wT, wbd) != (O, T, BD):
+                raise ValueError("VAETrainStep: wire layout is for O=%d T=%d box_dim=%d, the step for O=%d T=%d box_dim=%d" % (wO, wT, wbd, O, T, BD))
+            self.wire_dev = torch.zeros(lay[9], dtype=torch.uint8, device=dev)
+
+            def dv(off, n, dt):
+                return self.wire_dev[off: off + n * dt.itemsize].view(dt)
+            self.objs, self.angles, self.attrs = dv(lay[4], O, torch.int64), dv(lay[5], O, torch.int64), dv(lay[6], O, torch.int64)
+            self.triples = dv(lay[7], 3 * T, torch.int64).view(T, 3)
+            self.boxes = dv(lay[8], O * BD, torch.float32).view(O, BD)
+            self.obj_to_img = torch.zeros(O, **i64); self.triple_to_img = torch.zeros(T, **i64)
         self.mu = torch.zeros(O, E, **f32); self.logvar = torch.zeros(O, E, **f32); self.epsn = torch.zeros(O, E, **f32)
         self.z = torch.zeros(O, E, **f32); self.boxes_pred = torch.zeros(O, BD, **f32); self.angles_pred = torch.zeros(O, NA, **f32)
         self.d_boxes = torch.zeros(O, BD, **f32); self.d_logits = torch.zeros(O, NA, **f32)
@@ -332,4 +348,16 @@ class VAETrainStep(object):
 
     def step(self, batch):
         self.load_batch(batch)
+        return self.run()
+
+    def step_wire(self, pinned_wire):
+        """One train step from a host batch in wire layout (data.collate.packed_batch): one async H2D copy, the device half of the
+        batch assembly (global triple ids, obj_to_img / triple_to_img), then the step."""
+        if self.wire_meta is None:
+            raise RuntimeError("VAETrainStep.step_wire needs wire_meta= at construction")
+        B, O, T, bd, lay = self.wire_meta
+        self.wire_dev.copy_(pinned_wire[:lay[9]], non_blocking=True)
+        _lib.check(self.lib.sln_collate_finish(self.wire_dev.data_ptr(), self.wire_dev.numel(), B, O, T, bd, self.triples.data_ptr(),
+                                               self.obj_to_img.data_ptr(), self.triple_to_img.data_ptr(), None, _lib.cur_stream(self.dev)),
+                   "collate_finish")
         return self.run()

@@ -257,9 +257,12 @@ def run_vae(args):
                   gconv_num_layers=5, mlp_normalization='batch', vec_noise_dim=0, layout_noise_dim=32, use_AE=False).float().to(dev).train()
     _, objs, boxes, triples, angles, attrs, _, _ = syn.synthetic_batch(SCENES_PER_GPU, NODES_PER_SCENE, seed=42 + rank)
     host = [t.pin_memory() for t in (objs, triples, boxes, angles, attrs)]
-    h2d = sum(t.numel() * t.element_size() for t in host)
     O, T = objs.size(0), triples.size(0)
-    step = sutils.VAETrainStep(model, O, T, lr=1e-4, kl_weight=0.1, use_graph=True, process_group=pg, world_size=world)
+    # e2e input: the same scenes as un-collated samples, packed into one pinned wire buffer (what a DataLoader worker hands over)
+    collate = importlib.import_module("3d_sln_b200.data.collate")
+    wire, wire_meta = collate.packed_batch(syn.synthetic_samples(SCENES_PER_GPU, NODES_PER_SCENE, seed=42 + rank), lib)
+    h2d = int(wire_meta[4][9])
+    step = sutils.VAETrainStep(model, O, T, lr=1e-4, kl_weight=0.1, use_graph=True, process_group=pg, world_size=world, wire_meta=wire_meta)
     step.load_batch(host)
     n0 = lib.sln_launch_count()
     step._fwd_bwd(); step._allreduce(); step._opt()
@@ -288,11 +291,11 @@ def run_vae(args):
         b.record()
     barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    # ---- e2e: public API with pinned-host inputs: H2D of the batch, the step, D2H of the losses, every step
+    # ---- e2e: public API with pinned-host inputs: H2D of the (wire-packed) batch, device batch assembly, the step, D2H of the losses, every step
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = step.step(host)
+        out = step.step_wire(wire)     # one H2D copy of the packed batch + device-side batch assembly + the step
         losses_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
     barrier()

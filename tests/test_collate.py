@@ -90,3 +90,24 @@ def test_prefetcher_yields_every_batch_in_order():
     assert len(got) == 5
     for g, b in zip(got, batches):
         _same(g, col.suncg_collate_fn(b))
+
+
+@pytest.mark.gpu
+def test_train_step_from_wire_buffer_equals_step_from_collated_tensors():
+    """VAETrainStep.step_wire (one H2D copy of the packed batch + sln_collate_finish + the step) == VAETrainStep.step on the tensors
+    the reference collate produces, bit for bit."""
+    from helpers import our_model
+    sutils = importlib.import_module("3d_sln_b200.utils")
+    samples = syn.synthetic_samples(8, 12, seed=21, ragged=True)
+    ids, objs, boxes, triples, angles, attrs, o2i, t2i = col.suncg_collate_fn(samples)
+    wire, meta = col.packed_batch(samples)
+    losses = []
+    for use_wire in (False, True):
+        m = our_model(E=16, layers=2, norm="batch", seed=5).to("cuda:0").train()
+        st = sutils.VAETrainStep(m, objs.size(0), triples.size(0), use_graph=False, sample_eps=False, wire_meta=meta if use_wire else None)
+        st.epsn.copy_(torch.randn(st.epsn.shape, generator=torch.Generator().manual_seed(9)).to("cuda:0"))
+        out = st.step_wire(wire) if use_wire else st.step((objs, triples, boxes, angles, attrs))
+        losses.append(out.clone().cpu())
+        if use_wire:
+            assert torch.equal(st.triples.cpu(), triples) and torch.equal(st.obj_to_img.cpu(), o2i) and torch.equal(st.triple_to_img.cpu(), t2i)
+    assert torch.isfinite(losses[0]).all() and torch.equal(losses[0], losses[1])
