@@ -86,7 +86,9 @@ def packed_batch(batch, lib=None):
     if not kept:
         raise ValueError("packed_batch: every scene of the batch is empty")
     meta = wire_layout(lib, kept)
-    pin = torch.empty(meta[4][9], dtype=torch.uint8).pin_memory()
+    pin = torch.empty(meta[4][9], dtype=torch.uint8)
+    if torch.cuda.is_available():          # host-side packing also runs in loader workers / CPU tests, where there is nothing to pin for
+        pin = pin.pin_memory()
     pack_wire(kept, meta[4], pin)
     return pin, meta
 

@@ -111,3 +111,29 @@ def test_train_step_from_wire_buffer_equals_step_from_collated_tensors():
         if use_wire:
             assert torch.equal(st.triples.cpu(), triples) and torch.equal(st.obj_to_img.cpu(), o2i) and torch.equal(st.triple_to_img.cpu(), t2i)
     assert torch.isfinite(losses[0]).all() and torch.equal(losses[0], losses[1])
+
+
+def test_host_wire_packing_holds_the_collated_tensors():
+    """pack_wire (the host half of the batch assembly, CPU only): every section of the wire buffer equals what the reference collate
+    produces, except that triples still carry scene-local ids (the device kernel adds the object offsets)."""
+    samples = syn.synthetic_samples(9, 7, seed=4, ragged=True, empty_every=4)
+    ids, objs, boxes, triples, angles, attrs, o2i, t2i = col.suncg_collate_fn(samples)
+    wire, (B, O, T, bd, lay) = col.packed_batch(samples)
+    assert wire.is_pinned() or not torch.cuda.is_available()
+    assert (B, O, T, bd) == (ids.numel(), objs.numel(), triples.size(0), 6) and wire.numel() == lay[9]
+
+    def sec(k, n, dt):
+        return wire[lay[k]: lay[k] + n * dt.itemsize].view(dt)
+    i64 = torch.int64
+    kept = [i for i, s in enumerate(samples) if s[1].dim() > 0]
+    assert sec(0, B, i64).tolist() == kept                                     # positions in the DataLoader batch
+    obj_off, tri_off = sec(1, B + 1, i64), sec(2, B + 1, i64)
+    assert obj_off[0] == 0 and obj_off[-1] == O and tri_off[-1] == T
+    assert torch.equal(sec(3, B, i64), ids) and torch.equal(sec(4, O, i64), objs)
+    assert torch.equal(sec(5, O, i64), angles) and torch.equal(sec(6, O, i64), attrs)
+    assert torch.equal(sec(8, O * bd, torch.float32).view(O, bd), boxes)
+    local = sec(7, 3 * T, i64).view(T, 3).clone()
+    shift = torch.repeat_interleave(obj_off[:-1], tri_off[1:] - tri_off[:-1])
+    local[:, 0] += shift; local[:, 2] += shift
+    assert torch.equal(local, triples)
+    assert torch.equal(torch.repeat_interleave(sec(0, B, i64), obj_off[1:] - obj_off[:-1]), o2i)
