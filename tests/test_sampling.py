@@ -65,3 +65,26 @@ def test_device_mvn_draws_feed_the_decoder():
     m.train()
     with pytest.raises(RuntimeError):
         samp.decode_samples(m, objs, triples, attrs, 2)
+
+
+def test_decode_samples_chunking_with_a_stub_decoder_cpu():
+    """Host logic only (no CUDA): the chunked replica batches cover every draw exactly once, in order, whatever the chunk size."""
+    class Stub(object):
+        training, embedding_dim, box_dim, Nangle = False, 4, 6, 24
+        calls = []
+
+        def decoder(self, z, objs, triples, attributes):
+            self.calls.append((z.size(0), triples.size(0)))
+            assert int(triples[:, [0, 2]].max()) < objs.numel()                 # replica offsets stay inside the replicated graph
+            return z[:, :1].expand(-1, 6) + objs[:, None].float(), z[:, 1:2].expand(-1, 24)
+    objs, triples, _, _, attrs = syn.fixture_graph()
+    O = objs.numel()
+    z = torch.arange(11 * O * 4, dtype=torch.float32).view(11, O, 4)
+    for chunk in (1, 4, 11, 64):
+        m = Stub(); m.calls = []
+        boxes, angles = samp.decode_samples(m, objs, triples, attrs, 11, z=z, chunk=chunk)
+        assert boxes.shape == (11, O, 6) and angles.shape == (11, O, 24)
+        assert torch.equal(boxes[..., 0], z[..., 0] + objs[None].float()) and torch.equal(angles[..., 0], z[..., 1])
+        assert sum(c[0] for c in m.calls) == 11 * O and len(m.calls) == -(-11 // chunk)
+    with pytest.raises(ValueError):
+        samp.decode_samples(Stub(), objs, triples, attrs, 3, z=z)              # z has 11 draws, 3 requested
