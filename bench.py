@@ -104,8 +104,8 @@ def cpu_vae_steps(n_scenes, steps, warmup, budget_s):
     """The reference train-step body (train.py:70-84) restated in oracle/vae_oracle.py, fp32, all host threads.
     Returns (scene-graphs/s, seconds per step, scenes per step actually used, threads)."""
     from oracle import vae_oracle as vo
-    syn = importlib.import_module("3d_sln_b200.data.synthetic")
-    Model = importlib.import_module("3d_sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
+    syn = importlib.import_module("sln_b200.data.synthetic")
+    Model = importlib.import_module("sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     torch.manual_seed(42)
@@ -144,8 +144,8 @@ def eager_gpu_vae_steps(dev, n_scenes, steps=10, warmup=3):
     """Baseline only: the oracle's plain-torch restatement of the reference train step (train.py:70-84) run EAGERLY ON THE SAME GPU —
     the launch-per-aten-op execution the reference itself has after model.cuda() (the reference cannot travel to the GPU box)."""
     from oracle import vae_oracle as vo
-    syn = importlib.import_module("3d_sln_b200.data.synthetic")
-    Model = importlib.import_module("3d_sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
+    syn = importlib.import_module("sln_b200.data.synthetic")
+    Model = importlib.import_module("sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
     torch.manual_seed(42)
     m = Model(syn.default_vocab(), embedding_dim=64, batch_size=128, train_3d=True, decoder_cat=True, gconv_mode='feedforward',
               gconv_num_layers=5, mlp_normalization='batch', vec_noise_dim=0, layout_noise_dim=32, use_AE=False)
@@ -246,11 +246,11 @@ def run_vae(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
-    _lib = importlib.import_module("3d_sln_b200._lib")
+    _lib = importlib.import_module("sln_b200._lib")
     lib = _lib.load()
-    syn = importlib.import_module("3d_sln_b200.data.synthetic")
-    Model = importlib.import_module("3d_sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
-    sutils = importlib.import_module("3d_sln_b200.utils")
+    syn = importlib.import_module("sln_b200.data.synthetic")
+    Model = importlib.import_module("sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
+    sutils = importlib.import_module("sln_b200.utils")
 
     torch.manual_seed(42)   # reference options/options.py:59 — identical initial weights on every rank
     model = Model(syn.default_vocab(), embedding_dim=64, batch_size=128, train_3d=True, decoder_cat=True, gconv_mode='feedforward',
@@ -259,7 +259,7 @@ def run_vae(args):
     host = [t.pin_memory() for t in (objs, triples, boxes, angles, attrs)]
     O, T = objs.size(0), triples.size(0)
     # e2e input: the same scenes as un-collated samples, packed into one pinned wire buffer (what a DataLoader worker hands over)
-    collate = importlib.import_module("3d_sln_b200.data.collate")
+    collate = importlib.import_module("sln_b200.data.collate")
     wire, wire_meta = collate.packed_batch(syn.synthetic_samples(SCENES_PER_GPU, NODES_PER_SCENE, seed=42 + rank), lib)
     h2d = int(wire_meta[4][9])
     step = sutils.VAETrainStep(model, O, T, lr=1e-4, kl_weight=0.1, use_graph=True, process_group=pg, world_size=world, wire_meta=wire_meta)

@@ -24,7 +24,7 @@ def _config(n):
 
 
 def _scene(dev, seed=13):
-    meshes = importlib.import_module("3d_sln_b200.data.synthetic_meshes")
+    meshes = importlib.import_module("sln_b200.data.synthetic_meshes")
     boxes, angles, objs = meshes.synthetic_layout(10, seed=seed)
     g = torch.Generator().manual_seed(seed)
     start = boxes.clone()
@@ -43,10 +43,10 @@ def run(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    _lib = importlib.import_module("3d_sln_b200._lib")
+    _lib = importlib.import_module("sln_b200._lib")
     lib = _lib.load()
-    refine = importlib.import_module("3d_sln_b200.models.refine")
-    dr = importlib.import_module("3d_sln_b200.models.diff_render")
+    refine = importlib.import_module("sln_b200.models.refine")
+    dr = importlib.import_module("sln_b200.models.diff_render")
     boxes, angles, objs, start, a0 = _scene(dev, seed=13 + rank)
     objs_l = objs.tolist()
     step = refine.RefineStep(start, a0, objs, boxes, angles, lr=2e-4, use_graph=not args.no_graph)
@@ -158,8 +158,8 @@ def cpu_render_baseline(budget_s=25.0):
     pass and as many class passes as fit the budget are timed and the iteration is extrapolated to 1 + 32 passes."""
     import numpy as np
     from oracle import raster_oracle as ro
-    dr = importlib.import_module("3d_sln_b200.models.diff_render")
-    meshes = importlib.import_module("3d_sln_b200.data.synthetic_meshes")
+    dr = importlib.import_module("sln_b200.models.diff_render")
+    meshes = importlib.import_module("sln_b200.data.synthetic_meshes")
     boxes, angles, objs = meshes.synthetic_layout(10, seed=13)
     lib = meshes.MeshLibrary()
     v, fb, cls, kept, _ = dr.assemble_scene([boxes[i] for i in range(11)], [angles[i] for i in range(11)], objs.tolist(), lib)

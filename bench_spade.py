@@ -25,7 +25,7 @@ def _config(n):
 
 
 def _model(dev=None, ngf=64, crop=256):
-    spade = importlib.import_module("3d_sln_b200.models.SPADE_related")
+    spade = importlib.import_module("sln_b200.models.SPADE_related")
     torch.manual_seed(0)
     m = spade.SPADEGenerator4(semantic_nc=41, target_nc=3, nz=256, ngf=ngf, norm='spectralspadelayer3x3', crop_size=crop, n_up='normal').eval()
     return m.to(dev) if dev is not None else m
@@ -41,7 +41,7 @@ def run(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    _lib = importlib.import_module("3d_sln_b200._lib")
+    _lib = importlib.import_module("sln_b200._lib")
     lib = _lib.load()
     m = _model(dev)
     seg_h = so.synthetic_input(BATCH, S=256, seed=100 + rank).pin_memory()

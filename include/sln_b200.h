@@ -2,7 +2,7 @@
  * sln_b200.h — C ABI of the B200-native 3D_SLN hot path (libsln_b200.so).
  *
  * The reference (aluo-x/3D_SLN) has no FFI/plugin layer: its hot path is reached through Python nn.Module calls.
- * The drop-in boundary is therefore the Python class surface (3d_sln_b200/models/*.py mirrors the reference's
+ * The drop-in boundary is therefore the Python class surface (sln_b200/models/*.py mirrors the reference's
  * models/graph.py, models/Sg2ScVAE_model.py, ...) and THIS header is what those Python classes bind with ctypes.
  * Each entry point cites the reference code it replaces.
  *

@@ -20,7 +20,7 @@ import importlib  # noqa: E402
 
 from oracle import ref_shim  # noqa: E402
 
-syn = importlib.import_module("3d_sln_b200.data.synthetic")
+syn = importlib.import_module("sln_b200.data.synthetic")
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 

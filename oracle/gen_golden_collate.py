@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import ref_shim  # noqa: E402
 
-syn = importlib.import_module("3d_sln_b200.data.synthetic")
+syn = importlib.import_module("sln_b200.data.synthetic")
 NAMES = ("ids", "objs", "boxes", "triples", "angles", "attributes", "obj_to_img", "triple_to_img")
 
 

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY — CPU restatement (oracle) of the reference's SPADEGenerator4 forward.
 
-Nothing under ``3d_sln_b200/`` imports this file.  Functional form over a ``state_dict`` (keys as in the reference:
+Nothing under ``sln_b200/`` imports this file.  Functional form over a ``state_dict`` (keys as in the reference:
 ``head_0.conv_0.1.weight_orig`` ...), plain torch CPU ops, any dtype (fp64 = truth, fp32 = the reference's noise floor).
 Follows models/SPADE_related.py: LayerNorm2D :139-149, SEBlock2 :81-85, SPADE4 :1438-1454, SPADEResnetBlock4 :1487-1505,
 SPADEGenerator4.forward :1563-1605 (eval mode: spectral norm = W / (u^T W v), no power iteration).

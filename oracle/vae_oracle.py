@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE ONLY — CPU restatement (oracle) of the reference's VAE-graph hot path.
 
-Nothing under ``3d_sln_b200/`` imports this file.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+Nothing under ``sln_b200/`` imports this file.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs may use it, and only as the checker / CPU baseline — never as the product.
 
 It restates, as plain functional torch code over a ``state_dict``-style mapping (reference key names), what these

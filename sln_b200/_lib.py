@@ -1,7 +1,7 @@
 """ctypes binding of libsln_b200.so (C ABI declared in include/sln_b200.h).
 
 There is no CPU fallback: if the shared library cannot be loaded (and cannot be built with nvcc), every hot-path
-call raises.  The library is built in-tree (``3d_sln_b200/libsln_b200.so``) so that it travels with the repo snapshot.
+call raises.  The library is built in-tree (``sln_b200/libsln_b200.so``) so that it travels with the repo snapshot.
 """
 import ctypes
 import os
@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
-        raise RuntimeError("3d_sln_b200: nvcc not found and %s is missing/stale; cannot build the CUDA library" % LIB_PATH)
+        raise RuntimeError("sln_b200: nvcc not found and %s is missing/stale; cannot build the CUDA library" % LIB_PATH)
     objdir = os.path.join(_PKG_DIR, "build")
     os.makedirs(objdir, exist_ok=True)
     cflags = [f for f in NVCC_FLAGS if f != "-shared"]
@@ -69,13 +69,13 @@ def build(force=False, verbose=False):
         elif verbose:
             print(err)
     if errs:
-        raise RuntimeError("3d_sln_b200: nvcc failed\n" + "\n".join(errs))
+        raise RuntimeError("sln_b200: nvcc failed\n" + "\n".join(errs))
     objs = [os.path.join(objdir, os.path.basename(s)[:-3] + ".o") for s in _sources()]
     tmp = LIB_PATH + ".tmp.%d" % os.getpid()
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("3d_sln_b200: link failed\n%s\n%s" % (" ".join(cmd), res.stderr[-8000:]))
+        raise RuntimeError("sln_b200: link failed\n%s\n%s" % (" ".join(cmd), res.stderr[-8000:]))
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
@@ -180,7 +180,7 @@ def load():
         try:
             lib = ctypes.CDLL(LIB_PATH)
         except OSError as e:
-            raise RuntimeError("3d_sln_b200: cannot load %s (%s); the hot path has no CPU/PyTorch fallback" % (LIB_PATH, e))
+            raise RuntimeError("sln_b200: cannot load %s (%s); the hot path has no CPU/PyTorch fallback" % (LIB_PATH, e))
         for name, (res, args) in SIGNATURES.items():
             if not hasattr(lib, name):
                 continue  # optional components (raster/spade) may be absent in a partial build; checked by tests
@@ -188,7 +188,7 @@ def load():
             fn.restype = res
             fn.argtypes = args
         if lib.sln_version() != 2:
-            raise RuntimeError("3d_sln_b200: ABI version mismatch (library %d, binding 2)" % lib.sln_version())
+            raise RuntimeError("sln_b200: ABI version mismatch (library %d, binding 2)" % lib.sln_version())
         eng = os.environ.get("SLN_ENGINE")
         if eng in ("0", "1"):      # 0 = FP32 SIMT tiles, 1 = tcgen05 3xTF32 tiles (default) for the MLP contractions
             lib.sln_set_engine(int(eng))
@@ -199,7 +199,7 @@ def load():
 def check(rc, what=""):
     if rc != 0:
         msg = load().sln_last_error()
-        raise RuntimeError("3d_sln_b200 %s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+        raise RuntimeError("sln_b200 %s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
 
 
 def ptr(t):

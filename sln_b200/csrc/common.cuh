@@ -6,7 +6,7 @@
 #include <string.h>
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
-#error "3d_sln_b200 kernels are written for sm_100a only"
+#error "sln_b200 kernels are written for sm_100a only"
 #endif
 
 namespace sln {

@@ -4,6 +4,7 @@ pywavefront in models/misc.py:66-121).  SURVEY.md 8(d) config 3: 10 objects, eac
 """
 import math
 
+import numpy as np
 import torch
 
 from .synthetic import OBJECT_NAMES
@@ -45,12 +46,19 @@ class MeshLibrary(object):
         self.nu, self.nv = nu, nv
         g = torch.Generator().manual_seed(1234)
         self.models = {}
+        self.meta = {}
         for name in OBJECT_NAMES[1:]:
             size = (0.5 + torch.rand(3, generator=g)).tolist()      # canonical model extents 0.5 .. 1.5 m
             center = ((torch.rand(3, generator=g) - 0.5) * 0.2).tolist()
             v, f = box_mesh(nu, nv, size, center)
-            self.models[name] = dict(vertices=v.to(device), faces=f.to(device), size=torch.tensor(size, device=device),
-                                     center=torch.tensor(center, device=device))
+            # the metadata the reference reads from suncg_data_many.json ("bbox_min"/"bbox_max", models/diff_render.py:100-105);
+            # size / center are derived from it exactly as the reference does (float32 numpy arithmetic)
+            bbox_min = [c - s / 2 for c, s in zip(center, size)]
+            bbox_max = [c + s / 2 for c, s in zip(center, size)]
+            mn, mx = np.array(bbox_min, dtype=np.float32), np.array(bbox_max, dtype=np.float32)
+            self.models[name] = dict(vertices=v.to(device), faces=f.to(device), size=torch.from_numpy((mx - mn).astype("float32")).to(device),
+                                     center=torch.from_numpy(((mn + mx) / 2.0).astype("float32")).to(device))
+            self.meta[name] = dict(id=name, bbox_min=bbox_min, bbox_max=bbox_max)
 
     def to(self, device):
         for m in self.models.values():

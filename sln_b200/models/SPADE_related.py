@@ -47,7 +47,7 @@ class SPADE4(nn.Module):
         if not config_text.startswith('spade') or parsed is None:
             raise ValueError("not a SPADE norm specification: %r" % (config_text,))
         if str(parsed.group(1)) != 'layer' or int(parsed.group(2)) != 3:
-            raise NotImplementedError("3d_sln_b200 implements the configuration the reference runs: 'spadelayer3x3' (got %r)" % (config_text,))
+            raise NotImplementedError("sln_b200 implements the configuration the reference runs: 'spadelayer3x3' (got %r)" % (config_text,))
         self.param_free_norm = LayerNorm2D(norm_nc, affine=False)
         self.norm_nc = norm_nc
         self.mlp_preshared_depth = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(1, NHIDDEN // 8, kernel_size=3, padding=0), nn.LeakyReLU(inplace=True))
@@ -68,7 +68,7 @@ class SPADEResnetBlock4(nn.Module):
         if self.learned_shortcut:
             self.conv_s = nn.Conv2d(fin, fout, kernel_size=1, bias=False)
         if 'spectral' not in norm:
-            raise NotImplementedError("3d_sln_b200 implements the reference's 'spectralspadelayer3x3' blocks only")
+            raise NotImplementedError("sln_b200 implements the reference's 'spectralspadelayer3x3' blocks only")
         self.conv_0 = nn.Sequential(nn.ReflectionPad2d(1), spectral_norm(self.conv_0))
         self.conv_1 = nn.Sequential(nn.ReflectionPad2d(1), spectral_norm(self.conv_1))
         if self.learned_shortcut:
@@ -234,7 +234,7 @@ class SPADEGenerator4(nn.Module):
 
     def forward(self, input, z=None):
         if not input.is_cuda:
-            raise RuntimeError("3d_sln_b200 SPADEGenerator4 runs on CUDA (sm_100a) only; no CPU fallback")
+            raise RuntimeError("sln_b200 SPADEGenerator4 runs on CUDA (sm_100a) only; no CPU fallback")
         if self.training:
             raise NotImplementedError("SPADEGenerator4 is inference-only in the reference pipeline (test_SPADE_shade.py:12 .eval()); call .eval()")
         lib = _lib.load()

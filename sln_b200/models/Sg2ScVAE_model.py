@@ -224,7 +224,7 @@ class Sg2ScVAEModel(nn.Module):
     # ------------------------------------------------------------------ binding to the C ABI
     def _supported(self):
         if not (self.use_attr and self.decoder_cat and self.gconv_num_layers > 0):
-            raise NotImplementedError("3d_sln_b200 implements the released configuration only: use_attr=True, "
+            raise NotImplementedError("sln_b200 implements the released configuration only: use_attr=True, "
                                       "decoder_cat=True, gconv_num_layers>0")
         if self.mlp_normalization not in _NORMS:
             raise NotImplementedError("mlp_normalization=%r" % (self.mlp_normalization,))
@@ -261,9 +261,9 @@ class Sg2ScVAEModel(nn.Module):
         require_cuda(*ps)
         for t in ps + bufs:
             if not t.is_contiguous():
-                raise RuntimeError("3d_sln_b200 needs contiguous parameters")
+                raise RuntimeError("sln_b200 needs contiguous parameters")
         if any(p.dtype != torch.float32 for p in ps):
-            raise RuntimeError("3d_sln_b200 computes in fp32; call model.float()")
+            raise RuntimeError("sln_b200 computes in fp32; call model.float()")
         desc = self._desc()
         lib = _lib.load()
         assert lib.sln_vae_num_params(desc) == len(ps), (lib.sln_vae_num_params(desc), len(ps))

@@ -193,7 +193,7 @@ class _CompositeFn(torch.autograd.Function):
 def composite_fused(depth_data, images, static):
     """composite() as one library call each way (csrc/scene.cu); `static` carries the class -> channel tables of the scene."""
     if depth_data.device.type != "cuda":
-        raise RuntimeError("3d_sln_b200 compositing runs on CUDA only (composite() is the torch restatement)")
+        raise RuntimeError("sln_b200 compositing runs on CUDA only (composite() is the torch restatement)")
     return _CompositeFn.apply(depth_data, images, static)
 
 
@@ -201,7 +201,7 @@ def mesh_render_func(boxes, angles, objs, model_ids_old=None, obj_size_target=No
     """Same contract as the reference: -> (final [1,70,256,256], model_ids_return, obj_size_return, size_loss)."""
     dev = boxes[-1].device
     if dev.type != "cuda":
-        raise RuntimeError("3d_sln_b200 mesh_render_func runs on CUDA only (no CPU fallback)")
+        raise RuntimeError("sln_b200 mesh_render_func runs on CUDA only (no CPU fallback)")
     boxes = list(boxes)
     model_ids_return, obj_size_return = {}, []
     size_loss = 0.0
@@ -334,7 +334,7 @@ class _AssembleFn(torch.autograd.Function):
         ctx.hooks = refine_hooks
         b, a = boxes.contiguous().float(), angles.contiguous().float()
         if b.device.type != "cuda":
-            raise RuntimeError("3d_sln_b200 scene assembly runs on CUDA only (no CPU fallback)")
+            raise RuntimeError("sln_b200 scene assembly runs on CUDA only (no CPU fallback)")
         n_rows, n_obj, n_shell, F = b.size(0), st.mv.size(0), st.shell_v.size(0), st.faces.size(1)
         verts = torch.empty(1, n_obj + n_shell, 3, device=dev, dtype=torch.float32)
         size = torch.empty(st.n_kept, 3, device=dev, dtype=torch.float32)

@@ -57,7 +57,7 @@ def mlp_blocks(seq):
         elif isinstance(m, nn.Dropout) and m.p == 0:
             pass
         else:
-            raise NotImplementedError("3d_sln_b200: unsupported MLP stage %r (only Linear/BatchNorm1d/ReLU are fused)" % (m,))
+            raise NotImplementedError("sln_b200: unsupported MLP stage %r (only Linear/BatchNorm1d/ReLU are fused)" % (m,))
     if cur is not None:
         blocks.append(tuple(cur))
     return blocks
@@ -77,7 +77,7 @@ def block_params(blocks, want_bn):
 def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
-            raise RuntimeError("3d_sln_b200 runs on CUDA (sm_100a) only; got a %s tensor. There is no CPU fallback." % t.device)
+            raise RuntimeError("sln_b200 runs on CUDA (sm_100a) only; got a %s tensor. There is no CPU fallback." % t.device)
 
 
 class GradSink:
@@ -200,7 +200,7 @@ class GraphTripleConv(nn.Module):
         if self.mlp_normalization not in _NORMS:
             raise NotImplementedError("mlp_normalization=%r" % (self.mlp_normalization,))
         if self.input_dim != self.output_dim:
-            raise NotImplementedError("3d_sln_b200 GraphTripleConv kernels require output_dim == input_dim")
+            raise NotImplementedError("sln_b200 GraphTripleConv kernels require output_dim == input_dim")
         bn = [b for _, b, _ in self._blocks() if b is not None]
         return _lib.VaeDesc(embedding_dim=4, n_layers=1, recurrent=0, norm=_NORMS[self.mlp_normalization],
                             training=int(self.training), box_dim=6, n_angle=24, num_objs=1, num_preds=1, num_attrs=1,

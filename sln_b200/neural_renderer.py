@@ -24,7 +24,7 @@ RASTERIZER_EPS = 1e-3
 def _req_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
-            raise RuntimeError("3d_sln_b200.neural_renderer runs on CUDA (sm_100a) only; got a %s tensor. No CPU fallback." % t.device)
+            raise RuntimeError("sln_b200.neural_renderer runs on CUDA (sm_100a) only; got a %s tensor. No CPU fallback." % t.device)
 
 
 class _Raster(object):
@@ -92,7 +92,7 @@ class _Raster(object):
 def _prep(vertices, faces, K, R, t):
     _req_cuda(vertices, faces, K, R, t)
     if vertices.dim() != 3 or vertices.size(0) != 1 or faces.dim() != 3 or faces.size(0) != 1:
-        raise NotImplementedError("3d_sln_b200.neural_renderer renders one mesh per call (batch size 1), as the reference does")
+        raise NotImplementedError("sln_b200.neural_renderer renders one mesh per call (batch size 1), as the reference does")
     v = vertices[0].contiguous().float()
     f = faces[0].contiguous().to(torch.int32)
     return v, f, K.reshape(-1).contiguous().float(), R.reshape(-1).contiguous().float(), t.reshape(-1).contiguous().float()

@@ -82,7 +82,7 @@ class _FusedLossFn(torch.autograd.Function):
 def calculate_model_losses(args, model, bbox, bbox_pred, angles, angles_pred, mu=None, logvar=None, KL_weight=None):
     """Same contract as the reference: returns (total_loss tensor, {'bbox_pred','angle_pred','KLD_Gauss'} floats)."""
     if not bbox_pred.is_cuda:
-        raise RuntimeError("3d_sln_b200.calculate_model_losses runs on CUDA only (no CPU fallback)")
+        raise RuntimeError("sln_b200.calculate_model_losses runs on CUDA only (no CPU fallback)")
     use_kl = not args.use_AE
     holder = []
     total = _FusedLossFn.apply(bbox_pred, bbox, angles_pred, angles, mu if use_kl else None, logvar if use_kl else None,

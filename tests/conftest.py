@@ -25,4 +25,4 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def sln():
-    return importlib.import_module("3d_sln_b200")
+    return importlib.import_module("sln_b200")

@@ -9,7 +9,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
-syn = importlib.import_module("3d_sln_b200.data.synthetic")
+syn = importlib.import_module("sln_b200.data.synthetic")
 
 
 def load_golden(name):
@@ -23,7 +23,7 @@ def load_golden(name):
 
 
 def our_model(E=64, layers=5, norm="batch", mode="feedforward", use_AE=False, seed=42, device=None):
-    Model = importlib.import_module("3d_sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
+    Model = importlib.import_module("sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
     torch.manual_seed(seed)
     m = Model(syn.default_vocab(), embedding_dim=E, batch_size=128, train_3d=True, decoder_cat=True, gconv_mode=mode,
               gconv_num_layers=layers, mlp_normalization=norm, vec_noise_dim=0, layout_noise_dim=32, use_AE=use_AE)

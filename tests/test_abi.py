@@ -7,7 +7,7 @@ import torch
 
 
 def test_library_builds_and_exports_every_declared_symbol():
-    _lib = importlib.import_module("3d_sln_b200._lib")
+    _lib = importlib.import_module("sln_b200._lib")
     path = _lib.build()
     lib = ctypes.CDLL(path)
     declared = _lib.declared_symbols()
@@ -19,7 +19,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 
 def test_version_and_error_string():
-    _lib = importlib.import_module("3d_sln_b200._lib")
+    _lib = importlib.import_module("sln_b200._lib")
     lib = _lib.load()
     assert lib.sln_version() == 2
     # argument validation happens on the host before any launch: no GPU needed
@@ -31,7 +31,7 @@ def test_version_and_error_string():
 
 def test_parameter_table_matches_module_tree():
     from helpers import our_model
-    _lib = importlib.import_module("3d_sln_b200._lib")
+    _lib = importlib.import_module("sln_b200._lib")
     lib = _lib.load()
     for norm, mode, layers in (("batch", "feedforward", 5), ("none", "feedforward", 5), ("batch", "recurrent", 3)):
         m = our_model(E=64, layers=layers, norm=norm, mode=mode)
@@ -49,7 +49,7 @@ def test_cpu_tensors_fail_loudly():
     objs, triples, boxes, angles, attrs = syn.fixture_graph()
     with pytest.raises(RuntimeError, match="CUDA"):
         m(objs, triples, boxes, angles, attrs, None)
-    graph = importlib.import_module("3d_sln_b200.models.graph")
+    graph = importlib.import_module("sln_b200.models.graph")
     g = graph.GraphTripleConv(16, hidden_dim=32)
     with pytest.raises(RuntimeError, match="CUDA"):
         g(torch.zeros(4, 16), torch.zeros(3, 16), torch.zeros(3, 2, dtype=torch.long))
@@ -74,7 +74,7 @@ def test_state_dict_keys_and_init_match_reference_when_available():
 def test_host_side_argument_checks_of_collate_refine_scene_entry_points():
     """Argument validation happens on the host before any launch, so the error convention (negative code + message, no exception
     across the ABI) can be checked without a GPU: collate wire layout, refinement-loss pyramid limits, scene assembly / compositing."""
-    lib = importlib.import_module("3d_sln_b200._lib").load()
+    lib = importlib.import_module("sln_b200._lib").load()
     off = (ctypes.c_int64 * 10)()
     assert lib.sln_collate_layout(3, 50, 75, 6, off) == 0
     o = list(off)

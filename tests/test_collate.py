@@ -7,8 +7,8 @@ import numpy as np
 import pytest
 import torch
 
-syn = importlib.import_module("3d_sln_b200.data.synthetic")
-col = importlib.import_module("3d_sln_b200.data.collate")
+syn = importlib.import_module("sln_b200.data.synthetic")
+col = importlib.import_module("sln_b200.data.collate")
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "collate.npz")
 NAMES = ("ids", "objs", "boxes", "triples", "angles", "attributes", "obj_to_img", "triple_to_img")
 
@@ -97,7 +97,7 @@ def test_train_step_from_wire_buffer_equals_step_from_collated_tensors():
     """VAETrainStep.step_wire (one H2D copy of the packed batch + sln_collate_finish + the step) == VAETrainStep.step on the tensors
     the reference collate produces, bit for bit."""
     from helpers import our_model
-    sutils = importlib.import_module("3d_sln_b200.utils")
+    sutils = importlib.import_module("sln_b200.utils")
     samples = syn.synthetic_samples(8, 12, seed=21, ragged=True)
     ids, objs, boxes, triples, angles, attrs, o2i, t2i = col.suncg_collate_fn(samples)
     wire, meta = col.packed_batch(samples)

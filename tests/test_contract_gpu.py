@@ -6,7 +6,7 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-_lib = importlib.import_module("3d_sln_b200._lib")
+_lib = importlib.import_module("sln_b200._lib")
 DEV = "cuda:0"
 
 

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from oracle import vae_oracle as vo
 
-syn = importlib.import_module("3d_sln_b200.data.synthetic")
+syn = importlib.import_module("sln_b200.data.synthetic")
 
 
 def _free_port():
@@ -46,7 +46,7 @@ def _worker(rank, world, port, sd0, ret):
 
 
 def test_two_rank_gradient_average_matches_single_process():
-    Model = importlib.import_module("3d_sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
+    Model = importlib.import_module("sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
     torch.manual_seed(42)
     m = Model(syn.default_vocab(), embedding_dim=8, batch_size=128, train_3d=True, decoder_cat=True, gconv_mode='feedforward',
               gconv_num_layers=2, mlp_normalization='none', vec_noise_dim=0, layout_noise_dim=32, use_AE=False)

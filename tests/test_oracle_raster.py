@@ -9,7 +9,7 @@ import torch
 
 from oracle import raster_oracle as ro
 
-meshes = importlib.import_module("3d_sln_b200.data.synthetic_meshes")
+meshes = importlib.import_module("sln_b200.data.synthetic_meshes")
 
 
 def scene(n_objects=4, seed=3, nu=2, nv=3):

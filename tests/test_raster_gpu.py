@@ -11,9 +11,9 @@ from oracle import raster_oracle as ro
 from test_oracle_raster import scene
 
 pytestmark = pytest.mark.gpu
-nr = importlib.import_module("3d_sln_b200.neural_renderer")
-dr = importlib.import_module("3d_sln_b200.models.diff_render")
-meshes = importlib.import_module("3d_sln_b200.data.synthetic_meshes")
+nr = importlib.import_module("sln_b200.neural_renderer")
+dr = importlib.import_module("sln_b200.models.diff_render")
+meshes = importlib.import_module("sln_b200.data.synthetic_meshes")
 DEV = "cuda:0"
 
 
@@ -63,7 +63,7 @@ def test_texture_sampling_matches_oracle():
         want = ro.texture_sampling(fv_o, tex2, maps, ts)
         rgb = torch.empty(n, n, 3, device=DEV)
         lib = r.lib
-        L = importlib.import_module("3d_sln_b200._lib")
+        L = importlib.import_module("sln_b200._lib")
         td = torch.from_numpy(tex).to(DEV)
         L.check(lib.sln_raster_texture_sample(r.ws.data_ptr(), r.V, r.F, 1, n, td.data_ptr(), ts, 1e-3, fi.data_ptr(), w.data_ptr(),
                                               d.data_ptr(), rgb.data_ptr(), L.cur_stream(torch.device(DEV))), "tex")
@@ -190,7 +190,7 @@ def test_mesh_render_func_contract_and_gradients():
 def test_static_scene_fast_path_equals_mesh_render_func_and_graph_replays():
     """SceneStatic/render_static (no per-object Python loop, no host sync, fixed shapes) == mesh_render_func, and RefineStep's CUDA
     graph replays the same iteration as the eager path (identical losses over several Adam steps)."""
-    refine = importlib.import_module("3d_sln_b200.models.refine")
+    refine = importlib.import_module("sln_b200.models.refine")
     boxes, angles, objs = meshes.synthetic_layout(10, seed=13)
     boxes, angles = boxes.to(DEV), angles.to(DEV)
     final, ids, sizes, _ = dr.mesh_render_func([boxes[i] for i in range(11)], [angles[i] for i in range(11)], objs.tolist())

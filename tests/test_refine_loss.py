@@ -12,7 +12,7 @@ import torch
 
 from helpers import synthetic_render
 
-refine = importlib.import_module("3d_sln_b200.models.refine")
+refine = importlib.import_module("sln_b200.models.refine")
 Z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refine_loss.npz"))
 STRIDE = int(Z["grad_stride"])
 TOL = 1e-4
@@ -104,7 +104,7 @@ def test_fused_loss_matches_torch_restatement_everywhere_and_is_deterministic():
 
 @pytest.mark.gpu
 def test_refine_step_with_fused_loss_tracks_the_torch_loss():
-    syn_m = importlib.import_module("3d_sln_b200.data.synthetic_meshes")
+    syn_m = importlib.import_module("sln_b200.data.synthetic_meshes")
     dev = torch.device("cuda:0")
     boxes, angles, objs = [t.to(dev) for t in syn_m.synthetic_layout(6, seed=13)]
     start = boxes.clone(); start[:-1, [0, 3]] += 0.03

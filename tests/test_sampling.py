@@ -8,7 +8,7 @@ import torch
 
 from helpers import our_model, syn
 
-samp = importlib.import_module("3d_sln_b200.models.sampling")
+samp = importlib.import_module("sln_b200.models.sampling")
 DEV = "cuda:0"
 
 

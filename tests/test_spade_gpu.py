@@ -12,8 +12,8 @@ import torch
 from oracle import spade_oracle as so
 
 pytestmark = pytest.mark.gpu
-spade = importlib.import_module("3d_sln_b200.models.SPADE_related")
-_lib = importlib.import_module("3d_sln_b200._lib")
+spade = importlib.import_module("sln_b200.models.SPADE_related")
+_lib = importlib.import_module("sln_b200._lib")
 DEV = "cuda:0"
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spade_small.npz")
 NAMES = so.BLOCKS + ("pre_tanh",)

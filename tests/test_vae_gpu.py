@@ -17,9 +17,9 @@ from oracle import vae_oracle as vo
 
 pytestmark = pytest.mark.gpu
 
-_lib = importlib.import_module("3d_sln_b200._lib")
-graph = importlib.import_module("3d_sln_b200.models.graph")
-sutils = importlib.import_module("3d_sln_b200.utils")
+_lib = importlib.import_module("sln_b200._lib")
+graph = importlib.import_module("sln_b200.models.graph")
+sutils = importlib.import_module("sln_b200.utils")
 
 DEV = "cuda:0"
 

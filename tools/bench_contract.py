@@ -4,7 +4,7 @@ import importlib, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-_lib = importlib.import_module("3d_sln_b200._lib")
+_lib = importlib.import_module("sln_b200._lib")
 lib = _lib.load()
 eng = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 dev = torch.device("cuda:0")

@@ -10,8 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-_lib = importlib.import_module("3d_sln_b200._lib")
-syn = importlib.import_module("3d_sln_b200.data.synthetic")
+_lib = importlib.import_module("sln_b200._lib")
+syn = importlib.import_module("sln_b200.data.synthetic")
 lib = _lib.load()
 dev = torch.device("cuda:0")
 st = _lib.cur_stream(dev)

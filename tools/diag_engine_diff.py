@@ -4,8 +4,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import our_model, syn, with_eps
-_lib = importlib.import_module("3d_sln_b200._lib")
-sutils = importlib.import_module("3d_sln_b200.utils")
+_lib = importlib.import_module("sln_b200._lib")
+sutils = importlib.import_module("sln_b200.utils")
 lib = _lib.load()
 norm = sys.argv[1] if len(sys.argv) > 1 else "none"
 _, objs, boxes, triples, angles, attrs, _, _ = syn.synthetic_batch(64, 32, seed=42)

@@ -9,9 +9,9 @@ import torch  # noqa: E402
 
 n_steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 scenes = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-syn = importlib.import_module("3d_sln_b200.data.synthetic")
-Model = importlib.import_module("3d_sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
-sutils = importlib.import_module("3d_sln_b200.utils")
+syn = importlib.import_module("sln_b200.data.synthetic")
+Model = importlib.import_module("sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
+sutils = importlib.import_module("sln_b200.utils")
 dev = torch.device("cuda:0")
 torch.manual_seed(42)
 model = Model(syn.default_vocab(), embedding_dim=64, batch_size=128, train_3d=True, decoder_cat=True, gconv_mode='feedforward',
