@@ -75,8 +75,9 @@ def get_cam_mat(boxes):
     return int_mat.to(dev), R.reshape(1, 3, 3).to(dev), t.reshape(1, 1, 3).to(dev)
 
 
-def assemble_scene(boxes, angles, objs, library):
-    """Per-object similarity transforms (reference :76-159) for all objects at once.
+def assemble_scene(boxes, angles, objs, library, model_ids=None):
+    """Per-object similarity transforms (reference :76-159) for all objects at once.  model_ids: optional mesh id per object row
+    (the cached retrieval of an earlier iteration, reference :80-82); default = the class's canonical mesh.
 
     boxes: sequence of [6] tensors (objects normalised to the room; last row = room), angles: sequence of scalars (0..24),
     objs: class ids.  Returns vertices [1,V,3] (differentiable w.r.t. boxes and angles), faces [1,F,3] int32, face_cls [F]
@@ -96,7 +97,7 @@ def assemble_scene(boxes, angles, objs, library):
         A = torch.stack([torch.as_tensor(angles[i], device=dev, dtype=torch.float32).reshape(()) for i in kept])
         bmin, bmax = B[:, :3] * room, B[:, 3:] * room
         center, size = (bmax + bmin) / 2, bmax - bmin
-        models = [library.get(object_idx_to_name[int(objs[i])]) for i in kept]
+        models = [library.get(object_idx_to_name[int(objs[i])] if model_ids is None else model_ids[i]) for i in kept]
         msize = torch.stack([m["size"] for m in models])
         mcent = torch.stack([m["center"] for m in models])
         scale = (size / msize).min(dim=1).values                          # :106
@@ -197,24 +198,40 @@ def composite_fused(depth_data, images, static):
     return _CompositeFn.apply(depth_data, images, static)
 
 
+def room_metadata(room):
+    """The wall / floor record of the room shell in the reference's wall_data_wfc.json format (what `wall_retrieve` /
+    `floor_retrieve` return and `model_ids_return["wall"/"floor"]` cache, reference :171-175,243-247)."""
+    X, Y, Z = [float(v) for v in room]
+    return dict(house_id="synthetic", model_id="room", wall_bbox_min=[0.0, 0.0, 0.0], wall_bbox_max=[X, Y, Z],
+                floor_bbox_min=[0.0, 0.0, 0.0], floor_bbox_max=[X, 0.0, Z])
+
+
 def mesh_render_func(boxes, angles, objs, model_ids_old=None, obj_size_target=None):
-    """Same contract as the reference: -> (final [1,70,256,256], model_ids_return, obj_size_return, size_loss)."""
+    """Same contract as the reference: -> (final [1,70,256,256], model_ids_return, obj_size_return, size_loss).
+
+    Like the reference (:56-57) a later iteration (`model_ids_old` given) overwrites the caller's ``boxes[-1]`` IN PLACE with the
+    cached room box; `model_ids_return` holds `box_info`, one id per object row (recorded before the skip test, :84-89) and the
+    `wall` / `floor` records (first iteration only); `model_ids_old[idx]` selects the mesh on later iterations."""
     dev = boxes[-1].device
     if dev.type != "cuda":
         raise RuntimeError("sln_b200 mesh_render_func runs on CUDA only (no CPU fallback)")
-    boxes = list(boxes)
     model_ids_return, obj_size_return = {}, []
     size_loss = 0.0
     old_wall = boxes[-1].clone()
     if model_ids_old is not None:
-        boxes[-1] = torch.from_numpy(model_ids_old["box_info"]).float().to(dev)     # :56-57
+        boxes[-1] = torch.from_numpy(model_ids_old["box_info"]).float().to(dev)     # :56-57 (in place, as the reference)
     else:
         model_ids_return["box_info"] = boxes[-1].detach().cpu().numpy()            # :60
     lib = mesh_library(dev)
-    vertices, face_buf, face_cls, kept, sizes = assemble_scene(boxes, angles, objs, lib)
+    n_obj = len(boxes) - 1
+    if model_ids_old is None:
+        for i in range(n_obj):
+            model_ids_return[i] = object_idx_to_name[int(objs[i])]                  # :84-89 (one canonical mesh per class)
+        ids = None
+    else:
+        ids = [model_ids_old[i] for i in range(n_obj)]
+    vertices, face_buf, face_cls, kept, sizes = assemble_scene(boxes, angles, objs, lib, ids)
     for j, i in enumerate(kept):
-        if model_ids_old is None:
-            model_ids_return[i] = object_idx_to_name[int(objs[i])]
         if obj_size_target is not None:
             size_loss = size_loss + nn.functional.mse_loss(sizes[j], torch.from_numpy(obj_size_target[j]).float().to(dev))   # :98
         else:
@@ -223,6 +240,9 @@ def mesh_render_func(boxes, angles, objs, model_ids_old=None, obj_size_target=No
         size_loss = size_loss + nn.functional.mse_loss(old_wall, torch.from_numpy(obj_size_target[-1]).float().to(dev))      # :164
     else:
         obj_size_return.append(boxes[-1].detach().cpu().numpy())
+    if model_ids_old is None:
+        model_ids_return["wall"] = room_metadata(boxes[-1][3:].detach().cpu())      # :171-175
+        model_ids_return["floor"] = dict(model_ids_return["wall"])                  # :243-247
     K, R, t = get_cam_mat(boxes)
     face_buf, face_cls = cull_faces(vertices, face_buf, face_cls, R, t)
     names = desired_classes()
