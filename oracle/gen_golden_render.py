@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import raster_oracle as ro  # noqa: E402
 from sln_b200.data.synthetic import OBJECT_NAMES  # noqa: E402
-from sln_b200.data.synthetic_meshes import MeshLibrary, room_shell, synthetic_layout  # noqa: E402
+from sln_b200.data.synthetic_meshes import MeshLibrary, room_shell, room_walls, synthetic_layout  # noqa: E402
 
 REF_RENDER = "/root/reference/models/diff_render.py"
 REF_MISC = "/root/reference/models/misc.py"
@@ -116,7 +116,7 @@ def reference_namespace(library, rec, image_size):
           "suncg_data": {name: [dict(library.meta[name])] for name in library.meta},
           "load_suncg_obj": lambda mid: (library.get(mid)["vertices"].clone(), library.get(mid)["faces"].to(torch.int32)),
           "wall_data_json": [],
-          "load_wall_obj_new": lambda d: ([w[0].clone() for w in shell_for(d)["walls"]], [w[1].to(torch.int32) for w in shell_for(d)["walls"]]),
+          "load_wall_obj_new": lambda d: ([w[0].clone() for w in room_walls(d["wall_bbox_max"])], [w[1].to(torch.int32) for w in room_walls(d["wall_bbox_max"])]),
           "load_floor_obj": lambda d: (shell_for(d)["floor"][0].clone(), shell_for(d)["floor"][1].to(torch.int32)),
           "load_ceil_obj": lambda d: (shell_for(d)["ceiling"][0].clone(), shell_for(d)["ceiling"][1].to(torch.int32)),
           "print": lambda *a, **k: (sys.stderr.write("[ref] " + " ".join(str(x) for x in a) + "\n") if os.environ.get("REF_PRINT") else None)}

@@ -81,8 +81,15 @@ def room_shell(room, n=4):
     walls = [grid_quad(o, ex, ey, n, n), grid_quad(o, ey, ez, n, n), grid_quad(o + ex, ez, ey, n, n)]
     wv = torch.cat([w[0] for w in walls])
     wf = torch.cat([w[1] + i * walls[0][0].size(0) for i, w in enumerate(walls)])
-    # "walls": the three wall meshes separately, as the reference's load_wall_obj_new returns them (models/misc.py:157-165)
-    return {"floor": floor, "ceiling": ceiling, "wall": (wv, wf), "walls": walls}
+    return {"floor": floor, "ceiling": ceiling, "wall": (wv, wf)}
+
+
+def room_walls(room, n=4):
+    """The three wall meshes of room_shell separately, as the reference's load_wall_obj_new returns them (models/misc.py:157-165)."""
+    X, Y, Z = [float(v) for v in room]
+    o = torch.zeros(3)
+    ex, ey, ez = torch.tensor([X, 0, 0.]), torch.tensor([0, Y, 0.]), torch.tensor([0, 0, Z])
+    return [grid_quad(o, ex, ey, n, n), grid_quad(o, ey, ez, n, n), grid_quad(o + ex, ez, ey, n, n)]
 
 
 FURNITURE = ["bed", "chair", "sofa", "table", "desk", "cabinet", "dresser", "night_stand", "bookshelf", "television"]
