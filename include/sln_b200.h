@@ -85,6 +85,19 @@ int sln_vae_num_bn(const sln_vae_desc* d);      /* BatchNorm count; bn_bufs has 
  * 2 = one standalone GraphTripleConv layer. */
 size_t sln_vae_workspace_bytes(const sln_vae_desc* d, int64_t O, int64_t T, int which);
 
+/* Index validation.  The reference raises IndexError for an id outside its embedding table / node range (nn.Embedding,
+ * Sg2ScVAE_model.py:121-129; obj_vecs[s_idx], graph.py:78-79).  The kernels never read or write out of bounds: a bad id is
+ * remapped to row 0 and one of the bits below is OR-ed into an int32 flag that lives in the call's workspace at byte offset
+ * sln_vae_index_flag_offset(d, O, T, which) (which: 0 encoder, 1 decoder, 2 standalone layer; -1 on bad arguments).  The flag is
+ * rewritten by every *_fwd call; the CALLER reads it back (one 4-byte D2H copy) and raises — sln_b200's Python wrappers do so on
+ * the first call of every (O, T) shape and on every call when `check_indices=True`, VAETrainStep.check_indices() on demand. */
+#define SLN_IDX_OBJS 1      /* objs[i]       outside [0, num_objs)  */
+#define SLN_IDX_ATTRS 2     /* attributes[i] outside [0, num_attrs) */
+#define SLN_IDX_ANGLES 4    /* angles[i]     outside [0, n_angle)   */
+#define SLN_IDX_NODES 8     /* triples[t,0|2] / edges outside [0, O) */
+#define SLN_IDX_PREDS 16    /* triples[t,1]  outside [0, num_preds) */
+int64_t sln_vae_index_flag_offset(const sln_vae_desc* d, int64_t O, int64_t T, int which);
+
 /* Sg2ScVAEModel.encoder (reference Sg2ScVAE_model.py:115-143): objs[O] triples[T,3] boxes[O,box_dim] angles[O]
  * attributes[O] -> mu[O,E], logvar[O,E].  Saves what encoder_bwd needs in `ws`. */
 int sln_vae_encoder_fwd(const sln_vae_desc* d, const void* const* params, void* const* bn_bufs,
@@ -216,12 +229,25 @@ int sln_vae_loss(const float* boxes_pred, const float* boxes_gt, int32_t box_dim
                  float kl_weight, int64_t O, float* losses, float* d_boxes, float* d_angles, int32_t angles_grad_is_logits,
                  float* d_mu, float* d_logvar, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Same, with the KL weight read from device memory at launch time: a captured CUDA graph follows the reference's KL_linear_decay
+ * schedule (train.py:73-74) without re-capture. */
+int sln_vae_loss_dyn(const float* boxes_pred, const float* boxes_gt, int32_t box_dim, const float* angles_pred,
+                     const int64_t* angles_gt, int32_t n_angle, const float* mu, const float* logvar, int32_t Z,
+                     const float* kl_weight_dev, int64_t O, float* losses, float* d_boxes, float* d_angles,
+                     int32_t angles_grad_is_logits, float* d_mu, float* d_logvar, void* scratch, size_t scratch_bytes, void* stream);
+
 /* torch.optim.Adam step (reference train.py:15,82-84) over one flat fp32 arena.  *step is a device int64; when
  * advance_step != 0 it is incremented first, so the launch is identical every iteration (graph-safe); pass 0 for the
  * 2nd..nth arena of the same optimizer step.  grad_scale multiplies g (1/world_size for gradient averaging). */
 int sln_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, float grad_scale, int64_t* step, int32_t advance_step,
                   void* stream);
+/* Same, graph-friendly: the learning rate is read from device memory (*lr_dev) at launch time, and when guard_loss != NULL the
+ * whole update (moments, parameters, step counter) is skipped if *guard_loss is not finite — the reference's "not backpropping"
+ * guard of train.py:78-80 without a host round trip. */
+int sln_adam_step_dyn(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr_dev,
+                      float beta1, float beta2, float eps, float weight_decay, float grad_scale, int64_t* step,
+                      int32_t advance_step, const float* guard_loss, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ mesh rasterizer
  * Replaces what the reference reaches through the un-vendored `neural_renderer` package: nr.Renderer(camera_mode=

@@ -111,6 +111,7 @@ SIGNATURES = {
     "sln_vae_packed_bytes": (_SZ, [_DESC]),
     "sln_vae_pack_weights": (ctypes.c_int, [_DESC, _P, _P, _SZ, _P]),
     "sln_vae_workspace_bytes": (_SZ, [_DESC, _I64, _I64, ctypes.c_int]),
+    "sln_vae_index_flag_offset": (_I64, [_DESC, _I64, _I64, ctypes.c_int]),
     "sln_vae_encoder_fwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "sln_vae_encoder_bwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _I64, _I64, _P, _SZ, _P]),
     "sln_vae_decoder_fwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),
@@ -148,6 +149,8 @@ SIGNATURES = {
     "sln_reparam_bwd": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P, _P]),
     "sln_vae_loss": (ctypes.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P, _I32, _F, _I64, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P]),
     "sln_adam_step": (ctypes.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _P, _I32, _P]),
+    "sln_vae_loss_dyn": (ctypes.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P, _I32, _P, _I64, _P, _P, _P, _I32, _P, _P, _P, _SZ, _P]),
+    "sln_adam_step_dyn": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _F, _F, _F, _F, _F, _P, _I32, _P, _P]),
     "sln_packed_weights_bytes": (_SZ, [_I64, _I64]),
     "sln_pack_weights": (ctypes.c_int, [_P, _I64, _I64, _P, _P]),
     "sln_spade_conv": (ctypes.c_int, [_P, _I64, _I64, _I64, _I64, _I32, _I32, _P, _P, _P, _I64, _P, _P]),

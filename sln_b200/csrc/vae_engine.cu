@@ -58,7 +58,7 @@ struct BlkState {  // per-instance saved tensors (workspace)
 
 struct Dims {
   int E, D, H, Z, L, Lw, obj_w, attr_w, box_w, ang_w, box_dim, n_angle;
-  int norm, training;
+  int norm, training, num_preds;
   float eps, momentum;
 };
 
@@ -165,7 +165,7 @@ int make_dims(const sln_vae_desc* d, Dims* o) {
   o->L = d->n_layers; o->Lw = d->recurrent ? 1 : d->n_layers;
   o->obj_w = o->E * 3 / 4; o->attr_w = o->E / 4; o->box_w = o->E * 3 / 4; o->ang_w = o->E / 4;
   o->box_dim = d->box_dim; o->n_angle = d->n_angle;
-  o->norm = d->norm; o->training = d->training;
+  o->norm = d->norm; o->training = d->training; o->num_preds = d->num_preds;
   o->eps = d->bn_eps; o->momentum = d->bn_momentum;
   return SLN_OK;
 }
@@ -496,7 +496,7 @@ int graph_prep(const Ctx& c, NetPlan& p, const int64_t* triples_or_edges, int st
   SLN_CUDA_TRY(cudaMemsetAsync(p.err, 0, sizeof(int), c.st));
   (void)stride3;
   if (g.T > 0) {
-    k_split_triples<<<ceil_div(g.T, 256), 256, 0, c.st>>>((const long long*)triples_or_edges, g.T, g.O, g.s_idx, g.p_idx, g.o_idx, p.deg, p.err);
+    k_split_triples<<<ceil_div(g.T, 256), 256, 0, c.st>>>((const long long*)triples_or_edges, g.T, g.O, c.dm.num_preds, g.s_idx, g.p_idx, g.o_idx, p.deg, p.err);
     SLN_TRY(check_launch("split_triples"));
   }
   k_scan_deg<<<1, 1024, 0, c.st>>>(p.deg, g.O, g.row_ptr, g.cnt);
@@ -515,7 +515,7 @@ __global__ void k_split_edges(const long long* __restrict__ edges, int T, int O,
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   long long s = edges[(size_t)t * 2 + 0], o = edges[(size_t)t * 2 + 1];
-  if (s < 0 || s >= O || o < 0 || o >= O) { atomicExch(err, 1); s = 0; o = 0; }
+  if (s < 0 || s >= O || o < 0 || o >= O) { atomicOr(err, 8); s = 0; o = 0; }
   s_idx[t] = (int)s; o_idx[t] = (int)o;
   atomicAdd(deg + s, 1);
   atomicAdd(deg + o, 1);
@@ -653,9 +653,9 @@ int check_ws(const NetPlan& p, const void* ws, size_t ws_bytes) {
   if (ws_bytes < p.bytes) { set_error("workspace too small: %zu < %zu bytes", ws_bytes, p.bytes); return SLN_EWORKSPACE; }
   return SLN_OK;
 }
-int to_i32(const Ctx& c, const int64_t* src, int n, int* dst, int limit, int* err) {
+int to_i32(const Ctx& c, const int64_t* src, int n, int* dst, int limit, int* err, int bit) {
   if (n <= 0) return SLN_OK;
-  k_i64_to_i32<<<ceil_div(n, 256), 256, 0, c.st>>>((const long long*)src, n, dst, limit, err);
+  k_i64_to_i32<<<ceil_div(n, 256), 256, 0, c.st>>>((const long long*)src, n, dst, limit, err, bit);
   return check_launch("i64_to_i32");
 }
 int check_dims(int64_t O, int64_t T) {
@@ -719,6 +719,14 @@ size_t sln_vae_workspace_bytes(const sln_vae_desc* d, int64_t O, int64_t T, int 
   return p.bytes;
 }
 
+int64_t sln_vae_index_flag_offset(const sln_vae_desc* d, int64_t O, int64_t T, int which) {
+  Dims dm;
+  if (make_dims(d, &dm) || check_dims(O, T)) return -1;
+  static thread_local NetPlan p;
+  make_plan(dm, (int)O, (int)T, which, nullptr, &p);
+  return (int64_t)((char*)p.err - (char*)nullptr);
+}
+
 int sln_vae_encoder_fwd(const sln_vae_desc* d, const void* const* params, void* const* bn_bufs, const int64_t* objs,
                         const int64_t* triples, const float* boxes, const int64_t* angles, const int64_t* attributes, int64_t O64,
                         int64_t T64, float* mu, float* logvar, void* ws, size_t ws_bytes, void* stream) {
@@ -732,9 +740,9 @@ int sln_vae_encoder_fwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_TRY(check_ws(p, ws, ws_bytes));
   SLN_CUDA_TRY(cudaMemsetAsync(p.cp.base, 0, sizeof(unsigned) * kCounterCap, c.st));
   SLN_TRY(graph_prep(c, p, triples, 1));
-  SLN_TRY(to_i32(c, objs, O, p.objs32, d->num_objs, p.err));
-  SLN_TRY(to_i32(c, attributes, O, p.attrs32, d->num_attrs, p.err));
-  SLN_TRY(to_i32(c, angles, O, p.angles32, d->n_angle, p.err));
+  SLN_TRY(to_i32(c, objs, O, p.objs32, d->num_objs, p.err, SLN_IDX_OBJS));
+  SLN_TRY(to_i32(c, attributes, O, p.attrs32, d->num_attrs, p.err, SLN_IDX_ATTRS));
+  SLN_TRY(to_i32(c, angles, O, p.angles32, d->n_angle, p.err, SLN_IDX_ANGLES));
   // obj_vecs = [obj_emb | attr_emb | box_linear | angle_emb]   (Sg2ScVAE_model.py:121-129)
   SLN_TRY(gather_rows(c, m.emb[0], dm.obj_w, p.objs32, O, dm.obj_w, p.obj0, dm.D, 0));
   SLN_TRY(gather_rows(c, m.emb[1], dm.attr_w, p.attrs32, O, dm.attr_w, p.obj0, dm.D, dm.obj_w));
@@ -833,8 +841,8 @@ int sln_vae_decoder_fwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_TRY(check_ws(p, ws, ws_bytes));
   SLN_CUDA_TRY(cudaMemsetAsync(p.cp.base, 0, sizeof(unsigned) * kCounterCap, c.st));
   SLN_TRY(graph_prep(c, p, triples, 1));
-  SLN_TRY(to_i32(c, objs, O, p.objs32, d->num_objs, p.err));
-  SLN_TRY(to_i32(c, attributes, O, p.attrs32, d->num_attrs, p.err));
+  SLN_TRY(to_i32(c, objs, O, p.objs32, d->num_objs, p.err, SLN_IDX_OBJS));
+  SLN_TRY(to_i32(c, attributes, O, p.attrs32, d->num_attrs, p.err, SLN_IDX_ATTRS));
   // obj_vecs = [obj_emb_dc | attr_emb_dc | z]   (Sg2ScVAE_model.py:150-159, decoder_cat)
   SLN_TRY(gather_rows(c, m.emb[4], dm.obj_w, p.objs32, O, dm.obj_w, p.obj0, dm.D, 0));
   SLN_TRY(gather_rows(c, m.emb[5], dm.attr_w, p.attrs32, O, dm.attr_w, p.obj0, dm.D, dm.obj_w));
@@ -1054,8 +1062,8 @@ int sln_reparam_bwd(const float* d_z, const float* logvar, const float* eps, int
   return check_launch("reparam_bwd");
 }
 
-int sln_vae_loss(const float* boxes_pred, const float* boxes_gt, int32_t box_dim, const float* angles_pred, const int64_t* angles_gt,
-                 int32_t n_angle, const float* mu, const float* logvar, int32_t Z, float kl_weight, int64_t O, float* losses, float* d_boxes,
+static int vae_loss_impl(const float* boxes_pred, const float* boxes_gt, int32_t box_dim, const float* angles_pred, const int64_t* angles_gt,
+                 int32_t n_angle, const float* mu, const float* logvar, int32_t Z, float kl_weight, const float* kl_weight_dev, int64_t O, float* losses, float* d_boxes,
                  float* d_angles, int32_t angles_grad_is_logits, float* d_mu, float* d_logvar, void* scratch, size_t scratch_bytes, void* stream) {
   SLN_CHECK_ARG(boxes_pred && boxes_gt && angles_pred && angles_gt && losses && scratch, "null pointer");
   SLN_CHECK_ARG(O >= 1, "O must be >= 1");
@@ -1064,7 +1072,7 @@ int sln_vae_loss(const float* boxes_pred, const float* boxes_gt, int32_t box_dim
   SLN_CHECK_ARG(scratch_bytes >= 16 + (size_t)12 * blocks, "loss scratch too small");
   LossArgs a;
   a.boxes_pred = boxes_pred; a.boxes_gt = boxes_gt; a.BD = box_dim; a.logp = angles_pred; a.angles_gt = (const long long*)angles_gt;
-  a.NA = n_angle; a.mu = mu; a.logvar = logvar; a.Z = Z; a.kl_weight = kl_weight; a.O = (int)O;
+  a.NA = n_angle; a.mu = mu; a.logvar = logvar; a.Z = Z; a.kl_weight = kl_weight; a.kl_weight_dev = kl_weight_dev; a.O = (int)O;
   a.logits_grad = angles_grad_is_logits;
   a.d_boxes = d_boxes; a.d_logits = d_angles; a.d_mu = d_mu; a.d_logvar = d_logvar;
   a.counter = (unsigned*)scratch; a.partial = (float*)((char*)scratch + 16); a.losses = losses;
@@ -1072,20 +1080,46 @@ int sln_vae_loss(const float* boxes_pred, const float* boxes_gt, int32_t box_dim
   return check_launch("vae_loss");
 }
 
-int sln_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, float grad_scale, int64_t* step, int32_t advance_step, void* stream) {
+int sln_vae_loss(const float* boxes_pred, const float* boxes_gt, int32_t box_dim, const float* angles_pred, const int64_t* angles_gt,
+                 int32_t n_angle, const float* mu, const float* logvar, int32_t Z, float kl_weight, int64_t O, float* losses, float* d_boxes,
+                 float* d_angles, int32_t angles_grad_is_logits, float* d_mu, float* d_logvar, void* scratch, size_t scratch_bytes, void* stream) {
+  return vae_loss_impl(boxes_pred, boxes_gt, box_dim, angles_pred, angles_gt, n_angle, mu, logvar, Z, kl_weight, nullptr, O, losses, d_boxes,
+                       d_angles, angles_grad_is_logits, d_mu, d_logvar, scratch, scratch_bytes, stream);
+}
+int sln_vae_loss_dyn(const float* boxes_pred, const float* boxes_gt, int32_t box_dim, const float* angles_pred, const int64_t* angles_gt,
+                     int32_t n_angle, const float* mu, const float* logvar, int32_t Z, const float* kl_weight_dev, int64_t O, float* losses,
+                     float* d_boxes, float* d_angles, int32_t angles_grad_is_logits, float* d_mu, float* d_logvar, void* scratch,
+                     size_t scratch_bytes, void* stream) {
+  SLN_CHECK_ARG(kl_weight_dev != nullptr, "null kl_weight_dev");
+  return vae_loss_impl(boxes_pred, boxes_gt, box_dim, angles_pred, angles_gt, n_angle, mu, logvar, Z, 0.f, kl_weight_dev, O, losses, d_boxes,
+                       d_angles, angles_grad_is_logits, d_mu, d_logvar, scratch, scratch_bytes, stream);
+}
+
+static int adam_impl(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, const float* lr_dev, float beta1,
+                     float beta2, float eps, float weight_decay, float grad_scale, int64_t* step, int32_t advance_step, const float* guard,
+                     void* stream) {
   SLN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && step && n >= 0, "bad argument");
   SLN_CHECK_ARG(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0, "arenas must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (advance_step) {
-    k_inc_step<<<1, 1, 0, st>>>((long long*)step);
+    k_inc_step<<<1, 1, 0, st>>>((long long*)step, guard);
     SLN_TRY(check_launch("adam_inc_step"));
   }
   if (n == 0) return SLN_OK;
   long long threads = ceil_div64(n, 4);
   k_adam<<<(int)ceil_div64(threads, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, (long long)n, lr, beta1, beta2, eps, weight_decay,
-                                                       grad_scale, (const long long*)step);
+                                                       grad_scale, (const long long*)step, lr_dev, guard);
   return check_launch("adam");
+}
+int sln_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float grad_scale, int64_t* step, int32_t advance_step, void* stream) {
+  return adam_impl(params, grads, exp_avg, exp_avg_sq, n, lr, nullptr, beta1, beta2, eps, weight_decay, grad_scale, step, advance_step, nullptr, stream);
+}
+int sln_adam_step_dyn(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const float* lr_dev, float beta1,
+                      float beta2, float eps, float weight_decay, float grad_scale, int64_t* step, int32_t advance_step, const float* guard_loss,
+                      void* stream) {
+  SLN_CHECK_ARG(lr_dev != nullptr, "null lr_dev");
+  return adam_impl(params, grads, exp_avg, exp_avg_sq, n, 0.f, lr_dev, beta1, beta2, eps, weight_decay, grad_scale, step, advance_step, guard_loss, stream);
 }
 
 }  // extern "C"

@@ -19,12 +19,15 @@ struct Graph {
   int* cursor;     // [O]  scratch
 };
 
-__global__ void k_split_triples(const long long* __restrict__ triples, int T, int O, int* s_idx, int* p_idx, int* o_idx,
+// Index validation: out-of-range ids are remapped to row 0 (so no kernel ever reads or writes out of bounds) and recorded as a bit
+// in the workspace's index flag (include/sln_b200.h SLN_IDX_*), which the caller reads back — the reference raises IndexError.
+__global__ void k_split_triples(const long long* __restrict__ triples, int T, int O, int num_preds, int* s_idx, int* p_idx, int* o_idx,
                                 int* deg, int* err) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   long long s = triples[(size_t)t * 3 + 0], p = triples[(size_t)t * 3 + 1], o = triples[(size_t)t * 3 + 2];
-  if (s < 0 || s >= O || o < 0 || o >= O) { atomicExch(err, 1); s = 0; o = 0; }
+  if (s < 0 || s >= O || o < 0 || o >= O) { atomicOr(err, 8); s = 0; o = 0; }
+  if (p < 0 || p >= num_preds) { atomicOr(err, 16); p = 0; }
   s_idx[t] = (int)s; p_idx[t] = (int)p; o_idx[t] = (int)o;
   atomicAdd(deg + s, 1);
   atomicAdd(deg + o, 1);
@@ -85,11 +88,11 @@ __global__ void k_sort_rows(const int* __restrict__ row_ptr, int O, int* ent) {
   }
 }
 
-__global__ void k_i64_to_i32(const long long* __restrict__ src, int n, int* dst, int limit, int* err) {
+__global__ void k_i64_to_i32(const long long* __restrict__ src, int n, int* dst, int limit, int* err, int bit) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   long long v = src[i];
-  if (v < 0 || v >= limit) { atomicExch(err, 1); v = 0; }
+  if (v < 0 || v >= limit) { atomicOr(err, bit); v = 0; }
   dst[i] = (int)v;
 }
 
@@ -662,6 +665,7 @@ struct LossArgs {
   const float* logp; const long long* angles_gt; int NA;
   const float* mu; const float* logvar; int Z;  // mu == null -> AE mode, no KL
   float kl_weight;
+  const float* kl_weight_dev;  // non-null: read the KL weight from device memory (schedules change it without re-capturing a CUDA graph)
   int O;
   int logits_grad;  // 1: d_logits = d total / d logits (log-softmax backward fused); 0: gradient w.r.t. the log-probs
   float* d_boxes; float* d_logits; float* d_mu; float* d_logvar;  // gradient outputs (may be null: loss only)
@@ -673,6 +677,7 @@ __global__ void __launch_bounds__(256) k_vae_loss(const LossArgs a) {
   const int rows_per = 64;
   int r0 = blockIdx.x * rows_per, r1 = min(a.O, r0 + rows_per);
   float l1 = 0.f, nll = 0.f, kl = 0.f;
+  const float klw = a.kl_weight_dev ? __ldg(a.kl_weight_dev) : a.kl_weight;
   const float inv_bb = 1.f / ((float)a.O * (float)a.BD), inv_o = 1.f / (float)a.O;
   for (int e = threadIdx.x; e < (r1 - r0) * a.BD; e += blockDim.x) {
     size_t k = (size_t)r0 * a.BD + e;
@@ -692,7 +697,7 @@ __global__ void __launch_bounds__(256) k_vae_loss(const LossArgs a) {
       size_t k = (size_t)r0 * a.Z + e;
       float m = a.mu[k], lv = a.logvar[k], ex = expf(lv);
       kl += 1.f + lv - m * m - ex;
-      if (a.d_mu) { a.d_mu[k] = a.kl_weight * m * inv_o; a.d_logvar[k] = a.kl_weight * 0.5f * (ex - 1.f) * inv_o; }
+      if (a.d_mu) { a.d_mu[k] = klw * m * inv_o; a.d_logvar[k] = klw * 0.5f * (ex - 1.f) * inv_o; }
     }
   }
   __shared__ float red[3][8];
@@ -718,7 +723,7 @@ __global__ void __launch_bounds__(256) k_vae_loss(const LossArgs a) {
     }
     float bbox = (float)(t0 / ((double)a.O * a.BD));
     float ang = (float)(t1 / (double)a.O);
-    float kld = a.mu ? a.kl_weight * (float)(-0.5 * t2 / (double)a.O) : 0.f;
+    float kld = a.mu ? klw * (float)(-0.5 * t2 / (double)a.O) : 0.f;
     a.losses[0] = bbox; a.losses[1] = ang; a.losses[2] = kld; a.losses[3] = bbox + ang + kld;
     *a.counter = 0u;
   }
@@ -728,7 +733,12 @@ __global__ void __launch_bounds__(256) k_vae_loss(const LossArgs a) {
 // torch.optim.Adam semantics (train.py:15,82-84): m = b1*m+(1-b1)g ; v = b2*v+(1-b2)g^2 ;
 // p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps), bc_i = 1 - b_i^step.  `step` lives on the device so the launch is graph-safe.
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
-                       float lr, float b1, float b2, float eps, float weight_decay, float grad_scale, const long long* step_ptr) {
+                       float lr, float b1, float b2, float eps, float weight_decay, float grad_scale, const long long* step_ptr,
+                       const float* lr_dev, const float* guard) {
+  // guard: the reference skips backward + step when the loss is not finite (train.py:78-80 "not backpropping"); here the whole
+  // update (and k_inc_step) is predicated on the device-side loss so that one NaN step cannot poison parameters or moments
+  if (guard != nullptr && !isfinite(__ldg(guard))) return;
+  if (lr_dev != nullptr) lr = __ldg(lr_dev);
   long long step = *step_ptr;
   float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
   float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
@@ -754,6 +764,9 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
     }
   }
 }
-__global__ void k_inc_step(long long* step_ptr) { *step_ptr += 1; }
+__global__ void k_inc_step(long long* step_ptr, const float* guard) {
+  if (guard != nullptr && !isfinite(*guard)) return;
+  *step_ptr += 1;
+}
 
 }  // namespace sln

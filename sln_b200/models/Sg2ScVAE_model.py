@@ -12,6 +12,31 @@ from .. import _lib
 from .graph import make_mlp, GraphTripleConvNet, _init_weights, mlp_blocks, block_params, require_cuda, _NORMS
 
 
+_IDX_BITS = ((1, "objs"), (2, "attributes"), (4, "angles"), (8, "triples subject/object"), (16, "triples predicate"))
+
+
+def _check_index_flag(model, ws, desc, O, T, which, what):
+    """The reference raises IndexError for an out-of-range id (nn.Embedding / obj_vecs[s_idx]); the kernels remap it to row 0 and set a
+    bit in the workspace's index flag (include/sln_b200.h SLN_IDX_*).  Reading the flag is a 4-byte D2H copy + sync, so it is done on
+    the first call of every (which, O, T) shape, on every call when ``model.check_indices`` is True, never when it is False, and
+    never while a CUDA graph is being captured."""
+    mode = getattr(model, "check_indices", "first")
+    if mode is False or torch.cuda.is_current_stream_capturing():
+        return
+    key = (which, O, T)
+    if mode == "first":
+        if key in model._idx_checked:
+            return
+        model._idx_checked.add(key)
+    off = _lib.load().sln_vae_index_flag_offset(desc, O, T, which)
+    if off < 0:
+        return
+    flag = int(ws[off:off + 4].view(torch.int32).item())
+    if flag:
+        bad = ", ".join(name for bit, name in _IDX_BITS if flag & bit)
+        raise IndexError("index out of range in %s: %s" % (what, bad))
+
+
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, anchor, objs, triples, boxes_gt, angles_gt, attributes):
@@ -31,6 +56,7 @@ class _EncoderFn(torch.autograd.Function):
                                            boxes_gt.data_ptr(), angles_gt.data_ptr(), attributes.data_ptr(), O, T,
                                            mu.data_ptr(), logvar.data_ptr(), ws.data_ptr(), ws_bytes, _lib.cur_stream(dev)),
                    "vae_encoder_fwd")
+        _check_index_flag(model, ws, desc, O, T, 0, "Sg2ScVAEModel.encoder")
         ctx.model, ctx.desc, ctx.ws, ctx.dims, ctx.boxes = model, desc, ws, (O, T), boxes_gt
         return mu, logvar
 
@@ -68,6 +94,7 @@ class _DecoderFn(torch.autograd.Function):
         _lib.check(lib.sln_vae_decoder_fwd(desc, params, bufs, z.data_ptr(), objs.data_ptr(), _lib.ptr(triples) if T else None,
                                            attributes.data_ptr(), O, T, boxes_pred.data_ptr(), angles_pred.data_ptr(),
                                            ws.data_ptr(), ws_bytes, _lib.cur_stream(dev)), "vae_decoder_fwd")
+        _check_index_flag(model, ws, desc, O, T, 1, "Sg2ScVAEModel.decoder")
         ctx.model, ctx.desc, ctx.ws, ctx.dims = model, desc, ws, (O, T)
         ctx.z_needs_grad = z.requires_grad
         return boxes_pred, angles_pred
@@ -215,6 +242,8 @@ class Sg2ScVAEModel(nn.Module):
                   self.angle_mean, self.angle_var, self.box_net):
             m.apply(_init_weights)
 
+        self.check_indices = "first"      # "first" | True | False: see _check_index_flag
+        self._idx_checked = set()
         self._cache = None   # (params ptr table, bn ptr table, param list, enc/dec slot lists)
         self._sink = None
         self._gtable = None
@@ -269,13 +298,13 @@ class Sg2ScVAEModel(nn.Module):
         assert lib.sln_vae_num_params(desc) == len(ps), (lib.sln_vae_num_params(desc), len(ps))
         assert lib.sln_vae_num_bn(desc) * 3 == len(bufs)
         self._cache = dict(params=ps, bufs=bufs, enc=enc, dec=dec, ptable=_lib.ptr_array(ps), btable=_lib.ptr_array(bufs),
-                           key=tuple(p.data_ptr() for p in ps))
+                           key=tuple(p.data_ptr() for p in ps), bkey=tuple(b.data_ptr() for b in bufs))
         return self._cache
 
     def _tables(self):
         c = self._cache
-        if c is None or c['params'][0].data_ptr() != c['key'][0] or c['params'][-1].data_ptr() != c['key'][-1]:
-            c = self._build_cache()
+        if c is None or tuple(p.data_ptr() for p in c['params']) != c['key'] or tuple(b.data_ptr() for b in c['bufs']) != c['bkey']:
+            c = self._build_cache()      # any re-homed parameter / buffer (load_state_dict(assign=True), p.data = ...) drops the tables
         return c['ptable'], c['btable']
 
     def _grad_sink(self):
@@ -297,6 +326,12 @@ class Sg2ScVAEModel(nn.Module):
     def _apply(self, fn, *a, **kw):   # .cuda() / .float() / .to(): parameter storage moves -> drop pointer caches
         self._cache, self._sink, self._anchor = None, None, None
         return super(Sg2ScVAEModel, self)._apply(fn, *a, **kw)
+
+    def load_state_dict(self, state_dict, *a, **kw):   # assign=True swaps Parameter objects: drop every pointer cache
+        out = super(Sg2ScVAEModel, self).load_state_dict(state_dict, *a, **kw)
+        if kw.get("assign", False):
+            self._cache, self._sink, self._gtable = None, None, None
+        return out
 
     def _desc(self):
         if self._bn_cfg is None:

@@ -108,6 +108,44 @@ class FusedAdam(torch.optim.Optimizer):
         super(FusedAdam, self).__init__(params, defaults)
         self.grad_scale = grad_scale
         self._plans = {}
+        self._import_pending = False
+
+    # -- torch.optim.Adam-compatible checkpoints (reference train.py:25,95: optimizer.state_dict() / load_state_dict) --------------
+    def _export_state(self):
+        """Publish the arenas as per-parameter {'step', 'exp_avg', 'exp_avg_sq'} entries of Optimizer.state (views, no copy)."""
+        for plan in self._plans.values():
+            step = torch.tensor(float(plan['step'].item()))
+            for p in plan['params']:
+                o, k = plan['offsets'][id(p)], p.numel()
+                self.state[p] = {'step': step.clone(), 'exp_avg': plan['m'][o:o + k].view_as(p), 'exp_avg_sq': plan['v'][o:o + k].view_as(p)}
+
+    def state_dict(self):
+        self._export_state()
+        return super(FusedAdam, self).state_dict()
+
+    def load_state_dict(self, state_dict):
+        """Accepts a torch.optim.Adam (or FusedAdam) state_dict: moments and step are imported into the arenas — at once for
+        parameters that are already planned, at the first step() otherwise."""
+        super(FusedAdam, self).load_state_dict(state_dict)
+        self._import_pending = True
+        for plan in self._plans.values():
+            self._import_into(plan)
+
+    def _import_into(self, plan):
+        steps = []
+        for p in plan['params']:
+            st = self.state.get(p)
+            if not st or 'exp_avg' not in st:
+                continue
+            o, k = plan['offsets'][id(p)], p.numel()
+            if st['exp_avg'].data_ptr() != plan['m'][o:o + k].data_ptr():
+                plan['m'][o:o + k].copy_(st['exp_avg'].reshape(-1).to(plan['m']))
+                plan['v'][o:o + k].copy_(st['exp_avg_sq'].reshape(-1).to(plan['v']))
+            steps.append(int(float(st['step'])))
+        if steps:
+            if len(set(steps)) != 1:
+                raise RuntimeError("FusedAdam keeps one step counter per parameter group; the loaded state has steps %s" % sorted(set(steps)))
+            plan['step'].fill_(steps[0])
 
     @staticmethod
     def _key(ps):
@@ -150,6 +188,8 @@ class FusedAdam(torch.optim.Optimizer):
         step = old['step'] if old is not None else torch.zeros(1, device=dev, dtype=torch.int64)
         plan = dict(key=self._key(ps), arena=arena, m=m, v=v, runs=runs, step=step, offsets=offsets, params=ps)
         self._plans[gi] = plan
+        if self._import_pending:
+            self._import_into(plan)
         return plan
 
     @torch.no_grad()
@@ -165,6 +205,8 @@ class FusedAdam(torch.optim.Optimizer):
                 continue
             b1, b2 = group['betas']
             st = _lib.cur_stream(plan['arena'].device)
+            if gi == len(self.param_groups) - 1:
+                self._import_pending = False
             for ri, (off, k, gptr) in enumerate(plan['runs']):
                 if gptr % 16:
                     raise RuntimeError("FusedAdam: gradient run not 16-byte aligned")
@@ -243,6 +285,11 @@ class VAETrainStep(object):
         self.d_boxes = torch.zeros(O, BD, **f32); self.d_logits = torch.zeros(O, NA, **f32)
         self.d_mu = torch.zeros(O, E, **f32); self.d_logvar = torch.zeros(O, E, **f32); self.d_z = torch.zeros(O, E, **f32)
         self.losses = torch.zeros(4, **f32)
+        # [lr, kl_weight] on the device: read by k_adam / k_vae_loss at launch time, so set_lr() / set_kl_weight() (the reference's
+        # KL_linear_decay schedule, train.py:73-74) take effect on the next replay of the captured graph
+        self.hyper = torch.tensor([lr, kl_weight], **f32)
+        self.skip_nonfinite = True       # train.py:78-80: a non-finite total loss skips the update (device-side predicate in k_adam)
+        self._captured_training = None
         self.loss_scratch = _loss_scratch(dev, O)
         self.ws_enc = torch.empty(self.lib.sln_vae_workspace_bytes(model._desc(), O, T, 0), dtype=torch.uint8, device=dev)
         self.ws_dec = torch.empty(self.lib.sln_vae_workspace_bytes(model._desc(), O, T, 1), dtype=torch.uint8, device=dev)
@@ -281,12 +328,12 @@ class VAETrainStep(object):
         _lib.check(lib.sln_vae_decoder_fwd(desc, params, bufs, z.data_ptr(), self.objs.data_ptr(), self.triples.data_ptr(),
                                            self.attrs.data_ptr(), O, T, self.boxes_pred.data_ptr(), self.angles_pred.data_ptr(),
                                            self.ws_dec.data_ptr(), self.ws_dec.numel(), st), "decoder_fwd")
-        _lib.check(lib.sln_vae_loss(self.boxes_pred.data_ptr(), self.boxes.data_ptr(), m.box_dim, self.angles_pred.data_ptr(),
-                                    self.angles.data_ptr(), m.Nangle, self.mu.data_ptr() if use_kl else None,
-                                    self.logvar.data_ptr() if use_kl else None, E if use_kl else 0, self.kl_weight if use_kl else 0.0, O,
-                                    self.losses.data_ptr(), self.d_boxes.data_ptr(), self.d_logits.data_ptr(), 1,
-                                    self.d_mu.data_ptr() if use_kl else None, self.d_logvar.data_ptr() if use_kl else None,
-                                    self.loss_scratch.data_ptr(), self.loss_scratch.numel() * 4, st), "vae_loss")
+        _lib.check(lib.sln_vae_loss_dyn(self.boxes_pred.data_ptr(), self.boxes.data_ptr(), m.box_dim, self.angles_pred.data_ptr(),
+                                        self.angles.data_ptr(), m.Nangle, self.mu.data_ptr() if use_kl else None,
+                                        self.logvar.data_ptr() if use_kl else None, E if use_kl else 0, self.hyper.data_ptr() + 4, O,
+                                        self.losses.data_ptr(), self.d_boxes.data_ptr(), self.d_logits.data_ptr(), 1,
+                                        self.d_mu.data_ptr() if use_kl else None, self.d_logvar.data_ptr() if use_kl else None,
+                                        self.loss_scratch.data_ptr(), self.loss_scratch.numel() * 4, st), "vae_loss")
         _lib.check(lib.sln_vae_decoder_bwd(desc, params, grads, self.d_boxes.data_ptr(), self.d_logits.data_ptr(), 1, self.d_z.data_ptr(),
                                            O, T, self.ws_dec.data_ptr(), self.ws_dec.numel(), st), "decoder_bwd")
         if use_kl:
@@ -301,9 +348,76 @@ class VAETrainStep(object):
 
     def _opt(self):
         st = _lib.cur_stream(self.dev)
-        _lib.check(self.lib.sln_adam_step(self.p_arena.data_ptr(), self.sink.flat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                                          self.p_arena.numel(), self.lr, self.betas[0], self.betas[1], self.eps, 0.0,
-                                          1.0 / self.world_size, self.step_count.data_ptr(), 1, st), "adam_step")
+        _lib.check(self.lib.sln_adam_step_dyn(self.p_arena.data_ptr(), self.sink.flat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                              self.p_arena.numel(), self.hyper.data_ptr(), self.betas[0], self.betas[1], self.eps, 0.0,
+                                              1.0 / self.world_size, self.step_count.data_ptr(), 1,
+                                              self.losses.data_ptr() + 12 if self.skip_nonfinite else None, st), "adam_step")
+
+    # -- schedules / validation / checkpoints ----------------------------------------------------
+    def set_lr(self, lr):
+        self.lr = float(lr)
+        self.hyper[0:1].fill_(self.lr)
+
+    def set_kl_weight(self, w):
+        """reference train.py:73-74 (KL_linear_decay): takes effect on the next step, captured graph or not."""
+        self.kl_weight = float(w)
+        self.hyper[1:2].fill_(self.kl_weight)
+
+    def check_indices(self):
+        """Raise IndexError if the last step saw an out-of-range id (the kernels remap it to row 0 and set a flag; the reference raises
+        at the embedding lookup).  One 8-byte D2H read + sync: called automatically after the first step of a captured shape."""
+        from .models.Sg2ScVAE_model import _IDX_BITS
+        desc = self.model._desc()
+        for which, ws, what in ((0, self.ws_enc, "encoder"), (1, self.ws_dec, "decoder")):
+            off = self.lib.sln_vae_index_flag_offset(desc, self.O, self.T, which)
+            flag = int(ws[off:off + 4].view(torch.int32).item())
+            if flag:
+                raise IndexError("index out of range in VAETrainStep (%s): %s" % (what, ", ".join(n for b, n in _IDX_BITS if flag & b)))
+
+    def _param_slots(self):
+        """[(parameter, arena offset, numel)] in model.parameters() order (= the index order of torch.optim.Adam(model.parameters()))."""
+        cache = self.model._cache
+        off = {id(cache['params'][i]): self.sink.views[i].storage_offset() for i in self.sink.order}
+        return [(p, off[id(p)], p.numel()) for p in self.model.parameters()]
+
+    def optim_state_dict(self):
+        """Adam state in torch.optim.Adam(model.parameters()).state_dict() format — what the reference stores as checkpoint
+        ['optim_state'] (train.py:95) — so runs can resume in either implementation."""
+        step = float(self.step_count.item())
+        state = {}
+        for i, (p, o, k) in enumerate(self._param_slots()):
+            state[i] = {'step': torch.tensor(step), 'exp_avg': self.m[o:o + k].view_as(p).clone(), 'exp_avg_sq': self.v[o:o + k].view_as(p).clone()}
+        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None, capturable=False,
+                     differentiable=False, fused=None, decoupled_weight_decay=False, params=list(range(len(state))))
+        return {'state': state, 'param_groups': [group]}
+
+    def load_optim_state_dict(self, sd):
+        slots = self._param_slots()
+        steps = set()
+        with torch.no_grad():
+            for i, (p, o, k) in enumerate(slots):
+                st = sd['state'].get(i)
+                if st is None:
+                    self.m[o:o + k].zero_(); self.v[o:o + k].zero_()
+                    continue
+                self.m[o:o + k].copy_(st['exp_avg'].reshape(-1).to(self.m))
+                self.v[o:o + k].copy_(st['exp_avg_sq'].reshape(-1).to(self.v))
+                steps.add(int(float(st['step'])))
+        if len(steps) > 1:
+            raise RuntimeError("VAETrainStep keeps one Adam step counter; the loaded state has steps %s" % sorted(steps))
+        self.step_count.fill_(steps.pop() if steps else 0)
+        if sd.get('param_groups'):
+            self.set_lr(sd['param_groups'][0].get('lr', self.lr))
+
+    def state_dict(self):
+        return {'model_state': self.model.state_dict(), 'optim_state': self.optim_state_dict(), 'kl_weight': self.kl_weight}
+
+    def load_state_dict(self, sd):
+        """Parameters are copied INTO the step's arena (load_state_dict copies in place), moments and step into m / v / step_count."""
+        self.model.load_state_dict(sd['model_state'])
+        self.load_optim_state_dict(sd['optim_state'])
+        if 'kl_weight' in sd:
+            self.set_kl_weight(sd['kl_weight'])
 
     def _allreduce(self):
         if self.world_size > 1:
@@ -319,6 +433,8 @@ class VAETrainStep(object):
                 self._fwd_bwd(); self._allreduce(); self._opt()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
+        self._captured_training = self.model.training
+        self.check_indices_pending = True
         if not self.use_graph:
             return self
         self.graph_fb = torch.cuda.CUDAGraph()
@@ -337,6 +453,20 @@ class VAETrainStep(object):
             dst.copy_(src, non_blocking=True)
 
     def run(self):
+        if self._captured_training is not None and self.model.training != self._captured_training:
+            # the train/eval flag (BatchNorm batch vs running statistics; reference train.py:64-66 eval_mode_after) is baked into the
+            # captured launches: re-capture instead of silently running the old mode
+            if self.graph_fb is not None:
+                self.graph_fb = self.graph_opt = None
+                self.capture()
+            self._captured_training = self.model.training
+        out = self._run()
+        if getattr(self, "check_indices_pending", False):
+            self.check_indices_pending = False
+            self.check_indices()
+        return out
+
+    def _run(self):
         if self.graph_fb is not None:
             self.graph_fb.replay()
             if self.world_size > 1:
@@ -350,12 +480,16 @@ class VAETrainStep(object):
         self.load_batch(batch)
         return self.run()
 
-    def step_wire(self, pinned_wire):
+    def step_wire(self, pinned_wire, meta=None):
         """One train step from a host batch in wire layout (data.collate.packed_batch): one async H2D copy, the device half of the
         batch assembly (global triple ids, obj_to_img / triple_to_img), then the step."""
         if self.wire_meta is None:
             raise RuntimeError("VAETrainStep.step_wire needs wire_meta= at construction")
         B, O, T, bd, lay = self.wire_meta
+        if meta is not None and (tuple(meta[:4]) != (B, O, T, bd) or tuple(meta[4]) != tuple(lay)):
+            raise ValueError("VAETrainStep.step_wire: batch layout %r differs from the captured one %r" % (tuple(meta[:4]), (B, O, T, bd)))
+        if pinned_wire.numel() < lay[9]:
+            raise ValueError("VAETrainStep.step_wire: wire buffer holds %d bytes, the captured layout needs %d" % (pinned_wire.numel(), lay[9]))
         self.wire_dev.copy_(pinned_wire[:lay[9]], non_blocking=True)
         _lib.check(self.lib.sln_collate_finish(self.wire_dev.data_ptr(), self.wire_dev.numel(), B, O, T, bd, self.triples.data_ptr(),
                                                self.obj_to_img.data_ptr(), self.triple_to_img.data_ptr(), None, _lib.cur_stream(self.dev)),

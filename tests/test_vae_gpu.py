@@ -346,3 +346,149 @@ def test_fused_adam_matches_torch_adam():
         a.step(); b.step()
     for p, q in zip(ps, qs):
         assert (p - q).abs().max().item() < 1e-6
+
+
+def test_fused_adam_checkpoints_are_torch_adam_compatible():
+    """optimizer.state_dict() / load_state_dict (reference train.py:25,95) round-trip both ways between FusedAdam and torch.optim.Adam:
+    moments and the step counter (bias correction) continue, the continued trajectories agree."""
+    torch.manual_seed(1)
+    shapes = ((5, 3), (7,), (130, 9), (1,))
+    grads = [[torch.randn(s, device=DEV) for s in shapes] for _ in range(7)]
+
+    def run(opt, params, its):
+        for it in its:
+            for p, g in zip(params, grads[it]):
+                p.grad = g.clone()
+            opt.step()
+
+    init = [torch.randn(s, device=DEV) for s in shapes]
+    # truth: torch Adam for 7 steps
+    ref = [t.clone().requires_grad_(True) for t in init]
+    run(torch.optim.Adam(ref, lr=1e-2), ref, range(7))
+    # torch Adam 3 steps -> state_dict -> fresh FusedAdam (load before its first step) -> 4 more
+    p1 = [t.clone().requires_grad_(True) for t in init]
+    o1 = torch.optim.Adam(p1, lr=1e-2)
+    run(o1, p1, range(3))
+    f = sutils.FusedAdam(p1, lr=1e-2)
+    f.load_state_dict(o1.state_dict())
+    run(f, p1, range(3, 7))
+    for p, q in zip(p1, ref):
+        assert (p - q).abs().max().item() < 2e-6
+    # FusedAdam 3 steps -> state_dict -> torch Adam -> 4 more; and -> another FusedAdam that already stepped (import into live arenas)
+    p2 = [t.clone().requires_grad_(True) for t in init]
+    f2 = sutils.FusedAdam(p2, lr=1e-2)
+    run(f2, p2, range(3))
+    sd = f2.state_dict()
+    assert set(sd["state"].keys()) == {0, 1, 2, 3} and all(float(v["step"]) == 3.0 for v in sd["state"].values())
+    assert all(tuple(v["exp_avg"].shape) == s for v, s in zip(sd["state"].values(), shapes))
+    p3 = [p.detach().clone().requires_grad_(True) for p in p2]
+    o3 = torch.optim.Adam(p3, lr=1e-2)
+    o3.load_state_dict(sd)
+    run(o3, p3, range(3, 7))
+    for p, q in zip(p3, ref):
+        assert (p - q).abs().max().item() < 2e-6
+    p4 = [t.clone().requires_grad_(True) for t in init]
+    f4 = sutils.FusedAdam(p4, lr=1e-2)
+    run(f4, p4, [6])                                  # plans exist, wrong state
+    with torch.no_grad():
+        for p, q in zip(p4, p2):
+            p.copy_(q)
+    f4.load_state_dict(sd)
+    run(f4, p4, range(3, 7))
+    for p, q in zip(p4, ref):
+        assert (p - q).abs().max().item() < 2e-6
+
+
+def test_out_of_range_ids_raise_index_error_like_the_reference():
+    """nn.Embedding / obj_vecs[s_idx] raise IndexError in the reference; the kernels remap to row 0 + flag, the wrappers raise."""
+    _, objs, boxes, triples, angles, attrs, _, _ = syn.synthetic_batch(2, 6, seed=2)
+    dev = [t.to(DEV) for t in (objs, triples, boxes, angles, attrs)]
+    cases = {"objs": (0, lambda t: t.__setitem__(1, 10 ** 6)), "triples predicate": (1, lambda t: t.__setitem__((2, 1), 99)),
+             "triples subject/object": (1, lambda t: t.__setitem__((0, 2), objs.size(0))), "angles": (3, lambda t: t.__setitem__(0, 24)),
+             "attributes": (4, lambda t: t.__setitem__(2, -1))}
+    for what, (slot, poke) in cases.items():
+        m = our_model(E=16, layers=2, norm="none", device=DEV).eval()
+        bad = [t.clone() for t in dev]
+        poke(bad[slot])
+        with pytest.raises(IndexError, match=what):
+            m(bad[0], bad[1], bad[2], bad[3], bad[4], None)
+        assert all(torch.isfinite(p).all() for p in m.parameters())
+    m = our_model(E=16, layers=2, norm="none", device=DEV).eval()
+    m(*dev, None)                                                   # clean ids: no error, and "first" mode does not re-check this shape
+    bad = [t.clone() for t in dev]; bad[0][0] = 777
+    m(*bad, None)
+    m.check_indices = True
+    with pytest.raises(IndexError):
+        m(*bad, None)
+    with pytest.raises(IndexError, match="decoder"):
+        m.decoder(torch.zeros(objs.size(0), 16, device=DEV), bad[0], bad[1], bad[4])
+    # the captured train step validates after its first replay
+    m2 = our_model(E=16, layers=2, norm="none", device=DEV).train()
+    step = sutils.VAETrainStep(m2, objs.size(0), triples.size(0)).capture()
+    step.step(dev)
+    bad = [t.clone() for t in dev]; bad[1][1, 1] = 16
+    step.step(bad)
+    with pytest.raises(IndexError, match="predicate"):
+        step.check_indices()
+
+
+def test_train_step_schedules_guard_and_checkpoint_resume():
+    """Device-side hyper-parameters (KL weight schedule, lr) take effect on a captured graph; a non-finite loss skips the update
+    (reference train.py:78-80); optim_state_dict()/load_optim_state_dict resume in torch.optim.Adam's format (train.py:25,95)."""
+    B, n, E, L = 6, 8, 16, 2
+    _, objs, boxes, triples, angles, attrs, _, _ = syn.synthetic_batch(B, n, seed=9)
+    batch = [t.to(DEV) for t in (objs, triples, boxes, angles, attrs)]
+    gen = torch.Generator().manual_seed(3)
+    eps = [torch.randn(objs.size(0), E, generator=gen).to(DEV) for _ in range(6)]
+
+    def make():
+        m = our_model(E=E, layers=L, norm="none", seed=5, device=DEV).train()
+        st = sutils.VAETrainStep(m, objs.size(0), triples.size(0), lr=1e-3, kl_weight=0.1, sample_eps=False).capture()
+        return m, st
+    m, st = make()
+    init = {k: v.clone() for k, v in m.state_dict().items()}
+
+    def reset(model, step):
+        with torch.no_grad():
+            for k, p in model.state_dict().items():
+                p.copy_(init[k])
+        step.m.zero_(); step.v.zero_(); step.step_count.zero_()
+
+    def run(step, its):
+        out = []
+        for it in its:
+            step.load_batch(batch); step.epsn.copy_(eps[it])
+            out.append(step.run().tolist())
+        return out
+    reset(m, st)
+    base = run(st, range(2))
+    # KL weight: same parameters, doubled weight -> the KL term doubles exactly on the replayed graph
+    reset(m, st)
+    st.set_kl_weight(0.2)
+    l2 = run(st, range(1))[0]
+    assert abs(l2[2] - 2 * base[0][2]) <= 1e-6 * abs(base[0][2]) and abs(l2[0] - base[0][0]) <= 1e-7
+    st.set_kl_weight(0.1)
+    # non-finite loss: parameters, moments and the step counter stay put
+    reset(m, st)
+    run(st, range(1))
+    snap = (st.p_arena.clone(), st.m.clone(), st.v.clone(), int(st.step_count.item()))
+    poisoned = [t.clone() for t in batch]; poisoned[2][0, 0] = float("nan")
+    st.load_batch(poisoned); st.epsn.copy_(eps[1])
+    assert not torch.isfinite(st.run()[3])
+    assert torch.equal(st.p_arena, snap[0]) and torch.equal(st.m, snap[1]) and torch.equal(st.v, snap[2]) and int(st.step_count.item()) == snap[3] == 1
+    # resume: 3 steps -> checkpoint -> fresh step object + 3 more == 6 straight steps; the checkpoint loads into torch.optim.Adam too
+    reset(m, st)
+    straight = run(st, range(6))
+    want = {k: v.clone() for k, v in m.state_dict().items()}
+    reset(m, st)
+    run(st, range(3))
+    ckpt = st.state_dict()
+    m2, st2 = make()
+    st2.load_state_dict(ckpt)
+    resumed = run(st2, range(3, 6))
+    assert max(abs(a - b) for x, y in zip(resumed, straight[3:]) for a, b in zip(x, y)) <= 1e-6
+    for k, v in m2.state_dict().items():
+        assert torch.allclose(v, want[k], rtol=0, atol=1e-6), k
+    ref_opt = torch.optim.Adam(m2.parameters(), lr=1e-3)
+    ref_opt.load_state_dict(ckpt['optim_state'])
+    assert all(float(s['step']) == 3.0 for s in ref_opt.state_dict()['state'].values())
