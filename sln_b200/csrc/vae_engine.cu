@@ -724,7 +724,7 @@ int64_t sln_vae_index_flag_offset(const sln_vae_desc* d, int64_t O, int64_t T, i
   if (make_dims(d, &dm) || check_dims(O, T)) return -1;
   static thread_local NetPlan p;
   make_plan(dm, (int)O, (int)T, which, nullptr, &p);
-  return (int64_t)((char*)p.err - (char*)nullptr);
+  return (int64_t)((uintptr_t)p.err - 256);   // dry-run arenas hand out fake addresses 256 + offset (common.cuh Arena::take)
 }
 
 int sln_vae_encoder_fwd(const sln_vae_desc* d, const void* const* params, void* const* bn_bufs, const int64_t* objs,

@@ -380,7 +380,7 @@ def test_fused_adam_checkpoints_are_torch_adam_compatible():
     run(f2, p2, range(3))
     sd = f2.state_dict()
     assert set(sd["state"].keys()) == {0, 1, 2, 3} and all(float(v["step"]) == 3.0 for v in sd["state"].values())
-    assert all(tuple(v["exp_avg"].shape) == s for v, s in zip(sd["state"].values(), shapes))
+    assert all(tuple(sd["state"][i]["exp_avg"].shape) == s for i, s in enumerate(shapes))
     p3 = [p.detach().clone().requires_grad_(True) for p in p2]
     o3 = torch.optim.Adam(p3, lr=1e-2)
     o3.load_state_dict(sd)
