@@ -35,14 +35,12 @@ def _scene(dev, seed=13):
 
 
 def run(args):
+    """The process group (world > 1) is created and destroyed by bench.main()."""
     import bench as B
     rank, local_rank, world = B.dist_env()
     n = max(args.gpus, 1)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
     _lib = importlib.import_module("sln_b200._lib")
     lib = _lib.load()
     refine = importlib.import_module("sln_b200.models.refine")
@@ -123,7 +121,6 @@ def run(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s = t.tolist()
         dist.barrier()
-        dist.destroy_process_group()
     if rank != 0:
         return None
     peaks = B.measured_peaks()
@@ -133,8 +130,8 @@ def run(args):
     if fwd:
         gbs = fwd["work"] / (fwd["ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "raster_fwd class (k_project, k_face_setup, k_raster_tiles, k_scene_sval, k_scene_class_images)",
-                    "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": 0.57e6,
-                    "traffic_source": "dram bytes of one k_raster_tiles launch, ncu --set full (profiles/r1_prof_raster.csv): the scene is L2-resident",
+                    "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                    **B.profile_traffic("raster", "k_raster_tiles"),
                     "algorithmic_bytes_per_iter": fwd["work"], "launches_per_iter": fwd["launches"], "ms_per_iter": fwd["ms"],
                     "peak_source": peaks["source"],
                     "note": "a 256x256 scene moves ~5 MB: the rasterizer is latency/launch-bound, not HBM-bound (SURVEY 8d); backward class: %s" % (

@@ -38,9 +38,6 @@ def run(args):
     n = max(args.gpus, 1)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
     _lib = importlib.import_module("sln_b200._lib")
     lib = _lib.load()
     m = _model(dev)
@@ -97,7 +94,6 @@ def run(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s = t.tolist()
         dist.barrier()
-        dist.destroy_process_group()
     if rank != 0:
         return None
     peaks = B.measured_peaks()
@@ -107,9 +103,8 @@ def run(args):
     if conv:
         tf = conv["work"] / (conv["ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<Im2col, MatView, TcEpiStore|TcEpiSpade> (3xTF32 implicit-GEMM convolutions)",
-                    "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"], "traffic": 1.591e9,
-                    "traffic_source": "dram bytes of the largest launch (up_3 modulation conv), ncu --set full (profiles/r1_prof_tc_spade.csv): 1.076 GB read + 0.515 GB "
-                                      "written = activation in, x in, modulated activation out",
+                    "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"],
+                    **B.profile_traffic("tc_spade", "tc_gemm_kernel", pick="max"),
                     "algorithmic_flops_per_step": conv["work"], "launches_per_step": conv["launches"], "ms_per_step": conv["ms"],
                     "share_of_step": conv["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9),
                     "peak_source": peaks["source"] + ", sustained bf16",
@@ -118,7 +113,14 @@ def run(args):
     cpu = None
     if n == 1 and not args.no_cpu_baseline:
         cpu = cpu_spade_baseline(budget_s=25.0)
-    return {"metric": METRIC, "value": BATCH * n * 1e3 / ms_per_step, "unit": "images/s", "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
+    eager, batch1 = None, None
+    if n == 1:
+        try:
+            eager = eager_gpu_spade(dev, m, seg, z)
+            batch1 = batch1_latency(dev, m, seg, z)
+        except Exception as e:       # comparators only: never fail the bench line because of them
+            eager = {"unavailable": repr(e)[:300]}
+    return {"eager_gpu_baseline": eager, "batch1": batch1, "metric": METRIC, "value": BATCH * n * 1e3 / ms_per_step, "unit": "images/s", "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": _config(n),
             "e2e": {"value": BATCH * n * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": seg_h.numel() * 4 + z_h.numel() * 4,
@@ -126,6 +128,55 @@ def run(args):
             "gpu_launches": launches * args.steps, "launches_per_step": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "kernel_classes_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
             "useful_tflops": FLOP_PER_IMAGE * BATCH * n / (ms_per_step * 1e-3) / 1e12}
+
+
+def batch1_latency(dev, m, seg, z, reps=10):
+    """What testing/test_SPADE_shade.py:77-79 actually runs: 50 z draws at batch 1.  ms per image of this path at batch 1."""
+    s1, z1 = seg[:1].contiguous(), z[:1].contiguous()
+    for _ in range(3):
+        m(s1, z1)
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        m(s1, z1)
+    b.record()
+    torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / reps
+    return {"ms_per_image": ms, "images_per_s": 1e3 / ms, "what": "batch 1 (the reference's own call pattern, test_SPADE_shade.py:77-79), CUDA events, %d forwards" % reps}
+
+
+def eager_gpu_spade(dev, m, seg, z, reps=3):
+    """Comparators on the SAME GPU: the oracle port (the reference's forward as plain torch ops -> stock cuDNN / cuBLAS kernels, what
+    SPADEGenerator4.forward executes after .cuda()) with cudnn.allow_tf32 False (fp32 parity class of this path) and True (torch's
+    default for convolutions: faster, ~1e-3 relative error), at batch 16 and batch 1.  Baselines only."""
+    from oracle import spade_oracle as so
+    sd = {k: v.detach().to(dev) for k, v in m.state_dict().items()}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    out = {}
+    try:
+        for tf32 in (False, True):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            for nb in (BATCH, 1):
+                s_, z_ = seg[:nb].contiguous(), z[:nb].contiguous()
+                with torch.no_grad():
+                    for _ in range(2):
+                        so.forward(sd, s_, z_, 64, 8, torch.float32)
+                    torch.cuda.synchronize(dev)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for _ in range(reps):
+                        so.forward(sd, s_, z_, 64, 8, torch.float32)
+                    b.record()
+                    torch.cuda.synchronize(dev)
+                ms = a.elapsed_time(b) / reps
+                out["tf32_%s_batch%d" % ("on" if tf32 else "off", nb)] = {"ms_per_step": ms, "images_per_s": nb * 1e3 / ms,
+                                                                          "useful_tflops": FLOP_PER_IMAGE * nb / (ms * 1e-3) / 1e12}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    out["kind"] = "port, torch eager (cuDNN/cuBLAS) on the same GPU; tf32_off = fp32 arithmetic class of this path, tf32_on = torch's conv default"
+    return out
 
 
 def cpu_spade_baseline(budget_s=25.0):

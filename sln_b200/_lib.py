@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("sln_b200: nvcc not found and %s is missing/stale; cannot build the CUDA library" % LIB_PATH)
     objdir = os.path.join(_PKG_DIR, "build")
     os.makedirs(objdir, exist_ok=True)
-    cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("SLN_NVCC_EXTRA", "").split()   # e.g. -DSLN_TC_TRACE (tuning builds)
     jobs = []
     for src in _sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
@@ -178,12 +178,13 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if _stale():
+        path = os.environ.get("SLN_LIB_PATH") or LIB_PATH      # SLN_LIB_PATH: an instrumented tuning build (tools/build_trace.sh)
+        if path == LIB_PATH and _stale():
             build()
         try:
-            lib = ctypes.CDLL(LIB_PATH)
+            lib = ctypes.CDLL(path)
         except OSError as e:
-            raise RuntimeError("sln_b200: cannot load %s (%s); the hot path has no CPU/PyTorch fallback" % (LIB_PATH, e))
+            raise RuntimeError("sln_b200: cannot load %s (%s); the hot path has no CPU/PyTorch fallback" % (path, e))
         for name, (res, args) in SIGNATURES.items():
             if not hasattr(lib, name):
                 continue  # optional components (raster/spade) may be absent in a partial build; checked by tests
