@@ -345,12 +345,25 @@ struct SmemLayout {
 constexpr int SEG_CHUNKS = 40;
 
 // tuning aid: SM-clock timestamps of CTA (0,0,0) at the phase boundaries of the last tc_gemm launch (sln_debug_tc_trace)
-__device__ long long g_tc_trace[16];
+__device__ long long g_tc_trace[48];
 #ifdef SLN_TC_TRACE
 #define TC_TRACE(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid & 31) == 0 && (tid == 0 || tid == MMA_WARP * 32)) g_tc_trace[(slot) + (tid ? 8 : 0)] = clock64(); } while (0)
+#define TC_TRACE2(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0 || tid == MMA_WARP * 32)) g_tc_trace[16 + (slot) + (tid ? 16 : 0)] = clock64(); } while (0)
 #else
 #define TC_TRACE(slot) do { } while (0)
+#define TC_TRACE2(slot) do { } while (0)
 #endif
+
+// One lane of a CONVERGED warp, chosen by the hardware (elect.sync).  ptxas knows the elected lane is unique, so tcgen05.mma /
+// cp.async.bulk / tcgen05.commit issued under it compile to straight-line UTCHMMA / UBLKCP / UTCBAR with uniform-register operands.
+// Under a plain `if (lane == 0)` the compiler cannot prove uniformity and wraps EVERY such instruction in an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall loop (~100 cycles per MMA, measured: the issue loop, not the tensor core, paced
+// the BN <= 64 tiles).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -427,7 +440,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
 
   if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(BN, !A_RC, !B_RC), idesc2 = make_idesc(2 * BN, !A_RC, !B_RC);
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % S, use = c / S;
@@ -439,6 +452,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
         }
         mbar_wait(full + s, (uint32_t)(use & 1));
         tc_fence_after();
+        if (c < 8) TC_TRACE2(c);
         const uint32_t a_hi = smem_u32(smem + s * L::STAGE), a_lo = a_hi + L::A_TILE, b_hi = a_hi + 2 * L::A_TILE;   // b_lo = b_hi + B_TILE: rows BN..2BN-1 of the same tile
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {               // UMMA_K = 8 tf32: one 32-byte slice of every K-major row / one MN-major k-atom
@@ -495,8 +509,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
       const int s = c % S, use = c / S;
       const uint32_t st = sbase + s * L::STAGE;
       if (use > 0) mbar_wait(empty + s, (uint32_t)((use - 1) & 1));   // the MMAs that read this stage have retired
+      if (c < 4) TC_TRACE2(2 * c);
       if constexpr (BP) {
-        if (tid == 0) {                                   // B_hi | B_lo tiles of this stage: BN/32 units, two 4 KB bulk copies each
+        if (warp == 0 && elect_one()) {                   // B_hi | B_lo tiles of this stage: BN/32 units, two 4 KB bulk copies each
           mbar_expect_tx(full + s, 2 * L::B_TILE);
           const float* u0 = B.units + ((size_t)(n0 / 32) * B.kchunks + (size_t)(kbeg / BK + c)) * PACK_UNIT_FLOATS;
 #pragma unroll
@@ -514,6 +529,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
         la.template store<false>(A, BA, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
         if constexpr (!BP) lb.template store<false>(B, BB, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
       }
+      if (c < 4) TC_TRACE2(2 * c + 1);
       if (c + PF < nchunks) fetch(BA, BB, c + PF);        // refill the register buffer: these loads fly during the next PF chunks
       fence_async_smem();                                 // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
@@ -525,8 +541,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
     };
     la.init(A, m0, tid);
     if constexpr (!BP) lb.init(B, n0, tid);
+    TC_TRACE2(8);
     if (nchunks > 0) fetch(a0, b0, 0);
     if (PF == 2 && nchunks > 1) fetch(a1, b1, 1);
+    TC_TRACE2(9);
     for (int c = 0; c < nchunks; c += PF) {
       produce(a0, b0, c);
       if (PF == 2 && c + 1 < nchunks) produce(a1, b1, c + 1);

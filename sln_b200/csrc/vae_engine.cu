@@ -1042,9 +1042,9 @@ int sln_contract(const float* A, int64_t lda, int32_t a_rc, const float* B, int6
 }
 
 // tuning aid (not part of the public header): SM-clock trace of the last tcgen05 contraction launched by sln_contract
-int sln_debug_tc_trace(long long* out16) {
+int sln_debug_tc_trace(long long* out16) {   /* 48 slots */
   SLN_CUDA_TRY(cudaDeviceSynchronize());
-  SLN_CUDA_TRY(cudaMemcpyFromSymbol(out16, tc::g_tc_trace, sizeof(long long) * 16));   // all zero unless built with -DSLN_TC_TRACE
+  SLN_CUDA_TRY(cudaMemcpyFromSymbol(out16, tc::g_tc_trace, sizeof(long long) * 48));   // all zero unless built with -DSLN_TC_TRACE
   return SLN_OK;
 }
 

@@ -378,12 +378,13 @@ def test_fused_adam_checkpoints_are_torch_adam_compatible():
     p2 = [t.clone().requires_grad_(True) for t in init]
     f2 = sutils.FusedAdam(p2, lr=1e-2)
     run(f2, p2, range(3))
-    sd = f2.state_dict()
+    import copy
+    sd = copy.deepcopy(f2.state_dict())      # like torch's, the dict references the live moments; load_state_dict does not clone same-device tensors
     assert set(sd["state"].keys()) == {0, 1, 2, 3} and all(float(v["step"]) == 3.0 for v in sd["state"].values())
     assert all(tuple(sd["state"][i]["exp_avg"].shape) == s for i, s in enumerate(shapes))
     p3 = [p.detach().clone().requires_grad_(True) for p in p2]
     o3 = torch.optim.Adam(p3, lr=1e-2)
-    o3.load_state_dict(sd)
+    o3.load_state_dict(copy.deepcopy(sd))
     run(o3, p3, range(3, 7))
     for p, q in zip(p3, ref):
         assert (p - q).abs().max().item() < 2e-6
