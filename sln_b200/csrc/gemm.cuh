@@ -18,6 +18,7 @@ namespace sln {
 // ---------------------------------------------------------------- operand functors
 // Row-major matrix with an optional lazy per-column affine + ReLU: v(r,c) = act(p[r*ld+c]*scale[c]+shift[c]).
 struct MatView {
+  static constexpr bool kTwoLoads = false;   // fetch4 fills only `a` (tc_gemm.cuh: prefetch depth)
   const float* p;
   int ld, rows, cols;
   const float* scale;  // null -> identity
@@ -82,6 +83,7 @@ inline MatView make_view(const float* p, int ld, int rows, int cols, const float
 
 // Virtual [T, 3D] matrix  [ obj[s_t] | pred[t] | obj[o_t] ]   (reference graph.py:78-83), D % 4 == 0.
 struct GatherCat {
+  static constexpr bool kTwoLoads = false;
   MatView obj, pred;
   const int* s_idx;
   const int* o_idx;
@@ -123,6 +125,7 @@ struct GatherCat {
 // Virtual [rows, a.cols + b.cols] matrix [ a | b ]  (decoder box_net input: cat([obj_vecs, attr_vecs]),
 // reference Sg2ScVAE_model.py:166-167).  a.cols % 4 == 0.
 struct Concat2 {
+  static constexpr bool kTwoLoads = false;
   MatView a, b;
   int rows, cols;
   __device__ __forceinline__ float4 ld4(int r, int c) const {
@@ -161,6 +164,7 @@ struct Concat2 {
 //   q == null        : dy = g*p                       (eval-mode BN: p = gamma*rstd_running)
 //   otherwise        : training-mode BN backward, see bn_bwd_finalize()
 struct DyView {
+  static constexpr bool kTwoLoads = true;    // g and y: two 16-byte loads per quad
   const float* g;
   int ldg;
   const float* y;

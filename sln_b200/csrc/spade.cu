@@ -20,6 +20,7 @@ __device__ __forceinline__ int reflect(int v, int n) { return v < 0 ? -v : (v >=
 // input at the REFLECTED position (y + ky - ks/2, x + kx - ks/2)   (nn.ReflectionPad2d(1) + Conv2d(k=3, padding=0)), or the
 // pixel itself for ks == 1.  Optional lazy ReLU on load.
 struct Im2col {
+  static constexpr bool kTwoLoads = false;
   const float* p;
   int H, W, C, ks, rows, cols, relu, vec;
   int cshift;   // log2(C) when C is a power of two (the usual case), else -1: k -> (tap, c) without an integer division

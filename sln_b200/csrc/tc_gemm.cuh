@@ -136,6 +136,7 @@ __device__ __forceinline__ void split_store4(uint32_t hi_addr, uint32_t lo_addr,
 // engine's linear mode, SASS UBLKCP) straight into shared memory — no registers, no producer instructions, completion counted on the
 // stage's `full` mbarrier — instead of loading, splitting and storing them with the producer warps.
 struct PackedB {
+  static constexpr bool kTwoLoads = false;
   const float* units;   // [ceil(N/128)*4][ceil(K/32)][2][32][32] floats
   int kchunks;          // ceil(K/32)
   // functor API stubs (never called: the kernel takes the bulk-copy path for this type)
@@ -379,7 +380,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int BN, bool A_RC, bool B_RC, bool MSEG, class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const BOp B, const Epi epi, int M, int N, int K, int kchunk) {
   using L = SmemLayout<BN>;
-  constexpr int S = L::STAGES, PF = MSEG ? 1 : 2;   // chunks prefetched into registers per producer thread
+  // chunks prefetched into registers per producer thread.  The loads of chunk c + PF are issued at the end of produce(c) and consumed
+  // at the start of produce(c + PF), i.e. PF - 1 chunk periods later: with PF = 2 the period settled at the (loaded) L2 latency of
+  // ~900 cycles (phase trace, profiles/r2_trace_contract.txt).  Operands that arrive as a pre-split image (PackedB) need no B
+  // registers, so the single-load A functors can afford 4 chunks in flight (64 registers; one CTA per SM allows 224).
+  constexpr int S = L::STAGES, PF = MSEG ? 1 : ((is_packed<BOp>::value && !AOp::kTwoLoads) ? 4 : 2);
   constexpr bool BP = is_packed<BOp>::value;       // B tiles arrive by cp.async.bulk from a pre-split, pre-tiled image
   extern __shared__ char smem_raw[];
   char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -492,8 +497,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
     // loop invariants once per operand; PF register buffers (named, not arrays, so that they stay in registers)
     Loader<BM, A_RC, AOp> la;
     Loader<BN, B_RC, BOp> lb;
-    typename Loader<BM, A_RC, AOp>::Buf a0, a1;
-    typename Loader<BN, B_RC, BOp>::Buf b0, b1;
+    typename Loader<BM, A_RC, AOp>::Buf abuf[PF];
+    typename Loader<BN, B_RC, BOp>::Buf bbuf[PF];          // indexed by compile-time constants only (fully unrolled): registers
     const bool tail = ((kend - kbeg) & (BK - 1)) != 0;     // only the last chunk can have K padding
     const uint32_t sbase = smem_u32(smem);
     auto fetch = [&](auto& BA, auto& BB, int c) {
@@ -542,12 +547,14 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
     la.init(A, m0, tid);
     if constexpr (!BP) lb.init(B, n0, tid);
     TC_TRACE2(8);
-    if (nchunks > 0) fetch(a0, b0, 0);
-    if (PF == 2 && nchunks > 1) fetch(a1, b1, 1);
+#pragma unroll
+    for (int i = 0; i < PF; ++i)
+      if (i < nchunks) fetch(abuf[i], bbuf[i], i);
     TC_TRACE2(9);
     for (int c = 0; c < nchunks; c += PF) {
-      produce(a0, b0, c);
-      if (PF == 2 && c + 1 < nchunks) produce(a1, b1, c + 1);
+#pragma unroll
+      for (int i = 0; i < PF; ++i)
+        if (c + i < nchunks) produce(abuf[i], bbuf[i], c + i);
     }
     if (MSEG && nchunks > 0) drain((nchunks - 1) / SEG_CHUNKS);
     if (!MSEG && nchunks > 0) {                           // single segment: every MMA has retired when segfull completes
