@@ -59,7 +59,32 @@ typedef struct sln_vae_desc {
   const void* packed_weights;    /* NULL, or the buffer sln_vae_pack_weights() filled FROM THE CURRENT PARAMETER VALUES: pre-split
                                     (TF32 hi | lo), pre-tiled images of every Linear weight, pulled into shared memory by cp.async.bulk
                                     instead of being split on the fly (forward and backward-data contractions) */
+  const void* bn_sync;           /* NULL (per-rank BatchNorm statistics), or a DEVICE pointer to an sln_bn_sync table: training-mode
+                                    BatchNorm statistics are then summed over all ranks INSIDE the finalising kernels (SyncBatchNorm) */
 } sln_vae_desc;
+
+/* Cross-rank BatchNorm statistics (SURVEY 8e policy P1: the N-GPU step equals the 1-GPU step at the global batch; reference
+ * models/graph.py:14-15 nn.BatchNorm1d over ALL rows of the batch).  The kernel that finalises a BatchNorm layer's column sums (the
+ * last CTA of a column block in the contraction epilogue / k_prep) stores its (sum, sum of squares | sum g, sum g*yhat, rows) to
+ * EVERY rank's receive buffer with peer stores over NVLink, bumps every rank's flag for that slot with a system-scope atomic, spins
+ * on its own flag until `world` arrivals, and reduces the `world` contributions in rank order (fixed order: bit-identical statistics
+ * on every rank, run-to-run deterministic).  No NCCL call, no host round trip, capturable in a CUDA graph.
+ * The table lives in device memory; all pointers are device addresses valid ON THIS RANK (peer-mapped, e.g. from
+ * torch.distributed._symmetric_memory).  recv / flag / use must be zero-initialised once and never reset.
+ *   slot  = direction * 2 * SLN_BN_SYNC_SLOTS + which * SLN_BN_SYNC_SLOTS + (layer's first counter + column block)
+ *   recv[r] + ((slot * world + src_rank) * SLN_BN_SYNC_COLS + col) * 3   (doubles: a, b, rows)
+ * Cross-step reuse of a slot is ordered by the per-step gradient all-reduce. */
+#define SLN_BN_SYNC_MAX_WORLD 8
+#define SLN_BN_SYNC_COLS 128
+#define SLN_BN_SYNC_SLOTS 2304        /* counters of one encoder / decoder workspace */
+typedef struct sln_bn_sync {
+  int32_t world, rank;
+  double* recv[SLN_BN_SYNC_MAX_WORLD];      /* recv[r]: rank r's receive buffer: 4 * SLN_BN_SYNC_SLOTS * world * SLN_BN_SYNC_COLS * 3 doubles */
+  uint32_t* flag[SLN_BN_SYNC_MAX_WORLD];    /* flag[r]: rank r's arrival counters: 4 * SLN_BN_SYNC_SLOTS */
+  uint32_t* use;                            /* this rank's use counters: 4 * SLN_BN_SYNC_SLOTS */
+} sln_bn_sync;
+size_t sln_bn_sync_recv_bytes(int32_t world);     /* bytes of one rank's receive buffer */
+size_t sln_bn_sync_flag_bytes(void);              /* bytes of one rank's flag array (and of `use`) */
 
 /* Parameter table.  `params[i]` / `grads[i]` are device pointers in this canonical order (grads may be NULL
  * for forward-only calls; individual entries may be NULL to skip a gradient):

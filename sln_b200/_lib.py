@@ -88,8 +88,17 @@ class VaeDesc(ctypes.Structure):
         ("n_angle", ctypes.c_int32), ("num_objs", ctypes.c_int32), ("num_preds", ctypes.c_int32),
         ("num_attrs", ctypes.c_int32), ("bn_eps", ctypes.c_float), ("bn_momentum", ctypes.c_float),
         ("gconv_dim_override", ctypes.c_int32), ("gconv_hidden_override", ctypes.c_int32),
-        ("packed_weights", ctypes.c_void_p),
+        ("packed_weights", ctypes.c_void_p), ("bn_sync", ctypes.c_void_p),
     ]
+
+
+BN_SYNC_MAX_WORLD = 8
+
+
+class BnSync(ctypes.Structure):
+    """Mirror of ``sln_bn_sync`` (include/sln_b200.h): the device-resident table of the in-kernel SyncBatchNorm exchange."""
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("recv", ctypes.c_void_p * BN_SYNC_MAX_WORLD),
+                ("flag", ctypes.c_void_p * BN_SYNC_MAX_WORLD), ("use", ctypes.c_void_p)]
 
 
 _P = ctypes.c_void_p
@@ -112,6 +121,8 @@ SIGNATURES = {
     "sln_vae_pack_weights": (ctypes.c_int, [_DESC, _P, _P, _SZ, _P]),
     "sln_vae_workspace_bytes": (_SZ, [_DESC, _I64, _I64, ctypes.c_int]),
     "sln_vae_index_flag_offset": (_I64, [_DESC, _I64, _I64, ctypes.c_int]),
+    "sln_bn_sync_recv_bytes": (_SZ, [_I32]),
+    "sln_bn_sync_flag_bytes": (_SZ, []),
     "sln_vae_encoder_fwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "sln_vae_encoder_bwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _I64, _I64, _P, _SZ, _P]),
     "sln_vae_decoder_fwd": (ctypes.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _SZ, _P]),

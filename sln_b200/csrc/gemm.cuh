@@ -245,6 +245,8 @@ inline DyView make_dy(const float* g, int ldg, int rows, int cols, const float* 
 enum NormMode { NORM_NONE = 0, NORM_BN_TRAIN = 1, NORM_BN_EVAL = 2 };
 
 struct BnFwdFin {  // forward: batch statistics -> scale/shift (+ running stats), reference graph.py:14-15
+  const sln_bn_sync* sync;   // null: per-rank statistics; else SyncBatchNorm over all ranks (include/sln_b200.h)
+  int slot0;                 // sync slot of this layer's column block 0
   int enabled;     // 0: no statistics wanted
   float* partial;  // [row_tiles][2][N]
   unsigned* counter;
@@ -261,7 +263,9 @@ struct BnFwdFin {  // forward: batch statistics -> scale/shift (+ running stats)
   int M;
 };
 
-__device__ __forceinline__ void bn_fwd_apply(const BnFwdFin& f, int col, double s, double q) {
+// (s, q) and M are the GLOBAL sums / row count when statistics are synchronised across ranks
+__device__ __forceinline__ void bn_fwd_apply(const BnFwdFin& f0, int col, double s, double q, int M) {
+  BnFwdFin f = f0; f.M = M;
   double mean = s / f.M;
   double var = q / f.M - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -280,6 +284,8 @@ __device__ __forceinline__ void bn_fwd_apply(const BnFwdFin& f, int col, double 
 }
 
 struct BnBwdFin {  // backward: column sums of g and g*yhat -> (p,q,r) of DyView + parameter gradients
+  const sln_bn_sync* sync;   // null: per-rank statistics (set only for training-mode BatchNorm layers)
+  int slot0;
   int mode;        // NormMode of the layer whose pre-activation gradient is being formed
   float* partial;  // [row_tiles][2][N]
   unsigned* counter;
@@ -296,7 +302,10 @@ struct BnBwdFin {  // backward: column sums of g and g*yhat -> (p,q,r) of DyView
   int M;
 };
 
-__device__ __forceinline__ void bn_bwd_apply(const BnBwdFin& f, int col, double sg, double sgy) {
+// (sg, sgy): this rank's sums -> parameter gradients (the gradient all-reduce sums them over ranks);
+// (sg_all, sgy_all, M): sums / rows over all ranks -> the dy formula of training-mode BatchNorm (equal to the local ones without sync)
+__device__ __forceinline__ void bn_bwd_apply(const BnBwdFin& f0, int col, double sg, double sgy, double sg_all, double sgy_all, int M) {
+  BnBwdFin f = f0; f.M = M;
   if (f.mode == NORM_NONE) {
     if (f.dbias) f.dbias[col] += (float)sg;
     return;
@@ -310,7 +319,7 @@ __device__ __forceinline__ void bn_bwd_apply(const BnBwdFin& f, int col, double 
     return;
   }
   // training-mode BN:  dy = s*(g - c1 - yhat*c2),  yhat = (y-mean)*rstd,  c1 = sum(g)/M, c2 = sum(g*yhat)/M
-  double c1 = sg / f.M, c2 = sgy / f.M;
+  double c1 = sg_all / f.M, c2 = sgy_all / f.M;
   double rs = f.rstd[col], mu = f.mean[col];
   f.p[col] = s;
   f.q[col] = (float)(-(double)s * rs * c2);
@@ -327,9 +336,16 @@ __device__ __forceinline__ void bn_bwd_apply(const BnBwdFin& f, int col, double 
 // other CTAs (a single "last CTA reduces everything" tail cost ~60 us per Linear at config 2).
 constexpr int kCounterStride = 16;   // counters reserved per BatchNorm layer (>= number of column blocks)
 
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// fin(col, S_local, Q_local, S_all, Q_all, rows_all)
 template <int NT, class FinFn>
 __device__ __forceinline__ void finalize_column_block(const float* partial, unsigned* counter, int n0, int ncols, int N, int tid,
-                                                      double* sred, int* s_last, FinFn fin) {
+                                                      double* sred, int* s_last, FinFn fin, const sln_bn_sync* sync = nullptr,
+                                                      int slot0 = 0, int Mlocal = 0) {
   const int tiles = gridDim.y;
   __threadfence();
   __syncthreads();
@@ -365,10 +381,38 @@ __device__ __forceinline__ void finalize_column_block(const float* partial, unsi
   sred[2 * tid] = s;
   sred[2 * tid + 1] = q;
   __syncthreads();
+  double S = 0.0, Q = 0.0;
   if (live && g == 0) {
-    double S = 0.0, Q = 0.0;
     for (int gg = 0; gg < G; ++gg) { S += sred[2 * (gg * W + c)]; Q += sred[2 * (gg * W + c) + 1]; }
-    fin(n0 + c, S, Q);
+  }
+  if (sync == nullptr) {
+    if (live && g == 0) fin(n0 + c, S, Q, S, Q, Mlocal);
+  } else {
+    // SyncBatchNorm: one-shot all-gather of this column block's sums over peer memory (NVLink), reduced in rank order
+    const int world = sync->world, rank = sync->rank;
+    const size_t slot = (size_t)slot0 + blockIdx.x;
+    if (live && g == 0) {
+      for (int r = 0; r < world; ++r) {
+        double* dst = sync->recv[r] + ((slot * world + rank) * SLN_BN_SYNC_COLS + c) * 3;
+        dst[0] = S; dst[1] = Q; dst[2] = (double)Mlocal;
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned expect = (sync->use[slot] += 1u) * (unsigned)world;
+      for (int r = 0; r < world; ++r) atomicAdd_system(sync->flag[r] + slot, 1u);
+      while (ld_acquire_sys(sync->flag[rank] + slot) < expect) { __nanosleep(64); }
+    }
+    __syncthreads();
+    if (live && g == 0) {
+      double Sa = 0.0, Qa = 0.0, Ma = 0.0;
+      for (int r = 0; r < world; ++r) {
+        const volatile double* src = sync->recv[rank] + ((slot * world + r) * SLN_BN_SYNC_COLS + c) * 3;
+        Sa += src[0]; Qa += src[1]; Ma += src[2];
+      }
+      fin(n0 + c, S, Q, Sa, Qa, (int)Ma);
+    }
   }
   if (tid == 0) counter[blockIdx.x] = 0u;
 }
@@ -454,7 +498,7 @@ struct EpiStore {
       __shared__ int s_last;
       const BnFwdFin& f = fin;
       finalize_column_block<NT>(fin.partial, fin.counter, tc.n0, BN, N, tc.tid, reinterpret_cast<double*>(smem), &s_last,
-                                [&](int col, double S, double Q) { bn_fwd_apply(f, col, S, Q); });
+                                [&](int col, double, double, double S, double Q, int Mt) { bn_fwd_apply(f, col, S, Q, Mt); }, f.sync, f.slot0, f.M);
     }
   }
 };
@@ -501,7 +545,7 @@ struct EpiMaskReduce {
     __shared__ int s_last;
     const BnBwdFin& f = fin;
     finalize_column_block<NT>(fin.partial, fin.counter, tc.n0, BN, N, tc.tid, reinterpret_cast<double*>(smem), &s_last,
-                              [&](int col, double S, double Q) { bn_bwd_apply(f, col, S, Q); });
+                              [&](int col, double S, double Q, double Sa, double Qa, int Mt) { bn_bwd_apply(f, col, S, Q, Sa, Qa, Mt); }, f.sync, f.slot0, f.M);
   }
 };
 

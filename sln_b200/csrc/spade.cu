@@ -112,7 +112,10 @@ struct TcEpiSpade {
     o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
     *reinterpret_cast<float4*>(out + (size_t)i * C + c) = o;
   }
-  __device__ __forceinline__ void finalize(int, double, double) const {}
+  __device__ __forceinline__ void finalize(int, double, double, double, double, int) const {}
+  __device__ __forceinline__ const sln_bn_sync* sync() const { return nullptr; }
+  __device__ __forceinline__ int slot0() const { return 0; }
+  __device__ __forceinline__ int rows() const { return 0; }
   __device__ __forceinline__ float* partial() const { return nullptr; }
   __device__ __forceinline__ unsigned* counter() const { return nullptr; }
 };

@@ -90,7 +90,17 @@ struct Ctx {
   cudaStream_t st;
   Dims dm;
   bool side = false;   // weight gradients go to the side stream during this call
+  // SyncBatchNorm (sln_vae_desc.bn_sync): table pointer, first slot of this call (direction / encoder|decoder) and the workspace's
+  // counter base, so that a layer's slot is slot_off + (its counter - cbase)
+  const sln_bn_sync* sync = nullptr;
+  int slot_off = 0;
+  const unsigned* cbase = nullptr;
 };
+inline void ctx_sync(Ctx& c, const sln_vae_desc* d, const unsigned* cbase, int which, int direction) {
+  c.sync = (d->bn_sync && d->norm == 1 && d->training) ? (const sln_bn_sync*)d->bn_sync : nullptr;
+  c.slot_off = (direction * 2 + which) * SLN_BN_SYNC_SLOTS;
+  c.cbase = cbase;
+}
 
 // Decide whether this call uses the side stream (creating it on first use; never created while the caller is capturing).
 void side_begin(Ctx& c) {
@@ -323,6 +333,7 @@ struct NetPlan {
 };
 
 constexpr int kCounterCap = (4 * kMaxLayers + 16) * kCounterStride;
+static_assert(kCounterCap <= SLN_BN_SYNC_SLOTS, "one sync slot per BatchNorm counter");
 
 // which: 0 encoder, 1 decoder, 2 single standalone layer
 void make_plan(const Dims& dm, int O, int T, int which, void* ws, NetPlan* p) {
@@ -385,6 +396,7 @@ int block_fwd(const Ctx& c, const AOp& A, int M, const Blk& b, BlkState& s, floa
     f.running_mean = b.rm; f.running_var = b.rv; f.nbt = b.nbt;
     f.mean = s.mean; f.rstd = s.rstd; f.scale = s.scale; f.shift = s.shift;
     f.eps = c.dm.eps; f.momentum = c.dm.momentum; f.M = M;
+    if (c.sync) { f.sync = c.sync; f.slot0 = c.slot_off + (int)(s.counter - c.cbase); }
   } else if (mode == NORM_BN_EVAL) {
     SLN_CHECK_ARG(b.rm && b.rv, "eval-mode BatchNorm needs running statistics");
     k_bn_eval_prep<<<ceil_div(b.lin.out, 128), 128, 0, c.st>>>(b.gamma, b.beta, b.rm, b.rv, c.dm.eps, b.lin.out, s.mean, s.rstd, s.scale, s.shift);
@@ -414,6 +426,7 @@ BnBwdFin blk_fin(const Ctx& c, const Blk& b, const BlkState& s) {
   f.mode = norm_mode(c, b); f.partial = s.partial; f.counter = s.counter; f.gamma = b.gamma;
   f.mean = s.mean; f.rstd = s.rstd; f.scale = s.scale; f.p = s.p; f.q = s.q; f.r = s.r;
   f.dgamma = b.dgamma; f.dbeta = b.dbeta; f.dbias = b.lin.db; f.M = s.M;
+  if (c.sync && f.mode == NORM_BN_TRAIN) { f.sync = c.sync; f.slot0 = c.slot_off + (int)(s.counter - c.cbase); }
   return f;
 }
 ActInfo blk_act(const Blk& b, const BlkState& s) {
@@ -719,6 +732,11 @@ size_t sln_vae_workspace_bytes(const sln_vae_desc* d, int64_t O, int64_t T, int 
   return p.bytes;
 }
 
+size_t sln_bn_sync_recv_bytes(int32_t world) {
+  return (size_t)4 * SLN_BN_SYNC_SLOTS * (size_t)(world > 0 ? world : 1) * SLN_BN_SYNC_COLS * 3 * sizeof(double);
+}
+size_t sln_bn_sync_flag_bytes(void) { return (size_t)4 * SLN_BN_SYNC_SLOTS * sizeof(uint32_t); }
+
 int64_t sln_vae_index_flag_offset(const sln_vae_desc* d, int64_t O, int64_t T, int which) {
   Dims dm;
   if (make_dims(d, &dm) || check_dims(O, T)) return -1;
@@ -737,6 +755,7 @@ int sln_vae_encoder_fwd(const sln_vae_desc* d, const void* const* params, void* 
   static thread_local Model m; static thread_local NetPlan p;
   SLN_TRY(parse_model(dm, params, nullptr, bn_bufs, &m, d->packed_weights));
   make_plan(dm, O, T, 0, ws, &p);
+  ctx_sync(c, d, p.cp.base, 0, 0);
   SLN_TRY(check_ws(p, ws, ws_bytes));
   SLN_CUDA_TRY(cudaMemsetAsync(p.cp.base, 0, sizeof(unsigned) * kCounterCap, c.st));
   SLN_TRY(graph_prep(c, p, triples, 1));
@@ -778,6 +797,7 @@ int sln_vae_encoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   static thread_local Model m; static thread_local NetPlan p;
   SLN_TRY(parse_model(dm, params, grads, nullptr, &m, d->packed_weights));
   make_plan(dm, O, T, 0, ws, &p);
+  ctx_sync(c, d, p.cp.base, 0, 1);
   SLN_TRY(check_ws(p, ws, ws_bytes));
   side_begin(c);
   const int L = dm.L;
@@ -838,6 +858,7 @@ int sln_vae_decoder_fwd(const sln_vae_desc* d, const void* const* params, void* 
   static thread_local Model m; static thread_local NetPlan p;
   SLN_TRY(parse_model(dm, params, nullptr, bn_bufs, &m, d->packed_weights));
   make_plan(dm, O, T, 1, ws, &p);
+  ctx_sync(c, d, p.cp.base, 1, 0);
   SLN_TRY(check_ws(p, ws, ws_bytes));
   SLN_CUDA_TRY(cudaMemsetAsync(p.cp.base, 0, sizeof(unsigned) * kCounterCap, c.st));
   SLN_TRY(graph_prep(c, p, triples, 1));
@@ -872,6 +893,7 @@ int sln_vae_decoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   static thread_local Model m; static thread_local NetPlan p;
   SLN_TRY(parse_model(dm, params, grads, nullptr, &m, d->packed_weights));
   make_plan(dm, O, T, 1, ws, &p);
+  ctx_sync(c, d, p.cp.base, 1, 1);
   SLN_TRY(check_ws(p, ws, ws_bytes));
   side_begin(c);
   const int L = dm.L;

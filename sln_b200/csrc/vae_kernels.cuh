@@ -453,7 +453,8 @@ __global__ void __launch_bounds__(512) k_prep(const Src src, const ActInfo act, 
   const int tid = threadIdx.y * 128 + threadIdx.x;
   __shared__ double sred[2 * 512];
   finalize_column_block<512>(fin.partial, fin.counter, blockIdx.x * 128, 128, N, tid, sred, &s_last,
-                             [&](int col, double S, double Q) { bn_bwd_apply(fin, col, S, Q); });
+                             [&](int col, double S, double Q, double Sa, double Qa, int Mt) { bn_bwd_apply(fin, col, S, Q, Sa, Qa, Mt); },
+                             fin.sync, fin.slot0, fin.M);
 }
 
 template <class Src>

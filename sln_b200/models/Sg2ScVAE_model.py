@@ -242,6 +242,7 @@ class Sg2ScVAEModel(nn.Module):
                   self.angle_mean, self.angle_var, self.box_net):
             m.apply(_init_weights)
 
+        self._bn_sync = None              # utils.enable_sync_batchnorm(): cross-rank BatchNorm statistics (SyncBatchNorm)
         self.check_indices = "first"      # "first" | True | False: see _check_index_flag
         self._idx_checked = set()
         self._cache = None   # (params ptr table, bn ptr table, param list, enc/dec slot lists)
@@ -343,7 +344,8 @@ class Sg2ScVAEModel(nn.Module):
                             num_objs=self.obj_embeddings_ec.num_embeddings, num_preds=self.pred_embeddings_ec.num_embeddings,
                             num_attrs=self.attr_embedding_ec.num_embeddings,
                             bn_eps=self._bn_cfg[0], bn_momentum=self._bn_cfg[1],
-                            gconv_dim_override=0, gconv_hidden_override=0)
+                            gconv_dim_override=0, gconv_hidden_override=0,
+                            bn_sync=self._bn_sync.table.data_ptr() if getattr(self, "_bn_sync", None) is not None else None)
 
     def _get_anchor(self, dev):
         if self._anchor is None or self._anchor.device != dev:

@@ -217,6 +217,49 @@ class FusedAdam(torch.optim.Optimizer):
         return loss
 
 
+# ---------------------------------------------------------------------------------------------- SyncBatchNorm (multi-GPU policy P1)
+class BnSyncTable(object):
+    """Peer-mapped buffers + the device table (``sln_bn_sync``, include/sln_b200.h) of the in-kernel SyncBatchNorm exchange.
+
+    Every rank allocates one symmetric buffer [receive area | arrival flags] (torch.distributed._symmetric_memory: CUDA VMM
+    allocations mapped into every peer over NVLink), zeroes it, and records all ranks' addresses in a small device struct that the
+    BatchNorm-finalising kernels read.  No NCCL call happens on the data path afterwards."""
+
+    def __init__(self, device, group=None):
+        import ctypes
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        lib = _lib.load()
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.BN_SYNC_MAX_WORLD:
+            raise ValueError("in-kernel SyncBatchNorm supports up to %d ranks of one NVLink domain" % _lib.BN_SYNC_MAX_WORLD)
+        nrecv, nflag = lib.sln_bn_sync_recv_bytes(self.world), lib.sln_bn_sync_flag_bytes()
+        self.buf = symm_mem.empty(nrecv + nflag, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group.group_name if hasattr(group, "group_name") else group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.use = torch.zeros(nflag // 4, dtype=torch.int32, device=device)
+        t = _lib.BnSync()
+        t.world, t.rank = self.world, self.rank
+        for r in range(self.world):
+            t.recv[r] = ptrs[r]
+            t.flag[r] = ptrs[r] + nrecv
+        t.use = self.use.data_ptr()
+        self.table = torch.frombuffer(bytearray(bytes(t)), dtype=torch.uint8).clone().to(device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)               # every rank's buffer is zeroed before any peer can write into it
+
+
+def enable_sync_batchnorm(model, group=None):
+    """Training-mode BatchNorm statistics of `model` (Sg2ScVAEModel) become global over the process group — SURVEY 8e policy P1: the
+    N-GPU sharded step equals the 1-GPU step at the global batch (the reference's nn.BatchNorm1d normalises over all rows of the
+    batch, models/graph.py:14-15).  Returns the BnSyncTable (keep it alive as long as the model trains)."""
+    dev = next(model.parameters()).device
+    model._bn_sync = BnSyncTable(dev, group)
+    return model._bn_sync
+
+
 # ---------------------------------------------------------------------------------------------- fused train step
 class VAETrainStep(object):
     """The reference train-loop body (train.py:69-84) for a fixed batch shape, replayed as a CUDA graph.
@@ -228,9 +271,17 @@ class VAETrainStep(object):
     """
 
     def __init__(self, model, O, T, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, kl_weight=0.1, use_graph=True, process_group=None,
-                 world_size=1, sample_eps=True, pack_weights=True, wire_meta=None):
+                 world_size=1, sample_eps=True, pack_weights=True, wire_meta=None, bn_policy="local"):
+        """bn_policy: 'local' = per-rank BatchNorm statistics (DDP semantics, SURVEY 8e P2: no extra communication);
+        'sync' = statistics over all ranks, exchanged inside the finalising kernels over NVLink peer memory (P1: the sharded step
+        equals the single-GPU step on the global batch)."""
         self.lib = _lib.load()
         self.model = model
+        if bn_policy not in ("local", "sync"):
+            raise ValueError("bn_policy must be 'local' or 'sync'")
+        self.bn_policy = bn_policy
+        if bn_policy == "sync" and world_size > 1 and getattr(model, "_bn_sync", None) is None:
+            enable_sync_batchnorm(model, process_group)
         dev = next(model.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError("VAETrainStep needs a CUDA model")
