@@ -256,12 +256,14 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def vae_config(n):
+def vae_config(n, bn_policy="local"):
+    bn_note = "per-rank BatchNorm statistics" if bn_policy == "local" or n == 1 else "SyncBatchNorm inside the finalising kernels over NVLink peer memory"
     return {"workload": "BASELINE configs[1]: VAE-graph train step, %d scenes x %d nodes per GPU (O=%d, T=%d per GPU), embedding_dim=64, "
                         "5+5 GraphTripleConv layers, mlp_normalization=batch, Adam lr 1e-4" % (
                             SCENES_PER_GPU, NODES_PER_SCENE, SCENES_PER_GPU * NODES_PER_SCENE, SCENES_PER_GPU * (NODES_PER_SCENE - 1) * 2),
-            "global_batch_scenes": SCENES_PER_GPU * n, "parallelism": "dp%d (scene-sharded, NCCL all-reduce of one flat 15.5 MB gradient arena; "
-                                                                     "per-rank BatchNorm statistics)" % n,
+            "global_batch_scenes": SCENES_PER_GPU * n, "parallelism": "dp%d (scene-sharded; NCCL all-reduce of the 15.5 MB gradient arena in two buckets, the decoder's in flight "
+                                                                     "during the encoder's backward pass, captured inside the step graph; %s)" % (
+                                                                         n, bn_note),
             "l2": "L2 flushed (256 MiB write) before every timed step"}
 
 
@@ -293,7 +295,8 @@ def run_vae(args):
     collate = importlib.import_module("sln_b200.data.collate")
     wire, wire_meta = collate.packed_batch(syn.synthetic_samples(SCENES_PER_GPU, NODES_PER_SCENE, seed=42 + rank), lib)
     h2d = int(wire_meta[4][9])
-    step = sutils.VAETrainStep(model, O, T, lr=1e-4, kl_weight=0.1, use_graph=True, process_group=pg, world_size=world, wire_meta=wire_meta)
+    step = sutils.VAETrainStep(model, O, T, lr=1e-4, kl_weight=0.1, use_graph=True, process_group=pg, world_size=world, wire_meta=wire_meta,
+                               bn_policy=args.bn_policy if world > 1 else "local")
     step.load_batch(host)
     n0 = lib.sln_launch_count()
     step._fwd_bwd(); step._allreduce(); step._opt()
@@ -340,15 +343,18 @@ def run_vae(args):
         dev_ms, e2e_s = t.tolist()
     # ---- roofline: one un-graphed step with an event pair around every launch of the library
     prof = None
-    if rank == 0:
+    sync_bn = world > 1 and args.bn_policy == "sync"
+    if rank == 0 or sync_bn:     # under SyncBatchNorm the kernels of every rank wait for each other: all ranks run the pass
         barrier_local = lambda: torch.cuda.synchronize(dev)   # noqa: E731
         rows = {}
         reps = 3
-        lib.sln_prof_enable(1)
+        lib.sln_prof_enable(1 if rank == 0 else 0)
+        step.overlap_allreduce = False       # no NCCL collective is issued from this pass (rank 0 may be alone in it)
         for _ in range(reps):
             flush.zero_()
             step._fwd_bwd(); step._opt()
         barrier_local()
+    if rank == 0:
         total_ms = 0.0
         for ci, cname in enumerate(PROF_CLASSES):
             ms, work, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
@@ -418,7 +424,7 @@ def run_vae(args):
     line = {
         "metric": "scene-graphs/sec VAE train step (batch64, 32obj)", "value": value, "unit": "scene-graphs/s", "n_gpus": n,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": vae_config(n),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": vae_config(n, args.bn_policy),
         "e2e": {"value": e2e, "unit": "scene-graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16},
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "roofline": roofline, "roofline_scatter": roofline_scatter, "cpu_baseline": cpu, "eager_gpu_baseline": eager, "clocks": clocks,
@@ -571,6 +577,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="vae", choices=["vae", "render", "spade"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bn-policy", default="local", choices=["local", "sync"],
+                    help="N > 1: per-rank BatchNorm statistics (P2, default) or SyncBatchNorm inside the kernels over NVLink (P1)")
     ap.add_argument("--no-extra", action="store_true", help="vae workload: skip the render / spade sub-records")
     ap.add_argument("--no-graph", action="store_true", help="render workload: run the refinement iteration eagerly instead of as a CUDA graph")
     args = ap.parse_args()

@@ -277,6 +277,10 @@ class VAETrainStep(object):
         equals the single-GPU step on the global batch)."""
         self.lib = _lib.load()
         self.model = model
+        # overlap_allreduce: two gradient buckets (decoder | encoder), the first in flight during the encoder's backward pass, and the
+        # whole step (kernels + NCCL) captured as ONE graph; False = one all-reduce between a forward/backward graph and an Adam graph
+        self.overlap_allreduce = True
+        self._pending = []
         if bn_policy not in ("local", "sync"):
             raise ValueError("bn_policy must be 'local' or 'sync'")
         self.bn_policy = bn_policy
@@ -387,6 +391,13 @@ class VAETrainStep(object):
                                         self.loss_scratch.data_ptr(), self.loss_scratch.numel() * 4, st), "vae_loss")
         _lib.check(lib.sln_vae_decoder_bwd(desc, params, grads, self.d_boxes.data_ptr(), self.d_logits.data_ptr(), 1, self.d_z.data_ptr(),
                                            O, T, self.ws_dec.data_ptr(), self.ws_dec.numel(), st), "decoder_bwd")
+        self._pending = []
+        if self.world_size > 1 and self.overlap_allreduce:
+            # the decoder's gradients are final half a backward pass before the encoder's: their bucket goes out now, on NCCL's own
+            # stream, and crosses NVLink while sln_vae_encoder_bwd runs (a parallel branch of the captured graph)
+            import torch.distributed as dist
+            lo, hi = self.sink.ranges['dec']
+            self._pending.append(dist.all_reduce(self.sink.flat[lo:hi], group=self.pg, async_op=True))
         if use_kl:
             _lib.check(lib.sln_reparam_bwd(self.d_z.data_ptr(), self.logvar.data_ptr(), self.epsn.data_ptr(), O * E, self.d_mu.data_ptr(),
                                            self.d_logvar.data_ptr(), st), "reparam_bwd")
@@ -473,7 +484,14 @@ class VAETrainStep(object):
     def _allreduce(self):
         if self.world_size > 1:
             import torch.distributed as dist
-            dist.all_reduce(self.sink.flat, group=self.pg)
+            if self.overlap_allreduce:
+                lo, hi = self.sink.ranges['enc']
+                self._pending.append(dist.all_reduce(self.sink.flat[lo:hi], group=self.pg, async_op=True))
+                for w in self._pending:
+                    w.wait()              # the current stream waits for NCCL's stream (an event edge, also under capture)
+                self._pending = []
+            else:
+                dist.all_reduce(self.sink.flat, group=self.pg)
 
     def capture(self):
         """Warm up on a side stream, then capture forward+backward (and Adam) into CUDA graphs."""
@@ -488,6 +506,19 @@ class VAETrainStep(object):
         self.check_indices_pending = True
         if not self.use_graph:
             return self
+        if self.world_size > 1 and self.overlap_allreduce:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._fwd_bwd(); self._allreduce(); self._opt()
+                self.graph_fb, self.graph_opt, self.single_graph = g, None, True
+                return self
+            except RuntimeError as e:          # NCCL capture unavailable in this build: fall back to graph | all-reduce | graph
+                import warnings
+                warnings.warn("VAETrainStep: capturing NCCL inside the step graph failed (%s); using the two-graph path" % (str(e)[:200],))
+                torch.cuda.synchronize(self.dev)
+                self.overlap_allreduce = False
+        self.single_graph = self.world_size == 1
         self.graph_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_fb):
             self._fwd_bwd()
@@ -520,7 +551,7 @@ class VAETrainStep(object):
     def _run(self):
         if self.graph_fb is not None:
             self.graph_fb.replay()
-            if self.world_size > 1:
+            if self.graph_opt is not None:
                 self._allreduce()
                 self.graph_opt.replay()
         else:
