@@ -139,7 +139,14 @@ def run(args):
     cpu = None
     if n == 1 and not args.no_cpu_baseline:
         cpu = cpu_render_baseline(budget_s=25.0)
+    ref60 = None
+    if n == 1:
+        try:
+            ref60 = reference60(dev)
+        except Exception as e:      # secondary variant: never fail the bench line because of it
+            ref60 = {"unavailable": repr(e)[:300]}
     return {
+        "reference60": ref60,
         "metric": METRIC, "value": n * 1e3 / ms_per_step, "unit": "iters/s", "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": _config(n), "e2e": {"value": n * args.steps / e2e_s, "unit": "iters/s", "h2d_bytes_per_step": 11 * 6 * 4 + 11 * 4, "d2h_bytes_per_step": 4,
@@ -147,6 +154,40 @@ def run(args):
         "gpu_launches": launches_per_iter * args.steps, "launches_per_step": launches_per_iter, "roofline": roofline, "cpu_baseline": cpu,
         "clocks": clocks, "kernel_classes_ms": {k: round(v["ms"], 4) for k, v in prof.items()}, "first_loss": first, "loss_after_timed_iters": loss_after_value_loop,
     }
+
+
+def reference60(dev, iters=60):
+    """the reference's OWN loop (test_render_refine.py:279-359) — z -> decoder (eval BatchNorm) -> hooks -> softargmax +
+    jitter -> render -> loss -> backward through the decoder -> re-created nesterov SGD on z and the parameters, 60 iterations, one
+    CUDA-graph replay each (ReferenceRefineStep).  Seeded random-init Sg2ScVAEModel (no checkpoint offline), 10 objects + room."""
+    syn = importlib.import_module("sln_b200.data.synthetic")
+    Model = importlib.import_module("sln_b200.models.Sg2ScVAE_model").Sg2ScVAEModel
+    refine = importlib.import_module("sln_b200.models.refine")
+    boxes, angles, objs, _, _ = _scene(dev, seed=13)
+    n = objs.numel()
+    torch.manual_seed(42)
+    model = Model(syn.default_vocab(), embedding_dim=64, batch_size=128, train_3d=True, decoder_cat=True, gconv_mode='feedforward',
+                  gconv_num_layers=5, mlp_normalization='batch', vec_noise_dim=0, layout_noise_dim=32, use_AE=False).float().to(dev).eval()
+    refine.bias_box_head(model)      # no trained checkpoint offline: make the random-init decoder's boxes visible (all objects render)
+    triples = torch.tensor([[i, 0, n - 1] for i in range(n - 1)] + [[i, 1 + i % 9, (i + 1) % (n - 1)] for i in range(n - 1)], dtype=torch.long, device=dev)
+    attrs = torch.zeros(n, dtype=torch.long, device=dev)
+    torch.manual_seed(13)                                     # test_render_refine.py:274
+    z = torch.randn(n, 64, device=dev)
+    step = refine.ReferenceRefineStep(model, z, objs.to(dev), triples, attrs, boxes, angles, lr_z=2e-4, lr_model=1e-5, noise=True, use_graph=True)
+    for _ in range(3):
+        step.step()
+    torch.cuda.synchronize(dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    first = None
+    for a, b in evs:
+        a.record(); loss = step.step(); b.record()
+        if first is None:
+            first = float(loss)
+    torch.cuda.synchronize(dev)
+    ms = sum(a.elapsed_time(b) for a, b in evs) / iters
+    return {"ms_per_iter": ms, "iters_per_s": 1e3 / ms, "iterations": iters, "first_loss": first, "last_loss": float(loss),
+            "what": "reference loop variant: decoder (5 gconv layers, eval BatchNorm) inside the graph, SGD(nesterov, momentum 0.1, stateless) on z "
+                    "[11,64] lr 2e-4 and on the decoder parameters lr 1e-5; CUDA events around each graph replay"}
 
 
 def cpu_render_baseline(budget_s=25.0):

@@ -275,3 +275,121 @@ class RefineStep(object):
         else:
             self._iteration()
         return self.loss
+
+
+def bias_box_head(model, box=(0.3, 0.0, 0.3, 0.6, 0.4, 0.6), weight_scale=0.1):
+    """Synthetic stand-in for a trained checkpoint (none is available offline): a random-init decoder predicts boxes around 0 with
+    non-positive sizes, which render nothing and give the refinement loop no gradient.  Shrink the box head's last Linear and set its
+    bias to a visible box, so that every object renders and d loss / d z is non-trivial.  Benchmarks and tests only."""
+    last = [m for m in model.box_net if isinstance(m, torch.nn.Linear)][-1]
+    with torch.no_grad():
+        last.weight.mul_(weight_scale)
+        last.bias.copy_(torch.tensor(box, dtype=last.bias.dtype, device=last.bias.device))
+    return model
+
+
+class ReferenceRefineStep(object):
+    """The reference's OWN refinement iteration (testing/test_render_refine.py:279-359), one CUDA-graph replay per iteration:
+
+        z (leaf) -> model.decoder(z, objs, triples, attributes) [eval-mode BatchNorm]            :287
+        boxes_pred.register_hook(fix_grad); boxes_pred[-1] = boxes_gt[-1]                         :288-291
+        angles = softargmax(angles_pred, 1) + randn(n) / 10; register_hook(quad_grad); [-1] = gt  :293-298
+        render (scene assembly, ONE rasterization, compositing)                                   :324
+        null-fill, PSP pyramids, 100 * depth + 100 * semantic + 2 * size loss                     :332-352
+        backward THROUGH THE DECODER to z and to the model parameters                             :356
+        SGD(nesterov, momentum 0.1) re-created every iteration (:286) => stateless: p -= lr * 1.1 * grad,
+            lr = 2e-4 for z, learning_rate / 10 for the parameters                                :286,357
+
+    (RefineStep above optimises the layout itself with Adam — BASELINE.json configs[2]; this class is the loop the reference runs.)
+    The gradient hooks are applied inside the scene-assembly backward kernel; the size targets are the object sizes of the first
+    render of the prediction (:325-328), the target image is the render of the ground-truth layout (:318-321)."""
+
+    def __init__(self, model, z, objs, triples, attributes, boxes_gt, angles_gt, lr_z=2e-4, lr_model=1e-5, noise=True, use_graph=True,
+                 library=None, update_model=True):
+        from . import diff_render as dr
+        dev = z.device
+        if dev.type != "cuda":
+            raise RuntimeError("ReferenceRefineStep runs on CUDA only (no CPU fallback)")
+        if model.training:
+            raise RuntimeError("ReferenceRefineStep: the reference refines with model.eval() (test_render_refine.py:264)")
+        self._dr, self.model, self.dev = dr, model, dev
+        self.objs, self.triples, self.attrs = objs.to(dev), triples.to(dev), attributes.to(dev)
+        self.boxes_gt, self.angles_gt = boxes_gt.to(dev).float(), angles_gt.to(dev).float()
+        lib = library if library is not None else dr.mesh_library(dev)
+        self.static = dr.SceneStatic(objs, self.boxes_gt[-1], lib, dev)
+        with torch.no_grad():
+            target, _ = dr.render_static(self.static, self.boxes_gt, self.angles_gt, fused=True)          # "Rendering gt" :318-321
+        self.t_depth, self.t_labels = refine_targets(target)
+        self.fused_loss = FusedRefineLoss(self.t_depth, self.t_labels)
+        self.z = z.detach().clone().float().requires_grad_(True)
+        self.noise_on = bool(noise)
+        self.noise = torch.zeros(objs.size(0), device=dev)
+        self.lr_z, self.lr_model, self.update_model = float(lr_z), float(lr_model), bool(update_model)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.loss = torch.zeros((), device=dev)
+        self.boxes_pred = torch.zeros(objs.size(0), 6, device=dev)
+        self.angles_pred = torch.zeros(objs.size(0), device=dev)
+        with torch.no_grad():                                                                            # size targets = first render of the prediction
+            b, a = self._layout(sample_noise=False)
+            _, size = dr.render_static(self.static, b, a, fused=True)
+        self.size_target = size.detach().clone()
+        self.graph = None
+        if use_graph:
+            self.capture()
+
+    def _layout(self, sample_noise=True):
+        boxes_pred, angles_pred = self.model.decoder(self.z, self.objs, self.triples, self.attrs)
+        n = boxes_pred.size(0)
+        boxes = torch.cat([boxes_pred[:-1], self.boxes_gt[-1:]], 0)                                      # boxes_pred[-1] = boxes_gt[-1]
+        ang = softargmax(angles_pred, sum_dim=1)
+        if self.noise_on and sample_noise:
+            self.noise.normal_()
+            ang = ang + self.noise / 10.0
+        ang = torch.cat([ang[:-1], self.angles_gt[-1:]], 0)                                              # angles_pred_idx2[-1] = angles[-1]
+        return boxes, ang
+
+    def _iteration(self):
+        boxes, ang = self._layout()
+        image, size = self._dr.render_static(self.static, boxes, ang, fused=True, refine_hooks=True)     # hooks fused into the assembly backward
+        loss = self.fused_loss(image) + _SizeLossFn.apply(size, self.size_target, 2.0)
+        if self.z.grad is not None:
+            self.z.grad.zero_()
+        for p in self.params:                                                                            # optimizer.zero_grad() :355
+            if p.grad is not None:
+                p.grad.zero_()
+        loss.backward()
+        with torch.no_grad():
+            # torch.optim.SGD(nesterov=True, momentum=0.1) with a FRESH momentum buffer: buf = g, update = g + 0.1 * buf
+            self.z.add_(self.z.grad, alpha=-self.lr_z * 1.1)
+            if self.update_model:
+                ps = [p for p in self.params if p.grad is not None]
+                if ps:
+                    torch._foreach_add_(ps, [p.grad for p in ps], alpha=-self.lr_model * 1.1)
+            self.loss.copy_(loss.detach())
+            self.boxes_pred.copy_(boxes.detach()); self.angles_pred.copy_(ang.detach())
+
+    def capture(self):
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        z0 = self.z.detach().clone()
+        p0 = [p.detach().clone() for p in self.params]
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._iteration()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._iteration()
+        with torch.no_grad():                                  # undo the warm-up / capture iterations
+            self.z.copy_(z0)
+            for p, q in zip(self.params, p0):
+                p.copy_(q)
+        return self
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._iteration()
+        return self.loss
