@@ -8,6 +8,10 @@
 // interleaved weight rows whose epilogue (TcEpiSpade) computes lrelu(x_hat * (1 + gamma) + beta) directly: gamma and beta
 // never reach HBM (they are 61 % of the generator's FLOPs and would be 2 x C x H x W floats per SPADE4 otherwise).
 #include "../../include/sln_b200.h"
+// The convolutions run 128 x 128 tiles over K = 1152 .. 9216 (multi-segment accumulation: 64 extra registers per thread); at 16
+// producer warps ptxas is held to 96 registers and spills in exactly those variants (measured: 346 -> 332 images/s).  This
+// translation unit keeps 8 producer warps; the VAE engine (small tiles, short K) takes 16 (3.44 -> 3.15 ms per train step).
+#define SLN_TC_PROD_WARPS 8
 #include "gemm.cuh"
 #include "tc_gemm.cuh"
 

@@ -24,7 +24,13 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 32;            // floats per K chunk: 128 bytes = one SWIZZLE_128B row
-constexpr int PROD_WARPS = 8;               // producer / epilogue warps
+#ifndef SLN_TC_PROD_WARPS
+#define SLN_TC_PROD_WARPS 16
+#endif
+// producer / epilogue warps.  16 (4 per SM sub-partition): with 8 the producer instruction stream (operand transform, hi/lo split,
+// index arithmetic: ~2000 warp-instructions per 32-k chunk) ran 2 warps per scheduler and was latency-bound — ncu on the largest
+// SPADE kernel: issue slots 32 % busy, top stalls `wait` / `long_scoreboard`, tensor pipe 39 % (profiles/r2_prof_tc_spade_*).
+constexpr int PROD_WARPS = SLN_TC_PROD_WARPS;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int MMA_WARP = PROD_WARPS;        // the ninth warp issues the tcgen05.mma stream
 constexpr int THREADS = PROD_THREADS + 32;
@@ -175,38 +181,49 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 // the last chunk (CHECK == true) is zeroed.
 template <int ROWS, bool RC, class Op>
 struct LoaderBuf {   // the registers holding one fetched chunk (PF of these per operand)
-  static constexpr int NV = ROWS * BK / 4 / PROD_THREADS;   // quads per thread per chunk
+  static constexpr int NVR = ROWS * BK / 4 / PROD_THREADS;  // quads per thread per chunk (0: the tile has fewer quads than threads)
+  static constexpr int NV = NVR > 0 ? NVR : 1;
   float4 ra[NV], rb[NV];
   typename Op::Tok ktok;               // RC == false: the token of this chunk's k-row
 };
 template <int ROWS, bool RC, class Op>
 struct Loader {      // per-thread loop invariants, shared by all register buffers
-  static constexpr int NV = ROWS * BK / 4 / PROD_THREADS;
-  static_assert(NV >= 1, "tile too small for 256 loader threads");
+  static constexpr int NVR = ROWS * BK / 4 / PROD_THREADS;
+  static constexpr int NV = NVR > 0 ? NVR : 1;
+  static constexpr int ACTIVE = NVR > 0 ? PROD_THREADS : ROWS * BK / 4;   // threads that own a quad (small B tiles: the first ROWS * 8)
+  static constexpr int RPP = ACTIVE / 8;               // RC: tile rows covered per pass (quad i: + RPP rows)
+  static constexpr int KB = ACTIVE / 256 > 0 ? ACTIVE / 256 : 1;   // !RC: 32-row blocks covered per pass by the 32 k-rows x 8 row-quads
   using Buf = LoaderBuf<ROWS, RC, Op>;
   typename Op::Tok tok[RC ? NV : 1];   // RC: one token per owned tile row
   int col[RC ? 1 : NV];                // !RC: clamped storage column of quad i
-  uint32_t soff;                       // byte offset of quad 0 inside the tile (quad i: + 4096 i)
+  uint32_t soff;                       // byte offset of quad 0 inside the tile
+  bool active;
   __device__ __forceinline__ void init(const Op& op, int row0, int tid) {
-    if (RC) soff = sw128(tid >> 3, (tid & 7) * 4);                                   // K-major SWIZZLE_128B: (row, k-quad)
-    else soff = (uint32_t)((tid >> 3) * 128 + (((((tid & 7) >> 1) ^ ((tid >> 3) & 3)) << 5) | ((tid & 1) << 4)));   // MN-major 128B_BASE32B: (k-row, row-quad)
+    active = tid < ACTIVE;
+    const int t = active ? tid : 0;
     if (RC) {
+      soff = sw128(t >> 3, (t & 7) * 4);                                   // K-major SWIZZLE_128B: (row, k-quad); quad i: + RPP rows
 #pragma unroll
-      for (int i = 0; i < NV; ++i) tok[i] = op.token(row0 + (tid >> 3) + 32 * i);
+      for (int i = 0; i < NV; ++i) tok[i] = op.token(row0 + (t >> 3) + RPP * i);
     } else {
+      // MN-major 128B_BASE32B: thread = (k-row kr = (t >> 3) & 31, row-quad t & 7, 32-row block t >> 8); quad i: block + KB i
+      const int kr = (t >> 3) & 31, blk = t >> 8;
+      soff = (uint32_t)(kr * 128 + (((((t & 7) >> 1) ^ (kr & 3)) << 5) | ((t & 1) << 4))) + (uint32_t)blk * 4096u;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) col[i] = op.clampc(row0 + 32 * i + 4 * (tid & 7));
+      for (int i = 0; i < NV; ++i) col[i] = op.clampc(row0 + 32 * (blk + KB * i) + 4 * (t & 7));
     }
   }
+  static constexpr uint32_t QSTEP = RC ? (uint32_t)RPP * 128u : (uint32_t)KB * 4096u;   // tile bytes between a thread's consecutive quads
   template <bool CHECK>
   __device__ __forceinline__ void fetch(const Op& op, Buf& b, int k0, int kend, int tid) const {
+    if (!active) return;
     if (RC) {
       int k = k0 + (tid & 7) * 4;
       if (CHECK) k = min(k, kend - 4);
 #pragma unroll
       for (int i = 0; i < NV; ++i) op.fetch4(tok[i], k, b.ra[i], b.rb[i]);
     } else {
-      int k = k0 + (tid >> 3);
+      int k = k0 + ((tid >> 3) & 31);
       if (CHECK) k = min(k, kend - 1);
       b.ktok = op.token(k);
 #pragma unroll
@@ -216,6 +233,7 @@ struct Loader {      // per-thread loop invariants, shared by all register buffe
   // (k0, kend, CHECK) must be the ones passed to the matching fetch()
   template <bool CHECK>
   __device__ __forceinline__ void store(const Op& op, const Buf& b, int k0, int kend, uint32_t hi_tile, uint32_t lo_tile, int tid) const {
+    if (!active) return;
     if (RC) {
       const int k = k0 + (tid & 7) * 4;
       const bool valid = !CHECK || k < kend;
@@ -224,15 +242,15 @@ struct Loader {      // per-thread loop invariants, shared by all register buffe
       for (int i = 0; i < NV; ++i) {
         float4 v = op.finish4(tok[i], kc, b.ra[i], b.rb[i]);
         if (CHECK && !valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
-        split_store4(hi_tile + soff + i * 4096, lo_tile + soff + i * 4096, v);
+        split_store4(hi_tile + soff + i * QSTEP, lo_tile + soff + i * QSTEP, v);
       }
     } else {
-      const bool valid = !CHECK || (k0 + (tid >> 3)) < kend;
+      const bool valid = !CHECK || (k0 + ((tid >> 3) & 31)) < kend;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         float4 v = op.finish4(b.ktok, col[i], b.ra[i], b.rb[i]);
         if (CHECK && !valid) v = make_float4(0.f, 0.f, 0.f, 0.f);
-        split_store4(hi_tile + soff + i * 4096, lo_tile + soff + i * 4096, v);
+        split_store4(hi_tile + soff + i * QSTEP, lo_tile + soff + i * QSTEP, v);
       }
     }
   }
@@ -334,7 +352,7 @@ struct SmemLayout {
   static constexpr int B_TILE = BN * 128;
   static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
   static constexpr int STAGES = BN >= 128 ? 3 : 4;     // 192 KB / 192 KB / 160 KB of operand ring
-  static constexpr int STAT = 2 * 8 * BN * 4;          // per-warp column statistics [2][8 warps][BN]
+  static constexpr int STAT = 2 * PROD_WARPS * BN * 4;  // per-warp column statistics [2][PROD_WARPS][BN]
   static constexpr int OUT_LD = BN + 4;                // floats per staged accumulator row
   static_assert(BM * OUT_LD * 4 <= STAGES * STAGE, "accumulator staging must fit the (idle) stage buffers");
   static constexpr int NBARS = 2 * STAGES + 4;         // full[S] empty[S] segfull[2] accempty[2]
@@ -441,7 +459,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   const int quad = warp & 3, half = (warp >> 2) & 1;    // TMEM lane quadrant (fixed by warp id % 4), column half
   // BN >= 64: warps 0-3 own the left half of the columns, warps 4-7 the right half; BN = 32: only warps 0-3 hold accumulators
   constexpr int CH2 = BN >= 64 ? BN / 64 : 1;           // 32-column chunks owned by one thread
-  const bool has_acc = warp < PROD_WARPS && (BN >= 64 || half == 0);
+  const bool has_acc = warp < 8 && (BN >= 64 || half == 0);     // warps 0-7 read the accumulators (quadrant x column half); all producer warps apply the epilogue
   const int col_off = BN >= 64 ? half * (BN / 2) : 0;
   const uint32_t tmem_mine = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_off;
   float racc[MSEG ? CH2 : 1][32];      // MSEG: running sum over the drained segments (otherwise the sum is formed in the epilogue)
@@ -639,7 +657,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
       }
       if (rsub == 0) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { stat[(0 * 8 + warp) * BN + cq * 4 + e] = s1[e]; stat[(1 * 8 + warp) * BN + cq * 4 + e] = s2[e]; }
+        for (int e = 0; e < 4; ++e) { stat[(0 * PROD_WARPS + warp) * BN + cq * 4 + e] = s1[e]; stat[(1 * PROD_WARPS + warp) * BN + cq * 4 + e] = s2[e]; }
       }
     }
     __syncthreads();
@@ -648,7 +666,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
       if (n0 + j < N) {
         float a = 0.f, b = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { a += stat[(0 * 8 + w) * BN + j]; b += stat[(1 * 8 + w) * BN + j]; }
+        for (int w = 0; w < PROD_WARPS; ++w) { a += stat[(0 * PROD_WARPS + w) * BN + j]; b += stat[(1 * PROD_WARPS + w) * BN + j]; }
         partial[((size_t)blockIdx.y * 2 + 0) * N + n0 + j] = a;
         partial[((size_t)blockIdx.y * 2 + 1) * N + n0 + j] = b;
       }
