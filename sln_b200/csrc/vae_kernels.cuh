@@ -337,7 +337,7 @@ inline void launch_pool_fwd(cudaStream_t st, const MatView& a2, const int* row_p
   PoolPlan p = pool_plan(a2, O, H, D);
   if (p.V == 4 && p.batch == 16) k_pool_fwd<4, 16, 1><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);
   else if (p.V == 4 && p.batch == 4) k_pool_fwd<4, 4, 4><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);
-  else if (p.V == 4) k_pool_fwd<4, 8, 3><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);
+  else if (p.V == 4) k_pool_fwd<4, 8, 4><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);   // <= 64 registers: 4 CTAs / SM
   else if (p.V == 2) k_pool_fwd<2, 16, 3><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);
   else k_pool_fwd<1, 32, 4><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);
 }
