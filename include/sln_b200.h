@@ -358,9 +358,33 @@ size_t sln_packed_weights_bytes(int64_t N, int64_t K);
 int sln_pack_weights(const float* W, int64_t N, int64_t K, float* out, void* stream);
 int sln_spade_conv(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, const float* Wp, const float* Wpacked,
                    const float* bias, int64_t Cout, float* out, void* stream);
+/* The same implicit-GEMM convolution with the padding selectable: pad_mode 0 = ReflectionPad2d(1) (SPADE4 / SPADEResnetBlock4,
+ * reference SPADE_related.py:9-14,1429-1436), 1 = zeros = nn.Conv2d(kernel_size=3, padding=1) of the plain SPADE / SPADEResnetBlock
+ * (:261-263,322-326). */
+int sln_conv2d_nhwc(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, int32_t pad_mode,
+                    const float* Wp, const float* Wpacked, const float* bias, int64_t Cout, float* out, void* stream);
+
 int sln_spade_modulate(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* Wgb_packed, const float* bias_g,
                        const float* bias_b, int64_t C, int32_t pair, const float* x, const float* mean, const float* inv, float slope, float* out,
                        void* stream);
+/* sln_spade_modulate with the parameter-free normalisation's statistics per (sample, channel): the value of (b, c) is read at
+ * [b * stat_stride_b + c * stat_stride_c] — (1, 0) LayerNorm2D (SPADE4), (C, 1) nn.InstanceNorm2d(affine=False), (0, 1) eval-mode
+ * nn.BatchNorm2d(affine=False) (plain SPADE, SPADE_related.py:308-316,328,337) — and the convolution padding selectable (pad_mode as
+ * in sln_conv2d_nhwc).  inv is the multiplier: 1 / (std + eps) or 1 / sqrt(var + eps). */
+int sln_spade_modulate_ex(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* Wgb_packed,
+                          const float* bias_g, const float* bias_b, int64_t C, int32_t pair, const float* x, const float* mean,
+                          const float* inv, int32_t stat_stride_b, int32_t stat_stride_c, int32_t pad_mode, float slope, float* out,
+                          void* stream);
+/* nn.InstanceNorm2d(affine=False, track_running_stats=False) statistics of an NHWC tensor: mean[B*C], inv[B*C] = 1/sqrt(biased var + eps). */
+int sln_instnorm_stats(const float* x, int64_t B, int64_t HW, int64_t C, float eps, float* mean, float* inv, void* stream);
+/* out = act((x - mean[b,c]) * inv[b,c]), act 0 none / 1 ReLU: the norm + activation of a Conv2dBlock (SPADE_related.py:58-63). */
+int sln_norm_act(const float* x, int64_t B, int64_t HW, int64_t C, const float* mean, const float* inv, int32_t stat_stride_b,
+                 int32_t stat_stride_c, int32_t act, float* out, void* stream);
+/* F.interpolate of the NCHW label map [B, nc, S, S] to (h, w), bilinear (align_corners=False, SPADE_related.py:330) or nearest (:226),
+ * written NHWC with the channels zero-padded to cpad (a multiple of 4). */
+int sln_seg_resize_nhwc(const float* seg, int64_t B, int32_t nc, int32_t S, int32_t nearest, int64_t h, int64_t w, int32_t cpad, float* out,
+                        void* stream);
+
 int sln_spade_ln_stats(const float* x, int64_t B, int64_t n_per_sample, float eps, void* scratch, float* mean, float* inv, void* stream);
 int sln_spade_seg_features(const float* seg, int64_t B, int32_t nc, int32_t S, int32_t mode, int64_t h, int64_t w, const float* dw, const float* db,
                            int32_t nd, float* out, void* stream);

@@ -87,3 +87,60 @@ def synthetic_input(B, S=256, n_labels=40, seed=0):
     lab = torch.gather(labels, 1, owner.view(B, -1)).view(B, S, S)
     onehot = F.one_hot(lab, n_labels).permute(0, 3, 1, 2).float()
     return torch.cat([depth, onehot], 1).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Plain SPADEGenerator (reference models/SPADE_related.py:151-346; Conv2dBlock :16-68, SEResBlock2 :87-101), eval mode.
+PLAIN_BLOCKS = ("head_0", "G_middle_0", "G_middle_1", "up_0", "up_1", "up_2", "up_3")
+
+
+def _cw(sd, prefix, dt):
+    """conv weight: spectral-normalised (eval: W / u^T W v) when the checkpoint holds weight_orig, else plain."""
+    return _sn(sd, prefix, dt) if (prefix + ".weight_orig") in sd else _w(sd, prefix + ".weight", dt)
+
+
+def spade_plain(sd, p, x, segmap, dt, kind):
+    if kind == "instance":
+        normalized = F.instance_norm(x, eps=1e-5)
+    else:      # eval-mode BatchNorm2d(affine=False)
+        normalized = F.batch_norm(x, _w(sd, p + ".param_free_norm.running_mean", dt), _w(sd, p + ".param_free_norm.running_var", dt), training=False, eps=1e-5)
+    segmap = F.interpolate(segmap, size=x.shape[2:], mode='bilinear', align_corners=False)
+    actv = F.relu(F.conv2d(segmap, _w(sd, p + ".mlp_shared.0.weight", dt), _w(sd, p + ".mlp_shared.0.bias", dt), padding=1))
+    gamma = F.conv2d(actv, _w(sd, p + ".mlp_gamma.weight", dt), _w(sd, p + ".mlp_gamma.bias", dt), padding=1)
+    beta = F.conv2d(actv, _w(sd, p + ".mlp_beta.weight", dt), _w(sd, p + ".mlp_beta.bias", dt), padding=1)
+    return normalized * (1 + gamma) + beta
+
+
+def resblock_plain(sd, p, x, seg, dt, kind):
+    learned = any(k.startswith(p + ".conv_s.") for k in sd)
+    x_s = F.conv2d(spade_plain(sd, p + ".norm_s", x, seg, dt, kind), _cw(sd, p + ".conv_s", dt)) if learned else x
+    dx = F.conv2d(F.leaky_relu(spade_plain(sd, p + ".norm_0", x, seg, dt, kind), 0.2), _cw(sd, p + ".conv_0", dt), _w(sd, p + ".conv_0.bias", dt), padding=1)
+    dx = F.conv2d(F.leaky_relu(spade_plain(sd, p + ".norm_1", dx, seg, dt, kind), 0.2), _cw(sd, p + ".conv_1", dt), _w(sd, p + ".conv_1.bias", dt), padding=1)
+    return x_s + dx
+
+
+def forward_plain(sd, seg, z, nf, sh, kind="instance", dtype=torch.float64, taps=None):
+    """SPADEGenerator.forward (:209-250) with n_up='normal' -> tanh image [B, 3, S, S]."""
+    dt = dtype
+    seg, z = seg.to(dt), z.to(dt)
+    x = F.linear(z, _w(sd, "fc.weight", dt), _w(sd, "fc.bias", dt)).view(-1, 16 * nf, sh, sh)
+    x = resblock_plain(sd, "head_0", x, F.interpolate(seg, size=[sh, sh]), dt, kind)
+    if taps is not None: taps["head_0"] = x
+    for name, up in (("G_middle_0", True), ("G_middle_1", False), ("up_0", True), ("up_1", True), ("up_2", True), ("up_3", True)):
+        if up:
+            x = F.interpolate(x, scale_factor=2, mode='nearest')
+        x = resblock_plain(sd, name, x, seg, dt, kind)
+        if taps is not None: taps[name] = x
+    y = x                                                                  # conv_img_pre = SEResBlock2
+    for i, act in ((0, True), (1, False)):
+        y = F.conv2d(F.pad(y, (1, 1, 1, 1), mode='reflect'), _w(sd, "conv_img_pre.model.%d.conv.weight" % i, dt), _w(sd, "conv_img_pre.model.%d.conv.bias" % i, dt))
+        y = F.instance_norm(y, eps=1e-5)
+        if act:
+            y = F.relu(y)
+    s = y.mean(dim=(2, 3))
+    s = torch.sigmoid(F.linear(F.relu(F.linear(s, _w(sd, "conv_img_pre.model.2.fc.0.weight", dt))), _w(sd, "conv_img_pre.model.2.fc.2.weight", dt)))
+    y = y * s[:, :, None, None] + x
+    if taps is not None: taps["conv_img_pre"] = y
+    pre = F.conv2d(F.leaky_relu(y, 0.2), _w(sd, "conv_img.weight", dt), _w(sd, "conv_img.bias", dt), padding=2)
+    if taps is not None: taps["pre_tanh"] = pre
+    return torch.tanh(pre)

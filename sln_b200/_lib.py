@@ -165,6 +165,11 @@ SIGNATURES = {
     "sln_packed_weights_bytes": (_SZ, [_I64, _I64]),
     "sln_pack_weights": (ctypes.c_int, [_P, _I64, _I64, _P, _P]),
     "sln_spade_conv": (ctypes.c_int, [_P, _I64, _I64, _I64, _I64, _I32, _I32, _P, _P, _P, _I64, _P, _P]),
+    "sln_conv2d_nhwc": (ctypes.c_int, [_P, _I64, _I64, _I64, _I64, _I32, _I32, _I32, _P, _P, _P, _I64, _P, _P]),
+    "sln_spade_modulate_ex": (ctypes.c_int, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P]),
+    "sln_instnorm_stats": (ctypes.c_int, [_P, _I64, _I64, _I64, _F, _P, _P, _P]),
+    "sln_norm_act": (ctypes.c_int, [_P, _I64, _I64, _I64, _P, _P, _I32, _I32, _I32, _P, _P]),
+    "sln_seg_resize_nhwc": (ctypes.c_int, [_P, _I64, _I32, _I32, _I32, _I64, _I64, _I32, _P, _P]),
     "sln_spade_modulate": (ctypes.c_int, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _F, _P, _P]),
     "sln_spade_ln_stats": (ctypes.c_int, [_P, _I64, _I64, _F, _P, _P, _P, _P]),
     "sln_spade_seg_features": (ctypes.c_int, [_P, _I64, _I32, _I32, _I32, _I64, _I64, _P, _P, _I32, _P, _P]),

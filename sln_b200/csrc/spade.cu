@@ -28,10 +28,12 @@ struct Im2col {
   const float* p;
   int H, W, C, ks, rows, cols, relu, vec;
   int cshift;   // log2(C) when C is a power of two (the usual case), else -1: k -> (tap, c) without an integer division
+  int zpad;     // 0: ReflectionPad2d(1) (SPADE4 / SPADEResnetBlock4); 1: zero padding = nn.Conv2d(padding=1) of the plain SPADE blocks
   __device__ __forceinline__ float elem(int r, int k) const {
     const int tap = ks == 3 ? k / C : 0, c = k - tap * C;
     const int ky = ks == 3 ? tap / 3 : 1, kx = ks == 3 ? tap - 3 * (tap / 3) : 1;
     const int hw = H * W, b = r / hw, rem = r - b * hw, y = rem / W, x = rem - y * W;
+    if (ks == 3 && zpad && ((unsigned)(y + ky - 1) >= (unsigned)H || (unsigned)(x + kx - 1) >= (unsigned)W)) return 0.f;
     const int yy = ks == 3 ? reflect(y + ky - 1, H) : y, xx = ks == 3 ? reflect(x + kx - 1, W) : x;
     float v = __ldg(p + ((size_t)b * hw + (size_t)yy * W + xx) * C + c);
     return relu ? fmaxf(v, 0.f) : v;
@@ -44,6 +46,7 @@ struct Im2col {
       const int tap = ks == 3 ? k / C : 0, c = k - tap * C;
       const int ky = ks == 3 ? tap / 3 : 1, kx = ks == 3 ? tap - 3 * (tap / 3) : 1;
       const int hw = H * W, b = r / hw, rem = r - b * hw, y = rem / W, x = rem - y * W;
+      if (ks == 3 && zpad && ((unsigned)(y + ky - 1) >= (unsigned)H || (unsigned)(x + kx - 1) >= (unsigned)W)) return v;
       const int yy = ks == 3 ? reflect(y + ky - 1, H) : y, xx = ks == 3 ? reflect(x + kx - 1, W) : x;
       v = ldg4(p + ((size_t)b * hw + (size_t)yy * W + xx) * C + c);
       if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
@@ -56,15 +59,17 @@ struct Im2col {
     return v;
   }
   // two-phase API of the tensor-core loader: the token holds the image base and the three reflected row / column offsets
-  struct Tok { const float* base; int y0, y1, y2, x0, x1, x2; };
+  struct Tok { const float* base; int y0, y1, y2, x0, x1, x2; int valid; };   // valid: bit ky = row tap inside the image, bit 3 + kx = column tap
   __device__ __forceinline__ Tok token(int r) const {
     r = min(r, rows - 1);
     const int hw = H * W, b = r / hw, rem = r - b * hw, y = rem / W, x = rem - y * W;
     Tok t;
     t.base = p + (size_t)b * hw * C;
+    t.valid = 63;
     if (ks == 3) {
       t.y0 = reflect(y - 1, H) * W; t.y1 = y * W; t.y2 = reflect(y + 1, H) * W;
       t.x0 = reflect(x - 1, W); t.x1 = x; t.x2 = reflect(x + 1, W);
+      if (zpad) t.valid = (y >= 1 ? 1 : 0) | 2 | (y + 1 < H ? 4 : 0) | (x >= 1 ? 8 : 0) | 16 | (x + 1 < W ? 32 : 0);
     } else {
       t.y0 = t.y1 = t.y2 = y * W; t.x0 = t.x1 = t.x2 = x;
     }
@@ -75,6 +80,7 @@ struct Im2col {
     const int tap = ks == 3 ? (cshift >= 0 ? (k >> cshift) : k / C) : 0, c = k - tap * C;
     const int ky = ks == 3 ? (tap * 11) >> 5 : 1, kx = ks == 3 ? tap - 3 * ky : 1;      // tap / 3 for tap < 9
     const int yo = ky == 0 ? t.y0 : (ky == 1 ? t.y1 : t.y2), xo = kx == 0 ? t.x0 : (kx == 1 ? t.x1 : t.x2);
+    if (zpad && !(((t.valid >> ky) & 1) && ((t.valid >> (3 + kx)) & 1))) { a = make_float4(0.f, 0.f, 0.f, 0.f); return; }   // outside: zero
     a = ldg4(t.base + (size_t)(unsigned)((yo + xo) * C + c));
   }
   __device__ __forceinline__ float4 finish4(const Tok&, int, float4 v, float4) const {
@@ -84,8 +90,9 @@ struct Im2col {
   bool vec_ok() const { return vec != 0; }
 };
 
-Im2col make_im2col(const float* p, int B, int H, int W, int C, int ks, int relu) {
+Im2col make_im2col(const float* p, int B, int H, int W, int C, int ks, int relu, int zpad = 0) {
   Im2col a;
+  a.zpad = zpad;
   a.p = p; a.H = H; a.W = W; a.C = C; a.ks = ks; a.rows = B * H * W; a.cols = ks * ks * C; a.relu = relu;
   a.vec = (C % 4 == 0 && (uintptr_t)p % 16 == 0) ? 1 : 0;
   a.cshift = -1;
@@ -99,19 +106,23 @@ struct TcEpiSpade {
   float* out; const float* x; int C;
   const float* bias_g; const float* bias_b;
   const float* mean; const float* inv; int HW; float slope;
+  int sb, sc;   // statistics layout: value of (sample b, channel c) at [b * sb + c * sc] — (1, 0): one per sample (LayerNorm2D);
+                // (C, 1): one per sample and channel (InstanceNorm2d); (0, 1): one per channel (eval-mode BatchNorm2d)
   static constexpr bool kStats = false;
   static constexpr bool kPaired = true;
   __device__ __forceinline__ bool wants_stats() const { return false; }
   __device__ __forceinline__ void apply4(int, int, int, float4, float (&)[4], float (&)[4]) const {}
   __device__ __forceinline__ void apply_pair(int i, int c, float4 g, float4 b) const {
     const int bi = i / HW;
-    const float m = __ldg(mean + bi), iv = __ldg(inv + bi);
+    float4 m, iv;
+    if (sc) { m = ldg4(mean + (size_t)bi * sb + c); iv = ldg4(inv + (size_t)bi * sb + c); }
+    else { const float m1 = __ldg(mean + bi * sb), i1 = __ldg(inv + bi * sb); m = make_float4(m1, m1, m1, m1); iv = make_float4(i1, i1, i1, i1); }
     const float4 xv = ldg4(x + (size_t)i * C + c), bg = ldg4(bias_g + c), bb = ldg4(bias_b + c);
     float4 o;
-    o.x = fmaf((xv.x - m) * iv, 1.f + (g.x + bg.x), b.x + bb.x);
-    o.y = fmaf((xv.y - m) * iv, 1.f + (g.y + bg.y), b.y + bb.y);
-    o.z = fmaf((xv.z - m) * iv, 1.f + (g.z + bg.z), b.z + bb.z);
-    o.w = fmaf((xv.w - m) * iv, 1.f + (g.w + bg.w), b.w + bb.w);
+    o.x = fmaf((xv.x - m.x) * iv.x, 1.f + (g.x + bg.x), b.x + bb.x);
+    o.y = fmaf((xv.y - m.y) * iv.y, 1.f + (g.y + bg.y), b.y + bb.y);
+    o.z = fmaf((xv.z - m.z) * iv.z, 1.f + (g.z + bg.z), b.z + bb.z);
+    o.w = fmaf((xv.w - m.w) * iv.w, 1.f + (g.w + bg.w), b.w + bb.w);
     o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
     o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
     *reinterpret_cast<float4*>(out + (size_t)i * C + c) = o;
@@ -127,7 +138,7 @@ struct TcEpiSpade {
 // direct fallback of the modulation for channel counts the paired tiles cannot hold (2C < 32: reduced test models only)
 __global__ void k_modulate_direct(const Im2col A, const float* __restrict__ Wg, const float* __restrict__ Wb, const float* __restrict__ bg,
                                   const float* __restrict__ bb, int C, const float* __restrict__ x, const float* __restrict__ mean,
-                                  const float* __restrict__ inv, int HW, float slope, float* out) {
+                                  const float* __restrict__ inv, int HW, float slope, float* out, int sb, int sc) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= A.rows * C) return;
   const int i = idx / C, c = idx - i * C;
@@ -138,8 +149,75 @@ __global__ void k_modulate_direct(const Im2col A, const float* __restrict__ Wg, 
     b = fmaf(a, __ldg(Wb + (size_t)c * A.cols + k), b);
   }
   const int bi = i / HW;
-  float o = fmaf((__ldg(x + idx) - __ldg(mean + bi)) * __ldg(inv + bi), 1.f + g, b);
+  float o = fmaf((__ldg(x + idx) - __ldg(mean + (size_t)bi * sb + c * sc)) * __ldg(inv + (size_t)bi * sb + c * sc), 1.f + g, b);
   out[idx] = o > 0.f ? o : o * slope;
+}
+
+// ------------------------------------------------------------------------------------------------ InstanceNorm2d (plain SPADE / Conv2dBlock)
+// per (sample, channel): mean and 1 / sqrt(biased var + eps) over H*W of an NHWC tensor (nn.InstanceNorm2d(affine=False,
+// track_running_stats=False), reference SPADE_related.py:34,311).  CTA = (32 channels, sample); 8 pixel lanes per channel, fp64,
+// fixed-order shared-memory fold: deterministic.
+__global__ void __launch_bounds__(256) k_in_stats(const float* __restrict__ x, int HW, int C, float eps, float* mean, float* inv) {
+  const int b = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), pl = threadIdx.x >> 5;
+  double s = 0.0, q = 0.0;
+  if (c < C) {
+    const float* xb = x + (size_t)b * HW * C + c;
+    for (int p = pl; p < HW; p += 8) { const double v = (double)__ldg(xb + (size_t)p * C); s += v; q += v * v; }
+  }
+  __shared__ double sh[2][8][32];
+  sh[0][pl][threadIdx.x & 31] = s; sh[1][pl][threadIdx.x & 31] = q;
+  __syncthreads();
+  if (pl == 0 && c < C) {
+    double S = 0.0, Q = 0.0;
+    for (int k = 0; k < 8; ++k) { S += sh[0][k][threadIdx.x]; Q += sh[1][k][threadIdx.x]; }
+    const double m = S / HW;
+    double var = Q / HW - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[(size_t)b * C + c] = (float)m;
+    inv[(size_t)b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+// out = act((x - mean[b,c]) * inv[b,c]);  act: 0 none, 1 ReLU   (Conv2dBlock.norm + activation, SPADE_related.py:58-63)
+__global__ void k_norm_act(const float* __restrict__ x, long long n4, int HWC, int C, const float* __restrict__ mean, const float* __restrict__ inv,
+                           int sb, int sc, int act, float* out) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= n4) return;
+  const long long i = i4 * 4;
+  const int b = (int)(i / HWC), c = (int)(i % C);
+  const float4 v = ldg4(x + i);
+  float4 m, iv;
+  if (sc) { m = ldg4(mean + (size_t)b * sb + c); iv = ldg4(inv + (size_t)b * sb + c); }
+  else { const float m1 = __ldg(mean + b * sb), i1 = __ldg(inv + b * sb); m = make_float4(m1, m1, m1, m1); iv = make_float4(i1, i1, i1, i1); }
+  float4 o = make_float4((v.x - m.x) * iv.x, (v.y - m.y) * iv.y, (v.z - m.z) * iv.z, (v.w - m.w) * iv.w);
+  if (act == 1) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+  *reinterpret_cast<float4*>(out + i) = o;
+}
+// NCHW label map [B, nc, S, S] -> NHWC [B, h, w, cpad] (channels >= nc zero): bilinear with align_corners=False (F.interpolate(...,
+// mode='bilinear'), SPADE_related.py:330) or nearest (F.interpolate default, :226,228).  A thread per output pixel and channel quad.
+__global__ void k_seg_resize(const float* __restrict__ seg, int B, int nc, int S, int h, int w, int cpad, int nearest, float* out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = cpad / 4;
+  if (idx >= (long long)B * h * w * q) return;
+  const int cq = (int)(idx % q) * 4;
+  const long long pix = idx / q;
+  const int x = (int)(pix % w), y = (int)((pix / w) % h), b = (int)(pix / ((long long)w * h));
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  if (nearest) {
+    const int sy = min((int)floorf(y * ((float)S / h)), S - 1), sx = min((int)floorf(x * ((float)S / w)), S - 1);
+    for (int e = 0; e < 4; ++e) if (cq + e < nc) o[e] = __ldg(seg + (((size_t)b * nc + cq + e) * S + sy) * S + sx);
+  } else {
+    float fy = ((float)y + 0.5f) * ((float)S / h) - 0.5f, fx = ((float)x + 0.5f) * ((float)S / w) - 0.5f;
+    fy = fmaxf(fy, 0.f); fx = fmaxf(fx, 0.f);
+    const int y0 = min((int)fy, S - 1), x0 = min((int)fx, S - 1), y1 = min(y0 + 1, S - 1), x1 = min(x0 + 1, S - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+    for (int e = 0; e < 4; ++e) {
+      if (cq + e >= nc) continue;
+      const float* pl = seg + ((size_t)b * nc + cq + e) * S * S;
+      o[e] = hy * (hx * __ldg(pl + (size_t)y0 * S + x0) + lx * __ldg(pl + (size_t)y0 * S + x1)) +
+             ly * (hx * __ldg(pl + (size_t)y1 * S + x0) + lx * __ldg(pl + (size_t)y1 * S + x1));
+    }
+  }
+  *reinterpret_cast<float4*>(out + idx * 4) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm2D statistics
@@ -383,14 +461,20 @@ int sln_pack_weights(const float* Wm, int64_t N, int64_t K, float* out, void* st
 
 int sln_spade_conv(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, const float* Wp, const float* Wpacked,
                    const float* bias, int64_t Cout, float* out, void* stream) {
+  return sln_conv2d_nhwc(x, B, H, W, Cin, ks, relu_in, 0, Wp, Wpacked, bias, Cout, out, stream);
+}
+
+int sln_conv2d_nhwc(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, int32_t pad_mode, const float* Wp,
+                    const float* Wpacked, const float* bias, int64_t Cout, float* out, void* stream) {
   SLN_TRY(check_img(B, H, W, Cin));
+  SLN_CHECK_ARG(pad_mode == 0 || pad_mode == 1, "pad_mode: 0 reflection, 1 zeros");
   SLN_CHECK_ARG(x && Wp && out && Cout >= 1, "null pointer");
   SLN_CHECK_ARG(ks == 1 || ks == 3, "kernel size must be 1 or 3 (reflection-padded)");
   SLN_CHECK_ARG(ks == 1 || (H >= 2 && W >= 2), "reflection padding needs at least 2 rows and columns");
   SLN_CHECK_ARG(H * W * Cin < (1ll << 31), "one image must have fewer than 2^31 elements");
   cudaStream_t st = (cudaStream_t)stream;
   const int M = (int)(B * H * W), N = (int)Cout, K = (int)(ks * ks * Cin);
-  Im2col A = make_im2col(x, (int)B, (int)H, (int)W, (int)Cin, ks, relu_in);
+  Im2col A = make_im2col(x, (int)B, (int)H, (int)W, (int)Cin, ks, relu_in, pad_mode);
   MatView Wv = make_view(Wp, K, N, K);
   EpiStore epi; memset(&epi, 0, sizeof(epi));
   epi.C = out; epi.ldc = N; epi.bias = bias;
@@ -409,18 +493,26 @@ int sln_spade_conv(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin,
 int sln_spade_modulate(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* Wgb_packed, const float* bias_g,
                        const float* bias_b, int64_t C, int32_t pair, const float* x, const float* mean, const float* inv, float slope, float* out,
                        void* stream) {
+  return sln_spade_modulate_ex(actv, B, H, W, Ca, Wgb, Wgb_packed, bias_g, bias_b, C, pair, x, mean, inv, 1, 0, 0, slope, out, stream);
+}
+
+int sln_spade_modulate_ex(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* Wgb_packed,
+                          const float* bias_g, const float* bias_b, int64_t C, int32_t pair, const float* x, const float* mean, const float* inv,
+                          int32_t stat_stride_b, int32_t stat_stride_c, int32_t pad_mode, float slope, float* out, void* stream) {
   SLN_TRY(check_img(B, H, W, Ca));
+  SLN_CHECK_ARG((pad_mode == 0 || pad_mode == 1) && (stat_stride_c == 0 || stat_stride_c == 1) && stat_stride_b >= 0, "bad statistics layout / pad mode");
+  SLN_CHECK_ARG(stat_stride_c == 0 || (((uintptr_t)mean | (uintptr_t)inv) % 16 == 0 && stat_stride_b % 4 == 0), "per-channel statistics must be 16-byte aligned rows");
   SLN_CHECK_ARG(actv && Wgb && bias_g && bias_b && x && mean && inv && out, "null pointer");
   SLN_CHECK_ARG(H >= 2 && W >= 2 && C >= 1 && pair >= 2 && (2 * C) % pair == 0, "bad modulation shape");
   cudaStream_t st = (cudaStream_t)stream;
   const int M = (int)(B * H * W), N = (int)(2 * C), K = (int)(9 * Ca);
-  Im2col A = make_im2col(actv, (int)B, (int)H, (int)W, (int)Ca, 3, 1);   // ReLU of mlp_shared applied on load
+  Im2col A = make_im2col(actv, (int)B, (int)H, (int)W, (int)Ca, 3, 1, pad_mode);   // ReLU of mlp_shared applied on load
   MatView Wv = make_view(Wgb, K, N, K);
   const bool tc_ok = (pair == 32 || pair == 64 || pair == 128) && C % 4 == 0 && A.vec_ok() && Wv.vec_ok() && ((uintptr_t)x % 16 == 0) &&
                      ((uintptr_t)out % 16 == 0) && ((uintptr_t)bias_g % 16 == 0) && ((uintptr_t)bias_b % 16 == 0);
   ProfScope prof(st, PROF_SPADE_CONV, 2.0 * (double)M * N * K);
   if (tc_ok) {
-    TcEpiSpade te{out, x, (int)C, bias_g, bias_b, mean, inv, (int)(H * W), slope};
+    TcEpiSpade te{out, x, (int)C, bias_g, bias_b, mean, inv, (int)(H * W), slope, stat_stride_b, stat_stride_c};
     tc::TcChoice ch{pair, 1, ceil_div(K, tc::BK) * tc::BK};
     int rc;
     if (Wgb_packed) {
@@ -438,7 +530,7 @@ int sln_spade_modulate(const float* actv, int64_t B, int64_t H, int64_t W, int64
   // interleaved weight rows: tile t = [gamma of channels t*half .. | beta of the same]; the direct kernel needs them per channel
   SLN_CHECK_ARG(pair == 2 * C, "the direct modulation fallback expects a single pair tile (pair == 2C)");
   const long long total = (long long)M * C;
-  k_modulate_direct<<<(int)ceil_div64(total, 256), 256, 0, st>>>(A, Wgb, Wgb + (size_t)C * K, bias_g, bias_b, (int)C, x, mean, inv, (int)(H * W), slope, out);
+  k_modulate_direct<<<(int)ceil_div64(total, 256), 256, 0, st>>>(A, Wgb, Wgb + (size_t)C * K, bias_g, bias_b, (int)C, x, mean, inv, (int)(H * W), slope, out, stat_stride_b, stat_stride_c);
   return check_launch("spade_modulate_direct");
 }
 
@@ -453,6 +545,36 @@ int sln_spade_ln_stats(const float* x, int64_t B, int64_t n_per_sample, float ep
   SLN_TRY(check_launch("ln_partial"));
   k_ln_final<<<ceil_div((int)B, 128), 128, 0, st>>>((const double*)scratch, (int)B, n_per_sample, eps, mean, inv);
   return check_launch("ln_final");
+}
+
+int sln_instnorm_stats(const float* x, int64_t B, int64_t HW, int64_t C, float eps, float* mean, float* inv, void* stream) {
+  SLN_CHECK_ARG(x && mean && inv && B >= 1 && B <= 65535 && HW >= 1 && C >= 1 && HW < (1ll << 31) && C < (1ll << 24), "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(st, PROF_SPADE_MISC, 4.0 * (double)B * HW * C);
+  k_in_stats<<<dim3((unsigned)ceil_div64(C, 32), (unsigned)B), 256, 0, st>>>(x, (int)HW, (int)C, eps, mean, inv);
+  return check_launch("instnorm_stats");
+}
+
+int sln_norm_act(const float* x, int64_t B, int64_t HW, int64_t C, const float* mean, const float* inv, int32_t stat_stride_b, int32_t stat_stride_c,
+                 int32_t act, float* out, void* stream) {
+  SLN_CHECK_ARG(x && mean && inv && out && B >= 1 && HW >= 1 && C >= 4 && C % 4 == 0 && (act == 0 || act == 1), "bad argument (C must be a multiple of 4)");
+  SLN_CHECK_ARG(((uintptr_t)x | (uintptr_t)out) % 16 == 0 && HW * C < (1ll << 31), "tensors must be 16-byte aligned");
+  SLN_CHECK_ARG(stat_stride_c == 0 || (stat_stride_c == 1 && ((uintptr_t)mean | (uintptr_t)inv) % 16 == 0 && stat_stride_b % 4 == 0), "bad statistics layout");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n4 = (long long)B * HW * C / 4;
+  ProfScope prof(st, PROF_SPADE_MISC, 8.0 * (double)n4 * 4);
+  k_norm_act<<<(unsigned)ceil_div64(n4, 256), 256, 0, st>>>(x, n4, (int)(HW * C), (int)C, mean, inv, stat_stride_b, stat_stride_c, act, out);
+  return check_launch("norm_act");
+}
+
+int sln_seg_resize_nhwc(const float* seg, int64_t B, int32_t nc, int32_t S, int32_t nearest, int64_t h, int64_t w, int32_t cpad, float* out, void* stream) {
+  SLN_CHECK_ARG(seg && out && B >= 1 && nc >= 1 && S >= 1 && h >= 1 && w >= 1 && cpad >= nc && cpad % 4 == 0 && (nearest == 0 || nearest == 1), "bad argument");
+  SLN_CHECK_ARG((uintptr_t)out % 16 == 0, "output must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)B * h * w * (cpad / 4);
+  ProfScope prof(st, PROF_SPADE_MISC, 4.0 * (double)n * 4);
+  k_seg_resize<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(seg, (int)B, nc, S, (int)h, (int)w, cpad, nearest, out);
+  return check_launch("seg_resize");
 }
 
 int sln_spade_seg_features(const float* seg, int64_t B, int32_t nc, int32_t S, int32_t mode, int64_t h, int64_t w, const float* dw, const float* db,
