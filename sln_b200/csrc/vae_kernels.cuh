@@ -305,6 +305,69 @@ __global__ void __launch_bounds__(256, MINB) k_pool_fwd(const MatView a2, const 
   }
 }
 
+// Small graphs (BASELINE configs[1]: 2048 nodes, 10 MB, L2-resident): ONE WARP PER NODE, lanes along the columns (QPL float4 per lane),
+// 8 rows in flight per lane, sums in CSR order (bit-identical to k_pool_fwd and to scatter_add + clamp + divide).  The streaming
+// kernel above is unrolled for bandwidth (32 entries x 16 rows per iteration: ~7000 SASS instructions that every warp steps through
+// even for a 3-entry node — ncu at 64 scenes: 14.5 us, issue slots 47 % busy, DRAM idle, profiles/r2_prof_pool64_*); this one is a
+// short loop whose makespan is the 62-entry room node of a scene (8 dependent batches).
+template <int QPL>
+__global__ void __launch_bounds__(256) k_pool_fwd_node(const MatView a2, const int* __restrict__ row_ptr, const int* __restrict__ ent,
+                                                       int O, int H, int D, float* pooled) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int node = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (node >= O) return;
+  const int b = __ldg(row_ptr + node), e = __ldg(row_ptr + node + 1);
+  const bool bn = a2.scale != nullptr;
+  float4 acc[QPL], ss[QPL], hs[QPL], so[QPL], ho[QPL];
+#pragma unroll
+  for (int q = 0; q < QPL; ++q) {
+    acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = (lane + 32 * q) * 4;
+    if (bn) { ss[q] = ldg4(a2.scale + c); hs[q] = ldg4(a2.shift + c); so[q] = ldg4(a2.scale + H + D + c); ho[q] = ldg4(a2.shift + H + D + c); }
+  }
+  int mine = (b + lane < e) ? __ldg(ent + b + lane) : 0;             // 32 entries per outer step, one per lane
+  for (int k0 = b; k0 < e; k0 += 32) {
+    const int next = (k0 + 32 + lane < e) ? __ldg(ent + k0 + 32 + lane) : 0;   // in flight while this step's rows are summed
+    for (int k = k0; k < min(e, k0 + 32); k += 8) {
+      const int n = min(8, e - k), base = k - k0;
+      float4 v[8][QPL];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int x = __shfl_sync(0xffffffffu, mine, (base + u) & 31);
+        if (u < n) {
+          const float* row = a2.p + (size_t)(x & ((1 << 30) - 1)) * a2.ld + ((x >> 30) ? (H + D) : 0);
+#pragma unroll
+          for (int q = 0; q < QPL; ++q) v[u][q] = ldg4(row + (lane + 32 * q) * 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int x = __shfl_sync(0xffffffffu, mine, (base + u) & 31);
+        if (u < n) {
+          const bool oside = (x >> 30) != 0;
+#pragma unroll
+          for (int q = 0; q < QPL; ++q) {
+            float4 t = v[u][q];
+            if (bn) {
+              const float4 sc = oside ? so[q] : ss[q], sh = oside ? ho[q] : hs[q];
+              t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y); t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
+            }
+            if (a2.relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+            acc[q].x += t.x; acc[q].y += t.y; acc[q].z += t.z; acc[q].w += t.w;
+          }
+        }
+      }
+    }
+    mine = next;
+  }
+  const float ic = (float)max(e - b, 1);                              // = clamp(count, min=1) of graph.py:102-107
+#pragma unroll
+  for (int q = 0; q < QPL; ++q) {
+    float4 o = make_float4(__fdiv_rn(acc[q].x, ic), __fdiv_rn(acc[q].y, ic), __fdiv_rn(acc[q].z, ic), __fdiv_rn(acc[q].w, ic));
+    *reinterpret_cast<float4*>(pooled + (size_t)node * H + (lane + 32 * q) * 4) = o;
+  }
+}
+
 // Launch plan of k_pool_fwd.  V = 4 needs 16-byte aligned rows and halves; anything else takes the scalar-column variant.
 // Tuning override (sweeps only): env SLN_POOL="V,npg,batch".
 struct PoolPlan { int V, lanes, npg, batch; dim3 grid; size_t smem; };
@@ -334,6 +397,18 @@ inline PoolPlan pool_plan(const MatView& a2, int O, int H, int D) {
   return p;
 }
 inline void launch_pool_fwd(cudaStream_t st, const MatView& a2, const int* row_ptr, const int* ent, int O, int H, int D, float* pooled) {
+  static int small_ok = -1;                                            // env SLN_POOL_NODE=0 disables the warp-per-node kernel (A/B measurements)
+  if (small_ok < 0) { const char* e = getenv("SLN_POOL_NODE"); small_ok = (e && e[0] == '0') ? 0 : 1; }
+  const bool aligned = a2.vec && H % 128 == 0 && D % 4 == 0 && ((uintptr_t)pooled % 16 == 0) &&
+                       (!a2.scale || (((uintptr_t)a2.scale | (uintptr_t)a2.shift) % 16 == 0));
+  if (small_ok && aligned && H <= 512 && O <= 16 * kNumSMs * 2 && !getenv("SLN_POOL")) {   // every node's warp resident at once (<= 2 CTAs of 8 warps per SM)
+    const int grid = ceil_div(O, 8);
+    if (H == 128) k_pool_fwd_node<1><<<grid, 256, 0, st>>>(a2, row_ptr, ent, O, H, D, pooled);
+    else if (H == 256) k_pool_fwd_node<2><<<grid, 256, 0, st>>>(a2, row_ptr, ent, O, H, D, pooled);
+    else if (H == 384) k_pool_fwd_node<3><<<grid, 256, 0, st>>>(a2, row_ptr, ent, O, H, D, pooled);
+    else k_pool_fwd_node<4><<<grid, 256, 0, st>>>(a2, row_ptr, ent, O, H, D, pooled);
+    return;
+  }
   PoolPlan p = pool_plan(a2, O, H, D);
   if (p.V == 4 && p.batch == 16) k_pool_fwd<4, 16, 1><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);
   else if (p.V == 4 && p.batch == 4) k_pool_fwd<4, 4, 4><<<p.grid, 256, p.smem, st>>>(a2, row_ptr, ent, O, H, D, pooled, p.lanes, p.npg);
