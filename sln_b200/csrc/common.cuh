@@ -77,6 +77,17 @@ __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------- bump allocator over caller workspace
+// cudaFuncSetAttribute is per DEVICE: `mask` (one static per call site / template instantiation) remembers which devices of this
+// process have been configured.  Returns true when the current device still needs the attribute set.
+inline bool first_use_on_device(unsigned long long& mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 struct Arena {
   char* base;
   size_t cap;

@@ -628,10 +628,9 @@ int sln_spade_to_rgb(const float* x, int64_t B, int64_t H, int64_t W, int64_t Ci
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)ks * ks * Cin * 4 * sizeof(float);
   SLN_CHECK_ARG(smem <= 200 * 1024, "to_rgb weights do not fit shared memory");
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0ull;   // devices configured (per call site / instantiation)
+  if (first_use_on_device(configured)) {
     SLN_CUDA_TRY(cudaFuncSetAttribute(k_to_rgb<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
   }
   const int P = (int)(B * H * W);
   ProfScope prof(st, PROF_SPADE_CONV, 2.0 * (double)P * ks * ks * Cin * Cout);

@@ -732,11 +732,10 @@ template <int BN, bool A_RC, bool B_RC, bool MSEG, class AOp, class BOp, class E
 int launch_tc_bn_seg(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, const TcChoice& c) {
   auto kern = tc_gemm_kernel<BN, A_RC, B_RC, MSEG, AOp, BOp, Epi>;
   constexpr int bytes = SmemLayout<BN>::BYTES;
-  static bool configured = false;   // per template instantiation
-  if (!configured) {
+  static unsigned long long configured = 0ull;   // devices configured (per call site / instantiation)
+  if (first_use_on_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(tc_gemm, %d B smem) failed: %s", bytes, cudaGetErrorString(e)); return SLN_ECUDA; }
-    configured = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

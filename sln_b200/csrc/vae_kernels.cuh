@@ -186,11 +186,10 @@ inline int launch_embed_bwd(cudaStream_t st, const float* a, int lda, const floa
     const int per_warp = 16;
     const size_t smem = (size_t)rows * width * 8 * sizeof(float);
     if (smem > 48 * 1024) {
-      static bool configured = false;
-      if (!configured) {
+      static unsigned long long configured = 0ull;   // devices configured (per call site / instantiation)
+      if (first_use_on_device(configured)) {
         cudaError_t e = cudaFuncSetAttribute(k_embed_bwd_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_embed_bwd_tab) failed: %s", cudaGetErrorString(e)); return SLN_ECUDA; }
-        configured = true;
       }
     }
     k_embed_bwd_tab<<<ceil_div(n, 8 * per_warp), 256, smem, st>>>(a, lda, b, ldb, idx, n, width, rows, table_grad, per_warp);
@@ -585,11 +584,10 @@ int launch_skinny_fwd(cudaStream_t st, const AOp& A, const float* W, const float
   if (M <= 0) return SLN_OK;
   size_t smem = (size_t)K * 33 * sizeof(float);
   if (smem > 48 * 1024) {
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0ull;   // devices configured (per call site / instantiation)
+    if (first_use_on_device(configured)) {
       cudaError_t e = cudaFuncSetAttribute(k_skinny_fwd<AOp>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_skinny_fwd) failed: %s", cudaGetErrorString(e)); return SLN_ECUDA; }
-      configured = true;
     }
   }
   ProfScope prof(st, PROF_GEMM_FWD, 2.0 * (double)M * N * K);
