@@ -1,10 +1,12 @@
 """TEST INFRASTRUCTURE ONLY — Python face of the rasterizer oracle (oracle/raster_oracle.c, built by oracle/build_oracle.py)
 plus a torch-CPU restatement of the reference's compositing (models/diff_render.py:344-434) and camera (:13-46).
 
-PARITY UNPINNED for the rasterizer itself: see the header of raster_oracle.c (third-party `neural_renderer`, un-pinned,
+PARITY UNPINNED for the rasterizer core itself: see the header of raster_oracle.c (third-party `neural_renderer`, un-pinned,
 not installed, CUDA-only; restated from its published algorithm).  The compositing / camera parts restate reference code
 that IS in /root/reference (models/diff_render.py) but cannot be imported there (its `models/misc.py` needs pywavefront,
-pymesh, SUNCG metadata and `np.float`), so they are checked by reading, not by execution.
+pymesh, SUNCG metadata and `np.float`); they ARE pinned by execution: oracle/gen_golden_render.py runs the reference's own
+get_cam_mat / mesh_render_func from the file's AST (renderer stubbed by this C oracle) into tests/golden/render_*.npz, and
+tests/test_oracle_render.py checks `get_cam_mat` (bit-exact) and `composite` (1e-6) below against those goldens.
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
 """
