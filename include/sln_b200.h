@@ -293,7 +293,8 @@ int sln_adam_step_dyn(float* params, const float* grads, float* exp_avg, float* 
  *                            face_index_map: a face that shows nowhere contributes to neither sweep and is skipped)
  * sln_raster_backward_depth  gradient of depth_map w.r.t. face vertices: grad_faces [F2,9] +=.
  * sln_raster_vertex_grad     grad_faces [F2,9] -> grad w.r.t. the world vertices [V,3] (transpose of vertices_to_faces, then
- *                            the projection's Jacobian); grad_proj_scratch [V,3] is caller-owned scratch.
+ *                            the projection's Jacobian); grad_proj_scratch is caller-owned scratch of 24 V BYTES (64-bit fixed-point accumulators:
+ *                            order-independent, hence bit-reproducible, scatter of the face gradients onto shared vertices).
  * sln_scene_classes_fwd/bwd  the 32 per-class mask renders of mesh_render_func (diff_render.py:381-431) from ONE rasterization:
  *                            class image c = what a 0/1 texture of class c renders to (torch.sum(images,1)/3), written in OUTPUT
  *                            orientation [n_cls,is,is]; the backward applies Kato's per-render clamp per class. */

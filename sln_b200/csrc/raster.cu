@@ -44,8 +44,9 @@ __global__ void k_project(const float* __restrict__ verts, int V, const float* _
   out[3 * i] = u; out[3 * i + 1] = v; out[3 * i + 2] = zc;
 }
 
+__device__ __forceinline__ float fix_to_float(long long v);
 __global__ void k_project_bwd(const float* __restrict__ verts, int V, const float* __restrict__ K, const float* __restrict__ R,
-                              const float* __restrict__ t, float orig_size, const float* __restrict__ grad_out, float* __restrict__ grad_verts) {
+                              const float* __restrict__ t, float orig_size, const long long* __restrict__ grad_fix, float* __restrict__ grad_verts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= V) return;
   const float eps = 1e-9f;
@@ -54,10 +55,11 @@ __global__ void k_project_bwd(const float* __restrict__ verts, int V, const floa
   const float yc = x * R[3] + y * R[4] + z * R[5] + t[1];
   const float zc = x * R[6] + y * R[7] + z * R[8] + t[2];
   const float zi = 1.0f / (zc + eps);
-  const float du = grad_out[3 * i] * (2.0f / orig_size), dv = -grad_out[3 * i + 1] * (2.0f / orig_size);
+  const float grad_out[3] = {fix_to_float(grad_fix[3 * i]), fix_to_float(grad_fix[3 * i + 1]), fix_to_float(grad_fix[3 * i + 2])};
+  const float du = grad_out[0] * (2.0f / orig_size), dv = -grad_out[1] * (2.0f / orig_size);
   const float dx_ = K[0] * du + K[3] * dv, dy_ = K[1] * du + K[4] * dv;
   const float dxc = dx_ * zi, dyc = dy_ * zi;
-  const float dzc = grad_out[3 * i + 2] - (dx_ * xc + dy_ * yc) * zi * zi;
+  const float dzc = grad_out[2] - (dx_ * xc + dy_ * yc) * zi * zi;
   grad_verts[3 * i] = R[0] * dxc + R[3] * dyc + R[6] * dzc;
   grad_verts[3 * i + 1] = R[1] * dxc + R[4] * dyc + R[7] * dzc;
   grad_verts[3 * i + 2] = R[2] * dxc + R[5] * dyc + R[8] * dzc;
@@ -342,6 +344,8 @@ struct RgbBwdArgs {
   // fused class mode
   const int* face_cls; const float* sval; const float* gcls; int n_cls;   // gcls [n_cls, is, is] in internal orientation
   float* grad_faces;
+  float* jobg;       // [6 F2][2]: every (face, edge, axis) job's two partial sums, written exactly once; k_rgb_combine adds them
+                     // into grad_faces in a fixed order (no floating-point atomics: bit-reproducible gradients)
 };
 
 // The reference pixel of a sweep is fixed (the in-pixel for the out sweep, the out-pixel for the in sweep): its class and sample
@@ -474,14 +478,10 @@ __global__ void __launch_bounds__(256) k_backward_rgb_warp(const RgbBwdArgs a, i
   if (job >= a.F2 * 6) return;
   float g0, g1; int pi[3], axis;
   const int r = rgb_job<1>(a, job, 0, lane, g0, g1, pi, axis);
-  if (r == 2) { if (lane == 0) big_jobs[1 + atomicAdd(big_jobs, 1)] = job; return; }
-  if (r == 0) return;
+  if (r == 2) { if (lane == 0) big_jobs[1 + atomicAdd(big_jobs, 1)] = job; return; }   // (integer atomic: the ORDER of the list does not matter)
+  if (r == 0) { g0 = 0.f; g1 = 0.f; }
   g0 = warp_sum(g0); g1 = warp_sum(g1);
-  if (lane == 0) {
-    const int fn = job / 6;
-    if (g0 != 0.f) atomicAdd(a.grad_faces + 9 * (size_t)fn + pi[0] * 3 + (1 - axis), g0);
-    if (g1 != 0.f) atomicAdd(a.grad_faces + 9 * (size_t)fn + pi[1] * 3 + (1 - axis), g1);
-  }
+  if (lane == 0) { a.jobg[2 * (size_t)job] = g0; a.jobg[2 * (size_t)job + 1] = g1; }
 }
 
 __global__ void __launch_bounds__(32 * kBigWarps) k_backward_rgb_cta(const RgbBwdArgs a, const int* __restrict__ big_jobs) {
@@ -492,19 +492,27 @@ __global__ void __launch_bounds__(32 * kBigWarps) k_backward_rgb_cta(const RgbBw
     const int job = big_jobs[1 + li];
     float g0, g1; int pi[3], axis;
     const int r = rgb_job<kBigWarps>(a, job, w_idx, lane, g0, g1, pi, axis);   // CTA-uniform return value
-    if (r != 1) continue;
+    if (r != 1) { g0 = 0.f; g1 = 0.f; }
     g0 = warp_sum(g0); g1 = warp_sum(g1);
     if (lane == 0) { sh[0][w_idx] = g0; sh[1][w_idx] = g1; }
     __syncthreads();
     if (threadIdx.x == 0) {
       float t0 = 0.f, t1 = 0.f;
       for (int w = 0; w < kBigWarps; ++w) { t0 += sh[0][w]; t1 += sh[1][w]; }
-      const int fn = job / 6;
-      if (t0 != 0.f) atomicAdd(a.grad_faces + 9 * (size_t)fn + pi[0] * 3 + (1 - axis), t0);
-      if (t1 != 0.f) atomicAdd(a.grad_faces + 9 * (size_t)fn + pi[1] * 3 + (1 - axis), t1);
+      a.jobg[2 * (size_t)job] = t0; a.jobg[2 * (size_t)job + 1] = t1;
     }
     __syncthreads();
   }
+}
+// grad_faces[fn, k, c] += partial of job (fn, edge k, axis 1-c) for vertex pi[0] = k  +  partial of job (fn, edge k+2, axis 1-c) for
+// vertex pi[1] = k: the only two jobs that touch the slot, added in this order.
+__global__ void k_rgb_combine(const float* __restrict__ jobg, int F2, float* __restrict__ grad_faces) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;     // (fn, k, c)
+  if (i >= F2 * 6) return;
+  const int fn = i / 6, k = (i % 6) >> 1, c = i & 1, axis = 1 - c;
+  const float a0 = jobg[2 * ((size_t)fn * 6 + k * 2 + axis)], a1 = jobg[2 * ((size_t)fn * 6 + ((k + 2) % 3) * 2 + axis) + 1];
+  const float t = a0 + a1;
+  if (t != 0.f) grad_faces[9 * (size_t)fn + 3 * k + c] += t;
 }
 __global__ void k_mark_visible(const int* __restrict__ face_index_map, int P, int F2, int* __restrict__ fvis) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -512,7 +520,8 @@ __global__ void k_mark_visible(const int* __restrict__ face_index_map, int P, in
   const int f = face_index_map[p];
   if (f >= 0 && f < F2) fvis[f] = 1;   // benign race: every writer stores the same value
 }
-inline int launch_backward_rgb(RgbBwdArgs a, int* fvis, int* big_jobs, cudaStream_t st, const char* what) {
+inline int launch_backward_rgb(RgbBwdArgs a, int* fvis, int* big_jobs, float* jobg, cudaStream_t st, const char* what) {
+  a.jobg = jobg;
   const int P = a.is * a.is;
   // fvis [F2] and the job counter big_jobs[0] are adjacent in the workspace plan: one memset clears both
   cudaError_t e = cudaMemsetAsync(fvis, 0, ((size_t)a.F2 + 1) * sizeof(int), st);
@@ -523,43 +532,101 @@ inline int launch_backward_rgb(RgbBwdArgs a, int* fvis, int* big_jobs, cudaStrea
   k_backward_rgb_warp<<<ceil_div(a.F2 * 6, 8), 256, 0, st>>>(a, big_jobs);
   SLN_TRY(check_launch(what));
   k_backward_rgb_cta<<<min(a.F2 * 6, 4 * kNumSMs), 32 * kBigWarps, 0, st>>>(a, big_jobs);
+  SLN_TRY(check_launch(what));
+  k_rgb_combine<<<ceil_div(a.F2 * 6, 256), 256, 0, st>>>(jobg, a.F2, a.grad_faces);
   return check_launch(what);
 }
 
 // ------------------------------------------------------------------------------------------------ backward: depth
-__global__ void k_backward_depth(const float* __restrict__ fv, const float* __restrict__ finv, const float* __restrict__ depth_map,
-                                 const int* __restrict__ face_index_map, const float* __restrict__ weight_map,
-                                 const float* __restrict__ grad_depth_map, int is, float* grad_faces) {
-  int pn = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pn >= is * is) return;
-  const int fn = face_index_map[pn];
-  if (fn < 0) return;
-  const float g = grad_depth_map[pn];
-  if (g == 0.f) return;
-  const float* face = fv + 9 * (size_t)fn;
-  const float* fi = finv + 9 * (size_t)fn;
-  const float depth = depth_map[pn], depth2 = depth * depth;
-  float* gf = grad_faces + 9 * (size_t)fn;
-  float w[3] = {weight_map[3 * pn], weight_map[3 * pn + 1], weight_map[3 * pn + 2]};
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const float zk = face[3 * k + 2];
-    atomicAdd(gf + 3 * k + 2, g * w[k] * depth2 / (zk * zk));
-  }
+// One warp per face gathers the pixels that show the face inside its pixel box (lanes stride the box row-major, fixed-order
+// shuffle tree): a single writer per face, no floating-point atomics.  Per pixel the arithmetic is the per-pixel scatter of the
+// published kernel (d depth / d z_k through the barycentric weights, d depth / d xy through the pixel-space inverse).
+constexpr int kDepthBigPixels = 256;      // pixel boxes above this are gathered by a whole CTA (room-shell faces can span the image)
+struct DepthBwdArgs {
+  const float* fv; const float* finv; const int4* fbox; const float* depth_map; const int* face_index_map; const float* weight_map;
+  const float* grad_depth_map; int is, F2; float* grad_faces;
+};
+// partial sums of face fn over the pixels i = first, first + stride, ... of its box (row-major): 9 accumulators per thread
+__device__ __forceinline__ bool depth_face_partial(const DepthBwdArgs& a, int fn, const int4 bx, int first, int stride, float (&acc)[9]) {
+  const float* face = a.fv + 9 * (size_t)fn;
+  const float* fi = a.finv + 9 * (size_t)fn;
   float tmp[2] = {0.f, 0.f};
 #pragma unroll
   for (int k = 0; k < 2; ++k)
 #pragma unroll
     for (int l = 0; l < 3; ++l) tmp[k] += -fi[3 * l + k] / face[3 * l + 2];
-  const float fis = (float)is;
+  const float fis = (float)a.is;
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
+  for (int j = 0; j < 9; ++j) acc[j] = 0.f;
+  const int w = bx.y - bx.x + 1, n = w * (bx.w - bx.z + 1);
+  bool any = false;
+  for (int i = first; i < n; i += stride) {
+    const int pn = (bx.z + i / w) * a.is + bx.x + i % w;
+    if (a.face_index_map[pn] != fn) continue;
+    const float g = a.grad_depth_map[pn];
+    if (g == 0.f) continue;
+    any = true;
+    const float depth = a.depth_map[pn], depth2 = depth * depth;
 #pragma unroll
-    for (int l = 0; l < 2; ++l) atomicAdd(gf + 3 * k + l, -g * tmp[l] * w[k] * depth2 * fis / 2.f);
+    for (int k = 0; k < 3; ++k) {
+      const float wk = a.weight_map[3 * pn + k], zk = face[3 * k + 2];
+      acc[3 * k + 2] += g * wk * depth2 / (zk * zk);
+#pragma unroll
+      for (int l = 0; l < 2; ++l) acc[3 * k + l] += -g * tmp[l] * wk * depth2 * fis / 2.f;
+    }
+  }
+  return any;
+}
+__global__ void __launch_bounds__(256) k_backward_depth(const DepthBwdArgs a, int* __restrict__ big_list) {
+  const int fn = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (fn >= a.F2) return;
+  const int4 bx = a.fbox[fn];                                // x0, x1, y0, y1 inclusive; x0 > x1: never drawn
+  if (bx.x > bx.y || bx.z > bx.w) return;
+  if ((bx.y - bx.x + 1) * (bx.w - bx.z + 1) > kDepthBigPixels) {   // deferred to the CTA-per-face launch (integer atomic: list order is irrelevant)
+    if (lane == 0) big_list[1 + atomicAdd(big_list, 1)] = fn;
+    return;
+  }
+  float acc[9];
+  const bool any = depth_face_partial(a, fn, bx, lane, 32, acc);
+  if (!__any_sync(0xffffffffu, any)) return;
+#pragma unroll
+  for (int j = 0; j < 9; ++j) acc[j] = warp_sum(acc[j]);
+  if (lane == 0) {
+    float* gf = a.grad_faces + 9 * (size_t)fn;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) if (acc[j] != 0.f) gf[j] += acc[j];
+  }
+}
+__global__ void __launch_bounds__(1024) k_backward_depth_cta(const DepthBwdArgs a, const int* __restrict__ big_list) {
+  __shared__ float sh[32][9];
+  const int lane = threadIdx.x & 31, w_idx = threadIdx.x >> 5;
+  const int n = big_list[0];
+  for (int li = blockIdx.x; li < n; li += gridDim.x) {
+    const int fn = big_list[1 + li];
+    float acc[9];
+    depth_face_partial(a, fn, a.fbox[fn], threadIdx.x, 1024, acc);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) sh[w_idx][j] = acc[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+      float t = 0.f;
+      for (int w = 0; w < 32; ++w) t += sh[w][threadIdx.x];
+      if (t != 0.f) a.grad_faces[9 * (size_t)fn + threadIdx.x] += t;
+    }
+    __syncthreads();
+  }
 }
 
-// grad_fv [F2,9] -> grad_pv [V,3]  (transpose of vertices_to_faces incl. the fill_back copies)
-__global__ void k_faces_to_vertices_bwd(const float* __restrict__ grad_fv, const int* __restrict__ faces, int F, int fill_back, float* grad_pv) {
+// grad_fv [F2,9] -> grad_pv [V,3]  (transpose of vertices_to_faces incl. the fill_back copies).  A vertex is shared by a handful of
+// faces whose ids are arbitrary, so the scatter stays — but into 64-bit FIXED-POINT accumulators (2^-32 resolution, +-2.1e9 range):
+// integer addition is associative, the result does not depend on the order in which the atomics land.
+constexpr double kFixScale = 4294967296.0;   // 2^32
+__device__ __forceinline__ float fix_to_float(long long v) { return (float)((double)v * (1.0 / kFixScale)); }
+__global__ void k_faces_to_vertices_bwd(const float* __restrict__ grad_fv, const int* __restrict__ faces, int F, int fill_back, long long* grad_pv) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;   // one (face, corner) per thread
   const int F2 = fill_back ? 2 * F : F;
   if (e >= F2 * 3) return;
@@ -569,7 +636,10 @@ __global__ void k_faces_to_vertices_bwd(const float* __restrict__ grad_fv, const
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     float g = grad_fv[9 * (size_t)f + 3 * k + d];
-    if (g != 0.f) atomicAdd(grad_pv + 3 * (size_t)vi + d, g);
+    if (g != 0.f) {
+      g = fminf(fmaxf(g, -2.0e9f), 2.0e9f);
+      atomicAdd(reinterpret_cast<unsigned long long*>(grad_pv + 3 * (size_t)vi + d), (unsigned long long)__double2ll_rn((double)g * kFixScale));
+    }
   }
 }
 
@@ -631,7 +701,7 @@ using namespace sln;
 
 // workspace layout (all 256-byte aligned): pv [V,3] | fv [F2,9] | finv [F2,9] | fbox [F2] int4
 namespace {
-struct RasterPlan { float* pv; float* fv; float* finv; int4* fbox; int* fvis; size_t bytes; };
+struct RasterPlan { float* pv; float* fv; float* finv; int4* fbox; int* fvis; float* jobg; size_t bytes; };
 RasterPlan plan_raster(void* ws, int64_t V, int64_t F2) {
   Arena ar(ws, (size_t)-1);
   RasterPlan p;
@@ -640,6 +710,7 @@ RasterPlan plan_raster(void* ws, int64_t V, int64_t F2) {
   p.finv = ar.take<float>(9 * (size_t)F2);
   p.fbox = ar.take<int4>((size_t)F2);
   p.fvis = ar.take<int>((size_t)F2 + 1 + 6 * (size_t)F2);   // backward scratch: fvis [F2] (does the face own a pixel?) | big_jobs [1 + 6 F2] (count, job ids)
+  p.jobg = ar.take<float>(12 * (size_t)F2);                 // backward scratch: the two partial sums of every (face, edge, axis) job
   p.bytes = ar.off;
   return p;
 }
@@ -736,7 +807,7 @@ int sln_raster_backward_rgb(const void* ws, int64_t V, int64_t F, int32_t fill_b
   a.fv = p.fv; a.face_index_map = face_index_map; a.F2 = (int)F2; a.is = image_size; a.eps = eps;
   a.img = rgb_map; a.gimg = grad_rgb_map; a.C = 3; a.grad_faces = grad_faces;
   ProfScope prof((cudaStream_t)stream, PROF_RASTER_BWD, 36.0 * F2 + 28.0 * image_size * image_size);
-  return launch_backward_rgb(a, p.fvis, p.fvis + F2, (cudaStream_t)stream, "backward_rgb");
+  return launch_backward_rgb(a, p.fvis, p.fvis + F2, p.jobg, (cudaStream_t)stream, "backward_rgb");
 }
 
 int sln_raster_backward_depth(const void* ws, int64_t V, int64_t F, int32_t fill_back, int32_t image_size, const int32_t* face_index_map,
@@ -746,9 +817,17 @@ int sln_raster_backward_depth(const void* ws, int64_t V, int64_t F, int32_t fill
   RasterPlan p = plan_raster((void*)ws, V, fill_back ? 2 * F : F);
   const int P = image_size * image_size;
   ProfScope prof((cudaStream_t)stream, PROF_RASTER_BWD, 24.0 * P);
-  k_backward_depth<<<ceil_div(P, 256), 256, 0, (cudaStream_t)stream>>>(p.fv, p.finv, depth_map, face_index_map, weight_map, grad_depth_map,
-                                                                      image_size, grad_faces);
-  return check_launch("backward_depth");
+  const int F2 = (int)(fill_back ? 2 * F : F);
+  (void)P;
+  if (F2 == 0) return SLN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int* big_list = p.fvis + F2;                               // the deferred-job list of the workspace plan (count, ids): shared with the rgb pass, used in turn
+  SLN_CUDA_TRY(cudaMemsetAsync(big_list, 0, sizeof(int), st));
+  DepthBwdArgs a{p.fv, p.finv, p.fbox, depth_map, face_index_map, weight_map, grad_depth_map, image_size, F2, grad_faces};
+  k_backward_depth<<<ceil_div(F2, 8), 256, 0, st>>>(a, big_list);
+  SLN_TRY(check_launch("backward_depth"));
+  k_backward_depth_cta<<<min(F2, 2 * kNumSMs), 1024, 0, st>>>(a, big_list);
+  return check_launch("backward_depth_cta");
 }
 
 int sln_raster_vertex_grad(const void* ws, const float* vertices, int64_t V, const int32_t* faces, int64_t F, int32_t fill_back,
@@ -758,12 +837,14 @@ int sln_raster_vertex_grad(const void* ws, const float* vertices, int64_t V, con
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t F2 = fill_back ? 2 * F : F;
   ProfScope prof(st, PROF_RASTER_BWD, 36.0 * F2 + 36.0 * V);
-  SLN_CUDA_TRY(cudaMemsetAsync(grad_proj_scratch, 0, sizeof(float) * 3 * (size_t)V, st));
+  SLN_CHECK_ARG((uintptr_t)grad_proj_scratch % 8 == 0, "grad_proj_scratch must be 8-byte aligned (24 V bytes of fixed-point accumulators)");
+  long long* acc = reinterpret_cast<long long*>(grad_proj_scratch);
+  SLN_CUDA_TRY(cudaMemsetAsync(acc, 0, sizeof(long long) * 3 * (size_t)V, st));
   if (F2 > 0) {
-    k_faces_to_vertices_bwd<<<ceil_div((int)F2 * 3, 256), 256, 0, st>>>(grad_faces, faces, (int)F, fill_back, grad_proj_scratch);
+    k_faces_to_vertices_bwd<<<ceil_div((int)F2 * 3, 256), 256, 0, st>>>(grad_faces, faces, (int)F, fill_back, acc);
     SLN_TRY(check_launch("faces_to_vertices_bwd"));
   }
-  k_project_bwd<<<ceil_div((int)V, 256), 256, 0, st>>>(vertices, (int)V, K, R, t, orig_size, grad_proj_scratch, grad_vertices);
+  k_project_bwd<<<ceil_div((int)V, 256), 256, 0, st>>>(vertices, (int)V, K, R, t, orig_size, acc, grad_vertices);
   return check_launch("project_bwd");
 }
 
@@ -794,7 +875,7 @@ int sln_scene_classes_bwd(const void* ws, int64_t V, int64_t F, int32_t fill_bac
   a.fv = p.fv; a.face_index_map = face_index_map; a.F2 = (int)F2; a.is = image_size; a.eps = eps;
   a.face_cls = face_cls; a.sval = sval; a.gcls = grad_class_images_internal; a.n_cls = n_cls; a.grad_faces = grad_faces;
   ProfScope prof((cudaStream_t)stream, PROF_RASTER_BWD, 36.0 * F2 + (12.0 + 4.0 * n_cls) * image_size * image_size);
-  return launch_backward_rgb(a, p.fvis, p.fvis + F2, (cudaStream_t)stream, "scene_backward_rgb");
+  return launch_backward_rgb(a, p.fvis, p.fvis + F2, p.jobg, (cudaStream_t)stream, "scene_backward_rgb");
 }
 
 }  // extern "C"

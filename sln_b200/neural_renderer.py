@@ -81,7 +81,7 @@ class _Raster(object):
         return view(pv, 3 * self.V).view(self.V, 3), view(fv, 9 * self.F2).view(self.F2, 9), view(finv, 9 * self.F2).view(self.F2, 9)
 
     def vertex_grad(self, grad_faces):
-        scratch = torch.empty(self.V, 3, dtype=torch.float32, device=self.dev)
+        scratch = torch.empty(self.V, 3, dtype=torch.int64, device=self.dev)     # 64-bit fixed-point accumulators (deterministic scatter)
         gv = torch.empty(self.V, 3, dtype=torch.float32, device=self.dev)
         _lib.check(self.lib.sln_raster_vertex_grad(self.ws.data_ptr(), self.vertices.data_ptr(), self.V, self.faces.data_ptr(), self.F,
                                                    self.fill_back, self.K.data_ptr(), self.R.data_ptr(), self.t.data_ptr(), self.orig,
