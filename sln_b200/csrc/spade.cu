@@ -7,11 +7,14 @@
 // TF32/BF16 miss the 1e-4 contract by 40-300x).  The gamma and beta convolutions of a SPADE4 are ONE contraction over
 // interleaved weight rows whose epilogue (TcEpiSpade) computes lrelu(x_hat * (1 + gamma) + beta) directly: gamma and beta
 // never reach HBM (they are 61 % of the generator's FLOPs and would be 2 x C x H x W floats per SPADE4 otherwise).
+#include <type_traits>
+
 #include "../../include/sln_b200.h"
 // The convolutions run 128 x 128 tiles over K = 1152 .. 9216 (multi-segment accumulation: 64 extra registers per thread); at 16
 // producer warps ptxas is held to 96 registers and spills in exactly those variants (measured: 346 -> 332 images/s).  This
 // translation unit keeps 8 producer warps; the VAE engine (small tiles, short K) takes 16 (3.44 -> 3.15 ms per train step).
 #define SLN_TC_PROD_WARPS 8
+#define SLN_TC_PF_DEEP 2        // long K (1152 .. 9216): two chunks in flight suffice and leave registers to the im2col arithmetic (4: -3 %)
 #include "gemm.cuh"
 #include "tc_gemm.cuh"
 
@@ -23,12 +26,13 @@ __device__ __forceinline__ int reflect(int v, int n) { return v < 0 ? -v : (v >=
 // Virtual [B*H*W, ks*ks*C] matrix over an NHWC tensor: row = output pixel, column k = (ky*ks + kx)*C + c, reading the
 // input at the REFLECTED position (y + ky - ks/2, x + kx - ks/2)   (nn.ReflectionPad2d(1) + Conv2d(k=3, padding=0)), or the
 // pixel itself for ks == 1.  Optional lazy ReLU on load.
-struct Im2col {
+template <bool ZP>   // ZP: zero padding (compile-time: the reflect variant carries no validity bits and no extra branch in its hot loop)
+struct Im2colT {
   static constexpr bool kTwoLoads = false;
   const float* p;
   int H, W, C, ks, rows, cols, relu, vec;
   int cshift;   // log2(C) when C is a power of two (the usual case), else -1: k -> (tap, c) without an integer division
-  int zpad;     // 0: ReflectionPad2d(1) (SPADE4 / SPADEResnetBlock4); 1: zero padding = nn.Conv2d(padding=1) of the plain SPADE blocks
+  static constexpr int zpad = ZP ? 1 : 0;   // 0: ReflectionPad2d(1) (SPADE4 / SPADEResnetBlock4); 1: zero padding = nn.Conv2d(padding=1) of the plain SPADE blocks
   __device__ __forceinline__ float elem(int r, int k) const {
     const int tap = ks == 3 ? k / C : 0, c = k - tap * C;
     const int ky = ks == 3 ? tap / 3 : 1, kx = ks == 3 ? tap - 3 * (tap / 3) : 1;
@@ -59,19 +63,21 @@ struct Im2col {
     return v;
   }
   // two-phase API of the tensor-core loader: the token holds the image base and the three reflected row / column offsets
-  struct Tok { const float* base; int y0, y1, y2, x0, x1, x2; int valid; };   // valid: bit ky = row tap inside the image, bit 3 + kx = column tap
+  struct TokR { const float* base; int y0, y1, y2, x0, x1, x2; };
+  struct TokZ { const float* base; int y0, y1, y2, x0, x1, x2; int valid; };   // valid: bit ky = row tap inside the image, bit 3 + kx = column tap
+  using Tok = typename std::conditional<ZP, TokZ, TokR>::type;
   __device__ __forceinline__ Tok token(int r) const {
     r = min(r, rows - 1);
     const int hw = H * W, b = r / hw, rem = r - b * hw, y = rem / W, x = rem - y * W;
     Tok t;
     t.base = p + (size_t)b * hw * C;
-    t.valid = 63;
     if (ks == 3) {
       t.y0 = reflect(y - 1, H) * W; t.y1 = y * W; t.y2 = reflect(y + 1, H) * W;
       t.x0 = reflect(x - 1, W); t.x1 = x; t.x2 = reflect(x + 1, W);
-      if (zpad) t.valid = (y >= 1 ? 1 : 0) | 2 | (y + 1 < H ? 4 : 0) | (x >= 1 ? 8 : 0) | 16 | (x + 1 < W ? 32 : 0);
+      if constexpr (ZP) t.valid = (y >= 1 ? 1 : 0) | 2 | (y + 1 < H ? 4 : 0) | (x >= 1 ? 8 : 0) | 16 | (x + 1 < W ? 32 : 0);
     } else {
       t.y0 = t.y1 = t.y2 = y * W; t.x0 = t.x1 = t.x2 = x;
+      if constexpr (ZP) t.valid = 63;
     }
     return t;
   }
@@ -80,7 +86,9 @@ struct Im2col {
     const int tap = ks == 3 ? (cshift >= 0 ? (k >> cshift) : k / C) : 0, c = k - tap * C;
     const int ky = ks == 3 ? (tap * 11) >> 5 : 1, kx = ks == 3 ? tap - 3 * ky : 1;      // tap / 3 for tap < 9
     const int yo = ky == 0 ? t.y0 : (ky == 1 ? t.y1 : t.y2), xo = kx == 0 ? t.x0 : (kx == 1 ? t.x1 : t.x2);
-    if (zpad && !(((t.valid >> ky) & 1) && ((t.valid >> (3 + kx)) & 1))) { a = make_float4(0.f, 0.f, 0.f, 0.f); return; }   // outside: zero
+    if constexpr (ZP) {
+      if (!(((t.valid >> ky) & 1) && ((t.valid >> (3 + kx)) & 1))) { a = make_float4(0.f, 0.f, 0.f, 0.f); return; }   // outside: zero
+    }
     a = ldg4(t.base + (size_t)(unsigned)((yo + xo) * C + c));
   }
   __device__ __forceinline__ float4 finish4(const Tok&, int, float4 v, float4) const {
@@ -90,9 +98,11 @@ struct Im2col {
   bool vec_ok() const { return vec != 0; }
 };
 
-Im2col make_im2col(const float* p, int B, int H, int W, int C, int ks, int relu, int zpad = 0) {
-  Im2col a;
-  a.zpad = zpad;
+using Im2col = Im2colT<false>;
+using Im2colZ = Im2colT<true>;
+template <bool ZP>
+Im2colT<ZP> make_im2col(const float* p, int B, int H, int W, int C, int ks, int relu) {
+  Im2colT<ZP> a;
   a.p = p; a.H = H; a.W = W; a.C = C; a.ks = ks; a.rows = B * H * W; a.cols = ks * ks * C; a.relu = relu;
   a.vec = (C % 4 == 0 && (uintptr_t)p % 16 == 0) ? 1 : 0;
   a.cshift = -1;
@@ -136,7 +146,8 @@ struct TcEpiSpade {
 };
 
 // direct fallback of the modulation for channel counts the paired tiles cannot hold (2C < 32: reduced test models only)
-__global__ void k_modulate_direct(const Im2col A, const float* __restrict__ Wg, const float* __restrict__ Wb, const float* __restrict__ bg,
+template <class AT>
+__global__ void k_modulate_direct(const AT A, const float* __restrict__ Wg, const float* __restrict__ Wb, const float* __restrict__ bg,
                                   const float* __restrict__ bb, int C, const float* __restrict__ x, const float* __restrict__ mean,
                                   const float* __restrict__ inv, int HW, float slope, float* out, int sb, int sc) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -464,17 +475,12 @@ int sln_spade_conv(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin,
   return sln_conv2d_nhwc(x, B, H, W, Cin, ks, relu_in, 0, Wp, Wpacked, bias, Cout, out, stream);
 }
 
-int sln_conv2d_nhwc(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, int32_t pad_mode, const float* Wp,
-                    const float* Wpacked, const float* bias, int64_t Cout, float* out, void* stream) {
-  SLN_TRY(check_img(B, H, W, Cin));
-  SLN_CHECK_ARG(pad_mode == 0 || pad_mode == 1, "pad_mode: 0 reflection, 1 zeros");
-  SLN_CHECK_ARG(x && Wp && out && Cout >= 1, "null pointer");
-  SLN_CHECK_ARG(ks == 1 || ks == 3, "kernel size must be 1 or 3 (reflection-padded)");
-  SLN_CHECK_ARG(ks == 1 || (H >= 2 && W >= 2), "reflection padding needs at least 2 rows and columns");
-  SLN_CHECK_ARG(H * W * Cin < (1ll << 31), "one image must have fewer than 2^31 elements");
-  cudaStream_t st = (cudaStream_t)stream;
+}  // extern "C" (templates cannot have C linkage)
+template <bool ZP>
+static int conv2d_impl(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, const float* Wp,
+                       const float* Wpacked, const float* bias, int64_t Cout, float* out, cudaStream_t st) {
   const int M = (int)(B * H * W), N = (int)Cout, K = (int)(ks * ks * Cin);
-  Im2col A = make_im2col(x, (int)B, (int)H, (int)W, (int)Cin, ks, relu_in, pad_mode);
+  Im2colT<ZP> A = make_im2col<ZP>(x, (int)B, (int)H, (int)W, (int)Cin, ks, relu_in);
   MatView Wv = make_view(Wp, K, N, K);
   EpiStore epi; memset(&epi, 0, sizeof(epi));
   epi.C = out; epi.ldc = N; epi.bias = bias;
@@ -490,23 +496,33 @@ int sln_conv2d_nhwc(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin
   return launch_gemm<true, true>(st, A, Wv, epi, M, N, K, false, "spade_conv", PROF_SPADE_CONV);
 }
 
+extern "C" {
+int sln_conv2d_nhwc(const float* x, int64_t B, int64_t H, int64_t W, int64_t Cin, int32_t ks, int32_t relu_in, int32_t pad_mode, const float* Wp,
+                    const float* Wpacked, const float* bias, int64_t Cout, float* out, void* stream) {
+  SLN_TRY(check_img(B, H, W, Cin));
+  SLN_CHECK_ARG(pad_mode == 0 || pad_mode == 1, "pad_mode: 0 reflection, 1 zeros");
+  SLN_CHECK_ARG(x && Wp && out && Cout >= 1, "null pointer");
+  SLN_CHECK_ARG(ks == 1 || ks == 3, "kernel size must be 1 or 3");
+  SLN_CHECK_ARG(ks == 1 || pad_mode == 1 || (H >= 2 && W >= 2), "reflection padding needs at least 2 rows and columns");
+  SLN_CHECK_ARG(H * W * Cin < (1ll << 31), "one image must have fewer than 2^31 elements");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pad_mode == 1 && ks == 3) return conv2d_impl<true>(x, B, H, W, Cin, ks, relu_in, Wp, Wpacked, bias, Cout, out, st);
+  return conv2d_impl<false>(x, B, H, W, Cin, ks, relu_in, Wp, Wpacked, bias, Cout, out, st);
+}
+
 int sln_spade_modulate(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* Wgb_packed, const float* bias_g,
                        const float* bias_b, int64_t C, int32_t pair, const float* x, const float* mean, const float* inv, float slope, float* out,
                        void* stream) {
   return sln_spade_modulate_ex(actv, B, H, W, Ca, Wgb, Wgb_packed, bias_g, bias_b, C, pair, x, mean, inv, 1, 0, 0, slope, out, stream);
 }
 
-int sln_spade_modulate_ex(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* Wgb_packed,
-                          const float* bias_g, const float* bias_b, int64_t C, int32_t pair, const float* x, const float* mean, const float* inv,
-                          int32_t stat_stride_b, int32_t stat_stride_c, int32_t pad_mode, float slope, float* out, void* stream) {
-  SLN_TRY(check_img(B, H, W, Ca));
-  SLN_CHECK_ARG((pad_mode == 0 || pad_mode == 1) && (stat_stride_c == 0 || stat_stride_c == 1) && stat_stride_b >= 0, "bad statistics layout / pad mode");
-  SLN_CHECK_ARG(stat_stride_c == 0 || (((uintptr_t)mean | (uintptr_t)inv) % 16 == 0 && stat_stride_b % 4 == 0), "per-channel statistics must be 16-byte aligned rows");
-  SLN_CHECK_ARG(actv && Wgb && bias_g && bias_b && x && mean && inv && out, "null pointer");
-  SLN_CHECK_ARG(H >= 2 && W >= 2 && C >= 1 && pair >= 2 && (2 * C) % pair == 0, "bad modulation shape");
-  cudaStream_t st = (cudaStream_t)stream;
+}  // extern "C"
+template <bool ZP>
+static int modulate_impl(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* Wgb_packed,
+                         const float* bias_g, const float* bias_b, int64_t C, int32_t pair, const float* x, const float* mean, const float* inv,
+                         int32_t stat_stride_b, int32_t stat_stride_c, float slope, float* out, cudaStream_t st) {
   const int M = (int)(B * H * W), N = (int)(2 * C), K = (int)(9 * Ca);
-  Im2col A = make_im2col(actv, (int)B, (int)H, (int)W, (int)Ca, 3, 1, pad_mode);   // ReLU of mlp_shared applied on load
+  Im2colT<ZP> A = make_im2col<ZP>(actv, (int)B, (int)H, (int)W, (int)Ca, 3, 1);   // ReLU of mlp_shared applied on load
   MatView Wv = make_view(Wgb, K, N, K);
   const bool tc_ok = (pair == 32 || pair == 64 || pair == 128) && C % 4 == 0 && A.vec_ok() && Wv.vec_ok() && ((uintptr_t)x % 16 == 0) &&
                      ((uintptr_t)out % 16 == 0) && ((uintptr_t)bias_g % 16 == 0) && ((uintptr_t)bias_b % 16 == 0);
@@ -530,8 +546,23 @@ int sln_spade_modulate_ex(const float* actv, int64_t B, int64_t H, int64_t W, in
   // interleaved weight rows: tile t = [gamma of channels t*half .. | beta of the same]; the direct kernel needs them per channel
   SLN_CHECK_ARG(pair == 2 * C, "the direct modulation fallback expects a single pair tile (pair == 2C)");
   const long long total = (long long)M * C;
-  k_modulate_direct<<<(int)ceil_div64(total, 256), 256, 0, st>>>(A, Wgb, Wgb + (size_t)C * K, bias_g, bias_b, (int)C, x, mean, inv, (int)(H * W), slope, out, stat_stride_b, stat_stride_c);
+  k_modulate_direct<<<(int)ceil_div64(total, 256), 256, 0, st>>>(A, Wgb, Wgb + (size_t)C * K, bias_g, bias_b, (int)C, x, mean, inv, (int)(H * W), slope, out,
+                                                                    stat_stride_b, stat_stride_c);
   return check_launch("spade_modulate_direct");
+}
+
+extern "C" {
+int sln_spade_modulate_ex(const float* actv, int64_t B, int64_t H, int64_t W, int64_t Ca, const float* Wgb, const float* Wgb_packed,
+                          const float* bias_g, const float* bias_b, int64_t C, int32_t pair, const float* x, const float* mean, const float* inv,
+                          int32_t stat_stride_b, int32_t stat_stride_c, int32_t pad_mode, float slope, float* out, void* stream) {
+  SLN_TRY(check_img(B, H, W, Ca));
+  SLN_CHECK_ARG((pad_mode == 0 || pad_mode == 1) && (stat_stride_c == 0 || stat_stride_c == 1) && stat_stride_b >= 0, "bad statistics layout / pad mode");
+  SLN_CHECK_ARG(stat_stride_c == 0 || (((uintptr_t)mean | (uintptr_t)inv) % 16 == 0 && stat_stride_b % 4 == 0), "per-channel statistics must be 16-byte aligned rows");
+  SLN_CHECK_ARG(actv && Wgb && bias_g && bias_b && x && mean && inv && out, "null pointer");
+  SLN_CHECK_ARG((pad_mode == 1 || (H >= 2 && W >= 2)) && C >= 1 && pair >= 2 && (2 * C) % pair == 0, "bad modulation shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pad_mode == 1) return modulate_impl<true>(actv, B, H, W, Ca, Wgb, Wgb_packed, bias_g, bias_b, C, pair, x, mean, inv, stat_stride_b, stat_stride_c, slope, out, st);
+  return modulate_impl<false>(actv, B, H, W, Ca, Wgb, Wgb_packed, bias_g, bias_b, C, pair, x, mean, inv, stat_stride_b, stat_stride_c, slope, out, st);
 }
 
 int sln_spade_ln_stats(const float* x, int64_t B, int64_t n_per_sample, float eps, void* scratch, float* mean, float* inv, void* stream) {

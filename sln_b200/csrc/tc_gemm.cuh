@@ -24,6 +24,9 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 32;            // floats per K chunk: 128 bytes = one SWIZZLE_128B row
+#ifndef SLN_TC_PF_DEEP
+#define SLN_TC_PF_DEEP 4      // register-prefetch depth for single-load A functors with pre-split B (per translation unit)
+#endif
 #ifndef SLN_TC_PROD_WARPS
 #define SLN_TC_PROD_WARPS 16
 #endif
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   // at the start of produce(c + PF), i.e. PF - 1 chunk periods later: with PF = 2 the period settled at the (loaded) L2 latency of
   // ~900 cycles (phase trace, profiles/r2_trace_contract.txt).  Operands that arrive as a pre-split image (PackedB) need no B
   // registers, so the single-load A functors can afford 4 chunks in flight (64 registers; one CTA per SM allows 224).
-  constexpr int S = L::STAGES, PF = MSEG ? 1 : ((is_packed<BOp>::value && !AOp::kTwoLoads) ? 4 : 2);
+  constexpr int S = L::STAGES, PF = MSEG ? 1 : ((is_packed<BOp>::value && !AOp::kTwoLoads) ? SLN_TC_PF_DEEP : 2);
   constexpr bool BP = is_packed<BOp>::value;       // B tiles arrive by cp.async.bulk from a pre-split, pre-tiled image
   extern __shared__ char smem_raw[];
   char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
