@@ -10,10 +10,11 @@
 #include <type_traits>
 
 #include "../../include/sln_b200.h"
-// The convolutions run 128 x 128 tiles over K = 1152 .. 9216 (multi-segment accumulation: 64 extra registers per thread); at 16
-// producer warps ptxas is held to 96 registers and spills in exactly those variants (measured: 346 -> 332 images/s).  This
-// translation unit keeps 8 producer warps; the VAE engine (small tiles, short K) takes 16 (3.44 -> 3.15 ms per train step).
-#define SLN_TC_PROD_WARPS 8
+// 16 producer warps, like the VAE engine: the long-K convolutions accumulate over several TMEM segments into a per-thread
+// running sum, and with the accumulator columns split over PROD_WARPS/4 column groups (tc_gemm.cuh) that sum is 32 registers
+// at 16 warps, which fits the 96-register cap (with the 64-register sum of an 8-warp-style split the 16-warp build spilled
+// and lost: 346 -> 332 images/s).  Measured, same box: 8 warps 349 images/s, 16 warps 392.
+#define SLN_TC_PROD_WARPS 16
 #define SLN_TC_PF_DEEP 2        // long K (1152 .. 9216): two chunks in flight suffice and leave registers to the im2col arithmetic (4: -3 %)
 #include "gemm.cuh"
 #include "tc_gemm.cuh"

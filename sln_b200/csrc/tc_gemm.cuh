@@ -99,6 +99,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+
 // Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in [0,14), leading byte
 // offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
 //   K-major tile  [rows][32 floats]: canonical ((8,n),2):((8,SBO),1) in 16-byte units — 8-row groups 1024 B apart (SBO), LBO unused;
@@ -459,18 +475,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   asm volatile("griddepcontrol.wait;" ::: "memory");   // everything above overlapped the previous kernel's tail; its results are visible from here on
   TC_TRACE(1);
 
-  const int quad = warp & 3, half = (warp >> 2) & 1;    // TMEM lane quadrant (fixed by warp id % 4), column half
-  // BN >= 64: warps 0-3 own the left half of the columns, warps 4-7 the right half; BN = 32: only warps 0-3 hold accumulators
-  constexpr int CH2 = BN >= 64 ? BN / 64 : 1;           // 32-column chunks owned by one thread
-  const bool has_acc = warp < 8 && (BN >= 64 || half == 0);     // warps 0-7 read the accumulators (quadrant x column half); all producer warps apply the epilogue
-  const int col_off = BN >= 64 ? half * (BN / 2) : 0;
+  const int quad = warp & 3, cg = warp >> 2;            // TMEM lane quadrant (fixed by warp id % 4), column group
+  // the BN accumulator columns are split over the PROD_WARPS/4 column groups in chunks of CW = 32 (or 16) columns: with 8 warps
+  // and BN = 128 a thread owns 2 x 32 columns, with 16 warps 32 (BN = 128) or 16 (BN = 64): half the registers of the
+  // multi-segment running sum and half the TMEM reads per warp; groups past BN/CW idle
+  constexpr int NCG = PROD_WARPS / 4, CW = BN / NCG >= 32 ? 32 : 16;   // column groups, chunk width
+  constexpr int CGA = BN / CW < NCG ? BN / CW : NCG;    // groups that hold accumulators
+  constexpr int CH2 = BN / CW / CGA;                    // CW-column chunks owned by one thread
+  const bool has_acc = cg < CGA;                        // all producer warps apply the epilogue, these read the accumulators
+  const int col_off = cg * (BN / CGA);
   const uint32_t tmem_mine = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_off;
-  float racc[MSEG ? CH2 : 1][32];      // MSEG: running sum over the drained segments (otherwise the sum is formed in the epilogue)
+  float racc[MSEG ? CH2 : 1][CW];      // MSEG: running sum over the drained segments (otherwise the sum is formed in the epilogue)
   if (MSEG) {
 #pragma unroll
     for (int j = 0; j < (MSEG ? CH2 : 1); ++j)
 #pragma unroll
-      for (int e = 0; e < 32; ++e) racc[j][e] = 0.f;
+      for (int e = 0; e < CW; ++e) racc[j][e] = 0.f;
   }
 
   if (warp == MMA_WARP) {
@@ -513,10 +533,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
         for (int rg = 0; rg < NREG; ++rg) {
 #pragma unroll
           for (int j = 0; j < (MSEG ? CH2 : 1); ++j) {
-            float v[32];
-            tmem_ld32(tmem_mine + (uint32_t)(rg * BN + j * 32), v);
+            float v[CW];
+            tmem_ldw(tmem_mine + (uint32_t)(rg * BN + j * CW), v);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) racc[j][e] += v[e];
+            for (int e = 0; e < CW; ++e) racc[j][e] += v[e];
           }
         }
       }
@@ -599,26 +619,26 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
     const int r = quad * 32 + lane;
 #pragma unroll
     for (int j = 0; j < CH2; ++j) {
-      float acc[32];
+      float acc[CW];
       if (MSEG) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] = racc[MSEG ? j : 0][e];
+        for (int e = 0; e < CW; ++e) acc[e] = racc[MSEG ? j : 0][e];
       } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+        for (int e = 0; e < CW; ++e) acc[e] = 0.f;
         if (nchunks > 0) {
 #pragma unroll
           for (int rg = 0; rg < NREG; ++rg) {
-            float v[32];
-            tmem_ld32(tmem_mine + (uint32_t)(rg * BN + j * 32), v);
+            float v[CW];
+            tmem_ldw(tmem_mine + (uint32_t)(rg * BN + j * CW), v);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) acc[e] += v[e];
+            for (int e = 0; e < CW; ++e) acc[e] += v[e];
           }
         }
       }
 #pragma unroll
-      for (int e = 0; e < 32; e += 4)
-        *reinterpret_cast<float4*>(outs + (size_t)r * L::OUT_LD + col_off + j * 32 + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
+      for (int e = 0; e < CW; e += 4)
+        *reinterpret_cast<float4*>(outs + (size_t)r * L::OUT_LD + col_off + j * CW + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
     }
   }
   __syncthreads();
