@@ -140,7 +140,7 @@ def run(args):
     if n == 1 and not args.no_cpu_baseline:
         cpu = cpu_render_baseline(budget_s=25.0)
     ref60 = None
-    if n == 1:
+    if n == 1 and not args.no_graph:        # --no-graph is the profiling mode: keep its launch list to the headline iteration
         try:
             ref60 = reference60(dev)
         except Exception as e:      # secondary variant: never fail the bench line because of it

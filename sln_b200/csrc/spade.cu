@@ -239,7 +239,19 @@ __global__ void __launch_bounds__(256) k_ln_partial(const float* __restrict__ x,
   const float* xb = x + (size_t)b * n;
   double s = 0.0, q = 0.0;
   const long long n4 = n / 4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {           // four loads in flight per thread
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(xb) + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s += (double)v[u].x + (double)v[u].y + (double)v[u].z + (double)v[u].w;
+      q += (double)v[u].x * v[u].x + (double)v[u].y * v[u].y + (double)v[u].z * v[u].z + (double)v[u].w * v[u].w;
+    }
+  }
+  for (; i < n4; i += stride) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(xb) + i);
     s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
     q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
@@ -286,37 +298,62 @@ __device__ __forceinline__ float seg_sample(const float* __restrict__ ch, int S,
   const float v10 = __ldg(ch + (size_t)y1 * S + x0), v11 = __ldg(ch + (size_t)y1 * S + x1);
   return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
 }
-__global__ void __launch_bounds__(128) k_seg_features(const float* __restrict__ seg, int B, int nc, int S, int mode, int h, int w,
-                                                      const float* __restrict__ dw, const float* __restrict__ db, int nd, float* out) {
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= B * h * w) return;
-  const int b = pix / (h * w), rem = pix - b * h * w, y = rem / w, x = rem - y * w;
-  const float* sb = seg + (size_t)b * nc * S * S;
-  float d[9];
+// A CTA of 256 threads owns 64 consecutive pixels: thread (pixel p = tid % 64, group g = tid / 64) computes the features
+// j = g, g + 4, ... of pixel p (a thread-per-pixel loop is a chain of nc dependent-latency loads: 33 us even for an 8 x 8 map).
+// The 64 rows are contiguous in `out`: they are staged in shared memory (odd row stride: conflict-free) and written out as one
+// coalesced block (thread-per-row stores touch 32 sectors per instruction).
+constexpr int kSegPix = 64, kSegGroups = 4;
+__global__ void __launch_bounds__(kSegPix * kSegGroups) k_seg_features(const float* __restrict__ seg, int B, int nc, int S, int mode, int h, int w,
+                                                                       const float* __restrict__ dw, const float* __restrict__ db, int nd,
+                                                                       float* __restrict__ out) {
+  extern __shared__ float s_row[];   // [kSegPix][C | 1]
+  const int C = nd + nc - 1, LD = C | 1;
+  const int p = threadIdx.x % kSegPix, g = threadIdx.x / kSegPix;
+  const int pix0 = blockIdx.x * kSegPix, pix = pix0 + p, P = B * h * w;
+  if (pix < P) {
+    const int b = pix / (h * w), rem = pix - b * h * w, y = rem / w, x = rem - y * w;
+    const float* sb = seg + (size_t)b * nc * S * S;
+    float* o = s_row + p * LD;
+    if (g < nd) {                     // warp-uniform (64 pixels per group = 2 warps)
+      float d[9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) d[t] = seg_sample(sb, S, h, w, mode, reflect(y + t / 3 - 1, h), reflect(x + t % 3 - 1, w));
-  float* o = out + (size_t)pix * (nd + nc - 1);
-  for (int j = 0; j < nd; ++j) {
-    float acc = __ldg(db + j);
+      for (int t = 0; t < 9; ++t) d[t] = seg_sample(sb, S, h, w, mode, reflect(y + t / 3 - 1, h), reflect(x + t % 3 - 1, w));
+      for (int j = g; j < nd; j += kSegGroups) {
+        float acc = __ldg(db + j);
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc = fmaf(d[t], __ldg(dw + j * 9 + t), acc);
-    o[j] = acc > 0.f ? acc : acc * 0.01f;
+        for (int t = 0; t < 9; ++t) acc = fmaf(d[t], __ldg(dw + j * 9 + t), acc);
+        o[j] = acc > 0.f ? acc : acc * 0.01f;
+      }
+    }
+    int c = 1 + g;
+    for (; c + 3 * kSegGroups < nc; c += 4 * kSegGroups) {      // four independent samples in flight
+      const float v0 = seg_sample(sb + (size_t)c * S * S, S, h, w, mode, y, x);
+      const float v1 = seg_sample(sb + (size_t)(c + kSegGroups) * S * S, S, h, w, mode, y, x);
+      const float v2 = seg_sample(sb + (size_t)(c + 2 * kSegGroups) * S * S, S, h, w, mode, y, x);
+      const float v3 = seg_sample(sb + (size_t)(c + 3 * kSegGroups) * S * S, S, h, w, mode, y, x);
+      o[nd + c - 1] = v0; o[nd + c + kSegGroups - 1] = v1; o[nd + c + 2 * kSegGroups - 1] = v2; o[nd + c + 3 * kSegGroups - 1] = v3;
+    }
+    for (; c < nc; c += kSegGroups) o[nd + c - 1] = seg_sample(sb + (size_t)c * S * S, S, h, w, mode, y, x);
   }
-  for (int c = 1; c < nc; ++c) o[nd + c - 1] = seg_sample(sb + (size_t)c * S * S, S, h, w, mode, y, x);
+  __syncthreads();
+  const int n = min(kSegPix, P - pix0) * C;
+  float* ob = out + (size_t)pix0 * C;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int r = e / C;
+    ob[e] = s_row[r * LD + (e - r * C)];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ 2x upsampling (NHWC)
 // nn.Upsample(scale_factor=2, mode='nearest' | 'bilinear' [align_corners=False])   (reference :1544-1545)
-__global__ void k_upsample2x(const float* __restrict__ x, int B, int H, int W, int C, int bilinear, float* out) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// blockIdx.x = output row (b, oy), blockIdx.y = 256-float4 slice of the row: 32-bit index arithmetic only (a flat 64-bit index
+// costs four 64-bit divisions per float4: 293 us for the 128 -> 256 step, 1.1 TB/s).
+__global__ void __launch_bounds__(256) k_upsample2x(const float* __restrict__ x, int B, int H, int W, int C, int bilinear, float* __restrict__ out) {
   const int c4n = C / 4;
-  const long long total = (long long)B * 2 * H * 2 * W * c4n;
-  if (idx >= total) return;
-  const int c4 = (int)(idx % c4n);
-  long long pix = idx / c4n;
-  const int ox = (int)(pix % (2 * W)); pix /= 2 * W;
-  const int oy = (int)(pix % (2 * H));
-  const int b = (int)(pix / (2 * H));
+  const int e = blockIdx.y * blockDim.x + threadIdx.x;     // (ox, c4) within the row
+  if (e >= 2 * W * c4n) return;
+  const int ox = e / c4n, c4 = e - ox * c4n;
+  const int row = blockIdx.x, b = row / (2 * H), oy = row - b * 2 * H;
   const float* xb = x + (size_t)b * H * W * C + c4 * 4;
   float4 v;
   if (!bilinear) {
@@ -332,47 +369,81 @@ __global__ void k_upsample2x(const float* __restrict__ x, int B, int H, int W, i
     v.z = (1.f - ly) * ((1.f - lx) * a.z + lx * bq.z) + ly * ((1.f - lx) * c.z + lx * dq.z);
     v.w = (1.f - ly) * ((1.f - lx) * a.w + lx * bq.w) + ly * ((1.f - lx) * c.w + lx * dq.w);
   }
-  *reinterpret_cast<float4*>(out + ((size_t)b * 4 * H * W + (size_t)oy * 2 * W + ox) * C + c4 * 4) = v;
+  *reinterpret_cast<float4*>(out + ((size_t)row * 2 * W + ox) * C + c4 * 4) = v;
 }
 
 // ------------------------------------------------------------------------------------------------ squeeze-excite + residual
 // SEBlock2 (reference :81-85, reduction 8) and the block's residual add (:1493).
-__global__ void __launch_bounds__(256) k_se_pool(const float* __restrict__ dx, int HW, int C, int rows_per, float* partial) {
+// pooling partials: a CTA sums rows [r0, r1) of image b.  With C / 4 < 256 column lanes the threads also split the rows (RL row lanes
+// per column, combined through shared memory) — at C = 64 a column-only mapping left 240 of the 256 threads idle (248 us at 256 x 256).
+__global__ void __launch_bounds__(256) k_se_pool(const float* __restrict__ dx, int HW, int C, int rows_per, float* __restrict__ partial) {
+  __shared__ float4 s_acc[256];
   const int b = blockIdx.y, chunk = blockIdx.x, nch = gridDim.x;
   const int r0 = chunk * rows_per, r1 = min(HW, r0 + rows_per);
-  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = r0; r < r1; ++r) {
-      const float4 v = ldg4(dx + ((size_t)b * HW + r) * C + c);
+  const int c4n = C / 4;
+  if (c4n >= 256 || 256 % c4n != 0) {
+    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = r0; r < r1; ++r) {
+        const float4 v = ldg4(dx + ((size_t)b * HW + r) * C + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(partial + ((size_t)b * nch + chunk) * C + c) = acc;
+    }
+    return;
+  }
+  const int RL = 256 / c4n, cl = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* base = dx + (size_t)b * HW * C + cl * 4;
+  int r = r0 + rl;
+  for (; r + 3 * RL < r1; r += 4 * RL) {
+    const float4 v0 = ldg4(base + (size_t)r * C), v1 = ldg4(base + (size_t)(r + RL) * C);
+    const float4 v2 = ldg4(base + (size_t)(r + 2 * RL) * C), v3 = ldg4(base + (size_t)(r + 3 * RL) * C);
+    acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+    acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+  }
+  for (; r < r1; r += RL) {
+    const float4 v = ldg4(base + (size_t)r * C);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  s_acc[threadIdx.x] = acc;
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 1; k < RL; ++k) {             // fixed order: reproducible
+      const float4 v = s_acc[k * c4n + cl];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    *reinterpret_cast<float4*>(partial + ((size_t)b * nch + chunk) * C + c) = acc;
+    *reinterpret_cast<float4*>(partial + ((size_t)b * nch + chunk) * C + cl * 4) = acc;
   }
 }
-__global__ void __launch_bounds__(256) k_se_fc(const float* __restrict__ partial, int nch, int HW, int C, const float* __restrict__ W1,
-                                               const float* __restrict__ W2, int Ch, float* svec) {
+// 1024 threads per image: fc1 and fc2 are warp-per-output-row dot products with lanes along the (contiguous) reduction axis
+__global__ void __launch_bounds__(1024) k_se_fc(const float* __restrict__ partial, int nch, int HW, int C, const float* __restrict__ W1,
+                                                const float* __restrict__ W2, int Ch, float* __restrict__ svec) {
   extern __shared__ float sm[];   // pooled [C] | hidden [Ch]
   float* pooled = sm;
   float* hidden = sm + C;
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
-    for (int k = 0; k < nch; ++k) s += partial[((size_t)b * nch + k) * C + c];
+#pragma unroll 8
+    for (int k = 0; k < nch; ++k) s += __ldg(partial + ((size_t)b * nch + k) * C + c);
     pooled[c] = s / (float)HW;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int j = warp; j < Ch; j += blockDim.x >> 5) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = warp; j < Ch; j += nw) {
     float s = 0.f;
+#pragma unroll 4
     for (int c = lane; c < C; c += 32) s = fmaf(__ldg(W1 + (size_t)j * C + c), pooled[c], s);
     s = warp_sum(s);
     if (lane == 0) hidden[j] = fmaxf(s, 0.f);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = warp; c < C; c += nw) {
     float s = 0.f;
-    for (int j = 0; j < Ch; ++j) s = fmaf(__ldg(W2 + (size_t)c * Ch + j), hidden[j], s);
-    svec[(size_t)b * C + c] = 1.f / (1.f + expf(-s));
+    for (int j = lane; j < Ch; j += 32) s = fmaf(__ldg(W2 + (size_t)c * Ch + j), hidden[j], s);
+    s = warp_sum(s);
+    if (lane == 0) svec[(size_t)b * C + c] = 1.f / (1.f + expf(-s));
   }
 }
 __global__ void k_se_apply(const float* __restrict__ dx, const float* __restrict__ xs, const float* __restrict__ svec, long long n4, int HWC4, int C4,
@@ -427,6 +498,85 @@ __global__ void __launch_bounds__(128) k_to_rgb(const float* __restrict__ x, int
     const size_t o = ((size_t)b * Cout + co) * H * W + (size_t)y * W + xq;
     if (pre) pre[o] = acc[co];
     out[o] = tanhf(acc[co]);
+  }
+}
+
+// The same layer for the shapes the generators use (KS x KS, Cin % 16 == 0): a CTA of 128 threads owns a 32 x 16 pixel tile, stages
+// the activated input (tile + halo, 16 channels at a time, pixel stride 20 floats: conflict-free LDS.128) in shared memory with
+// coalesced loads, and every thread computes 4 vertically adjacent pixels so that one weight read feeds 4 pixels and one input
+// read up to KS taps (the thread-per-pixel kernel above re-reads the 25 x 256 B neighbourhood of every pixel with 32 cache lines
+// per load instruction: 1.9 ms at 16 x 256 x 256 x 64).
+constexpr int kRgbTX = 32, kRgbTY = 16, kRgbCC = 16, kRgbLD = kRgbCC + 4;
+template <int KS>
+__global__ void __launch_bounds__(128, 2) k_to_rgb_tiled(const float* __restrict__ x, int B, int H, int W, int Cin, const float* __restrict__ Wt,
+                                                         const float* __restrict__ bias, int Cout, float slope, float* pre, float* out) {
+  constexpr int PAD = KS / 2, SW = kRgbTX + KS - 1, SH = kRgbTY + KS - 1, NR = 4 + KS - 1;
+  extern __shared__ __align__(16) float s_rgb[];
+  float* s_w = s_rgb;                          // [KS*KS*Cin][4]
+  float* s_x = s_rgb + KS * KS * Cin * 4;      // [SH][SW][kRgbLD]
+  const int K = KS * KS * Cin;
+  for (int e = threadIdx.x; e < K * 4; e += blockDim.x) {
+    const int k = e >> 2, co = e & 3;
+    s_w[e] = co < Cout ? __ldg(Wt + (size_t)co * K + k) : 0.f;
+  }
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * kRgbTX, y0 = blockIdx.y * kRgbTY, b = blockIdx.z;
+  const float* xb = x + (size_t)b * H * W * Cin;
+  float acc[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int co = 0; co < 3; ++co) acc[i][co] = co < Cout ? __ldg(bias + co) : 0.f;
+  for (int cc = 0; cc < Cin; cc += kRgbCC) {
+    __syncthreads();                           // the previous chunk has been consumed (first pass: nothing to wait for but s_w's writers)
+    for (int e = threadIdx.x; e < SH * SW * (kRgbCC / 4); e += blockDim.x) {
+      const int p = e / (kRgbCC / 4), q = e - p * (kRgbCC / 4);
+      const int py = p / SW, px = p - py * SW;
+      const int gy = y0 + py - PAD, gx = x0 + px - PAD;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        v = ldg4(xb + ((size_t)gy * W + gx) * Cin + cc + q * 4);
+        v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+        v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+      }
+      *reinterpret_cast<float4*>(s_x + (size_t)p * kRgbLD + q * 4) = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int kx = 0; kx < KS; ++kx) {
+#pragma unroll 1
+      for (int c4 = 0; c4 < kRgbCC / 4; ++c4) {
+        float4 xv[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) xv[r] = *reinterpret_cast<const float4*>(s_x + (size_t)((ty * 4 + r) * SW + tx + kx) * kRgbLD + c4 * 4);
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) {
+          const float4* wk = reinterpret_cast<const float4*>(s_w) + (size_t)((ky * KS + kx) * Cin + cc + c4 * 4);
+          const float4 w0 = wk[0], w1 = wk[1], w2 = wk[2], w3 = wk[3];     // 4 input channels x (up to) 4 output channels, broadcast reads
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = xv[i + ky];
+            acc[i][0] = fmaf(v.x, w0.x, fmaf(v.y, w1.x, fmaf(v.z, w2.x, fmaf(v.w, w3.x, acc[i][0]))));
+            acc[i][1] = fmaf(v.x, w0.y, fmaf(v.y, w1.y, fmaf(v.z, w2.y, fmaf(v.w, w3.y, acc[i][1]))));
+            acc[i][2] = fmaf(v.x, w0.z, fmaf(v.y, w1.z, fmaf(v.z, w2.z, fmaf(v.w, w3.z, acc[i][2]))));
+          }
+        }
+      }
+    }
+  }
+  const int gx = x0 + tx;
+  if (gx >= W) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gy = y0 + ty * 4 + i;
+    if (gy >= H) break;
+#pragma unroll
+    for (int co = 0; co < 3; ++co) {
+      if (co >= Cout) break;
+      const size_t o = ((size_t)b * Cout + co) * H * W + (size_t)gy * W + gx;
+      if (pre) pre[o] = acc[i][co];
+      out[o] = tanhf(acc[i][co]);
+    }
   }
 }
 
@@ -616,7 +766,7 @@ int sln_spade_seg_features(const float* seg, int64_t B, int32_t nc, int32_t S, i
   cudaStream_t st = (cudaStream_t)stream;
   const int P = (int)(B * h * w);
   ProfScope prof(st, PROF_SPADE_MISC, 4.0 * P * (double)(nd + nc - 1));
-  k_seg_features<<<ceil_div(P, 128), 128, 0, st>>>(seg, (int)B, nc, S, mode, (int)h, (int)w, dw, db, nd, out);
+  k_seg_features<<<ceil_div(P, kSegPix), kSegPix * kSegGroups, (size_t)kSegPix * ((nd + nc - 1) | 1) * sizeof(float), st>>>(seg, (int)B, nc, S, mode, (int)h, (int)w, dw, db, nd, out);
   return check_launch("seg_features");
 }
 
@@ -626,7 +776,9 @@ int sln_spade_upsample2x(const float* x, int64_t B, int64_t H, int64_t W, int64_
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = (long long)B * 4 * H * W * (C / 4);
   ProfScope prof(st, PROF_SPADE_MISC, 20.0 * (double)total);
-  k_upsample2x<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(x, (int)B, (int)H, (int)W, (int)C, bilinear, out);
+  const long long rowlen = 2 * W * (C / 4);
+  SLN_CHECK_ARG(rowlen <= 65535ll * 256, "upsample2x row too long");
+  k_upsample2x<<<dim3((unsigned)(B * 2 * H), (unsigned)ceil_div64(rowlen, 256)), 256, 0, st>>>(x, (int)B, (int)H, (int)W, (int)C, bilinear, out);
   return check_launch("upsample2x");
 }
 
@@ -646,7 +798,7 @@ int sln_spade_se_residual(const float* dx, const float* xs, int64_t B, int64_t H
   ProfScope prof(st, PROF_SPADE_MISC, 16.0 * (double)B * HW * C);
   k_se_pool<<<dim3(nch, (unsigned)B), 256, 0, st>>>(dx, HW, (int)C, rows_per, partial);
   SLN_TRY(check_launch("se_pool"));
-  k_se_fc<<<(unsigned)B, 256, (size_t)(C + Ch) * sizeof(float), st>>>(partial, nch, HW, (int)C, W1, W2, Ch, svec);
+  k_se_fc<<<(unsigned)B, 1024, (size_t)(C + Ch) * sizeof(float), st>>>(partial, nch, HW, (int)C, W1, W2, Ch, svec);
   SLN_TRY(check_launch("se_fc"));
   const long long n4 = (long long)B * HW * (C / 4);
   k_se_apply<<<(unsigned)ceil_div64(n4, 256), 256, 0, st>>>(dx, xs, svec, n4, HW * (int)(C / 4), (int)(C / 4), out);
@@ -660,12 +812,22 @@ int sln_spade_to_rgb(const float* x, int64_t B, int64_t H, int64_t W, int64_t Ci
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)ks * ks * Cin * 4 * sizeof(float);
   SLN_CHECK_ARG(smem <= 200 * 1024, "to_rgb weights do not fit shared memory");
+  const int P = (int)(B * H * W);
+  ProfScope prof(st, PROF_SPADE_CONV, 2.0 * (double)P * ks * ks * Cin * Cout);
+  const size_t smem_t = smem + (size_t)(kRgbTX + 4) * (kRgbTY + 4) * kRgbLD * sizeof(float);
+  if (ks == 5 && Cin % kRgbCC == 0 && Cout <= 3 && smem_t <= 110 * 1024 && B <= 65535) {
+    static unsigned long long configured_t = 0ull;
+    if (first_use_on_device(configured_t)) {
+      SLN_CUDA_TRY(cudaFuncSetAttribute(k_to_rgb_tiled<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    }
+    k_to_rgb_tiled<5><<<dim3(ceil_div((int)W, kRgbTX), ceil_div((int)H, kRgbTY), (unsigned)B), 128, smem_t, st>>>(x, (int)B, (int)H, (int)W, (int)Cin, Wt, bias,
+                                                                                                            Cout, slope, pre, out);
+    return check_launch("to_rgb");
+  }
   static unsigned long long configured = 0ull;   // devices configured (per call site / instantiation)
   if (first_use_on_device(configured)) {
     SLN_CUDA_TRY(cudaFuncSetAttribute(k_to_rgb<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
-  const int P = (int)(B * H * W);
-  ProfScope prof(st, PROF_SPADE_CONV, 2.0 * (double)P * ks * ks * Cin * Cout);
   k_to_rgb<4><<<ceil_div(P, 128), 128, smem, st>>>(x, (int)B, (int)H, (int)W, (int)Cin, Wt, bias, Cout, ks, slope, pre, out);
   return check_launch("to_rgb");
 }
