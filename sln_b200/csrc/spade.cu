@@ -14,8 +14,7 @@
 // running sum, and with the accumulator columns split over PROD_WARPS/4 column groups (tc_gemm.cuh) that sum is 32 registers
 // at 16 warps, which fits the 96-register cap (with the 64-register sum of an 8-warp-style split the 16-warp build spilled
 // and lost: 346 -> 332 images/s).  Measured, same box: 8 warps 349 images/s, 16 warps 392.
-#define SLN_TC_PROD_WARPS 16
-#define SLN_TC_PF_DEEP 2        // long K (1152 .. 9216): two chunks in flight suffice and leave registers to the im2col arithmetic (4: -3 %)
+// Two producer groups of 8 warps alternate chunks, one chunk prefetched per group (tc_gemm.cuh defaults).
 #include "gemm.cuh"
 #include "tc_gemm.cuh"
 
@@ -831,5 +830,14 @@ int sln_spade_to_rgb(const float* x, int64_t B, int64_t H, int64_t W, int64_t Ci
   k_to_rgb<4><<<ceil_div(P, 128), 128, smem, st>>>(x, (int)B, (int)H, (int)W, (int)Cin, Wt, bias, Cout, ks, slope, pre, out);
   return check_launch("to_rgb");
 }
+
+#ifdef SLN_TC_TRACE
+// tuning build only (tools/build_trace.sh spade): the phase stamps of CTA (0,0,0) of this translation unit's last contraction launch
+int sln_debug_tc_trace_spade(long long* out48) {
+  SLN_CUDA_TRY(cudaDeviceSynchronize());
+  SLN_CUDA_TRY(cudaMemcpyFromSymbol(out48, tc::g_tc_trace, sizeof(long long) * 48));
+  return SLN_OK;
+}
+#endif
 
 }  // extern "C"

@@ -25,7 +25,7 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;            // floats per K chunk: 128 bytes = one SWIZZLE_128B row
 #ifndef SLN_TC_PF_DEEP
-#define SLN_TC_PF_DEEP 4      // register-prefetch depth for single-load A functors with pre-split B (per translation unit)
+#define SLN_TC_PF_DEEP 2      // chunks in flight per CTA (register prefetch) for single-load A functors with pre-split B
 #endif
 #ifndef SLN_TC_PROD_WARPS
 #define SLN_TC_PROD_WARPS 16
@@ -35,6 +35,17 @@ constexpr int BK = 32;            // floats per K chunk: 128 bytes = one SWIZZLE
 // SPADE kernel: issue slots 32 % busy, top stalls `wait` / `long_scoreboard`, tensor pipe 39 % (profiles/r2_prof_tc_spade_*).
 constexpr int PROD_WARPS = SLN_TC_PROD_WARPS;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
+// Producer groups: the producer warps split into PROD_GROUPS groups that take the chunks round-robin (group g: chunks g, g + G, ...),
+// each group building whole stages on its own.  One chunk is a serial chain per warp (wait empty -> consume the prefetched
+// registers -> st.shared -> proxy fence -> arrive -> issue the next loads): ~1400 cycles measured against 800 cycles of MMA work,
+// and with every warp on the same chunk nothing overlaps it.  Two groups keep two such chains in flight.
+// Measured (B200): SPADEGenerator4 419 -> 435 images/s, VAE train step 3.00 -> 2.82 ms (G = 2, one chunk prefetched per group;
+// two per group: 2.86 ms).
+#ifndef SLN_TC_PROD_GROUPS
+#define SLN_TC_PROD_GROUPS 2
+#endif
+constexpr int PROD_GROUPS = SLN_TC_PROD_GROUPS;
+static_assert(PROD_WARPS % PROD_GROUPS == 0 && (PROD_WARPS / PROD_GROUPS) % 4 == 0, "producer groups must be whole multiples of 4 warps");
 constexpr int MMA_WARP = PROD_WARPS;        // the ninth warp issues the tcgen05.mma stream
 constexpr int THREADS = PROD_THREADS + 32;
 
@@ -198,21 +209,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 //                segment of a storage row and write one full 128-byte swizzle row.
 // Bounds: tile rows beyond the operand are clamped by the functor (their products are never stored); only the K padding of
 // the last chunk (CHECK == true) is zeroed.
-template <int ROWS, bool RC, class Op>
+template <int ROWS, bool RC, class Op, int NT>
 struct LoaderBuf {   // the registers holding one fetched chunk (PF of these per operand)
-  static constexpr int NVR = ROWS * BK / 4 / PROD_THREADS;  // quads per thread per chunk (0: the tile has fewer quads than threads)
+  static constexpr int NVR = ROWS * BK / 4 / NT;  // quads per thread per chunk (0: the tile has fewer quads than threads)
   static constexpr int NV = NVR > 0 ? NVR : 1;
   float4 ra[NV], rb[NV];
   typename Op::Tok ktok;               // RC == false: the token of this chunk's k-row
 };
-template <int ROWS, bool RC, class Op>
+template <int ROWS, bool RC, class Op, int NT>      // NT: threads that build one tile (a producer group)
 struct Loader {      // per-thread loop invariants, shared by all register buffers
-  static constexpr int NVR = ROWS * BK / 4 / PROD_THREADS;
+  static constexpr int NVR = ROWS * BK / 4 / NT;
   static constexpr int NV = NVR > 0 ? NVR : 1;
-  static constexpr int ACTIVE = NVR > 0 ? PROD_THREADS : ROWS * BK / 4;   // threads that own a quad (small B tiles: the first ROWS * 8)
+  static constexpr int ACTIVE = NVR > 0 ? NT : ROWS * BK / 4;   // threads that own a quad (small B tiles: the first ROWS * 8)
   static constexpr int RPP = ACTIVE / 8;               // RC: tile rows covered per pass (quad i: + RPP rows)
   static constexpr int KB = ACTIVE / 256 > 0 ? ACTIVE / 256 : 1;   // !RC: 32-row blocks covered per pass by the 32 k-rows x 8 row-quads
-  using Buf = LoaderBuf<ROWS, RC, Op>;
+  using Buf = LoaderBuf<ROWS, RC, Op, NT>;
   typename Op::Tok tok[RC ? NV : 1];   // RC: one token per owned tile row
   int col[RC ? 1 : NV];                // !RC: clamped storage column of quad i
   uint32_t soff;                       // byte offset of quad 0 inside the tile
@@ -432,6 +443,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   // registers, so the single-load A functors can afford 4 chunks in flight (64 registers; one CTA per SM allows 224).
   constexpr int S = L::STAGES, PF = MSEG ? 1 : ((is_packed<BOp>::value && !AOp::kTwoLoads) ? SLN_TC_PF_DEEP : 2);
   constexpr bool BP = is_packed<BOp>::value;       // B tiles arrive by cp.async.bulk from a pre-split, pre-tiled image
+  // producer groups; the 128-column multi-segment variant has no registers for a second chunk in flight (96-register cap: 600 B of spills)
+  constexpr int G = (MSEG && BN >= 128) ? 1 : PROD_GROUPS, GROUP_WARPS = PROD_WARPS / G, GROUP_THREADS = GROUP_WARPS * 32;
+  constexpr int PFG = PF / G > 0 ? PF / G : 1;     // chunks prefetched per thread of a group (PFG * G chunks in flight per CTA)
   extern __shared__ char smem_raw[];
   char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
   float* stat = reinterpret_cast<float*>(smem + S * L::STAGE);             // [2][8][BN]
@@ -462,7 +476,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
     tmem_alloc(tmem_slot, TMEM_COLS);
     if (lane == 0) {
 #pragma unroll
-      for (int s = 0; s < S; ++s) { mbar_init(full + s, PROD_WARPS + (BP ? 1 : 0)); mbar_init(empty + s, 1); }
+      for (int s = 0; s < S; ++s) { mbar_init(full + s, GROUP_WARPS + (BP ? 1 : 0)); mbar_init(empty + s, 1); }
       mbar_init(segfull, 1); mbar_init(segfull + 1, 1);
       mbar_init(accempty, PROD_WARPS); mbar_init(accempty + 1, PROD_WARPS);
       fence_barrier_init();
@@ -544,20 +558,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
       __syncwarp();
       if (lane == 0) mbar_arrive(accempty);
     };
-    // loop invariants once per operand; PF register buffers (named, not arrays, so that they stay in registers)
-    Loader<BM, A_RC, AOp> la;
-    Loader<BN, B_RC, BOp> lb;
-    typename Loader<BM, A_RC, AOp>::Buf abuf[PF];
-    typename Loader<BN, B_RC, BOp>::Buf bbuf[PF];          // indexed by compile-time constants only (fully unrolled): registers
+    // loop invariants once per operand; PFG register buffers (indexed by compile-time constants only, so that they stay in registers)
+    const int grp = warp / GROUP_WARPS, gtid = tid - grp * GROUP_THREADS;   // this warp's producer group, thread index inside it
+    Loader<BM, A_RC, AOp, GROUP_THREADS> la;
+    Loader<BN, B_RC, BOp, GROUP_THREADS> lb;
+    typename Loader<BM, A_RC, AOp, GROUP_THREADS>::Buf abuf[PFG];
+    typename Loader<BN, B_RC, BOp, GROUP_THREADS>::Buf bbuf[PFG];
     const bool tail = ((kend - kbeg) & (BK - 1)) != 0;     // only the last chunk can have K padding
     const uint32_t sbase = smem_u32(smem);
+    int ndrained = 0;                                      // MSEG: segments this warp has drained (every warp drains every segment, in order)
     auto fetch = [&](auto& BA, auto& BB, int c) {
       if (tail && c == nchunks - 1) {
-        la.template fetch<true>(A, BA, kbeg + c * BK, kend, tid);
-        if constexpr (!BP) lb.template fetch<true>(B, BB, kbeg + c * BK, kend, tid);
+        la.template fetch<true>(A, BA, kbeg + c * BK, kend, gtid);
+        if constexpr (!BP) lb.template fetch<true>(B, BB, kbeg + c * BK, kend, gtid);
       } else {
-        la.template fetch<false>(A, BA, kbeg + c * BK, kend, tid);
-        if constexpr (!BP) lb.template fetch<false>(B, BB, kbeg + c * BK, kend, tid);
+        la.template fetch<false>(A, BA, kbeg + c * BK, kend, gtid);
+        if constexpr (!BP) lb.template fetch<false>(B, BB, kbeg + c * BK, kend, gtid);
       }
     };
     auto produce = [&](auto& BA, auto& BB, int c) {
@@ -566,7 +582,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
       if (use > 0) mbar_wait(empty + s, (uint32_t)((use - 1) & 1));   // the MMAs that read this stage have retired
       if (c < 4) TC_TRACE2(2 * c);
       if constexpr (BP) {
-        if (warp == 0 && elect_one()) {                   // B_hi | B_lo tiles of this stage: BN/32 units, two 4 KB bulk copies each
+        if (gtid < 32 && elect_one()) {                   // B_hi | B_lo tiles of this stage: BN/32 units, two 4 KB bulk copies each
           mbar_expect_tx(full + s, 2 * L::B_TILE);
           const float* u0 = B.units + ((size_t)(n0 / 32) * B.kchunks + (size_t)(kbeg / BK + c)) * PACK_UNIT_FLOATS;
 #pragma unroll
@@ -578,35 +594,40 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
         }
       }
       if (tail && c == nchunks - 1) {
-        la.template store<true>(A, BA, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
-        if constexpr (!BP) lb.template store<true>(B, BB, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
+        la.template store<true>(A, BA, kbeg + c * BK, kend, st, st + L::A_TILE, gtid);
+        if constexpr (!BP) lb.template store<true>(B, BB, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, gtid);
       } else {
-        la.template store<false>(A, BA, kbeg + c * BK, kend, st, st + L::A_TILE, tid);
-        if constexpr (!BP) lb.template store<false>(B, BB, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, tid);
+        la.template store<false>(A, BA, kbeg + c * BK, kend, st, st + L::A_TILE, gtid);
+        if constexpr (!BP) lb.template store<false>(B, BB, kbeg + c * BK, kend, st + 2 * L::A_TILE, st + 2 * L::A_TILE + L::B_TILE, gtid);
       }
       if (c < 4) TC_TRACE2(2 * c + 1);
-      if (c + PF < nchunks) fetch(BA, BB, c + PF);        // refill the register buffer: these loads fly during the next PF chunks
+      if (c + PFG * G < nchunks) fetch(BA, BB, c + PFG * G);   // refill the register buffer: these loads fly during the group's next PFG chunks
       fence_async_smem();                                 // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(full + s);
       if (MSEG) {
-        const int seg = c / SEG_CHUNKS;
-        if ((c % SEG_CHUNKS) == 0 && seg > 0) drain(seg - 1);
+        // a group's first chunk of a new segment: drain the segment before it (a group's consecutive chunks are G <= SEG_CHUNKS
+        // apart, so at most one segment is pending here)
+        if (c / SEG_CHUNKS > ndrained) drain(ndrained++);
       }
     };
-    la.init(A, m0, tid);
-    if constexpr (!BP) lb.init(B, n0, tid);
+    la.init(A, m0, gtid);
+    if constexpr (!BP) lb.init(B, n0, gtid);
     TC_TRACE2(8);
 #pragma unroll
-    for (int i = 0; i < PF; ++i)
-      if (i < nchunks) fetch(abuf[i], bbuf[i], i);
+    for (int i = 0; i < PFG; ++i)
+      if (grp + i * G < nchunks) fetch(abuf[i], bbuf[i], grp + i * G);
     TC_TRACE2(9);
-    for (int c = 0; c < nchunks; c += PF) {
+    for (int c = grp; c < nchunks; c += PFG * G) {
 #pragma unroll
-      for (int i = 0; i < PF; ++i)
-        if (c + i < nchunks) produce(abuf[i], bbuf[i], c + i);
+      for (int i = 0; i < PFG; ++i)
+        if (c + i * G < nchunks) produce(abuf[i], bbuf[i], c + i * G);
     }
-    if (MSEG && nchunks > 0) drain((nchunks - 1) / SEG_CHUNKS);
+    if (MSEG && nchunks > 0) {
+      const int last = (nchunks - 1) / SEG_CHUNKS;          // a group without a chunk in the last segment still owes the one before it
+      if (G > 1 && ndrained < last) drain(ndrained++);
+      drain(last);
+    }
     if (!MSEG && nchunks > 0) {                           // single segment: every MMA has retired when segfull completes
       mbar_wait(segfull, 0u);
       tc_fence_after();
@@ -735,6 +756,9 @@ inline TcChoice pick_tc(int M, int N, int K, bool allow_split) {
     }
     int kchunk = ceil_div(ceil_div(K, splits), BK) * BK;
     splits = ceil_div(K, kchunk);
+    // with producer groups the 128-column multi-segment variant runs a single group (no registers for a second chunk in flight):
+    // the 64-column tile with two groups is the faster multi-segment kernel (measured, K = 2304 / 9216: 2-5 %)
+    if (forced == 0 && PROD_GROUPS > 1 && bn == 128 && ceil_div(kchunk, BK) > SEG_CHUNKS) continue;
     int ctas = tiles * splits;
     int waves = ceil_div(ctas, kNumSMs);            // one CTA per SM (shared-memory bound)
     // cycles per CTA ~ prologue (TMEM alloc, first loads) + chunks x max(MMA time, producer time) + epilogue:
