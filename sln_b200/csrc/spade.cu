@@ -122,12 +122,13 @@ struct TcEpiSpade {
   static constexpr bool kPaired = true;
   __device__ __forceinline__ bool wants_stats() const { return false; }
   __device__ __forceinline__ void apply4(int, int, int, float4, float (&)[4], float (&)[4]) const {}
-  __device__ __forceinline__ void apply_pair(int i, int c, float4 g, float4 b) const {
+  __device__ __forceinline__ float4 load_pair(int i, int c) const { return ldg4(x + (size_t)i * C + c); }   // issued before the accumulator read-out
+  __device__ __forceinline__ void apply_pair(int i, int c, float4 g, float4 b, float4 xv) const {
     const int bi = i / HW;
     float4 m, iv;
     if (sc) { m = ldg4(mean + (size_t)bi * sb + c); iv = ldg4(inv + (size_t)bi * sb + c); }
     else { const float m1 = __ldg(mean + bi * sb), i1 = __ldg(inv + bi * sb); m = make_float4(m1, m1, m1, m1); iv = make_float4(i1, i1, i1, i1); }
-    const float4 xv = ldg4(x + (size_t)i * C + c), bg = ldg4(bias_g + c), bb = ldg4(bias_b + c);
+    const float4 bg = ldg4(bias_g + c), bb = ldg4(bias_b + c);
     float4 o;
     o.x = fmaf((xv.x - m.x) * iv.x, 1.f + (g.x + bg.x), b.x + bb.x);
     o.y = fmaf((xv.y - m.y) * iv.y, 1.f + (g.y + bg.y), b.y + bb.y);

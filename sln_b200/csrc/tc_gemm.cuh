@@ -634,7 +634,25 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
     }
   }
   TC_TRACE(4);
-  // ---- epilogue: stage the tile in shared memory (the stage buffers are idle: every MMA has retired) ...
+  // ---- epilogue.  Lanes run along the columns: LPR lanes cover one row (4 columns each), a warp covers 32/LPR rows per pass and
+  // NIT passes in all.  Paired epilogues first issue the loads of the tensor they modulate (HBM latency: they fly during the
+  // accumulator read-out and the staging barrier instead of once per pass).
+  constexpr int LPR = BN / 4, RPP = 32 / LPR, NIT = BM / (PROD_WARPS * RPP);           // BN = 128: 32 lanes per row, 1 row per pass
+  constexpr int HB = BN / 2, LPR2 = HB / 4, RPP2 = 32 / LPR2, NIT2 = BM / (PROD_WARPS * RPP2);
+  static_assert(BM % (PROD_WARPS * RPP) == 0 && BM % (PROD_WARPS * RPP2) == 0, "whole passes only");
+  const int cq2 = lane % LPR2, rsub2 = lane / LPR2;
+  const int ch = n0 / 2 + cq2 * 4;                     // paired tiles: first of the 4 output channels of this lane
+  float4 xin[Epi::kPaired ? NIT2 : 1];
+  if constexpr (Epi::kPaired) {
+    if (warp < PROD_WARPS && 2 * ch < N) {
+#pragma unroll
+      for (int it = 0; it < NIT2; ++it) {
+        const int r = warp * RPP2 + rsub2 + it * PROD_WARPS * RPP2;
+        xin[it] = m0 + r < M ? epi.load_pair(m0 + r, ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  // ... stage the tile in shared memory (the stage buffers are idle: every MMA has retired) ...
   float* outs = reinterpret_cast<float*>(smem);
   if (has_acc) {
     const int r = quad * 32 + lane;
@@ -662,10 +680,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
         *reinterpret_cast<float4*>(outs + (size_t)r * L::OUT_LD + col_off + j * CW + e) = make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]);
     }
   }
+  TC_TRACE2(10);
   __syncthreads();
-  // ... then lanes run along the columns: LPR lanes cover one row (4 columns each), a warp covers 32/LPR rows per pass
+  TC_TRACE2(11);
+  // ... then every warp reads its rows back (all passes first: independent shared-memory loads) and applies the epilogue
   const bool stats = Epi::kStats && epi.wants_stats();
-  constexpr int LPR = BN / 4, RPP = 32 / LPR;           // BN = 128: 32 lanes per row, 1 row per pass
   const int cq = lane % LPR, rsub = lane / LPR;
   const int jcol = n0 + cq * 4;
   const int nvalid = min(4, max(0, N - jcol));
@@ -673,22 +692,28 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   if constexpr (Epi::kPaired) {
     // paired tiles: columns [0, BN/2) and [BN/2, BN) of a tile belong to the SAME BN/2 output channels (gamma | beta of a SPADE
     // modulation); a lane takes 4 channels of one row from both halves
-    constexpr int HB = BN / 2, LPR2 = HB / 4, RPP2 = 32 / LPR2;
-    const int cq2 = lane % LPR2, rsub2 = lane / LPR2;
-    const int ch = n0 / 2 + cq2 * 4;
     if (warp < PROD_WARPS && 2 * ch < N) {
-      for (int r = warp * RPP2 + rsub2; r < BM; r += PROD_WARPS * RPP2) {
-        if (m0 + r >= M) break;
-        float4 a = *reinterpret_cast<const float4*>(outs + (size_t)r * L::OUT_LD + cq2 * 4);
-        float4 b = *reinterpret_cast<const float4*>(outs + (size_t)r * L::OUT_LD + HB + cq2 * 4);
-        epi.apply_pair(m0 + r, ch, a, b);
+      float4 ga[NIT2], be[NIT2];
+#pragma unroll
+      for (int it = 0; it < NIT2; ++it) {
+        const int r = warp * RPP2 + rsub2 + it * PROD_WARPS * RPP2;
+        ga[it] = *reinterpret_cast<const float4*>(outs + (size_t)r * L::OUT_LD + cq2 * 4);
+        be[it] = *reinterpret_cast<const float4*>(outs + (size_t)r * L::OUT_LD + HB + cq2 * 4);
+      }
+#pragma unroll
+      for (int it = 0; it < NIT2; ++it) {
+        const int r = warp * RPP2 + rsub2 + it * PROD_WARPS * RPP2;
+        if (m0 + r < M) epi.apply_pair(m0 + r, ch, ga[it], be[it], xin[Epi::kPaired ? it : 0]);
       }
     }
   } else if (nvalid > 0 && warp < PROD_WARPS) {
-    for (int r = warp * RPP + rsub; r < BM; r += PROD_WARPS * RPP) {
-      if (m0 + r >= M) break;
-      float4 a = *reinterpret_cast<const float4*>(outs + (size_t)r * L::OUT_LD + cq * 4);
-      epi.apply4(m0 + r, jcol, nvalid, a, s1, s2);
+    float4 av[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) av[it] = *reinterpret_cast<const float4*>(outs + (size_t)(warp * RPP + rsub + it * PROD_WARPS * RPP) * L::OUT_LD + cq * 4);
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {                   // rows in ascending order: the column statistics keep their summation order
+      const int r = warp * RPP + rsub + it * PROD_WARPS * RPP;
+      if (m0 + r < M) epi.apply4(m0 + r, jcol, nvalid, av[it], s1, s2);
     }
   }
   TC_TRACE(5);

@@ -35,8 +35,8 @@ for (M, N, K, arc, brc, acc) in shapes:
     if any(t):
         w = t[1]      # producer warp 0: time of griddepcontrol.wait return = origin
         rel = lambda x: (x - w) if x else None
-        print("   [cycles after the dependency wait]  producer: init done %s, first fetches issued %s | chunk c begin/stored: %s | main loop done %s, tile applied %s, stats %s, end %s" % (
-            rel(t[24]), rel(t[25]), " ".join("%s/%s" % (rel(t[16 + 2 * c]), rel(t[17 + 2 * c])) for c in range(4)), rel(t[4]), rel(t[5]), rel(t[6]), rel(t[7])))
+        print("   [cycles after the dependency wait]  producer: init done %s, first fetches issued %s | chunk c begin/stored: %s | main loop done %s, staged %s, barrier %s, tile applied %s, stats %s, end %s" % (
+            rel(t[24]), rel(t[25]), " ".join("%s/%s" % (rel(t[16 + 2 * c]), rel(t[17 + 2 * c])) for c in range(4)), rel(t[4]), rel(t[26]), rel(t[27]), rel(t[5]), rel(t[6]), rel(t[7])))
         print("   MMA warp: full[c] observed at %s | first chunk issued %s, all issued %s   (entry->wait %d)" % (
             " ".join(str(rel(t[32 + c])) for c in range(8)), rel(t[10]), rel(t[11]), t[1] - t[0]))
     print("M=%5d N=%4d K=%5d a_rc=%d b_rc=%d acc=%d : %8.2f us  %7.2f TFLOP/s" % (M, N, K, arc, brc, acc, us, 2.0 * M * N * K / us / 1e6))

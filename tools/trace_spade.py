@@ -45,7 +45,7 @@ for (H, Cin, ks, Cout) in shapes:
         t = list(tr)
         w0 = t[1]
         rel = lambda v: (v - w0) if v else None
-        print("   producer: init %s, fetches issued %s | chunk begin/stored: %s | main loop done %s, tile applied %s, stats %s, end %s" % (
-            rel(t[24]), rel(t[25]), " ".join("%s/%s" % (rel(t[16 + 2 * c]), rel(t[17 + 2 * c])) for c in range(4)), rel(t[4]), rel(t[5]), rel(t[6]), rel(t[7])))
+        print("   producer: init %s, fetches issued %s | chunk begin/stored: %s | main loop done %s, staged %s, barrier %s, tile applied %s, stats %s, end %s" % (
+            rel(t[24]), rel(t[25]), " ".join("%s/%s" % (rel(t[16 + 2 * c]), rel(t[17 + 2 * c])) for c in range(4)), rel(t[4]), rel(t[26]), rel(t[27]), rel(t[5]), rel(t[6]), rel(t[7])))
         print("   MMA warp: full[c] at %s | first chunk issued %s, all issued %s   (entry->wait %d)" % (
             " ".join(str(rel(t[32 + c])) for c in range(8)), rel(t[10]), rel(t[11]), t[1] - t[0]))
