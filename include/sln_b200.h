@@ -61,6 +61,10 @@ typedef struct sln_vae_desc {
                                     instead of being split on the fly (forward and backward-data contractions) */
   const void* bn_sync;           /* NULL (per-rank BatchNorm statistics), or a DEVICE pointer to an sln_bn_sync table: training-mode
                                     BatchNorm statistics are then summed over all ranks INSIDE the finalising kernels (SyncBatchNorm) */
+  const void* graph_ws;          /* decoder calls only (the encoder ignores it): NULL, or the workspace of the sln_vae_encoder_fwd call
+                                    of THIS step that ran on the same objs / triples / attributes (same O, T, still intact): the decoder
+                                    reads the encoder's CSR and int32 index arrays instead of rebuilding them (the reference's model
+                                    passes the same graph to both halves, Sg2ScVAE_model.py:118-172) */
 } sln_vae_desc;
 
 /* Cross-rank BatchNorm statistics (SURVEY 8e policy P1: the N-GPU step equals the 1-GPU step at the global batch; reference

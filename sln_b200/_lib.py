@@ -88,7 +88,7 @@ class VaeDesc(ctypes.Structure):
         ("n_angle", ctypes.c_int32), ("num_objs", ctypes.c_int32), ("num_preds", ctypes.c_int32),
         ("num_attrs", ctypes.c_int32), ("bn_eps", ctypes.c_float), ("bn_momentum", ctypes.c_float),
         ("gconv_dim_override", ctypes.c_int32), ("gconv_hidden_override", ctypes.c_int32),
-        ("packed_weights", ctypes.c_void_p), ("bn_sync", ctypes.c_void_p),
+        ("packed_weights", ctypes.c_void_p), ("bn_sync", ctypes.c_void_p), ("graph_ws", ctypes.c_void_p),
     ]
 
 

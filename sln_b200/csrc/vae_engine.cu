@@ -502,6 +502,16 @@ int bwd_x_masked(const Ctx& c, const DyView& dy, const Lin& lin, int M, const Bl
   return launch_gemm<true, false>(c.st, dy, weight_view(lin), epi, M, lin.in, lin.out, false, "linear_bwd_x_masked", PROF_GEMM_BWD_X);
 }
 
+// sln_vae_desc.graph_ws: the decoder borrows the graph (CSR, int32 index arrays) that this step's encoder call built in ITS workspace
+inline bool borrow_graph(const Dims& dm, const sln_vae_desc* d, int O, int T, NetPlan& p) {
+  if (!d->graph_ws) return false;
+  static thread_local NetPlan enc;
+  make_plan(dm, O, T, 0, const_cast<void*>(d->graph_ws), &enc);
+  p.g = enc.g;
+  p.objs32 = enc.objs32; p.attrs32 = enc.attrs32;
+  return true;
+}
+
 int graph_prep(const Ctx& c, NetPlan& p, const int64_t* triples_or_edges, int stride3) {
   const Graph& g = p.g;
   SLN_CUDA_TRY(cudaMemsetAsync(p.deg, 0, sizeof(int) * g.O, c.st));
@@ -861,9 +871,13 @@ int sln_vae_decoder_fwd(const sln_vae_desc* d, const void* const* params, void* 
   ctx_sync(c, d, p.cp.base, 1, 0);
   SLN_TRY(check_ws(p, ws, ws_bytes));
   SLN_CUDA_TRY(cudaMemsetAsync(p.cp.base, 0, sizeof(unsigned) * kCounterCap, c.st));
-  SLN_TRY(graph_prep(c, p, triples, 1));
-  SLN_TRY(to_i32(c, objs, O, p.objs32, d->num_objs, p.err, SLN_IDX_OBJS));
-  SLN_TRY(to_i32(c, attributes, O, p.attrs32, d->num_attrs, p.err, SLN_IDX_ATTRS));
+  if (borrow_graph(dm, d, O, T, p)) {                    // the encoder validated the indices; this call's flag stays clear
+    SLN_CUDA_TRY(cudaMemsetAsync(p.err, 0, sizeof(int), c.st));
+  } else {
+    SLN_TRY(graph_prep(c, p, triples, 1));
+    SLN_TRY(to_i32(c, objs, O, p.objs32, d->num_objs, p.err, SLN_IDX_OBJS));
+    SLN_TRY(to_i32(c, attributes, O, p.attrs32, d->num_attrs, p.err, SLN_IDX_ATTRS));
+  }
   // obj_vecs = [obj_emb_dc | attr_emb_dc | z]   (Sg2ScVAE_model.py:150-159, decoder_cat)
   SLN_TRY(gather_rows(c, m.emb[4], dm.obj_w, p.objs32, O, dm.obj_w, p.obj0, dm.D, 0));
   SLN_TRY(gather_rows(c, m.emb[5], dm.attr_w, p.attrs32, O, dm.attr_w, p.obj0, dm.D, dm.obj_w));
@@ -895,6 +909,7 @@ int sln_vae_decoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   make_plan(dm, O, T, 1, ws, &p);
   ctx_sync(c, d, p.cp.base, 1, 1);
   SLN_TRY(check_ws(p, ws, ws_bytes));
+  (void)borrow_graph(dm, d, O, T, p);
   side_begin(c);
   const int L = dm.L;
   MatView obj_f = block_out(m.dec[L - 1][3], p.st[L - 1][3]);

@@ -163,12 +163,20 @@ __global__ void __launch_bounds__(256) k_embed_bwd_tab(const float* __restrict__
   __syncthreads();
   float* mine = tab + warp * sz;
   const int i0 = (blockIdx.x * 8 + warp) * per_warp, i1 = min(n, i0 + per_warp);
-  for (int i = i0; i < i1; ++i) {
-    const int id = __ldg(idx + i);
+  for (int i = i0; i < i1; i += 4) {             // four rows per trip: their index and value loads are independent (adds stay in row order)
+    int id[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) id[u] = i + u < i1 ? __ldg(idx + i + u) : 0;
     for (int c = lane; c < width; c += 32) {
-      float v = __ldg(a + (size_t)i * lda + c);
-      if (b) v += __ldg(b + (size_t)i * ldb + c);
-      mine[id * width + c] += v;
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = i + u < i1 ? __ldg(a + (size_t)(i + u) * lda + c) : 0.f;
+        if (b && i + u < i1) v[u] += __ldg(b + (size_t)(i + u) * ldb + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u < i1) mine[id[u] * width + c] += v[u];
     }
   }
   __syncthreads();
@@ -465,6 +473,59 @@ struct PlainSrc {
   int ld;
   __device__ __forceinline__ float at(int i, int c) const { return __ldg(p + (size_t)i * ld + c); }
 };
+// the four rows i, i+4, i+8, i+12 (< r1) of column c that one k_prep thread handles per trip
+template <class Src>
+__device__ __forceinline__ void prep_at4(const Src& src, int i, int r1, int c, float (&d)[4]) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) d[u] = i + 4 * u < r1 ? src.at(i + 4 * u, c) : 0.f;
+}
+// NodeGatherSrc: at() is a loop of dependent (entry -> row) loads, and four calls in a row serialise their chains (measured: 15.6 us
+// per launch for 2048 x 128 outputs).  Here the first four entries of all four rows are loaded as 16 independent chains; nodes of
+// higher degree (the room node: 62) continue in batches of 16.  Sums run in CSR order exactly as in at() (bit-identical).
+__device__ __forceinline__ void prep_at4(const NodeGatherSrc& src, int i, int r1, int c, float (&d)[4]) {
+  const int mask30 = (1 << 30) - 1;
+  int b[4], n[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const bool ok = i + 4 * u < r1;
+    b[u] = ok ? __ldg(src.row_ptr + i + 4 * u) : 0;
+    n[u] = ok ? __ldg(src.row_ptr + i + 4 * u + 1) - b[u] : 0;
+  }
+  int en[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) en[u][k] = k < n[u] ? __ldg(src.ent + b[u] + k) : -1;
+  float v[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      v[u][k] = en[u][k] >= 0 ? __ldg(src.dcat + (size_t)(en[u][k] & mask30) * src.ld + ((en[u][k] >> 30) ? 2 * src.D + c : c)) : 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (k < n[u]) acc += v[u][k];
+    int k = b[u] + 4;
+    const int e = b[u] + n[u];
+    for (; k + 16 <= e; k += 16) {
+      int e16[16];
+      float v16[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) e16[q] = __ldg(src.ent + k + q);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) v16[q] = __ldg(src.dcat + (size_t)(e16[q] & mask30) * src.ld + ((e16[q] >> 30) ? 2 * src.D + c : c));
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += v16[q];
+    }
+    for (; k < e; ++k) {
+      const int e1 = __ldg(src.ent + k);
+      acc += __ldg(src.dcat + (size_t)(e1 & mask30) * src.ld + ((e1 >> 30) ? 2 * src.D + c : c));
+    }
+    d[u] = acc;
+  }
+}
 
 struct ActInfo {  // the activation whose input gradient is being formed: a = relu(y*scale+shift)
   int has_act;    // 0: plain copy (no mask, no statistics)
@@ -494,9 +555,9 @@ __global__ void __launch_bounds__(512) k_prep(const Src src, const ActInfo act, 
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int ii = i + 4 * u;
-        d[u] = ii < r1 ? src.at(ii, j) : 0.f;
         y[u] = (ii < r1 && act.has_act) ? __ldg(act.y + (size_t)ii * act.ldy + j) : 0.f;
       }
+      prep_at4(src, i, r1, j, d);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int ii = i + 4 * u;
@@ -537,7 +598,9 @@ int launch_prep(cudaStream_t st, const Src& src, const ActInfo& act, float* G, i
   if (M <= 0 || N <= 0) return SLN_OK;
   // aim for ~2 waves of CTAs; partial buffer is sized for max_row_tiles(M) = ceil(M/16) tiles
   int col_blocks = ceil_div(N, 128);
-  int want_tiles = max(1, (2 * kNumSMs) / col_blocks);
+  static int waves = -1;                                   // env SLN_PREP_WAVES (tuning experiments)
+  if (waves < 0) { const char* e = getenv("SLN_PREP_WAVES"); waves = e ? atoi(e) : 2; if (waves < 1) waves = 2; }
+  int want_tiles = max(1, (waves * kNumSMs) / col_blocks);
   int rows = max(16, ceil_div(M, want_tiles));
   rows = ceil_div(rows, 4) * 4;
   dim3 grid(col_blocks, ceil_div(M, rows));
@@ -568,6 +631,7 @@ __global__ void __launch_bounds__(256) k_skinny_fwd(const AOp A, const float* __
   for (int i = blockIdx.x * 8 + warp; i < M; i += gridDim.x * 8) {
     float acc0 = b, acc1 = 0.f;
     int k = 0;
+#pragma unroll 4                                        // 8 row loads in flight per warp (one iteration = one exposed L2 round trip otherwise)
     for (; k + 8 <= K; k += 8) {
       float4 a = A.ld4(i, k), c = A.ld4(i, k + 4);
       acc0 = fmaf(a.x, s_wt[(k + 0) * 33 + lane], acc0); acc1 = fmaf(a.y, s_wt[(k + 1) * 33 + lane], acc1);
@@ -604,6 +668,7 @@ struct SmallKSrc {
   const float* add; int ldadd;
   __device__ __forceinline__ float at(int i, int j) const {
     float acc = add ? __ldg(add + (size_t)i * ldadd + j) : 0.f;
+#pragma unroll 8
     for (int k = 0; k < Kt; ++k) acc = fmaf(__ldg(dy + (size_t)i * lddy + k), __ldg(W + (size_t)k * ldw + j), acc);
     return acc;
   }

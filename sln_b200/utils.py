@@ -380,6 +380,7 @@ class VAETrainStep(object):
             z = self.z
         else:
             z = self.mu
+        desc.graph_ws = self.ws_enc.data_ptr()     # same objs / triples / attributes: the decoder reuses the encoder's CSR and index arrays
         _lib.check(lib.sln_vae_decoder_fwd(desc, params, bufs, z.data_ptr(), self.objs.data_ptr(), self.triples.data_ptr(),
                                            self.attrs.data_ptr(), O, T, self.boxes_pred.data_ptr(), self.angles_pred.data_ptr(),
                                            self.ws_dec.data_ptr(), self.ws_dec.numel(), st), "decoder_fwd")
