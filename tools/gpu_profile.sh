@@ -19,6 +19,7 @@ timeout 300 $NCU_F -k regex:tc_gemm -s 171 -c 4 -o gpurun_out/prof_tc_vae python
 timeout 300 $NCU_F --import-source on -k regex:tc_gemm -s 47 -c 2 -o gpurun_out/prof_tc_spade python tools/prof_spade.py 16 > /dev/null 2>&1
 timeout 300 $NCU_F --import-source on -k regex:k_raster_tiles -s 3 -c 1 -o gpurun_out/prof_raster python bench.py --workload render --no-graph --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 timeout 300 $NCU_F -k regex:k_pool_fwd -s 3 -c 1 -o gpurun_out/prof_pool python tools/bench_pool.py 8192 > /dev/null 2>&1
+timeout 300 $NCU_F -k regex:k_pool_fwd_node -s 12 -c 1 -o gpurun_out/prof_pool64 python tools/prof_step.py 2 > /dev/null 2>&1
 for r in gpurun_out/*.ncu-rep; do
   ncu -i $r --page raw --csv > ${r%.ncu-rep}_raw.csv 2>/dev/null
   if [ $(stat -c %s $r) -gt 16000000 ]; then rm -f $r; fi
