@@ -77,14 +77,43 @@ __global__ void k_fill_csr(const int* __restrict__ s_idx, const int* __restrict_
   ent[row_ptr[o] + atomicAdd(cursor + o, 1)] = (1 << 30) | t;
 }
 
-__global__ void k_sort_rows(const int* __restrict__ row_ptr, int O, int* ent) {
-  int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= O) return;
-  int b = row_ptr[o], e = row_ptr[o + 1];
-  for (int i = b + 1; i < e; ++i) {  // insertion sort: rows are short (degree of a scene-graph node)
-    int key = ent[i], j = i - 1;
-    while (j >= b && ent[j] > key) { ent[j + 1] = ent[j]; --j; }
-    ent[j + 1] = key;
+// One thread per node sorts short rows by insertion; rows above 16 entries (the room node of a scene: one entry per object) are
+// rank-sorted by the whole warp — every lane counts, for its keys, the smaller keys of the row (keys are unique: entry = side bit |
+// triple index), then writes each key to its rank: no dependent chain (a 62-entry insertion sort in global memory took 17 us).
+constexpr int kSortShort = 16, kSortLaneKeys = 8;        // warp path: rows up to 32 * kSortLaneKeys entries
+__global__ void __launch_bounds__(128) k_sort_rows(const int* __restrict__ row_ptr, int O, int* ent) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  const int b = o < O ? row_ptr[o] : 0, n = o < O ? row_ptr[o + 1] - b : 0;
+  const bool warp_row = n > kSortShort && n <= 32 * kSortLaneKeys;
+  if (!warp_row) {
+    for (int i = b + 1; i < b + n; ++i) {  // insertion sort: rows are short (degree of a scene-graph node)
+      int key = ent[i], j = i - 1;
+      while (j >= b && ent[j] > key) { ent[j + 1] = ent[j]; --j; }
+      ent[j + 1] = key;
+    }
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, warp_row);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int bb = __shfl_sync(0xffffffffu, b, src), nn = __shfl_sync(0xffffffffu, n, src);
+    int key[kSortLaneKeys], rank[kSortLaneKeys];
+#pragma unroll
+    for (int q = 0; q < kSortLaneKeys; ++q) {
+      const int i = q * 32 + lane;
+      key[q] = i < nn ? ent[bb + i] : 0;
+      rank[q] = 0;
+    }
+    for (int m = 0; m < nn; ++m) {
+      const int other = ent[bb + m];                     // same address in every lane: one broadcast load
+#pragma unroll
+      for (int q = 0; q < kSortLaneKeys; ++q) rank[q] += other < key[q] ? 1 : 0;
+    }
+    __syncwarp();                                        // every lane has read the row before anyone overwrites it
+#pragma unroll
+    for (int q = 0; q < kSortLaneKeys; ++q)
+      if (q * 32 + lane < nn) ent[bb + rank[q]] = key[q];
+    __syncwarp();
   }
 }
 
@@ -621,6 +650,7 @@ __global__ void __launch_bounds__(256) k_skinny_fwd(const AOp A, const float* __
                                                     float* out, int ldo) {
   extern __shared__ float s_wt[];   // [K][33]: coalesced reads of W (k fastest), transposed writes with an odd row stride (conflict-free)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#pragma unroll 8                                          // 8 weight loads in flight per thread (24 dependent round trips otherwise)
   for (int e = threadIdx.x; e < N * K; e += blockDim.x) {
     int j = e / K, k = e - j * K;
     s_wt[k * 33 + j] = __ldg(W + e);
@@ -818,25 +848,32 @@ __global__ void __launch_bounds__(256) k_vae_loss(const LossArgs a) {
   float l1 = 0.f, nll = 0.f, kl = 0.f;
   const float klw = a.kl_weight_dev ? __ldg(a.kl_weight_dev) : a.kl_weight;
   const float inv_bb = 1.f / ((float)a.O * (float)a.BD), inv_o = 1.f / (float)a.O;
+  // inputs and gradient seeds never alias: restrict-qualified views let the unrolled loops keep several loads in flight
+  const float* __restrict__ bp = a.boxes_pred; const float* __restrict__ bg = a.boxes_gt; float* __restrict__ dbx = a.d_boxes;
+  const float* __restrict__ lpv = a.logp; const long long* __restrict__ ag = a.angles_gt; float* __restrict__ dlg = a.d_logits;
+  const float* __restrict__ muv = a.mu; const float* __restrict__ lvv = a.logvar; float* __restrict__ dmu = a.d_mu; float* __restrict__ dlv = a.d_logvar;
+#pragma unroll 2
   for (int e = threadIdx.x; e < (r1 - r0) * a.BD; e += blockDim.x) {
     size_t k = (size_t)r0 * a.BD + e;
-    float d = a.boxes_pred[k] - a.boxes_gt[k];
+    float d = bp[k] - bg[k];
     l1 += fabsf(d);
-    if (a.d_boxes) a.d_boxes[k] = (d > 0.f ? inv_bb : (d < 0.f ? -inv_bb : 0.f));
+    if (dbx) dbx[k] = (d > 0.f ? inv_bb : (d < 0.f ? -inv_bb : 0.f));
   }
+#pragma unroll 4
   for (int e = threadIdx.x; e < (r1 - r0) * a.NA; e += blockDim.x) {
     int i = r0 + e / a.NA, c = e % a.NA;
-    float lp = a.logp[(size_t)i * a.NA + c];
-    bool hit = ((long long)c == a.angles_gt[i]);
+    float lp = lpv[(size_t)i * a.NA + c];
+    bool hit = ((long long)c == ag[i]);
     if (hit) nll -= lp;
-    if (a.d_logits) a.d_logits[(size_t)i * a.NA + c] = a.logits_grad ? (expf(lp) - (hit ? 1.f : 0.f)) * inv_o : (hit ? -inv_o : 0.f);
+    if (dlg) dlg[(size_t)i * a.NA + c] = a.logits_grad ? (expf(lp) - (hit ? 1.f : 0.f)) * inv_o : (hit ? -inv_o : 0.f);
   }
-  if (a.mu) {
+  if (muv) {
+#pragma unroll 4
     for (int e = threadIdx.x; e < (r1 - r0) * a.Z; e += blockDim.x) {
       size_t k = (size_t)r0 * a.Z + e;
-      float m = a.mu[k], lv = a.logvar[k], ex = expf(lv);
+      float m = muv[k], lv = lvv[k], ex = expf(lv);
       kl += 1.f + lv - m * m - ex;
-      if (a.d_mu) { a.d_mu[k] = klw * m * inv_o; a.d_logvar[k] = klw * 0.5f * (ex - 1.f) * inv_o; }
+      if (dmu) { dmu[k] = klw * m * inv_o; dlv[k] = klw * 0.5f * (ex - 1.f) * inv_o; }
     }
   }
   __shared__ float red[3][8];
