@@ -75,8 +75,12 @@ struct Model {
 // concurrently with the data-gradient chain, filling the SMs that the 62..128-CTA grids of the chain leave idle.
 // Hazards: a dW kernel READS a masked-gradient buffer `g` that a later chain kernel overwrites (the g buffers are shared
 // by all layers), so every chain kernel that writes such a buffer first waits for the last side-stream reader of it.
+constexpr int kLeafStreams = 3;
 struct Side {
   cudaStream_t st = nullptr;
+  cudaStream_t leaf[kLeafStreams];   // the embedding-table gradients at the tail of a backward call: small independent kernels, one stream each
+  int leaf_next = 0;
+  unsigned leaf_used = 0u;
   cudaEvent_t ev[64];
   int next = 0;
   bool ready = false, active = false;
@@ -112,13 +116,27 @@ void side_begin(Ctx& c) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(c.st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { (void)cudaGetLastError(); return; }
     if (cudaStreamCreateWithFlags(&sd.st, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    for (int i = 0; i < kLeafStreams; ++i)
+      if (cudaStreamCreateWithFlags(&sd.leaf[i], cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return; }
     for (int i = 0; i < 64; ++i)
       if (cudaEventCreateWithFlags(&sd.ev[i], cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return; }
     sd.ready = true;
   }
   sd.readers.clear();
   sd.active = false;
+  sd.leaf_next = 0; sd.leaf_used = 0u;
   c.side = true;
+}
+// stream for a leaf kernel (reads chain results, feeds only the optimizer, nothing overwrites its inputs before side_end)
+cudaStream_t side_fork_leaf(const Ctx& c) {
+  if (!c.side) return c.st;
+  Side& sd = g_side;
+  const int k = sd.leaf_next++ % kLeafStreams;
+  cudaEvent_t e = sd.take();
+  cudaEventRecord(e, c.st);
+  cudaStreamWaitEvent(sd.leaf[k], e, 0);
+  sd.leaf_used |= 1u << k;
+  return sd.leaf[k];
 }
 // stream for a weight-gradient launch that reads buffer `g`: forks from the chain (everything issued so far is visible)
 cudaStream_t side_fork(const Ctx& c) {
@@ -155,6 +173,13 @@ int side_end(Ctx& c) {
     SLN_CUDA_TRY(cudaEventRecord(e, sd.st));
     SLN_CUDA_TRY(cudaStreamWaitEvent(c.st, e, 0));
   }
+  for (int k = 0; k < kLeafStreams; ++k) {
+    if (!(sd.leaf_used >> k & 1u)) continue;
+    cudaEvent_t e = sd.take();
+    SLN_CUDA_TRY(cudaEventRecord(e, sd.leaf[k]));
+    SLN_CUDA_TRY(cudaStreamWaitEvent(c.st, e, 0));
+  }
+  sd.leaf_used = 0u; sd.leaf_next = 0;
   sd.readers.clear();
   sd.active = false;
   c.side = false;
@@ -569,7 +594,7 @@ int gather_rows(const Ctx& c, const float* table, int ldt, const int* idx, int n
   return check_launch("gather_rows");
 }
 int embed_bwd(const Ctx& c, const float* a, int lda, const float* b, int ldb, const int* idx, int n, int width, float* tg, int rows) {
-  return launch_embed_bwd(c.st, a, lda, b, ldb, idx, n, width, tg, rows);
+  return launch_embed_bwd(side_fork_leaf(c), a, lda, b, ldb, idx, n, width, tg, rows);   // tail of a backward call: see Side::leaf
 }
 
 // ---------------------------------------------------------------- one GraphTripleConv layer
@@ -785,17 +810,24 @@ int sln_vae_encoder_fwd(const sln_vae_desc* d, const void* const* params, void* 
   MatView obj_f;
   SLN_TRY(gconv_net_fwd(c, p, m.enc, make_view(p.obj0, dm.D, O, dm.D), make_view(p.pred0, dm.D, T, dm.D), &obj_f));
   // heads (Sg2ScVAE_model.py:134-143)
+  // The box and the angle branch are independent 4-kernel chains on obj_f (disjoint states, disjoint column ranges of mu / logvar):
+  // the angle branch runs on the side stream (a parallel branch of a captured graph), joined before the call returns.
+  side_begin(c);
+  Ctx ca = c;
+  ca.side = false;
+  if (c.side) ca.st = side_fork(c);
+  BlkState dummy; memset(&dummy, 0, sizeof(dummy)); dummy.M = O;
+  SLN_TRY(block_fwd(ca, obj_f, O, m.amv[0], p.amv[0]));
+  SLN_TRY(block_fwd(ca, block_out(m.amv[0], p.amv[0]), O, m.amv[1], p.amv[1]));
+  MatView ha = block_out(m.amv[1], p.amv[1]);
+  SLN_TRY(block_fwd(ca, ha, O, m.angle_mean, dummy, mu + dm.box_w, dm.Z));
+  SLN_TRY(block_fwd(ca, ha, O, m.angle_var, dummy, logvar + dm.box_w, dm.Z));
   SLN_TRY(block_fwd(c, obj_f, O, m.bmv[0], p.bmv[0]));
   SLN_TRY(block_fwd(c, block_out(m.bmv[0], p.bmv[0]), O, m.bmv[1], p.bmv[1]));
-  SLN_TRY(block_fwd(c, obj_f, O, m.amv[0], p.amv[0]));
-  SLN_TRY(block_fwd(c, block_out(m.amv[0], p.amv[0]), O, m.amv[1], p.amv[1]));
-  BlkState dummy; memset(&dummy, 0, sizeof(dummy)); dummy.M = O;
-  MatView hb = block_out(m.bmv[1], p.bmv[1]), ha = block_out(m.amv[1], p.amv[1]);
+  MatView hb = block_out(m.bmv[1], p.bmv[1]);
   SLN_TRY(block_fwd(c, hb, O, m.box_mean, dummy, mu, dm.Z));
   SLN_TRY(block_fwd(c, hb, O, m.box_var, dummy, logvar, dm.Z));
-  SLN_TRY(block_fwd(c, ha, O, m.angle_mean, dummy, mu + dm.box_w, dm.Z));
-  SLN_TRY(block_fwd(c, ha, O, m.angle_var, dummy, logvar + dm.box_w, dm.Z));
-  return SLN_OK;
+  return side_end(c);
 }
 
 int sln_vae_encoder_bwd(const sln_vae_desc* d, const void* const* params, void* const* grads, const float* boxes, const float* d_mu,
@@ -849,9 +881,9 @@ int sln_vae_encoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
     const int off = dm.obj_w + dm.attr_w;
     // dW [box_w, box_dim] = dy^T boxes: the SMALL side is the input (6), so boxes play the role of the narrow operand
     if (m.box_emb.lin.dW)
-      SLN_TRY(launch_skinny_bwd_w(c.st, boxes, dm.box_dim, dm.box_dim, make_view(p.dobj0 + off, dm.D, O, dm.box_w), O, dm.box_w,
+      SLN_TRY(launch_skinny_bwd_w(side_fork_leaf(c), boxes, dm.box_dim, dm.box_dim, make_view(p.dobj0 + off, dm.D, O, dm.box_w), O, dm.box_w,
                                   m.box_emb.lin.dW, dm.box_dim, true, nullptr));
-    if (m.box_emb.lin.db) SLN_TRY(launch_embed_bwd(c.st, p.dobj0 + off, dm.D, nullptr, 0, nullptr, O, dm.box_w, m.box_emb.lin.db, 1));
+    if (m.box_emb.lin.db) SLN_TRY(launch_embed_bwd(side_fork_leaf(c), p.dobj0 + off, dm.D, nullptr, 0, nullptr, O, dm.box_w, m.box_emb.lin.db, 1));
   }
   SLN_TRY(embed_bwd(c, p.dobj0 + dm.obj_w + dm.attr_w + dm.box_w, dm.D, nullptr, 0, p.angles32, O, dm.ang_w, m.demb[2], d->n_angle));
   SLN_TRY(embed_bwd(c, dpred0, ldp, nullptr, 0, p.g.p_idx, T, dm.D, m.demb[3], d->num_preds));
@@ -887,15 +919,20 @@ int sln_vae_decoder_fwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_TRY(gconv_net_fwd(c, p, m.dec, make_view(p.obj0, dm.D, O, dm.D), make_view(p.pred0, dm.D, T, dm.D), &obj_f));
   // box_net on [obj_f | attr_vecs], angle_net on obj_f   (Sg2ScVAE_model.py:166-171)
   Concat2 cat{obj_f, make_view(p.obj0 + dm.obj_w, dm.D, O, dm.attr_w), O, dm.D + dm.attr_w};
-  SLN_TRY(block_fwd(c, cat, O, m.box_net[0], p.box_net0));
+  // box_net runs on the side stream while angle_net + log-softmax run on the chain (independent branches on obj_f)
+  side_begin(c);
+  Ctx cb = c;
+  cb.side = false;
+  if (c.side) cb.st = side_fork(c);
   BlkState dummy; memset(&dummy, 0, sizeof(dummy)); dummy.M = O;
-  SLN_TRY(block_fwd(c, block_out(m.box_net[0], p.box_net0), O, m.box_net[1], dummy, boxes_pred, dm.box_dim));
+  SLN_TRY(block_fwd(cb, cat, O, m.box_net[0], p.box_net0));
+  SLN_TRY(block_fwd(cb, block_out(m.box_net[0], p.box_net0), O, m.box_net[1], dummy, boxes_pred, dm.box_dim));
   SLN_TRY(block_fwd(c, obj_f, O, m.angle_net[0], p.angle_net0));
   SLN_TRY(block_fwd(c, block_out(m.angle_net[0], p.angle_net0), O, m.angle_net[1], dummy, p.logits, dm.n_angle));
   k_log_softmax_fwd<<<ceil_div(O, 8), 256, 0, c.st>>>(p.logits, O, dm.n_angle, angles_pred);
   SLN_TRY(check_launch("log_softmax_fwd"));
   SLN_CUDA_TRY(cudaMemcpyAsync(p.logp, angles_pred, sizeof(float) * (size_t)O * dm.n_angle, cudaMemcpyDeviceToDevice, c.st));
-  return SLN_OK;
+  return side_end(c);
 }
 
 int sln_vae_decoder_bwd(const sln_vae_desc* d, const void* const* params, void* const* grads, const float* d_boxes, const float* d_angles,
