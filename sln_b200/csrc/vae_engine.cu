@@ -164,6 +164,19 @@ void side_before_write(const Ctx& c, const void* g) {
   cudaStreamWaitEvent(c.st, it->second, 0);
   sd.readers.erase(it);
 }
+// the chain waits for everything issued to the leaf streams so far (a branch of the chain that ran there rejoins it)
+int side_join_leaf(const Ctx& c) {
+  if (!c.side) return SLN_OK;
+  Side& sd = g_side;
+  for (int k = 0; k < kLeafStreams; ++k) {
+    if (!(sd.leaf_used >> k & 1u)) continue;
+    cudaEvent_t e = sd.take();
+    SLN_CUDA_TRY(cudaEventRecord(e, sd.leaf[k]));
+    SLN_CUDA_TRY(cudaStreamWaitEvent(c.st, e, 0));
+  }
+  sd.leaf_used = 0u;
+  return SLN_OK;
+}
 // join: every weight gradient of this call is complete before anything the caller enqueues next
 int side_end(Ctx& c) {
   if (!c.side) return SLN_OK;
@@ -349,7 +362,7 @@ struct NetPlan {
   float* dobj0;
   // encoder heads
   BlkState bmv[2], amv[2];
-  float *tmpA, *tmpB;
+  float *tmpA, *tmpA2, *tmpB;
   // decoder heads
   BlkState box_net0, angle_net0;
   float *logits, *logp, *dlogits, *tmpC;
@@ -385,7 +398,7 @@ void make_plan(const Dims& dm, int O, int T, int which, void* ws, NetPlan* p) {
     plan_state(ar, p->cp, O, dm.H, &p->amv[0]); plan_state(ar, p->cp, O, dm.D, &p->amv[1]);
     p->bmv[0].g = ar.take<float>((size_t)O * dm.H); p->bmv[1].g = ar.take<float>((size_t)O * dm.D);
     p->amv[0].g = ar.take<float>((size_t)O * dm.H); p->amv[1].g = ar.take<float>((size_t)O * dm.D);
-    p->tmpA = ar.take<float>((size_t)O * dm.D); p->tmpB = ar.take<float>((size_t)O * dm.D);
+    p->tmpA = ar.take<float>((size_t)O * dm.D); p->tmpB = ar.take<float>((size_t)O * dm.D); p->tmpA2 = ar.take<float>((size_t)O * dm.D);
   } else if (which == 1) {
     plan_state(ar, p->cp, O, dm.H, &p->box_net0); plan_state(ar, p->cp, O, dm.H, &p->angle_net0);
     p->box_net0.g = ar.take<float>((size_t)O * dm.H); p->angle_net0.g = ar.take<float>((size_t)O * dm.H);
@@ -846,6 +859,20 @@ int sln_vae_encoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   MatView obj_f = block_out(m.enc[L - 1][3], p.st[L - 1][3]);
   MatView hb = block_out(m.bmv[1], p.bmv[1]), ha = block_out(m.amv[1], p.amv[1]);
   MatView hb1 = block_out(m.bmv[0], p.bmv[0]), ha1 = block_out(m.amv[0], p.amv[0]);
+  // --- angle branch: independent of the box branch up to the kernel that adds tmpB, so it runs on a leaf stream (its weight
+  // gradients fork from there to the side stream as usual) and rejoins the chain below
+  Ctx ca = c;
+  if (c.side) ca.st = side_fork_leaf(c);
+  DyView dmu_a = make_dy(d_mu + dm.box_w, dm.Z, O, dm.ang_w), dlv_a = make_dy(d_logvar + dm.box_w, dm.Z, O, dm.ang_w);
+  SLN_TRY(bwd_w(ca, dmu_a, ha, m.angle_mean.lin, O, true));
+  SLN_TRY(bwd_w(ca, dlv_a, ha, m.angle_var.lin, O, true));
+  SLN_TRY(bwd_x_plain(ca, dmu_a, m.angle_mean.lin, O, p.tmpA2, dm.D));
+  SLN_TRY(bwd_x_masked(ca, dlv_a, m.angle_var.lin, O, m.amv[1], p.amv[1], p.tmpA2, dm.D));
+  DyView dya2 = blk_dy(ca, m.amv[1], p.amv[1]);
+  SLN_TRY(bwd_w(ca, dya2, ha1, m.amv[1].lin, O));
+  SLN_TRY(bwd_x_masked(ca, dya2, m.amv[1].lin, O, m.amv[0], p.amv[0], nullptr, 0));
+  DyView dya1 = blk_dy(ca, m.amv[0], p.amv[0]);
+  SLN_TRY(bwd_w(ca, dya1, obj_f, m.amv[0].lin, O));
   // --- box branch
   DyView dmu_b = make_dy(d_mu, dm.Z, O, dm.box_w), dlv_b = make_dy(d_logvar, dm.Z, O, dm.box_w);
   SLN_TRY(bwd_w(c, dmu_b, hb, m.box_mean.lin, O, true));
@@ -858,17 +885,7 @@ int sln_vae_encoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   DyView dyb1 = blk_dy(c, m.bmv[0], p.bmv[0]);
   SLN_TRY(bwd_w(c, dyb1, obj_f, m.bmv[0].lin, O));
   SLN_TRY(bwd_x_plain(c, dyb1, m.bmv[0].lin, O, p.tmpB, dm.D));
-  // --- angle branch
-  DyView dmu_a = make_dy(d_mu + dm.box_w, dm.Z, O, dm.ang_w), dlv_a = make_dy(d_logvar + dm.box_w, dm.Z, O, dm.ang_w);
-  SLN_TRY(bwd_w(c, dmu_a, ha, m.angle_mean.lin, O, true));
-  SLN_TRY(bwd_w(c, dlv_a, ha, m.angle_var.lin, O, true));
-  SLN_TRY(bwd_x_plain(c, dmu_a, m.angle_mean.lin, O, p.tmpA, dm.D));
-  SLN_TRY(bwd_x_masked(c, dlv_a, m.angle_var.lin, O, m.amv[1], p.amv[1], p.tmpA, dm.D));
-  DyView dya2 = blk_dy(c, m.amv[1], p.amv[1]);
-  SLN_TRY(bwd_w(c, dya2, ha1, m.amv[1].lin, O));
-  SLN_TRY(bwd_x_masked(c, dya2, m.amv[1].lin, O, m.amv[0], p.amv[0], nullptr, 0));
-  DyView dya1 = blk_dy(c, m.amv[0], p.amv[0]);
-  SLN_TRY(bwd_w(c, dya1, obj_f, m.amv[0].lin, O));
+  SLN_TRY(side_join_leaf(c));
   // both branches meet at the last gconv layer's node output
   SLN_TRY(bwd_x_masked(c, dya1, m.amv[0].lin, O, m.enc[L - 1][3], p.st[L - 1][3], p.tmpB, dm.D));
   // --- graph conv stack
