@@ -550,11 +550,11 @@ inline bool borrow_graph(const Dims& dm, const sln_vae_desc* d, int O, int T, Ne
   return true;
 }
 
-int graph_prep(const Ctx& c, NetPlan& p, const int64_t* triples_or_edges, int stride3) {
+int graph_prep(const Ctx& c, NetPlan& p, const int64_t* triples_or_edges, int stride3, bool clear_err = true) {
   const Graph& g = p.g;
   SLN_CUDA_TRY(cudaMemsetAsync(p.deg, 0, sizeof(int) * g.O, c.st));
   SLN_CUDA_TRY(cudaMemsetAsync(g.cursor, 0, sizeof(int) * g.O, c.st));
-  SLN_CUDA_TRY(cudaMemsetAsync(p.err, 0, sizeof(int), c.st));
+  if (clear_err) SLN_CUDA_TRY(cudaMemsetAsync(p.err, 0, sizeof(int), c.st));
   (void)stride3;
   if (g.T > 0) {
     k_split_triples<<<ceil_div(g.T, 256), 256, 0, c.st>>>((const long long*)triples_or_edges, g.T, g.O, c.dm.num_preds, g.s_idx, g.p_idx, g.o_idx, p.deg, p.err);
@@ -742,16 +742,7 @@ size_t sln_vae_packed_bytes(const sln_vae_desc* d) {
   return floats * sizeof(float);
 }
 
-int sln_vae_pack_weights(const sln_vae_desc* d, const void* const* params, void* packed, size_t packed_bytes, void* stream) {
-  Dims dm;
-  SLN_TRY(make_dims(d, &dm));
-  SLN_CHECK_ARG(params && packed && (uintptr_t)packed % 16 == 0, "null or misaligned pointer");
-  static thread_local Model m;
-  std::vector<PackJob> jobs;
-  size_t floats = 0;
-  SLN_TRY(parse_model(dm, params, nullptr, nullptr, &m, packed, &jobs, &floats));
-  if (packed_bytes < floats * sizeof(float)) { set_error("packed weight buffer too small: %zu < %zu bytes", packed_bytes, floats * sizeof(float)); return SLN_EWORKSPACE; }
-  cudaStream_t st = (cudaStream_t)stream;
+int launch_pack_jobs(cudaStream_t st, const std::vector<PackJob>& jobs, size_t floats) {
   ProfScope prof(st, PROF_MISC, 12.0 * (double)floats);
   for (size_t j0 = 0; j0 < jobs.size(); j0 += kPackJobsPerLaunch) {
     PackJobs pj; memset(&pj, 0, sizeof(pj));
@@ -767,6 +758,18 @@ int sln_vae_pack_weights(const sln_vae_desc* d, const void* const* params, void*
     SLN_TRY(check_launch("pack_weights"));
   }
   return SLN_OK;
+}
+
+int sln_vae_pack_weights(const sln_vae_desc* d, const void* const* params, void* packed, size_t packed_bytes, void* stream) {
+  Dims dm;
+  SLN_TRY(make_dims(d, &dm));
+  SLN_CHECK_ARG(params && packed && (uintptr_t)packed % 16 == 0, "null or misaligned pointer");
+  static thread_local Model m;
+  std::vector<PackJob> jobs;
+  size_t floats = 0;
+  SLN_TRY(parse_model(dm, params, nullptr, nullptr, &m, packed, &jobs, &floats));
+  if (packed_bytes < floats * sizeof(float)) { set_error("packed weight buffer too small: %zu < %zu bytes", packed_bytes, floats * sizeof(float)); return SLN_EWORKSPACE; }
+  return launch_pack_jobs((cudaStream_t)stream, jobs, floats);
 }
 
 int sln_vae_num_params(const sln_vae_desc* d) { Dims dm; if (make_dims(d, &dm)) return -1; return count_params(dm); }
@@ -806,26 +809,34 @@ int sln_vae_encoder_fwd(const sln_vae_desc* d, const void* const* params, void* 
   ctx_sync(c, d, p.cp.base, 0, 0);
   SLN_TRY(check_ws(p, ws, ws_bytes));
   SLN_CUDA_TRY(cudaMemsetAsync(p.cp.base, 0, sizeof(unsigned) * kCounterCap, c.st));
-  SLN_TRY(graph_prep(c, p, triples, 1));
-  SLN_TRY(to_i32(c, objs, O, p.objs32, d->num_objs, p.err, SLN_IDX_OBJS));
-  SLN_TRY(to_i32(c, attributes, O, p.attrs32, d->num_attrs, p.err, SLN_IDX_ATTRS));
-  SLN_TRY(to_i32(c, angles, O, p.angles32, d->n_angle, p.err, SLN_IDX_ANGLES));
+  SLN_CUDA_TRY(cudaMemsetAsync(p.err, 0, sizeof(int), c.st));
+  // Two independent preparations run as parallel branches and meet before the first layer: the CSR build (chain) and the int32
+  // index copies + embedding gathers of the node features (leaf stream).  (Re-splitting the weight images on a third branch was
+  // measured too: no gain — the bandwidth kernel fills every SM slot and the small kernels queue behind it.)
+  side_begin(c);
+  Ctx ce = c;
+  ce.side = false;
+  if (c.side) ce.st = side_fork_leaf(c);
+  SLN_TRY(to_i32(ce, objs, O, p.objs32, d->num_objs, p.err, SLN_IDX_OBJS));
+  SLN_TRY(to_i32(ce, attributes, O, p.attrs32, d->num_attrs, p.err, SLN_IDX_ATTRS));
+  SLN_TRY(to_i32(ce, angles, O, p.angles32, d->n_angle, p.err, SLN_IDX_ANGLES));
   // obj_vecs = [obj_emb | attr_emb | box_linear | angle_emb]   (Sg2ScVAE_model.py:121-129)
-  SLN_TRY(gather_rows(c, m.emb[0], dm.obj_w, p.objs32, O, dm.obj_w, p.obj0, dm.D, 0));
-  SLN_TRY(gather_rows(c, m.emb[1], dm.attr_w, p.attrs32, O, dm.attr_w, p.obj0, dm.D, dm.obj_w));
+  SLN_TRY(gather_rows(ce, m.emb[0], dm.obj_w, p.objs32, O, dm.obj_w, p.obj0, dm.D, 0));
+  SLN_TRY(gather_rows(ce, m.emb[1], dm.attr_w, p.attrs32, O, dm.attr_w, p.obj0, dm.D, dm.obj_w));
   {
     dim3 blk(32, 8);
-    k_small_linear<<<ceil_div(O, 8), blk, 0, c.st>>>(boxes, O, dm.box_dim, m.box_emb.lin.W, m.box_emb.lin.b, dm.box_w, p.obj0, dm.D, dm.obj_w + dm.attr_w);
+    k_small_linear<<<ceil_div(O, 8), blk, 0, ce.st>>>(boxes, O, dm.box_dim, m.box_emb.lin.W, m.box_emb.lin.b, dm.box_w, p.obj0, dm.D, dm.obj_w + dm.attr_w);
     SLN_TRY(check_launch("box_embeddings"));
   }
-  SLN_TRY(gather_rows(c, m.emb[2], dm.ang_w, p.angles32, O, dm.ang_w, p.obj0, dm.D, dm.obj_w + dm.attr_w + dm.box_w));
+  SLN_TRY(gather_rows(ce, m.emb[2], dm.ang_w, p.angles32, O, dm.ang_w, p.obj0, dm.D, dm.obj_w + dm.attr_w + dm.box_w));
+  SLN_TRY(graph_prep(c, p, triples, 1, false));
   SLN_TRY(gather_rows(c, m.emb[3], dm.D, p.g.p_idx, T, dm.D, p.pred0, dm.D, 0));
+  SLN_TRY(side_join_leaf(c));
   MatView obj_f;
   SLN_TRY(gconv_net_fwd(c, p, m.enc, make_view(p.obj0, dm.D, O, dm.D), make_view(p.pred0, dm.D, T, dm.D), &obj_f));
   // heads (Sg2ScVAE_model.py:134-143)
   // The box and the angle branch are independent 4-kernel chains on obj_f (disjoint states, disjoint column ranges of mu / logvar):
   // the angle branch runs on the side stream (a parallel branch of a captured graph), joined before the call returns.
-  side_begin(c);
   Ctx ca = c;
   ca.side = false;
   if (c.side) ca.st = side_fork(c);
