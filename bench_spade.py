@@ -143,7 +143,23 @@ def batch1_latency(dev, m, seg, z, reps=10):
     b.record()
     torch.cuda.synchronize(dev)
     ms = a.elapsed_time(b) / reps
-    return {"ms_per_image": ms, "images_per_s": 1e3 / ms, "what": "batch 1 (the reference's own call pattern, test_SPADE_shade.py:77-79), CUDA events, %d forwards" % reps}
+    out = {"ms_per_image": ms, "images_per_s": 1e3 / ms, "what": "batch 1 (the reference's own call pattern, test_SPADE_shade.py:77-79), CUDA events, %d forwards" % reps}
+    try:     # the same forward as one CUDA graph (models/SPADE_related.py GraphedForward): launch-bound at batch 1
+        import importlib
+        run = importlib.import_module("sln_b200.models.SPADE_related").GraphedForward(m, s1, z1)
+        for _ in range(3):
+            run(s1, z1)
+        torch.cuda.synchronize(dev)
+        a.record()
+        for _ in range(reps):
+            run(s1, z1)
+        b.record()
+        torch.cuda.synchronize(dev)
+        out["graphed_ms_per_image"] = a.elapsed_time(b) / reps
+    except Exception as e:      # context only
+        out["graphed_ms_per_image"] = None
+        out["graphed_error"] = repr(e)[:200]
+    return out
 
 
 def eager_gpu_spade(dev, m, seg, z, reps=3):

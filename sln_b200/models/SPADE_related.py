@@ -109,6 +109,39 @@ def _pretile(w):
     return out
 
 
+class GraphedForward(object):
+    """One CUDA graph of ``generator(seg, z)`` for a fixed input shape: the ~190 launches of a forward become one replay.  The
+    reference draws 50 z vectors at batch 1 (testing/test_SPADE_shade.py:77-79), where a forward is launch-bound, not GPU-bound.
+
+        run = GraphedForward(netG, seg, z)        # warms up (packs the weights), captures
+        img = run(seg, z)                          # copies the inputs into the captured buffers, replays; ``img`` is overwritten by the next call
+
+    Built for the generator's CURRENT weights (their packed images are baked into the graph): rebuild after loading a checkpoint."""
+
+    def __init__(self, generator, seg, z, warmup=2):
+        if generator.training or getattr(generator, "taps", None) is not None:
+            raise RuntimeError("GraphedForward needs an eval-mode generator without taps")
+        dev = seg.device
+        self.generator = generator
+        self.seg = seg.detach().contiguous().float().clone()
+        self.z = z.detach().contiguous().float().clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):               # first-use initialisation (function attributes, weight packing) must not be captured
+            for _ in range(max(1, warmup)):
+                generator(self.seg, self.z)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = generator(self.seg, self.z)
+
+    def __call__(self, seg, z):
+        self.seg.copy_(seg)
+        self.z.copy_(z)
+        self.graph.replay()
+        return self.out
+
+
 class SPADEGenerator4(nn.Module):
     def __init__(self, semantic_nc, target_nc, nz, ngf, norm, crop_size, n_up):
         super().__init__()

@@ -106,3 +106,22 @@ def test_errors_are_loud():
         spade.SPADEGenerator4(semantic_nc=41, target_nc=3, nz=16, ngf=8, norm='spectralspadelayer3x3', crop_size=64, n_up='more')
     with pytest.raises(NotImplementedError):
         m.train().to(DEV)(torch.zeros(1, 41, 64, 64, device=DEV), torch.zeros(1, 16, device=DEV))
+
+
+def test_graphed_forward_replays_the_eager_forward():
+    """GraphedForward (one CUDA graph per input shape) returns bit-for-bit what the eager forward returns, for new inputs too."""
+    torch.manual_seed(0)
+    m = spade.SPADEGenerator4(semantic_nc=41, target_nc=3, nz=16, ngf=16, norm='spectralspadelayer3x3', crop_size=64, n_up='normal').eval().to(DEV)
+    seg = so.synthetic_input(1, S=64, seed=5).to(DEV)
+    z = torch.randn(1, 16, generator=torch.Generator().manual_seed(1)).to(DEV)
+    run = spade.GraphedForward(m, seg, z)
+    for seed in (2, 3):
+        seg2 = so.synthetic_input(1, S=64, seed=10 + seed).to(DEV)
+        z2 = torch.randn(1, 16, generator=torch.Generator().manual_seed(seed)).to(DEV)
+        got = run(seg2, z2).clone()
+        with torch.no_grad():
+            want = m(seg2, z2)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+    with pytest.raises(RuntimeError):
+        spade.GraphedForward(m.train(), seg, z)
