@@ -978,16 +978,18 @@ int sln_vae_decoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   side_begin(c);
   const int L = dm.L;
   MatView obj_f = block_out(m.dec[L - 1][3], p.st[L - 1][3]);
+  // angle_net's output layer (+ log-softmax backward) is independent of box_net's two layers: a parallel branch (leaf stream)
+  Ctx ca = c;
+  if (c.side) ca.st = side_fork_leaf(c);
   const float* dlogits = d_angles;
   if (!angles_are_logits) {
-    k_log_softmax_bwd<<<ceil_div(O, 8), 256, 0, c.st>>>(d_angles, p.logp, O, dm.n_angle, p.dlogits);
+    k_log_softmax_bwd<<<ceil_div(O, 8), 256, 0, ca.st>>>(d_angles, p.logp, O, dm.n_angle, p.dlogits);
     SLN_TRY(check_launch("log_softmax_bwd"));
     dlogits = p.dlogits;
   }
-  // angle_net
   DyView dyl = make_dy(dlogits, dm.n_angle, O, dm.n_angle);
-  SLN_TRY(bwd_w(c, dyl, block_out(m.angle_net[0], p.angle_net0), m.angle_net[1].lin, O, true));
-  SLN_TRY(bwd_x_masked(c, dyl, m.angle_net[1].lin, O, m.angle_net[0], p.angle_net0, nullptr, 0));
+  SLN_TRY(bwd_w(ca, dyl, block_out(m.angle_net[0], p.angle_net0), m.angle_net[1].lin, O, true));
+  SLN_TRY(bwd_x_masked(ca, dyl, m.angle_net[1].lin, O, m.angle_net[0], p.angle_net0, nullptr, 0));
   // box_net
   DyView dyb = make_dy(d_boxes, dm.box_dim, O, dm.box_dim);
   SLN_TRY(bwd_w(c, dyb, block_out(m.box_net[0], p.box_net0), m.box_net[1].lin, O, true));
@@ -997,6 +999,7 @@ int sln_vae_decoder_bwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_TRY(bwd_w(c, dyb0, cat, m.box_net[0].lin, O));
   const int ldc = dm.D + dm.attr_w;
   SLN_TRY(bwd_x_plain(c, dyb0, m.box_net[0].lin, O, p.tmpC, ldc));
+  SLN_TRY(side_join_leaf(c));
   DyView dya0 = blk_dy(c, m.angle_net[0], p.angle_net0);
   SLN_TRY(bwd_w(c, dya0, obj_f, m.angle_net[0].lin, O));
   SLN_TRY(bwd_x_masked(c, dya0, m.angle_net[0].lin, O, m.dec[L - 1][3], p.st[L - 1][3], p.tmpC, ldc));
