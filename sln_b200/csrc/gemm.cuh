@@ -347,10 +347,11 @@ __device__ __forceinline__ void finalize_column_block(const float* partial, unsi
                                                       double* sred, int* s_last, FinFn fin, const sln_bn_sync* sync = nullptr,
                                                       int slot0 = 0, int Mlocal = 0) {
   const int tiles = gridDim.y;
+  const int cb = n0 / ncols;            // column block (== blockIdx.x unless the launch covers a subset of the column tiles)
   __threadfence();
   __syncthreads();
   if (tid == 0) {
-    unsigned ticket = atomicAdd(counter + blockIdx.x, 1u);
+    unsigned ticket = atomicAdd(counter + cb, 1u);
     *s_last = (ticket == (unsigned)tiles - 1u) ? 1 : 0;
   }
   __syncthreads();
@@ -390,7 +391,7 @@ __device__ __forceinline__ void finalize_column_block(const float* partial, unsi
   } else {
     // SyncBatchNorm: one-shot all-gather of this column block's sums over peer memory (NVLink), reduced in rank order
     const int world = sync->world, rank = sync->rank;
-    const size_t slot = (size_t)slot0 + blockIdx.x;
+    const size_t slot = (size_t)slot0 + cb;
     if (live && g == 0) {
       for (int r = 0; r < world; ++r) {
         double* dst = sync->recv[r] + ((slot * world + rank) * SLN_BN_SYNC_COLS + c) * 3;
@@ -414,7 +415,7 @@ __device__ __forceinline__ void finalize_column_block(const float* partial, unsi
       fin(n0 + c, S, Q, Sa, Qa, (int)Ma);
     }
   }
-  if (tid == 0) counter[blockIdx.x] = 0u;
+  if (tid == 0) counter[cb] = 0u;
 }
 
 // ---------------------------------------------------------------- epilogues

@@ -435,7 +435,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 //   the MMAs of the previous chunks instead of being exposed once per chunk.
 // grid = (ceil(N/BN), ceil(M/128), splits); each z-slice reduces k in [z*kchunk, (z+1)*kchunk), kchunk % 32 == 0.
 template <int BN, bool A_RC, bool B_RC, bool MSEG, class AOp, class BOp, class Epi>
-__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const BOp B, const Epi epi, int M, int N, int K, int kchunk) {
+__global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const BOp B, const Epi epi, int M, int N, int K, int kchunk, int xmap) {
   using L = SmemLayout<BN>;
   // chunks prefetched into registers per producer thread.  The loads of chunk c + PF are issued at the end of produce(c) and consumed
   // at the start of produce(c + PF), i.e. PF - 1 chunk periods later: with PF = 2 the period settled at the (loaded) L2 latency of
@@ -457,7 +457,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // xmap != 0: the launch covers a subset of the column tiles — tile = blockIdx.x, plus (xmap >> 16) from tile (xmap & 0xffff) on
+  const int xtile = (int)blockIdx.x + (((xmap >> 16) != 0 && (int)blockIdx.x >= (xmap & 0xffff)) ? (xmap >> 16) : 0);
+  const int m0 = blockIdx.y * BM, n0 = xtile * BN;
   const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
   const int nchunks = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
   TC_TRACE(0);
@@ -760,6 +762,10 @@ inline bool pdl_enabled() {   // env SLN_PDL=0 disables programmatic dependent l
 }
 
 struct TcChoice { int bn, splits, kchunk; };
+// A launch over `count` column tiles of width `bn`: the tiles 0 .. count-1, with `skip_n` tiles left out from tile `skip_at` on
+// (e.g. count 4, skip_at 2, skip_n 1 -> tiles 0, 1, 3, 4; count 1, skip_at 0, skip_n 2 -> tile 2).  count == 0: every tile, width chosen
+// by pick_tc.  The epilogue state (BatchNorm partials, tickets, statistics) is per column block, so disjoint subsets are independent.
+struct TileSel { int count = 0, skip_at = 0, skip_n = 0, bn = 0; };
 
 inline TcChoice pick_tc(int M, int N, int K, bool allow_split) {
   const int bns[3] = {128, 64, 32};
@@ -801,7 +807,7 @@ inline TcChoice pick_tc(int M, int N, int K, bool allow_split) {
 inline bool tc_eligible(int M, int N, int K) { return M >= 1 && N >= 32 && K >= 32; }
 
 template <int BN, bool A_RC, bool B_RC, bool MSEG, class AOp, class BOp, class Epi>
-int launch_tc_bn_seg(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, const TcChoice& c) {
+int launch_tc_bn_seg(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, const TcChoice& c, const TileSel& sel) {
   auto kern = tc_gemm_kernel<BN, A_RC, B_RC, MSEG, AOp, BOp, Epi>;
   constexpr int bytes = SmemLayout<BN>::BYTES;
   static unsigned long long configured = 0ull;   // devices configured (per call site / instantiation)
@@ -811,7 +817,7 @@ int launch_tc_bn_seg(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(ceil_div(N, BN), ceil_div(M, BM), c.splits);
+  cfg.gridDim = dim3(sel.count > 0 ? sel.count : ceil_div(N, BN), ceil_div(M, BM), c.splits);
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = bytes;
   cfg.stream = st;
@@ -821,28 +827,30 @@ int launch_tc_bn_seg(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int kchunk = c.kchunk;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, A, B, epi, M, N, K, kchunk);
+  int xmap = sel.count > 0 ? ((sel.skip_n << 16) | sel.skip_at) : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, A, B, epi, M, N, K, kchunk, xmap);
   if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(tc_gemm) failed: %s", cudaGetErrorString(e)); return SLN_ECUDA; }
   return SLN_OK;
 }
 
 template <int BN, bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
-int launch_tc_bn(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, const TcChoice& c) {
+int launch_tc_bn(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, const TcChoice& c, const TileSel& sel = TileSel()) {
   // K ranges that fit one accumulation segment take the variant without in-loop drains (deeper register prefetch)
-  if (ceil_div(c.kchunk < K ? c.kchunk : K, BK) > SEG_CHUNKS) return launch_tc_bn_seg<BN, A_RC, B_RC, true>(st, A, B, epi, M, N, K, c);
-  return launch_tc_bn_seg<BN, A_RC, B_RC, false>(st, A, B, epi, M, N, K, c);
+  if (ceil_div(c.kchunk < K ? c.kchunk : K, BK) > SEG_CHUNKS) return launch_tc_bn_seg<BN, A_RC, B_RC, true>(st, A, B, epi, M, N, K, c, sel);
+  return launch_tc_bn_seg<BN, A_RC, B_RC, false>(st, A, B, epi, M, N, K, c, sel);
 }
 
 template <bool A_RC, bool B_RC, class AOp, class BOp, class Epi>
 int launch_tc(cudaStream_t st, const AOp& A, const BOp& B, const Epi& epi, int M, int N, int K, bool allow_split, const char* what,
-              int prof_cls) {
+              int prof_cls, const TileSel& sel = TileSel()) {
   if (M <= 0 || N <= 0) return SLN_OK;
-  ProfScope prof(st, prof_cls, 2.0 * (double)M * (double)N * (double)K);
-  TcChoice c = pick_tc(M, N, K, allow_split);
+  const int ncols = sel.count > 0 ? (sel.count * sel.bn < N ? sel.count * sel.bn : N) : N;
+  ProfScope prof(st, prof_cls, 2.0 * (double)M * (double)ncols * (double)K);
+  TcChoice c = sel.count > 0 ? TcChoice{sel.bn, 1, ceil_div(K, BK) * BK} : pick_tc(M, N, K, allow_split);
   int rc;
-  if (c.bn == 128) rc = launch_tc_bn<128, A_RC, B_RC>(st, A, B, epi, M, N, K, c);
-  else if (c.bn == 64) rc = launch_tc_bn<64, A_RC, B_RC>(st, A, B, epi, M, N, K, c);
-  else rc = launch_tc_bn<32, A_RC, B_RC>(st, A, B, epi, M, N, K, c);
+  if (c.bn == 128) rc = launch_tc_bn<128, A_RC, B_RC>(st, A, B, epi, M, N, K, c, sel);
+  else if (c.bn == 64) rc = launch_tc_bn<64, A_RC, B_RC>(st, A, B, epi, M, N, K, c, sel);
+  else rc = launch_tc_bn<32, A_RC, B_RC>(st, A, B, epi, M, N, K, c, sel);
   if (rc != SLN_OK) return rc;
   return check_launch(what);
 }

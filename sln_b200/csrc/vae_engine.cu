@@ -424,7 +424,8 @@ MatView slice_cols(const MatView& v, int off, int width) {
 MatView weight_view(const Lin& l) { return make_view(l.W, l.in, l.out, l.in); }
 
 template <class AOp>
-int block_fwd(const Ctx& c, const AOp& A, int M, const Blk& b, BlkState& s, float* out = nullptr, int ldo = 0) {
+int block_fwd(const Ctx& c, const AOp& A, int M, const Blk& b, BlkState& s, float* out = nullptr, int ldo = 0, const tc::TileSel* sel = nullptr,
+              bool skip_eval_prep = false) {
   EpiStore epi; memset(&epi, 0, sizeof(epi));
   epi.C = out ? out : s.y; epi.ldc = out ? ldo : b.lin.out; epi.bias = b.lin.b;
   int mode = norm_mode(c, b);
@@ -435,7 +436,7 @@ int block_fwd(const Ctx& c, const AOp& A, int M, const Blk& b, BlkState& s, floa
     f.mean = s.mean; f.rstd = s.rstd; f.scale = s.scale; f.shift = s.shift;
     f.eps = c.dm.eps; f.momentum = c.dm.momentum; f.M = M;
     if (c.sync) { f.sync = c.sync; f.slot0 = c.slot_off + (int)(s.counter - c.cbase); }
-  } else if (mode == NORM_BN_EVAL) {
+  } else if (mode == NORM_BN_EVAL && !skip_eval_prep) {
     SLN_CHECK_ARG(b.rm && b.rv, "eval-mode BatchNorm needs running statistics");
     k_bn_eval_prep<<<ceil_div(b.lin.out, 128), 128, 0, c.st>>>(b.gamma, b.beta, b.rm, b.rv, c.dm.eps, b.lin.out, s.mean, s.rstd, s.scale, s.shift);
     SLN_TRY(check_launch("bn_eval_prep"));
@@ -446,8 +447,9 @@ int block_fwd(const Ctx& c, const AOp& A, int M, const Blk& b, BlkState& s, floa
     tc::TcEpiStore te{epi.C, epi.ldc, epi.bias, epi.fin};
     if (b.lin.pf) {   // pre-split weight image: the B tiles arrive by cp.async.bulk
       tc::PackedB pb{b.lin.pf, ceil_div(b.lin.in, tc::BK)};
-      return tc::launch_tc<true, true>(c.st, A, pb, te, M, b.lin.out, b.lin.in, false, "linear_fwd_tc_packed", PROF_GEMM_FWD);
+      return tc::launch_tc<true, true>(c.st, A, pb, te, M, b.lin.out, b.lin.in, false, "linear_fwd_tc_packed", PROF_GEMM_FWD, sel ? *sel : tc::TileSel());
     }
+    if (sel) { set_error("internal: column-tile subsets need the packed tensor-core path"); return SLN_EINVAL; }
     return tc::launch_tc<true, true>(c.st, A, weight_view(b.lin), te, M, b.lin.out, b.lin.in, false, "linear_fwd_tc", PROF_GEMM_FWD);
   }
   return launch_gemm<true, true>(c.st, A, weight_view(b.lin), epi, M, b.lin.out, b.lin.in, false, "linear_fwd", PROF_GEMM_FWD);
@@ -616,7 +618,24 @@ int gconv_fwd(const Ctx& c, const Graph& g, const Blk* blk, BlkState* st, float*
   const int D = c.dm.D, H = c.dm.H, O = g.O, T = g.T;
   GatherCat gc{obj_in, pred_in, g.s_idx, g.o_idx, D, T, 3 * D};
   SLN_TRY(block_fwd(c, gc, T, blk[0], st[0]));
-  SLN_TRY(block_fwd(c, block_out(blk[0], st[0]), T, blk[1], st[1]));
+  // net1's second Linear writes [new_s | new_p | new_o] (2H + D columns).  At configs[1] that is 5 x 31 = 155 tiles of 128 x 128 on
+  // 148 SMs: a 7-CTA second wave doubles the kernel's time.  Only new_s / new_o feed the pooling and net2; new_p is needed by the
+  // NEXT layer.  So the s / o column tiles run on the chain (124 CTAs: one wave) and the p tiles as a parallel branch that overlaps
+  // the pooling and net2 and rejoins at the end of the layer.  Per-column-block BatchNorm state makes the two launches independent.
+  MatView a1 = block_out(blk[0], st[0]);
+  const int tm = ceil_div(T, tc::BM);
+  const bool split = c.side && blk[1].lin.pf && use_tc(T, blk[1].lin.out, blk[1].lin.in, SITE_FWD) && a1.vec_ok() && H % 128 == 0 && D % 128 == 0 &&
+                     blk[1].lin.out == 2 * H + D && tm * ((2 * H + D) / 128) > kNumSMs && tm * (2 * H / 128) <= kNumSMs;
+  if (split) {
+    const tc::TileSel so{2 * H / 128, H / 128, D / 128, 128}, sp{D / 128, 0, H / 128, 128};
+    SLN_TRY(block_fwd(c, a1, T, blk[1], st[1], nullptr, 0, &so));
+    Ctx cp = c;
+    cp.side = false;
+    cp.st = side_fork_leaf(c);
+    SLN_TRY(block_fwd(cp, a1, T, blk[1], st[1], nullptr, 0, &sp, true));
+  } else {
+    SLN_TRY(block_fwd(c, a1, T, blk[1], st[1]));
+  }
   MatView a2 = block_out(blk[1], st[1]);
   if (O > 0) {
     ProfScope prof(c.st, PROF_POOL, pool_bytes(O, T, H));
@@ -627,6 +646,7 @@ int gconv_fwd(const Ctx& c, const Graph& g, const Blk* blk, BlkState* st, float*
   SLN_TRY(block_fwd(c, block_out(blk[2], st[2]), O, blk[3], st[3]));
   *obj_out = block_out(blk[3], st[3]);
   *pred_out = slice_cols(a2, H, D);
+  if (split) SLN_TRY(side_join_leaf(c));
   return SLN_OK;
 }
 
@@ -943,12 +963,12 @@ int sln_vae_decoder_fwd(const sln_vae_desc* d, const void* const* params, void* 
   SLN_TRY(gather_rows(c, m.emb[5], dm.attr_w, p.attrs32, O, dm.attr_w, p.obj0, dm.D, dm.obj_w));
   SLN_TRY(gather_rows(c, z, dm.Z, nullptr, O, dm.Z, p.obj0, dm.D, dm.obj_w + dm.attr_w));
   SLN_TRY(gather_rows(c, m.emb[6], dm.D, p.g.p_idx, T, dm.D, p.pred0, dm.D, 0));
+  side_begin(c);
   MatView obj_f;
   SLN_TRY(gconv_net_fwd(c, p, m.dec, make_view(p.obj0, dm.D, O, dm.D), make_view(p.pred0, dm.D, T, dm.D), &obj_f));
   // box_net on [obj_f | attr_vecs], angle_net on obj_f   (Sg2ScVAE_model.py:166-171)
   Concat2 cat{obj_f, make_view(p.obj0 + dm.obj_w, dm.D, O, dm.attr_w), O, dm.D + dm.attr_w};
   // box_net runs on the side stream while angle_net + log-softmax run on the chain (independent branches on obj_f)
-  side_begin(c);
   Ctx cb = c;
   cb.side = false;
   if (c.side) cb.st = side_fork(c);
