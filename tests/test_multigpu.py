@@ -118,10 +118,18 @@ def test_two_rank_sharded_step_equals_single_gpu_step(tmp_path, norm, policy):
             continue
         if k in degenerate or k.endswith("running_mean"):
             continue          # running_mean tracks mean(xW + b): it inherits the +-lr noise of the (zero-gradient) bias b; running_var does not
-        d = (v.double() - two["sd"][k].double()).abs().max().item()
+        diff = (v.double() - two["sd"][k].double()).abs()
         scale = max(v.abs().max().item(), 1e-3)
-        worst = max(worst, d / scale)
-        assert d <= 2e-5 * scale + 2e-6, (k, d, scale)
+        tol = torch.full_like(diff, 2e-5 * scale + 2e-6)
+        g = grads.get(k)
+        if g is not None and g.shape == v.shape:
+            # element-wise version of the same argument.  Adam moves an element by ~lr * g / |g| per step, so a gradient perturbation dg
+            # (check (1) bounds it by 2e-5 * gmax; the split-K weight gradients are fp32 atomics, i.e. run-to-run noise) shifts the element
+            # by ~lr * dg / |g| per step — up to ~2 lr where |g| is at the noise floor.  Elements with solid gradients stay tightly bound.
+            tol = tol + STEPS * 1e-3 * torch.clamp(4e-5 * gmax / g.double().abs().clamp_min(1e-30), max=2.2)
+        worst = max(worst, (diff / scale).max().item())
+        bad = diff > tol
+        assert not bool(bad.any()), (k, diff[bad].max().item(), scale, int(bad.sum()))
     assert len(degenerate) < len(grads) // 2
     assert all(torch.isfinite(torch.tensor(l)).all() for l in two["losses"])
     print("max relative parameter difference 2 ranks vs 1 GPU (%s, %s): %.2e" % (norm, policy, worst))
