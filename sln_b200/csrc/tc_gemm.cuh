@@ -4,15 +4,18 @@
 // 3xTF32 stays at the fp32 noise floor).  Every fp32 operand x is split on the fly into hi = tf32(x) and lo = tf32(x - hi)
 // and the tensor core accumulates  lo*hi + hi*lo + hi*hi  in fp32 in TMEM (short chains only, see "Accumulation scheme").
 //
-// Structure of one CTA (288 threads, tile 128 x BN, K consumed in chunks of 32 floats = one 128-byte swizzle row):
-//   8 PRODUCER warps read A/B through the same operand functors as the SIMT kernel (gather+concat, lazy BatchNorm+ReLU,
-//     BN-backward dy, transposed reads ...), split hi/lo in registers and write four K-major SWIZZLE_128B tiles
-//     (A_hi, A_lo, B_hi, B_lo) of a shared-memory stage, then publish it (fence.proxy.async + mbarrier arrive);
-//   a ninth warp is the MMA ISSUER: per stage 4 k-slices x 2 tcgen05.mma.kind::tf32 (M=128, N=2BN and N=BN, K=8) into TMEM
-//     accumulators, tcgen05.commit hands the stage back.  A ring of 3-4 stages decouples the two sides;
-//   EPILOGUE (the producer warps): tcgen05.ld 32x32b (thread = accumulator row, 32 columns at a time) -> staging in shared
-//     memory -> epilogue functor with lanes along the columns (bias / ReLU mask / BatchNorm column statistics / RED.ADD).
-// TMA is not used for the operands because every operand needs a per-element transform (gather, BN, hi/lo split) between
+// Structure of one CTA (544 threads, tile 128 x BN, K consumed in chunks of 32 floats = one 128-byte swizzle row):
+//   16 PRODUCER warps in two groups of 8 that take the chunks alternately.  A group reads A (and B, unless it is a pre-split
+//     image) through the same operand functors as the SIMT kernel (gather+concat, lazy BatchNorm+ReLU, BN-backward dy,
+//     transposed reads, im2col ...), splits hi/lo in registers and writes the K-major SWIZZLE_128B tiles (A_hi, A_lo, B_hi,
+//     B_lo) of a shared-memory stage, then publishes it (fence.proxy.async + mbarrier arrive); pre-split weight images
+//     (PackedB) arrive by cp.async.bulk onto the same mbarrier;
+//   a seventeenth warp is the MMA ISSUER: per stage 4 k-slices x 2 tcgen05.mma.kind::tf32 (M=128, N=2BN and N=BN, K=8) into
+//     TMEM accumulators, tcgen05.commit hands the stage back.  A ring of 3-4 stages decouples the two sides;
+//   EPILOGUE (the producer warps): tcgen05.ld 32x32b (thread = accumulator row, 32 or 16 columns at a time, the columns split
+//     over the warps' column groups) -> staging in shared memory -> epilogue functor with lanes along the columns (bias /
+//     ReLU mask / BatchNorm column statistics / RED.ADD / the paired SPADE modulation).
+// TMA tensor maps are not used for the activations because every such operand needs a per-element transform (gather, BN, hi/lo split) between
 // global memory and the tensor core; the stores are laid out so that each st.shared.v4 phase covers one full 128-byte row.
 #pragma once
 #include <stdlib.h>
@@ -46,7 +49,7 @@ constexpr int PROD_THREADS = PROD_WARPS * 32;
 #endif
 constexpr int PROD_GROUPS = SLN_TC_PROD_GROUPS;
 static_assert(PROD_WARPS % PROD_GROUPS == 0 && (PROD_WARPS / PROD_GROUPS) % 4 == 0, "producer groups must be whole multiples of 4 warps");
-constexpr int MMA_WARP = PROD_WARPS;        // the ninth warp issues the tcgen05.mma stream
+constexpr int MMA_WARP = PROD_WARPS;        // the warp after the producers issues the tcgen05.mma stream
 constexpr int THREADS = PROD_THREADS + 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -427,7 +430,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// One CTA = 8 producer/epilogue warps + 1 MMA warp, decoupled by mbarriers (no CTA-wide barrier in the main loop):
+// One CTA = PROD_WARPS producer/epilogue warps (in PROD_GROUPS groups) + 1 MMA warp, decoupled by mbarriers (no CTA-wide barrier in the main loop):
 //   producers   wait empty[s] -> transform + hi/lo split + st.shared of chunk c (fetched PF chunks earlier into registers)
 //               -> issue the global loads of chunk c+PF -> fence.proxy.async -> one arrive per warp on full[s];
 //   MMA warp    (one lane) wait full[s] -> 12 tcgen05.mma.kind::tf32 -> tcgen05.commit -> empty[s]  (-> segfull at segment ends);
@@ -448,7 +451,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_gemm_kernel(const AOp A, const 
   constexpr int PFG = PF / G > 0 ? PF / G : 1;     // chunks prefetched per thread of a group (PFG * G chunks in flight per CTA)
   extern __shared__ char smem_raw[];
   char* smem = (char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
-  float* stat = reinterpret_cast<float*>(smem + S * L::STAGE);             // [2][8][BN]
+  float* stat = reinterpret_cast<float*>(smem + S * L::STAGE);             // [2][PROD_WARPS][BN]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S * L::STAGE + L::STAT);
   uint64_t* empty = full + S;
   uint64_t* segfull = empty + S;
