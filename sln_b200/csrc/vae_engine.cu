@@ -76,16 +76,17 @@ struct Model {
 // Hazards: a dW kernel READS a masked-gradient buffer `g` that a later chain kernel overwrites (the g buffers are shared
 // by all layers), so every chain kernel that writes such a buffer first waits for the last side-stream reader of it.
 constexpr int kLeafStreams = 3;
+constexpr int kSideEvents = 256;
 struct Side {
   cudaStream_t st = nullptr;
   cudaStream_t leaf[kLeafStreams];   // the embedding-table gradients at the tail of a backward call: small independent kernels, one stream each
   int leaf_next = 0;
   unsigned leaf_used = 0u;
-  cudaEvent_t ev[64];
+  cudaEvent_t ev[kSideEvents];   // ring: far more than one backward call takes between a reader's record and the matching wait
   int next = 0;
   bool ready = false, active = false;
   std::unordered_map<const void*, cudaEvent_t> readers;
-  cudaEvent_t take() { cudaEvent_t e = ev[next]; next = (next + 1) % 64; return e; }
+  cudaEvent_t take() { cudaEvent_t e = ev[next]; next = (next + 1) % kSideEvents; return e; }
 };
 thread_local Side g_side;
 int g_side_enabled = -1;
@@ -118,7 +119,7 @@ void side_begin(Ctx& c) {
     if (cudaStreamCreateWithFlags(&sd.st, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return; }
     for (int i = 0; i < kLeafStreams; ++i)
       if (cudaStreamCreateWithFlags(&sd.leaf[i], cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); return; }
-    for (int i = 0; i < 64; ++i)
+    for (int i = 0; i < kSideEvents; ++i)
       if (cudaEventCreateWithFlags(&sd.ev[i], cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return; }
     sd.ready = true;
   }
