@@ -1,6 +1,7 @@
 """CPU-side checks of the drop-in boundary: the library builds for sm_100a, loads, and exports every declared symbol."""
 import ctypes
 import importlib
+import os
 
 import pytest
 import torch
@@ -98,3 +99,40 @@ def test_host_side_argument_checks_of_collate_refine_scene_entry_points():
     assert lib.sln_composite_workspace_bytes(32) > 0
     assert lib.sln_composite_fwd(dummy, dummy, 32, 65536, 40, dummy, 41, dummy, 29, dummy, dummy, dummy, 1 << 20, None) < 0   # wall >= C
     assert b"composite_fwd" in lib.sln_last_error()
+
+
+def test_ctypes_struct_mirrors_match_the_header_layout(tmp_path):
+    """sln_vae_desc / sln_bn_sync are passed by pointer across the C ABI: the ctypes mirrors in _lib.py must have the size and the field
+    offsets that a C compiler gives the header's structs (a field added on one side only would shift every later field silently)."""
+    import ctypes
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    _lib = importlib.import_module("sln_b200._lib")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mirrors = {"sln_vae_desc": _lib.VaeDesc, "sln_bn_sync": _lib.BnSync}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sln_b200.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)], check=True)   # the header is plain C
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for line in out:
+        if not line:
+            continue
+        cname, fname, val = line.split()
+        cls = mirrors[cname]
+        if fname == "size":
+            assert ctypes.sizeof(cls) == int(val), (cname, ctypes.sizeof(cls), val)
+        else:
+            assert getattr(cls, fname).offset == int(val), (cname, fname, getattr(cls, fname).offset, val)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in mirrors.values())
